@@ -1,0 +1,206 @@
+/*
+ * b200prune.h — C-ABI of the B200-native pruning hot path.
+ *
+ * Drop-in boundary for EIDOSLAB/pruning-for-vision-representation's pruning path.  The
+ * reference has no FFI of its own (pure Python over torch ops); each entry point below
+ * names the reference lines whose arithmetic it replaces.  A reference maintainer binds
+ * this header with ctypes; `pruning_for_vision_representation_b200`
+ * is that binding plus a mirror of the reference's Python functions.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller (PyTorch); h_* is host.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - all entry points are asynchronous w.r.t. the host unless they say "synchronises".
+ *   - return value: 0 on success, negative B200P_E* on failure; b200p_last_error() gives
+ *     a thread-local message.  There is no CPU fallback: without a CUDA device every
+ *     compute entry point fails with B200P_ECUDA.
+ *
+ * Data model ("plan")
+ *   The prunable parameter set is a list of T segments (one per nn.Conv2d / nn.Linear
+ *   weight, in model.named_modules() order — train.py:263-265, 333-336).  The virtual
+ *   flat index space is their concatenation (the reference's torch.cat, train.py:294 /
+ *   parameters_to_vector, torch/nn/utils/prune.py:1114).  Each segment is cut into
+ *   chunks of B200P_CHUNK elements; a chunk never spans two segments.  The bit-packed
+ *   mask has one 32-bit word per 32 elements, chunk-major: chunk c owns words
+ *   [c*128, c*128+128); bit (e & 31) of word (e >> 5) inside the chunk is element e.
+ *   Bits past a segment's last element are always 0.  Bit = 1 means "kept".
+ */
+#ifndef B200PRUNE_H_
+#define B200PRUNE_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200P_CHUNK            4096
+#define B200P_WORDS_PER_CHUNK  128
+
+#define B200P_OK        0
+#define B200P_EINVAL   -1   /* bad argument (shape / alignment / range)        */
+#define B200P_ECUDA    -2   /* CUDA runtime error or no device                   */
+#define B200P_ESTATE   -3   /* call sequence error (e.g. slot not bound)          */
+#define B200P_ENOMEM   -4
+
+/* pointer-table slots of a plan: one device pointer per segment */
+#define B200P_SLOT_W        0   /* fp32 weights (weight_orig)                              */
+#define B200P_SLOT_G        1   /* fp32 gradients                                          */
+#define B200P_SLOT_SCORE    2   /* fp32 accumulated SNIP scores                            */
+#define B200P_SLOT_BUF      3   /* fp32 SGD momentum buffers                               */
+#define B200P_SLOT_WEFF     4   /* fp32 effective (masked) weight = module.weight          */
+#define B200P_SLOT_MASKF    5   /* fp32 0/1 masks = module.weight_mask (checkpoint compat) */
+#define B200P_SLOT_WEFF16   6   /* bf16 effective weight for autocast forward              */
+#define B200P_NUM_SLOTS     8
+
+/* emit / select modes */
+#define B200P_MODE_SNIP_STRICT  0  /* keep = score > thr (every tie pruned): train.py:316          */
+#define B200P_MODE_EXACT_K      1  /* prune exactly k alive entries, ties lowest flat index first: */
+                                   /* prune.L1Unstructured, torch/nn/utils/prune.py:520-540        */
+
+/* key source for select / emit */
+#define B200P_KEY_ABS_W   0   /* key = |w|  (magnitude pruning; |.| is fused into the read) */
+#define B200P_KEY_SCORE   1   /* key = SCORE slot (SNIP)                                    */
+
+typedef struct b200p_plan b200p_plan;
+
+/* result block written by the select stage (device memory inside the workspace; copy it
+ * out with b200p_select_result).  Mirrors the Python float `threshold` of train.py:307
+ * plus the tie bookkeeping of SURVEY §8(c). */
+typedef struct b200p_select_result_t {
+    uint64_t k;          /* requested rank (1-based k-th smallest among alive keys)          */
+    uint64_t n_valid;    /* alive keys considered                                            */
+    uint64_t n_less;     /* alive keys strictly below the threshold                          */
+    uint64_t n_equal;    /* alive keys equal to the threshold                                */
+    uint64_t quota;      /* EXACT_K: how many of the tied keys are pruned (= k - n_less)     */
+    uint64_t n_kept;     /* kept bits after the last emit                                    */
+    float    threshold;  /* the k-th smallest key as fp32 (NaN if the rank falls on a NaN)   */
+    uint32_t thr_key;    /* its 31-bit integer key                                           */
+    uint32_t passes_full;/* how many full-data passes the select needed (2 or 3)             */
+    uint32_t collected;  /* candidates gathered in pass 2 (0 if histogram mode)              */
+} b200p_select_result_t;
+
+const char* b200p_last_error(void);
+int  b200p_version(void);
+/* number of visible CUDA devices (0 if none / driver missing); never fails */
+int  b200p_device_count(void);
+
+/* ---- plan ------------------------------------------------------------------------- */
+/* Build the chunk tables for T segments with the given element counts (host array).
+ * Allocates the small device tables and a workspace (histograms, select state, candidate
+ * buffer of `cand_capacity` entries; 0 = default max(1<<20, N/16)).  Synchronises. */
+int  b200p_plan_create(int device, int n_segments, const int64_t* h_numel,
+                       int64_t cand_capacity, b200p_plan** out);
+int  b200p_plan_destroy(b200p_plan* plan);
+int64_t b200p_plan_total(const b200p_plan* plan);        /* N = sum numel               */
+int64_t b200p_plan_num_chunks(const b200p_plan* plan);
+int64_t b200p_plan_mask_words(const b200p_plan* plan);   /* = num_chunks * 128            */
+int64_t b200p_plan_seg_chunk_start(const b200p_plan* plan, int seg); /* first chunk of seg */
+/* Upload one device pointer per segment for `slot`.  16-byte aligned pointers take the
+ * 128-bit vector path; anything else is accepted and runs the scalar path. */
+int  b200p_plan_bind(b200p_plan* plan, int slot, const void* const* h_ptrs, void* stream);
+/* device address of the 4096-bin uint64 histogram and of the select state, so that the
+ * host side can run NCCL collectives on them between stages */
+void* b200p_plan_hist_ptr(b200p_plan* plan);
+void* b200p_plan_state_ptr(b200p_plan* plan);
+
+/* ---- K1: importance scores (train.py:258-261, 282-291) ----------------------------- */
+/* SCORE[t] (=|+=) |W[t] * G[t]|   (accumulate=0 assigns, 1 adds) over chunks [c0,c1) */
+int  b200p_score_accumulate(b200p_plan* plan, int accumulate,
+                            int64_t chunk_begin, int64_t chunk_end, void* stream);
+
+/* ---- K2: global k-th smallest (train.py:299-307; prune.py:526-536) ----------------- */
+/* Whole select on one GPU: radix passes + scans, no host sync.  `d_old_mask` (nullable)
+ * restricts the key set to alive entries (iterative magnitude pruning, prune.py:368-370).
+ * k is the 1-based rank among alive keys, 1 <= k <= n_alive. */
+int  b200p_select_kth(b200p_plan* plan, int key_source, const uint32_t* d_old_mask,
+                      uint64_t k, int mode, void* stream);
+/* staged variant for parameter-sharded multi-GPU select: the caller runs
+ *   begin -> [hist(pass) -> allreduce(hist) -> scan(pass)] for pass = 0,1,2 -> finish
+ * over its own chunk range; hist/state pointers come from b200p_plan_hist_ptr/state_ptr. */
+int  b200p_select_begin(b200p_plan* plan, uint64_t k, int mode, int allow_collect, void* stream);
+int  b200p_select_hist(b200p_plan* plan, int pass, int key_source, const uint32_t* d_old_mask,
+                       int64_t chunk_begin, int64_t chunk_end, void* stream);
+int  b200p_select_scan(b200p_plan* plan, int pass, void* stream);
+/* EXACT_K tie resolution over chunks [c0,c1): `tie_offset` = number of tied keys that
+ * live in lower-numbered chunks owned by other ranks (0 on one GPU). */
+int  b200p_select_ties(b200p_plan* plan, int key_source, const uint32_t* d_old_mask,
+                       int64_t chunk_begin, int64_t chunk_end, uint64_t tie_offset, void* stream);
+/* copy the result block to the host.  Synchronises the stream. */
+int  b200p_select_result(b200p_plan* plan, b200p_select_result_t* h_out, void* stream);
+
+/* ---- K3: mask emit (train.py:311-317; prune.py:538, 1149-1161) ---------------------- */
+/* new_mask = old_mask & keep(key, threshold, mode).  Optional fused outputs when the
+ * corresponding slots are bound and requested: MASKF (fp32 0/1), WEFF (= mask ? W : 0).
+ * force: 0 = use the selected threshold, 1 = keep everything alive, 2 = prune everything,
+ *        3 = SNIP_STRICT against `forced_threshold` (train.py:300-303: +inf / -1). */
+#define B200P_EMIT_MASKF   1
+#define B200P_EMIT_WEFF    2
+int  b200p_emit_masks(b200p_plan* plan, int key_source, int mode, int force,
+                      float forced_threshold, const uint32_t* d_old_mask, uint32_t* d_new_mask,
+                      int outputs, int64_t chunk_begin, int64_t chunk_end, void* stream);
+
+/* ---- K5: sparsity (train.py:347-369) ------------------------------------------------ */
+/* d_out[0] = # elements with (mask bit == 0 or W == 0)  (d_mask nullable -> counts W == 0),
+ * d_out[1] = # mask bits set.  d_out is 2 x uint64 device memory, zeroed by the call. */
+int  b200p_count_zeros(b200p_plan* plan, const uint32_t* d_mask, uint64_t* d_out,
+                       int use_weights, void* stream);
+/* fp32 0/1 masks -> packed (checkpoint load) and packed -> fp32 MASKF slot */
+int  b200p_mask_pack_from_f32(b200p_plan* plan, uint32_t* d_mask, void* stream);
+int  b200p_mask_unpack_to_f32(b200p_plan* plan, const uint32_t* d_mask, void* stream);
+/* WEFF = mask ? W : 0 (the forward pre-hook of prune.py:71-74), optionally bf16 too */
+int  b200p_apply_mask(b200p_plan* plan, const uint32_t* d_mask, int outputs, void* stream);
+/* G = mask ? G : 0 (the MulBackward of the reparametrisation) */
+int  b200p_mask_grads(b200p_plan* plan, const uint32_t* d_mask, void* stream);
+
+/* ---- K4: fused masked SGD step (train.py:54-67; torch/optim/sgd.py:343-380) -------- */
+#define B200P_SGD_NESTEROV    1
+#define B200P_SGD_FIRST_STEP  2   /* momentum buffer is initialised to the gradient */
+#define B200P_SGD_EMIT_WEFF   4   /* also write WEFF   = mask ? w_new : 0           */
+#define B200P_SGD_EMIT_WEFF16 8   /* also write WEFF16 = bf16(mask ? w_new : 0)     */
+int  b200p_masked_sgd_step(b200p_plan* plan, const uint32_t* d_mask, float lr, float momentum,
+                           float dampening, float weight_decay, int flags, void* stream);
+
+/* ---- LOST (object_discovery.py:23-134) ---------------------------------------------- */
+/* Batched LOST over B images that share d.  Image b has n_b = dims[2b]*dims[2b+1] patch
+ * keys stored row-major at d_feats + feat_offset[b] (elements), row stride `row_stride`
+ * elements (so a qkv buffer can be read in place, main_lost_original.py:251-263).
+ * Outputs (device): degree int32 [sum n_b], seed int32 [B], box int32 [B,4]
+ * (xmin,ymin,xmax,ymax in pixels, object_discovery.py:120-128), status int32 [B]
+ * (0 ok, 1 = "The seed is in the background component", object_discovery.py:110-111).
+ * d_A (nullable): fp32 Gram matrices, image b at d_A + a_offset[b], n_b x n_b row-major.
+ * h_meta is a host array of B records; it is copied to the device by the call. */
+typedef struct b200p_lost_image_t {
+    int64_t feat_offset;   /* elements from d_feats                      */
+    int64_t a_offset;      /* elements from d_A (ignored if d_A == NULL) */
+    int64_t out_offset;    /* elements from d_degree                     */
+    int32_t dim0, dim1;    /* dims = [w_featmap, h_featmap] (object_discovery.py:97) */
+    int32_t img_h, img_w;  /* init_image_size[1:] (object_discovery.py:66,126-128)   */
+    float   scale0, scale1;/* scales (object_discovery.py:120-121)                   */
+} b200p_lost_image_t;
+
+#define B200P_LOST_GRAM_FFMA   0   /* fp32 CUDA-core Gram (reference-accurate, slow)        */
+#define B200P_LOST_GRAM_TC     1   /* tcgen05 3xTF32 error-compensated Gram (default)       */
+int  b200p_lost_workspace_bytes(int n_images, int64_t total_patches, int64_t total_a, int64_t* out);
+int  b200p_lost_batched(int device, const float* d_feats, int64_t row_stride, int d,
+                        const b200p_lost_image_t* h_meta, int n_images, int k_patches,
+                        float* d_A, int32_t* d_degree, int32_t* d_seed, float* d_box,
+                        int32_t* d_status, void* d_workspace, int64_t workspace_bytes,
+                        int gram_impl, void* stream);
+
+/* ---- host-buffer convenience entry points (the "e2e" path of bench.py) -------------- */
+/* Complete SNIP mask build from HOST buffers: weights h_w [N], B gradient sets h_g[b] [N]
+ * (flat, segment-concatenated, pinned or pageable), sparsity -> packed mask on the host.
+ * H2D copies are double-buffered against the score kernels.  Synchronises. */
+int  b200p_snip_mask_build_host(b200p_plan* plan, const float* h_w, const float* const* h_g,
+                                int n_batches, uint64_t k, uint32_t* h_mask_out,
+                                b200p_select_result_t* h_result);
+int  b200p_magnitude_mask_build_host(b200p_plan* plan, const float* h_w, const uint32_t* h_old_mask,
+                                     uint64_t k, uint32_t* h_mask_out,
+                                     b200p_select_result_t* h_result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* B200PRUNE_H_ */

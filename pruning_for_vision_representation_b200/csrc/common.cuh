@@ -1,0 +1,186 @@
+// common.cuh — shared device helpers and the plan object of the B200 pruning hot path.
+// sm_100a only.  See include/b200prune.h for the data model (segments, chunks, packed masks).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/b200prune.h"
+
+namespace b200p {
+
+constexpr int kChunk   = B200P_CHUNK;            // elements per chunk
+constexpr int kThreads = 256;                    // threads per CTA of the streaming kernels
+constexpr int kVecPerThread = kChunk / (4 * kThreads);   // float4 per thread per chunk = 4
+constexpr int kWordsPerChunk = B200P_WORDS_PER_CHUNK;
+constexpr int kHistBins = 4096;                  // 12-bit digits
+constexpr uint32_t kNanKey = 0x7FFFFFFFu;        // every NaN sorts last (torch.sort semantics)
+
+// digit layout of the 31-bit key: pass 0 -> bits 30..19, pass 1 -> bits 18..7, pass 2 -> bits 6..0
+__host__ __device__ __forceinline__ uint32_t digit_of(uint32_t key, int pass) {
+    return pass == 0 ? (key >> 19) : pass == 1 ? ((key >> 7) & 0xFFFu) : (key & 0x7Fu);
+}
+__host__ __device__ __forceinline__ int digit_bins(int pass) { return pass == 2 ? 128 : 4096; }
+// mask selecting the bits already fixed before `pass`
+__host__ __device__ __forceinline__ uint32_t prefix_mask_before(int pass) {
+    return pass == 0 ? 0u : pass == 1 ? 0x7FF80000u : 0x7FFFFF80u;
+}
+
+// key of a score / weight: bit pattern of |x|, NaN canonicalised to the maximum key.
+// For non-negative fp32 the integer order of the bit patterns is the float order.
+__device__ __forceinline__ uint32_t key_of(float x) {
+    uint32_t u = __float_as_uint(x) & 0x7FFFFFFFu;
+    return u > 0x7F800000u ? kNanKey : u;
+}
+__host__ __device__ __forceinline__ float key_to_float(uint32_t key) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(key == kNanKey ? 0x7FC00000u : key);
+#else
+    union { uint32_t u; float f; } c; c.u = (key == kNanKey ? 0x7FC00000u : key); return c.f;
+#endif
+}
+
+// device-side view of the segment / chunk tables
+struct SegView {
+    const int32_t* chunk_seg;        // [n_chunks]  segment of each chunk
+    const int64_t* seg_chunk_start;  // [n_seg + 1] first chunk of each segment
+    const int64_t* seg_numel;        // [n_seg]
+};
+
+struct ChunkInfo {
+    int     seg;     // segment index
+    int64_t elem0;   // first element of the chunk inside its segment
+    int     n;       // valid elements in the chunk (1..kChunk)
+};
+
+__device__ __forceinline__ ChunkInfo chunk_info(const SegView& sv, int64_t c) {
+    ChunkInfo ci;
+    ci.seg = sv.chunk_seg[c];
+    int64_t lc = c - sv.seg_chunk_start[ci.seg];
+    ci.elem0 = lc * kChunk;
+    int64_t rem = sv.seg_numel[ci.seg] - ci.elem0;
+    ci.n = rem < kChunk ? (int)rem : kChunk;
+    return ci;
+}
+
+// 128-bit streaming loads / stores.  Read-only streams go through the non-coherent path
+// without allocating in L1; read-modify-write streams use plain (coherent) accesses.
+__device__ __forceinline__ float4 ld_nc_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_f4(float* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Combine the 4-bit nibbles of 8 consecutive lanes into one 32-bit mask word.
+// Lane L contributes bits [4*(L&7), 4*(L&7)+4).  Every lane of the group of 8 returns the word.
+__device__ __forceinline__ uint32_t gather_nibbles(uint32_t nib) {
+    uint32_t v = (nib & 0xFu) << (4 * (threadIdx.x & 7));
+    v |= __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+    v |= __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+    v |= __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+    return v;
+}
+// nibble of this thread out of a mask word shared by its group of 8 lanes
+__device__ __forceinline__ uint32_t nibble_of(uint32_t word) {
+    return (word >> (4 * (threadIdx.x & 7))) & 0xFu;
+}
+// In the vector path thread `tid` owns float4 number v = j*kThreads + tid of the chunk
+// (elements 4v..4v+3); the mask word holding them is word v/8 = j*32 + tid/8.
+__device__ __forceinline__ int vec_word_index(int j) { return j * (kThreads / 8) + (threadIdx.x >> 3); }
+
+// select state kept in the plan workspace (device).  Host mirror: b200p_select_result_t.
+struct SelState {
+    unsigned long long k;            // 1-based rank still to find inside the current bucket
+    unsigned long long k_request;    // rank as requested
+    unsigned long long n_valid;      // alive keys
+    unsigned long long n_less;       // alive keys below the current bucket
+    unsigned long long n_equal;      // final: keys equal to the threshold
+    unsigned long long quota;        // final: tied keys to prune (EXACT_K)
+    unsigned long long n_kept;       // kept bits of the last emit
+    unsigned long long bucket_count; // population of the bucket chosen by the last scan
+    unsigned long long tie_seen;     // ties located in chunks before tie_chunk (tie pass)
+    long long          tie_chunk;    // chunk in which the quota runs out (-1: every tie pruned)
+    uint32_t prefix;                 // key bits fixed so far
+    uint32_t thr_key;                // final key
+    float    threshold;              // final fp32 threshold
+    uint32_t mode;                   // B200P_MODE_*
+    uint32_t collect;                // 1: pass-1 bucket was gathered into the candidate buffer
+    uint32_t allow_collect;
+    uint32_t cand_count;             // candidates gathered
+    uint32_t tie_resid;              // ties to prune inside tie_chunk
+    uint32_t need_ties;              // EXACT_K and quota < n_equal
+    uint32_t passes_full;            // full-data passes executed
+    uint32_t pad_[2];
+};
+
+}  // namespace b200p
+
+// ---------------------------------------------------------------------------------------
+// plan object (host)
+struct b200p_plan {
+    int device = 0;
+    int n_seg = 0;
+    int64_t total = 0;
+    int64_t n_chunks = 0;
+    int64_t cand_capacity = 0;
+    int num_sms = 148;
+    std::vector<int64_t> numel;
+    std::vector<int64_t> seg_chunk_start;   // n_seg + 1
+    std::vector<int64_t> seg_flat_start;    // n_seg + 1
+    // device tables
+    int32_t* d_chunk_seg = nullptr;
+    int64_t* d_seg_chunk_start = nullptr;
+    int64_t* d_seg_numel = nullptr;
+    void**   d_ptrs[B200P_NUM_SLOTS] = {nullptr};
+    bool     bound[B200P_NUM_SLOTS] = {false};
+    bool     vec_ok[B200P_NUM_SLOTS] = {false};
+    // workspace
+    unsigned long long* d_hist = nullptr;   // kHistBins
+    b200p::SelState*    d_state = nullptr;
+    uint32_t* d_cand_key = nullptr;         // cand_capacity
+    uint32_t* d_cand_pos = nullptr;         // cand_capacity   (chunk * kChunk + element)
+    uint32_t* d_chunk_ties = nullptr;       // n_chunks
+    // lazily created arena for the host-buffer entry points
+    float* arena_w = nullptr; float* arena_g[2] = {nullptr, nullptr}; float* arena_score = nullptr;
+    uint32_t* arena_mask = nullptr; uint32_t* arena_old_mask = nullptr;
+    cudaStream_t arena_streams[2] = {nullptr, nullptr};
+    cudaEvent_t  arena_events[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    b200p::SegView view() const {
+        b200p::SegView sv; sv.chunk_seg = d_chunk_seg; sv.seg_chunk_start = d_seg_chunk_start;
+        sv.seg_numel = d_seg_numel; return sv;
+    }
+    template <typename T> T* const* ptrs(int slot) const { return (T* const*)d_ptrs[slot]; }
+    int grid_for(int64_t chunks, int ctas_per_sm) const {
+        int64_t g = (int64_t)num_sms * ctas_per_sm;
+        if (g > chunks) g = chunks;
+        return g < 1 ? 1 : (int)g;
+    }
+};
+
+namespace b200p {
+void set_error(const std::string& msg);
+int  cuda_fail(cudaError_t e, const char* what);
+}  // namespace b200p
+
+#define B200P_CUDA(call)                                                        \
+    do { cudaError_t e__ = (call);                                              \
+         if (e__ != cudaSuccess) return b200p::cuda_fail(e__, #call); } while (0)
+#define B200P_REQUIRE(cond, code, msg)                                          \
+    do { if (!(cond)) { b200p::set_error(msg); return (code); } } while (0)
+#define B200P_LAUNCH_CHECK(name)                                                \
+    do { cudaError_t e__ = cudaGetLastError();                                  \
+         if (e__ != cudaSuccess) return b200p::cuda_fail(e__, name); } while (0)

@@ -1,0 +1,356 @@
+// emit.cu — K3 mask emit, K5 sparsity count, mask format conversions, mask apply.
+//
+// K3 replaces train.py:311-317 (mask = (score > thr).float(); custom_from_mask) and the
+// index_put of torch/nn/utils/prune.py:538 + per-tensor slicing :1149-1161.  The kernel-side
+// truth is the bit-packed mask (1/8 B per parameter); the fp32 `weight_mask` buffers and the
+// masked `weight` tensors that the reference's checkpoint format needs are optional fused
+// outputs of the same pass.
+#include "common.cuh"
+
+namespace b200p {
+
+struct EmitArgs {
+    const float* const* key_ptrs;    // |w| or score source
+    const float* const* w_ptrs;      // weights (for WEFF output), may equal key_ptrs
+    float* const* maskf_ptrs;        // optional fp32 mask output
+    float* const* weff_ptrs;         // optional masked weight output
+    const uint32_t* old_mask;        // nullable
+    uint32_t* new_mask;
+    SelState* st;
+    int mode;                        // B200P_MODE_*
+    int force;                       // 0 none, 1 keep all, 2 prune all, 3 strict vs forced_threshold
+    float forced_threshold;
+    int outputs;                     // B200P_EMIT_*
+    int vec_ok;
+};
+
+// keep decision for one element
+__device__ __forceinline__ bool keep_decision(float x, int mode, int force, float thr_f, uint32_t thr_key,
+                                              bool ties_pruned) {
+    if (force == 1) return true;
+    if (force == 2) return false;
+    if (mode == B200P_MODE_SNIP_STRICT || force == 3) return x > thr_f;       // NaN -> false (pruned)
+    const uint32_t key = key_of(x);
+    return key > thr_key || (key == thr_key && !ties_pruned);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_emit_masks(SegView sv, EmitArgs a, int64_t c_begin, int64_t c_end) {
+    __shared__ unsigned long long s_kept;
+    if (threadIdx.x == 0) s_kept = 0;
+    __syncthreads();
+    const int tid = threadIdx.x;
+    float thr_f = a.forced_threshold;
+    uint32_t thr_key = 0;
+    long long tie_chunk = -1;
+    uint32_t need_ties = 0, tie_resid = 0;
+    if (a.force == 0) {
+        thr_f = a.st->threshold; thr_key = a.st->thr_key;
+        if (a.mode == B200P_MODE_EXACT_K) { need_ties = a.st->need_ties; tie_chunk = a.st->tie_chunk; tie_resid = a.st->tie_resid; }
+    }
+    unsigned long long kept = 0;
+
+    for (int64_t c = c_begin + blockIdx.x; c < c_end; c += gridDim.x) {
+        const ChunkInfo ci = chunk_info(sv, c);
+        const float* __restrict__ src = a.key_ptrs[ci.seg] + ci.elem0;
+        const uint32_t* mold = a.old_mask ? a.old_mask + c * kWordsPerChunk : nullptr;
+        uint32_t* mnew = a.new_mask + c * kWordsPerChunk;
+        float* mf = (a.outputs & B200P_EMIT_MASKF) ? a.maskf_ptrs[ci.seg] + ci.elem0 : nullptr;
+        float* wf = (a.outputs & B200P_EMIT_WEFF) ? a.weff_ptrs[ci.seg] + ci.elem0 : nullptr;
+        const float* wsrc = wf ? a.w_ptrs[ci.seg] + ci.elem0 : nullptr;
+        // ties: pruned everywhere unless the quota runs out at/before this chunk
+        const bool ties_pruned = !need_ties || tie_chunk < 0 || c < tie_chunk;
+
+        if (a.vec_ok && ci.n == kChunk) {
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) {
+                const int e = 4 * (j * kThreads + tid);
+                const float4 v = ld_nc_f4(src + e);
+                uint32_t oldn = 0xFu;
+                if (mold) oldn = nibble_of(__ldg(mold + vec_word_index(j)));
+                uint32_t nib = 0;
+                nib |= keep_decision(v.x, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 1u : 0u;
+                nib |= keep_decision(v.y, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 2u : 0u;
+                nib |= keep_decision(v.z, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 4u : 0u;
+                nib |= keep_decision(v.w, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 8u : 0u;
+                nib &= oldn;
+                const uint32_t word = gather_nibbles(nib);
+                if ((tid & 7) == 0) { mnew[vec_word_index(j)] = word; kept += __popc(word); }
+                if (mf) {
+                    float4 m; m.x = (nib & 1u) ? 1.f : 0.f; m.y = (nib & 2u) ? 1.f : 0.f;
+                    m.z = (nib & 4u) ? 1.f : 0.f; m.w = (nib & 8u) ? 1.f : 0.f;
+                    st_f4(mf + e, m);
+                }
+                if (wf) {
+                    const float4 wv = (wsrc == src) ? v : ld_nc_f4(wsrc + e);
+                    float4 o; o.x = (nib & 1u) ? wv.x : 0.f; o.y = (nib & 2u) ? wv.y : 0.f;
+                    o.z = (nib & 4u) ? wv.z : 0.f; o.w = (nib & 8u) ? wv.w : 0.f;
+                    st_f4(wf + e, o);
+                }
+            }
+        } else {
+            // scalar path: one 32-element word per warp iteration, lane = bit
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int wd = warp; wd < kWordsPerChunk; wd += kThreads / 32) {
+                const int e = wd * 32 + lane;
+                bool keep = false;
+                float x = 0.f;
+                if (e < ci.n) {
+                    x = src[e];
+                    keep = keep_decision(x, a.mode, a.force, thr_f, thr_key, ties_pruned);
+                    if (mold) keep = keep && ((__ldg(mold + wd) >> lane) & 1u);
+                    if (mf) mf[e] = keep ? 1.f : 0.f;
+                    if (wf) wf[e] = keep ? wsrc[e] : 0.f;
+                }
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, keep);
+                if (lane == 0) { mnew[wd] = word; kept += __popc(word); }
+            }
+        }
+
+        if (need_ties && c == tie_chunk) {
+            // The quota runs out inside this chunk: the first tie_resid tied+alive elements (in
+            // element order) are pruned, the remaining ties of the chunk stay.  One warp walks
+            // the chunk in order; everything above wrote the ties of this chunk as kept.
+            __syncthreads();
+            if (tid < 32) {
+                uint32_t left = tie_resid;
+                for (int wd = 0; wd < kWordsPerChunk && left > 0; ++wd) {
+                    const int e = wd * 32 + tid;
+                    bool tie = false;
+                    if (e < ci.n) {
+                        tie = key_of(src[e]) == thr_key;
+                        if (mold) tie = tie && ((mold[wd] >> tid) & 1u);
+                    }
+                    const uint32_t tmask = __ballot_sync(0xFFFFFFFFu, tie);
+                    if (tmask == 0) continue;
+                    const uint32_t rank = __popc(tmask & ((1u << tid) - 1u));
+                    const bool drop = tie && rank < left;
+                    const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, drop);
+                    if (drop) { if (mf) mf[e] = 0.f; if (wf) wf[e] = 0.f; }
+                    if (tid == 0) { mnew[wd] &= ~dmask; kept -= __popc(dmask); }
+                    left -= __popc(dmask);
+                }
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xFFFFFFFFu, kept, o);
+    if ((tid & 31) == 0 && kept) atomicAdd(&s_kept, kept);
+    __syncthreads();
+    if (tid == 0 && s_kept) atomicAdd(&a.st->n_kept, s_kept);
+}
+
+// ---- K5: zeros of the effective weight ---------------------------------------------------
+// out[0] += #(bit == 0 || w == 0)   out[1] += #(bit == 1)
+__global__ void __launch_bounds__(kThreads)
+k_count_zeros(SegView sv, const float* const* __restrict__ w_ptrs, const uint32_t* __restrict__ mask,
+              unsigned long long* __restrict__ out, int64_t n_chunks, int vec_ok, int use_weights) {
+    __shared__ unsigned long long s_z, s_b;
+    if (threadIdx.x == 0) { s_z = 0; s_b = 0; }
+    __syncthreads();
+    const int tid = threadIdx.x;
+    unsigned long long zeros = 0, bits = 0;
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const ChunkInfo ci = chunk_info(sv, c);
+        const uint32_t* m = mask ? mask + c * kWordsPerChunk : nullptr;
+        if (!use_weights) {
+            // packed-only fast path: zeros = n - popcount
+            if (tid < kWordsPerChunk) {
+                const uint32_t w = m ? __ldg(m + tid) : 0u;
+                bits += __popc(w);
+            }
+            if (tid == 0) zeros += ci.n;     // corrected below by subtracting the bits
+            continue;
+        }
+        const float* __restrict__ w = w_ptrs[ci.seg] + ci.elem0;
+        if (vec_ok && ci.n == kChunk) {
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) {
+                const float4 v = ld_nc_f4(w + 4 * (j * kThreads + tid));
+                uint32_t nib = 0xFu;
+                if (m) nib = nibble_of(__ldg(m + vec_word_index(j)));
+                bits += __popc(nib);
+                zeros += ((nib & 1u) == 0 || v.x == 0.f) + ((nib & 2u) == 0 || v.y == 0.f) +
+                         ((nib & 4u) == 0 || v.z == 0.f) + ((nib & 8u) == 0 || v.w == 0.f);
+            }
+        } else {
+            for (int e = tid; e < ci.n; e += kThreads) {
+                uint32_t bit = 1u;
+                if (m) bit = (__ldg(m + (e >> 5)) >> (e & 31)) & 1u;
+                bits += bit;
+                zeros += (bit == 0 || w[e] == 0.f);
+            }
+        }
+    }
+    if (!use_weights) zeros = zeros - bits;   // per-thread partials may wrap; the 64-bit sum is exact
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        zeros += __shfl_xor_sync(0xFFFFFFFFu, zeros, o);
+        bits += __shfl_xor_sync(0xFFFFFFFFu, bits, o);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&s_z, zeros); atomicAdd(&s_b, bits); }
+    __syncthreads();
+    if (tid == 0) { atomicAdd(out + 0, s_z); atomicAdd(out + 1, s_b); }
+}
+
+// ---- conversions ---------------------------------------------------------------------------
+// DIR 0: MASKF (fp32 0/1) -> packed.   DIR 1: packed -> MASKF.
+// DIR 2: WEFF = bit ? W : 0 (and/or bf16).   DIR 3: G = bit ? G : 0.
+template <int DIR>
+__global__ void __launch_bounds__(kThreads)
+k_mask_convert(SegView sv, float* const* __restrict__ f_ptrs, const float* const* __restrict__ w_ptrs,
+               __nv_bfloat16* const* __restrict__ h_ptrs, uint32_t* __restrict__ mask, int64_t n_chunks,
+               int vec_ok, int outputs) {
+    const int tid = threadIdx.x;
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const ChunkInfo ci = chunk_info(sv, c);
+        uint32_t* m = mask + c * kWordsPerChunk;
+        float* f = f_ptrs ? f_ptrs[ci.seg] + ci.elem0 : nullptr;
+        const float* w = w_ptrs ? w_ptrs[ci.seg] + ci.elem0 : nullptr;
+        __nv_bfloat16* h = h_ptrs ? h_ptrs[ci.seg] + ci.elem0 : nullptr;
+        if (vec_ok && ci.n == kChunk) {
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) {
+                const int e = 4 * (j * kThreads + tid);
+                if (DIR == 0) {
+                    const float4 v = ld_nc_f4(f + e);
+                    const uint32_t nib = (v.x != 0.f ? 1u : 0u) | (v.y != 0.f ? 2u : 0u) | (v.z != 0.f ? 4u : 0u) | (v.w != 0.f ? 8u : 0u);
+                    const uint32_t word = gather_nibbles(nib);
+                    if ((tid & 7) == 0) m[vec_word_index(j)] = word;
+                } else {
+                    const uint32_t nib = nibble_of(__ldg(m + vec_word_index(j)));
+                    if (DIR == 1) {
+                        float4 o; o.x = (nib & 1u) ? 1.f : 0.f; o.y = (nib & 2u) ? 1.f : 0.f; o.z = (nib & 4u) ? 1.f : 0.f; o.w = (nib & 8u) ? 1.f : 0.f;
+                        st_f4(f + e, o);
+                    } else if (DIR == 2) {
+                        const float4 v = ld_nc_f4(w + e);
+                        float4 o; o.x = (nib & 1u) ? v.x : 0.f; o.y = (nib & 2u) ? v.y : 0.f; o.z = (nib & 4u) ? v.z : 0.f; o.w = (nib & 8u) ? v.w : 0.f;
+                        if (outputs & B200P_EMIT_WEFF) st_f4(f + e, o);
+                        if (h) {
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                            *reinterpret_cast<uint2*>(h + e) = pk;
+                        }
+                    } else {
+                        float4 v = ld_f4(f + e);
+                        v.x = (nib & 1u) ? v.x : 0.f; v.y = (nib & 2u) ? v.y : 0.f; v.z = (nib & 4u) ? v.z : 0.f; v.w = (nib & 8u) ? v.w : 0.f;
+                        st_f4(f + e, v);
+                    }
+                }
+            }
+        } else {
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int wd = warp; wd < kWordsPerChunk; wd += kThreads / 32) {
+                const int e = wd * 32 + lane;
+                if (DIR == 0) {
+                    const bool on = e < ci.n && f[e] != 0.f;
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, on);
+                    if (lane == 0) m[wd] = word;
+                } else if (e < ci.n) {
+                    const bool on = (__ldg(m + wd) >> lane) & 1u;
+                    if (DIR == 1) f[e] = on ? 1.f : 0.f;
+                    else if (DIR == 2) {
+                        const float o = on ? w[e] : 0.f;
+                        if (outputs & B200P_EMIT_WEFF) f[e] = o;
+                        if (h) h[e] = __float2bfloat16_rn(o);
+                    } else f[e] = on ? f[e] : 0.f;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace b200p
+
+using namespace b200p;
+
+extern "C" int b200p_emit_masks(b200p_plan* p, int key_source, int mode, int force, float forced_threshold,
+                                const uint32_t* d_old_mask, uint32_t* d_new_mask, int outputs,
+                                int64_t chunk_begin, int64_t chunk_end, void* stream) {
+    B200P_REQUIRE(p != nullptr && d_new_mask != nullptr, B200P_EINVAL, "emit_masks: null argument");
+    B200P_REQUIRE(key_source == B200P_KEY_ABS_W || key_source == B200P_KEY_SCORE, B200P_EINVAL, "emit_masks: bad key_source");
+    B200P_REQUIRE(mode == B200P_MODE_SNIP_STRICT || mode == B200P_MODE_EXACT_K, B200P_EINVAL, "emit_masks: bad mode");
+    B200P_REQUIRE(force >= 0 && force <= 3, B200P_EINVAL, "emit_masks: bad force");
+    const int kslot = key_source == B200P_KEY_ABS_W ? B200P_SLOT_W : B200P_SLOT_SCORE;
+    B200P_REQUIRE(p->bound[kslot], B200P_ESTATE, "emit_masks: key slot is not bound");
+    if (outputs & B200P_EMIT_MASKF) B200P_REQUIRE(p->bound[B200P_SLOT_MASKF], B200P_ESTATE, "emit_masks: MASKF slot is not bound");
+    if (outputs & B200P_EMIT_WEFF) B200P_REQUIRE(p->bound[B200P_SLOT_WEFF] && p->bound[B200P_SLOT_W], B200P_ESTATE, "emit_masks: WEFF/W slots are not bound");
+    if (chunk_end < 0) chunk_end = p->n_chunks;
+    B200P_REQUIRE(chunk_begin >= 0 && chunk_begin <= chunk_end && chunk_end <= p->n_chunks, B200P_EINVAL, "emit_masks: bad chunk range");
+    B200P_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    B200P_CUDA(cudaMemsetAsync(&p->d_state->n_kept, 0, sizeof(unsigned long long), st));
+    if (chunk_begin == chunk_end) return B200P_OK;
+    EmitArgs a;
+    a.key_ptrs = p->ptrs<const float>(kslot);
+    a.w_ptrs = p->ptrs<const float>(B200P_SLOT_W);
+    a.maskf_ptrs = p->ptrs<float>(B200P_SLOT_MASKF);
+    a.weff_ptrs = p->ptrs<float>(B200P_SLOT_WEFF);
+    a.old_mask = d_old_mask; a.new_mask = d_new_mask; a.st = p->d_state;
+    a.mode = mode; a.force = force; a.forced_threshold = forced_threshold; a.outputs = outputs;
+    bool vec = p->vec_ok[kslot];
+    if (outputs & B200P_EMIT_MASKF) vec = vec && p->vec_ok[B200P_SLOT_MASKF];
+    if (outputs & B200P_EMIT_WEFF) vec = vec && p->vec_ok[B200P_SLOT_WEFF] && p->vec_ok[B200P_SLOT_W];
+    a.vec_ok = vec ? 1 : 0;
+    k_emit_masks<<<p->grid_for(chunk_end - chunk_begin, 4), kThreads, 0, st>>>(p->view(), a, chunk_begin, chunk_end);
+    B200P_LAUNCH_CHECK("k_emit_masks");
+    return B200P_OK;
+}
+
+extern "C" int b200p_count_zeros(b200p_plan* p, const uint32_t* d_mask, uint64_t* d_out, int use_weights, void* stream) {
+    B200P_REQUIRE(p != nullptr && d_out != nullptr, B200P_EINVAL, "count_zeros: null argument");
+    B200P_REQUIRE(use_weights || d_mask, B200P_EINVAL, "count_zeros: need a mask or the weights");
+    if (use_weights) B200P_REQUIRE(p->bound[B200P_SLOT_WEFF] || p->bound[B200P_SLOT_W], B200P_ESTATE, "count_zeros: W slot is not bound");
+    B200P_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    B200P_CUDA(cudaMemsetAsync(d_out, 0, 2 * sizeof(uint64_t), st));
+    k_count_zeros<<<p->grid_for(p->n_chunks, 4), kThreads, 0, st>>>(p->view(), p->ptrs<const float>(B200P_SLOT_W), d_mask,
+        (unsigned long long*)d_out, p->n_chunks, p->vec_ok[B200P_SLOT_W] ? 1 : 0, use_weights);
+    B200P_LAUNCH_CHECK("k_count_zeros");
+    return B200P_OK;
+}
+
+extern "C" int b200p_mask_pack_from_f32(b200p_plan* p, uint32_t* d_mask, void* stream) {
+    B200P_REQUIRE(p != nullptr && d_mask != nullptr, B200P_EINVAL, "mask_pack: null argument");
+    B200P_REQUIRE(p->bound[B200P_SLOT_MASKF], B200P_ESTATE, "mask_pack: MASKF slot is not bound");
+    B200P_CUDA(cudaSetDevice(p->device));
+    k_mask_convert<0><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->view(), p->ptrs<float>(B200P_SLOT_MASKF),
+        nullptr, nullptr, d_mask, p->n_chunks, p->vec_ok[B200P_SLOT_MASKF] ? 1 : 0, 0);
+    B200P_LAUNCH_CHECK("k_mask_convert<0>");
+    return B200P_OK;
+}
+extern "C" int b200p_mask_unpack_to_f32(b200p_plan* p, const uint32_t* d_mask, void* stream) {
+    B200P_REQUIRE(p != nullptr && d_mask != nullptr, B200P_EINVAL, "mask_unpack: null argument");
+    B200P_REQUIRE(p->bound[B200P_SLOT_MASKF], B200P_ESTATE, "mask_unpack: MASKF slot is not bound");
+    B200P_CUDA(cudaSetDevice(p->device));
+    k_mask_convert<1><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->view(), p->ptrs<float>(B200P_SLOT_MASKF),
+        nullptr, nullptr, const_cast<uint32_t*>(d_mask), p->n_chunks, p->vec_ok[B200P_SLOT_MASKF] ? 1 : 0, 0);
+    B200P_LAUNCH_CHECK("k_mask_convert<1>");
+    return B200P_OK;
+}
+extern "C" int b200p_apply_mask(b200p_plan* p, const uint32_t* d_mask, int outputs, void* stream) {
+    B200P_REQUIRE(p != nullptr && d_mask != nullptr, B200P_EINVAL, "apply_mask: null argument");
+    B200P_REQUIRE(p->bound[B200P_SLOT_W], B200P_ESTATE, "apply_mask: W slot is not bound");
+    const bool want32 = outputs & B200P_EMIT_WEFF, want16 = outputs & B200P_SGD_EMIT_WEFF16;
+    B200P_REQUIRE(want32 || want16, B200P_EINVAL, "apply_mask: no output requested");
+    if (want32) B200P_REQUIRE(p->bound[B200P_SLOT_WEFF], B200P_ESTATE, "apply_mask: WEFF slot is not bound");
+    if (want16) B200P_REQUIRE(p->bound[B200P_SLOT_WEFF16], B200P_ESTATE, "apply_mask: WEFF16 slot is not bound");
+    B200P_CUDA(cudaSetDevice(p->device));
+    bool vec = p->vec_ok[B200P_SLOT_W] && (!want32 || p->vec_ok[B200P_SLOT_WEFF]) && (!want16 || p->vec_ok[B200P_SLOT_WEFF16]);
+    k_mask_convert<2><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->view(),
+        want32 ? p->ptrs<float>(B200P_SLOT_WEFF) : nullptr, p->ptrs<const float>(B200P_SLOT_W),
+        want16 ? p->ptrs<__nv_bfloat16>(B200P_SLOT_WEFF16) : nullptr, const_cast<uint32_t*>(d_mask), p->n_chunks,
+        vec ? 1 : 0, want32 ? B200P_EMIT_WEFF : 0);
+    B200P_LAUNCH_CHECK("k_mask_convert<2>");
+    return B200P_OK;
+}
+extern "C" int b200p_mask_grads(b200p_plan* p, const uint32_t* d_mask, void* stream) {
+    B200P_REQUIRE(p != nullptr && d_mask != nullptr, B200P_EINVAL, "mask_grads: null argument");
+    B200P_REQUIRE(p->bound[B200P_SLOT_G], B200P_ESTATE, "mask_grads: G slot is not bound");
+    B200P_CUDA(cudaSetDevice(p->device));
+    k_mask_convert<3><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->view(), p->ptrs<float>(B200P_SLOT_G),
+        nullptr, nullptr, const_cast<uint32_t*>(d_mask), p->n_chunks, p->vec_ok[B200P_SLOT_G] ? 1 : 0, 0);
+    B200P_LAUNCH_CHECK("k_mask_convert<3>");
+    return B200P_OK;
+}

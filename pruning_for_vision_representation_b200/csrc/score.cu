@@ -1,0 +1,84 @@
+// score.cu — K1: SNIP importance score accumulation.
+//   SCORE (=|+=) |W * G|      reference: train.py:258-261 (|g|), train.py:289 (|w| * |g|)
+// |w|*|g| == |w*g| bit-for-bit in IEEE fp32 (one correctly rounded multiply, sign-symmetric),
+// so one multiply and one sign clear replace the reference's abs, clone, abs, mul.
+// HBM-bound stream: 16 B / parameter / mini-batch (read w, g, score; write score).
+#include "common.cuh"
+
+namespace b200p {
+
+template <bool ACCUMULATE, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+k_score_accumulate(SegView sv, const float* const* __restrict__ w_ptrs,
+                   const float* const* __restrict__ g_ptrs, float* const* __restrict__ s_ptrs,
+                   int64_t c_begin, int64_t c_end) {
+    const int tid = threadIdx.x;
+    for (int64_t c = c_begin + blockIdx.x; c < c_end; c += gridDim.x) {
+        const ChunkInfo ci = chunk_info(sv, c);
+        const float* __restrict__ w = w_ptrs[ci.seg] + ci.elem0;
+        const float* __restrict__ g = g_ptrs[ci.seg] + ci.elem0;
+        float* __restrict__ s = s_ptrs[ci.seg] + ci.elem0;
+        if (VEC && ci.n == kChunk) {
+            float4 wv[kVecPerThread], gv[kVecPerThread], sv4[kVecPerThread];
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) {
+                const int e = 4 * (j * kThreads + tid);
+                wv[j] = ld_nc_f4(w + e);
+                gv[j] = ld_nc_f4(g + e);
+                if (ACCUMULATE) sv4[j] = ld_f4(s + e);
+            }
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) {
+                const int e = 4 * (j * kThreads + tid);
+                float4 r;
+                r.x = fabsf(__fmul_rn(wv[j].x, gv[j].x));
+                r.y = fabsf(__fmul_rn(wv[j].y, gv[j].y));
+                r.z = fabsf(__fmul_rn(wv[j].z, gv[j].z));
+                r.w = fabsf(__fmul_rn(wv[j].w, gv[j].w));
+                if (ACCUMULATE) {
+                    r.x = __fadd_rn(sv4[j].x, r.x); r.y = __fadd_rn(sv4[j].y, r.y);
+                    r.z = __fadd_rn(sv4[j].z, r.z); r.w = __fadd_rn(sv4[j].w, r.w);
+                }
+                st_f4(s + e, r);
+            }
+        } else {
+            for (int e = tid; e < ci.n; e += kThreads) {
+                float r = fabsf(__fmul_rn(w[e], g[e]));
+                if (ACCUMULATE) r = __fadd_rn(s[e], r);
+                s[e] = r;
+            }
+        }
+    }
+}
+
+}  // namespace b200p
+
+using namespace b200p;
+
+extern "C" int b200p_score_accumulate(b200p_plan* p, int accumulate, int64_t chunk_begin,
+                                      int64_t chunk_end, void* stream) {
+    B200P_REQUIRE(p != nullptr, B200P_EINVAL, "score_accumulate: null plan");
+    B200P_REQUIRE(p->bound[B200P_SLOT_W] && p->bound[B200P_SLOT_G] && p->bound[B200P_SLOT_SCORE],
+                  B200P_ESTATE, "score_accumulate: W, G and SCORE slots must be bound");
+    if (chunk_end < 0) chunk_end = p->n_chunks;
+    B200P_REQUIRE(chunk_begin >= 0 && chunk_begin <= chunk_end && chunk_end <= p->n_chunks,
+                  B200P_EINVAL, "score_accumulate: bad chunk range");
+    if (chunk_begin == chunk_end) return B200P_OK;
+    B200P_CUDA(cudaSetDevice(p->device));
+    const bool vec = p->vec_ok[B200P_SLOT_W] && p->vec_ok[B200P_SLOT_G] && p->vec_ok[B200P_SLOT_SCORE];
+    const int grid = p->grid_for(chunk_end - chunk_begin, 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto w = p->ptrs<const float>(B200P_SLOT_W);
+    auto g = p->ptrs<const float>(B200P_SLOT_G);
+    auto s = p->ptrs<float>(B200P_SLOT_SCORE);
+    SegView sv = p->view();
+    if (accumulate) {
+        if (vec) k_score_accumulate<true, true><<<grid, kThreads, 0, st>>>(sv, w, g, s, chunk_begin, chunk_end);
+        else     k_score_accumulate<true, false><<<grid, kThreads, 0, st>>>(sv, w, g, s, chunk_begin, chunk_end);
+    } else {
+        if (vec) k_score_accumulate<false, true><<<grid, kThreads, 0, st>>>(sv, w, g, s, chunk_begin, chunk_end);
+        else     k_score_accumulate<false, false><<<grid, kThreads, 0, st>>>(sv, w, g, s, chunk_begin, chunk_end);
+    }
+    B200P_LAUNCH_CHECK("k_score_accumulate");
+    return B200P_OK;
+}

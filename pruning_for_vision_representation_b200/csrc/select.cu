@@ -1,0 +1,507 @@
+// select.cu — K2: global k-th smallest key by multi-pass MSD radix select.
+//
+// Replaces the full torch.sort of train.py:306-307 (SNIP) and the torch.topk of
+// torch/nn/utils/prune.py:536 (global magnitude): only the k-th smallest key and the
+// tie counts are needed, never the order.
+//
+// Keys are the 31-bit patterns of non-negative fp32 values (|w| or the SNIP score); NaN is
+// canonicalised to the largest key (torch.sort / topk place NaN last).  Three digits:
+//   pass 0: bits 30..19 (exponent + 4 mantissa bits, 4096 bins) over ALL alive keys
+//   pass 1: bits 18..7  (4096 bins)   pass 2: bits 6..0 (128 bins)
+// After pass 0 the bucket that holds rank k is known.  If it fits the candidate buffer the
+// second full-data pass gathers its (key, position) pairs ("collect" mode) and passes 1/2
+// run on that small list; otherwise passes 1 and 2 re-stream the full data ("histogram"
+// mode, degenerate inputs such as a constant tensor).  Per-CTA shared-memory histograms
+// are flushed with one global atomic per non-empty bin; the last CTA to finish (ticket
+// counter) scans the histogram and advances the select state, so no host round trip and
+// no extra launch is needed between passes.  The staged entry points (hist / scan
+// separately) exist so that a parameter-sharded multi-GPU select can all-reduce the
+// histogram between them.
+#include "common.cuh"
+
+namespace b200p {
+
+constexpr int kScanThreads = kThreads;           // the scan runs inside the last CTA
+constexpr int kBinsPerThread = kHistBins / kScanThreads;   // 16
+
+// ---- per-thread view of one chunk ------------------------------------------------------
+// VEC path:    slot i = 4*j+q  <->  element 4*(j*kThreads+tid)+q
+// scalar path: slot i          <->  element i*kThreads+tid
+template <bool VEC>
+__device__ __forceinline__ int slot_element(int i) {
+    return VEC ? 4 * ((i >> 2) * kThreads + threadIdx.x) + (i & 3) : i * kThreads + threadIdx.x;
+}
+
+// Loads the 16 keys this thread owns and a 16-bit "alive" bitmap (valid element, old mask set).
+template <bool VEC, bool ABS_ONLY = true>
+__device__ __forceinline__ void load_keys(const float* __restrict__ src, const uint32_t* __restrict__ mask_chunk,
+                                          int n, uint32_t (&key)[16], uint32_t& alive) {
+    alive = 0;
+    if (VEC) {
+#pragma unroll
+        for (int j = 0; j < kVecPerThread; ++j) {
+            const float4 v = ld_nc_f4(src + 4 * (j * kThreads + threadIdx.x));
+            key[4 * j + 0] = key_of(v.x); key[4 * j + 1] = key_of(v.y);
+            key[4 * j + 2] = key_of(v.z); key[4 * j + 3] = key_of(v.w);
+            uint32_t nib = 0xFu;
+            if (mask_chunk) nib = nibble_of(__ldg(mask_chunk + vec_word_index(j)));
+            alive |= nib << (4 * j);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = i * kThreads + threadIdx.x;
+            key[i] = 0;
+            if (e < n) {
+                key[i] = key_of(src[e]);
+                uint32_t bit = 1u;
+                if (mask_chunk) bit = (__ldg(mask_chunk + (e >> 5)) >> (e & 31)) & 1u;
+                alive |= bit << i;
+            }
+        }
+    }
+}
+
+// ---- scan of the global histogram by one CTA -------------------------------------------
+// Finds the bin that holds rank st->k, advances the state, clears the histogram.
+__device__ void scan_and_advance(int pass, unsigned long long* __restrict__ hist, SelState* __restrict__ st,
+                                 long long cand_capacity) {
+    __shared__ unsigned long long s_warp[kScanThreads / 32];
+    __shared__ unsigned long long s_total;
+    const int tid = threadIdx.x;
+    const int bins = digit_bins(pass);
+    unsigned long long local[kBinsPerThread];
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) {
+        const int b = tid * kBinsPerThread + i;
+        // volatile: the counts were produced by other CTAs' atomics (L2), never cached in L1
+        local[i] = b < bins ? ((volatile unsigned long long*)hist)[b] : 0ull;
+        sum += local[i];
+    }
+    // block exclusive scan of `sum`
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((tid & 31) >= o) incl += v;
+    }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        unsigned long long v = tid < kScanThreads / 32 ? s_warp[tid] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (tid >= o) inc += u;
+        }
+        if (tid < kScanThreads / 32) s_warp[tid] = inc - v;   // exclusive warp offsets
+        if (tid == kScanThreads / 32 - 1) s_total = inc;
+    }
+    __syncthreads();
+    unsigned long long running = s_warp[tid >> 5] + (incl - sum);
+    const unsigned long long total = s_total;
+    const unsigned long long k = st->k;
+    const uint32_t prefix = st->prefix;
+    __syncthreads();   // everyone has read the state before anyone writes it
+    if (pass == 0 && tid == 0) st->n_valid = total;
+    const int shift = pass == 0 ? 19 : pass == 1 ? 7 : 0;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) {
+        const int b = tid * kBinsPerThread + i;
+        if (!found && b < bins && local[i] != 0 && running < k && k <= running + local[i]) {
+            found = true;
+            st->n_less += running;
+            st->k = k - running;
+            st->bucket_count = local[i];
+            const uint32_t np = prefix | ((uint32_t)b << shift);
+            st->prefix = np;
+            if (pass == 0) {
+                st->collect = (st->allow_collect && local[i] <= (unsigned long long)cand_capacity) ? 1u : 0u;
+                st->cand_count = 0;
+            }
+            if (pass == 2) {
+                st->thr_key = np;
+                st->threshold = key_to_float(np);
+                st->n_equal = local[i];
+                st->quota = k - running;
+                st->need_ties = (st->mode == B200P_MODE_EXACT_K && (k - running) < local[i]) ? 1u : 0u;
+                st->tie_chunk = -1;
+                st->tie_resid = 0;
+                st->tie_seen = 0;
+            }
+        }
+        running += local[i];
+    }
+    if (tid == 0 && (k == 0 || k > total)) {
+        // rank outside the key set (host error): report the largest key so that nothing
+        // above it survives a strict compare; n_equal = 0 flags the condition.
+        st->prefix = kNanKey; st->thr_key = kNanKey; st->threshold = key_to_float(kNanKey);
+        st->bucket_count = 0; st->n_equal = 0; st->quota = 0; st->need_ties = 0; st->collect = 0;
+        st->tie_chunk = -1;
+    }
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) {
+        const int b = tid * kBinsPerThread + i;
+        if (b < kHistBins) hist[b] = 0ull;
+    }
+}
+
+// flush the CTA histogram and, if this is the last CTA, run the scan
+__device__ __forceinline__ void flush_and_maybe_scan(int pass, const uint32_t* s_hist,
+                                                     unsigned long long* hist, SelState* st,
+                                                     unsigned int* ticket, long long cand_capacity,
+                                                     bool fuse_scan) {
+    const int bins = digit_bins(pass);
+    for (int b = threadIdx.x; b < bins; b += kThreads) {
+        const uint32_t v = s_hist[b];
+        if (v) atomicAdd(hist + b, (unsigned long long)v);
+    }
+    if (!fuse_scan) return;
+    __shared__ unsigned int s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1) {
+        __threadfence();
+        scan_and_advance(pass, hist, st, cand_capacity);
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+// ---- full-data pass --------------------------------------------------------------------
+// PASS 0: histogram digit 0 of every alive key.
+// PASS 1: keys whose digit 0 matches the chosen bucket: gather (collect mode) or histogram.
+// PASS 2: (histogram mode only) keys matching 24 fixed bits: histogram digit 2.
+template <int PASS>
+__global__ void __launch_bounds__(kThreads)
+k_select_pass_full(SegView sv, const float* const* __restrict__ key_ptrs, const uint32_t* __restrict__ old_mask,
+                   unsigned long long* __restrict__ hist, SelState* __restrict__ st,
+                   uint32_t* __restrict__ cand_key, uint32_t* __restrict__ cand_pos, unsigned int* __restrict__ ticket,
+                   long long cand_capacity, int64_t c_begin, int64_t c_end, int vec_ok, int fuse_scan) {
+    __shared__ uint32_t s_hist[kHistBins];
+    uint32_t prefix = 0, collect = 0;
+    if (PASS > 0) {
+        prefix = st->prefix; collect = st->collect;
+        if (PASS == 2 && collect) return;            // candidates carry passes 1 and 2
+    }
+    const bool do_hist = !(PASS == 1 && collect);
+    if (do_hist) {
+        for (int b = threadIdx.x; b < kHistBins; b += kThreads) s_hist[b] = 0;
+        __syncthreads();
+    }
+    const uint32_t pmask = prefix_mask_before(PASS);
+    const int lane = threadIdx.x & 31;
+
+    for (int64_t c = c_begin + blockIdx.x; c < c_end; c += gridDim.x) {
+        const ChunkInfo ci = chunk_info(sv, c);
+        const float* __restrict__ src = key_ptrs[ci.seg] + ci.elem0;
+        const uint32_t* mchunk = old_mask ? old_mask + c * kWordsPerChunk : nullptr;
+        uint32_t key[16], alive;
+        const bool vec = vec_ok && ci.n == kChunk;
+        if (vec) load_keys<true>(src, mchunk, ci.n, key, alive);
+        else     load_keys<false>(src, mchunk, ci.n, key, alive);
+
+        if (PASS == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if ((alive >> i) & 1u) atomicAdd(&s_hist[key[i] >> 19], 1u);
+        } else {
+            uint32_t match = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (((alive >> i) & 1u) && ((key[i] & pmask) == prefix)) match |= 1u << i;
+            if (do_hist) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if ((match >> i) & 1u) atomicAdd(&s_hist[digit_of(key[i], PASS)], 1u);
+            } else {
+                // warp-aggregated append of (key, position) pairs
+                const int cnt = __popc(match);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                if (warp_total > 0) {
+                    uint32_t base = 0;
+                    if (lane == 31) base = atomicAdd(&st->cand_count, (uint32_t)warp_total);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 31);
+                    uint32_t off = base + (uint32_t)(incl - cnt);
+                    const uint32_t pos0 = (uint32_t)(c * kChunk);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if ((match >> i) & 1u) {
+                            if ((long long)off < cand_capacity) {
+                                cand_key[off] = key[i];
+                                cand_pos[off] = pos0 + (uint32_t)(vec ? slot_element<true>(i) : slot_element<false>(i));
+                            }
+                            ++off;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (do_hist) {
+        __syncthreads();
+        flush_and_maybe_scan(PASS, s_hist, hist, st, ticket, cand_capacity, fuse_scan != 0);
+    }
+}
+
+// ---- candidate passes (collect mode) ---------------------------------------------------
+template <int PASS>
+__global__ void __launch_bounds__(kThreads)
+k_select_pass_cand(const uint32_t* __restrict__ cand_key, unsigned long long* __restrict__ hist,
+                   SelState* __restrict__ st, unsigned int* __restrict__ ticket, long long cand_capacity,
+                   int fuse_scan) {
+    __shared__ uint32_t s_hist[kHistBins];
+    if (!st->collect) return;
+    const uint32_t n = st->cand_count;
+    const uint32_t prefix = st->prefix;
+    const uint32_t pmask = prefix_mask_before(PASS);
+    const int bins = digit_bins(PASS);
+    for (int b = threadIdx.x; b < bins; b += kThreads) s_hist[b] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const uint32_t key = cand_key[i];
+        if ((key & pmask) == prefix) atomicAdd(&s_hist[digit_of(key, PASS)], 1u);
+    }
+    __syncthreads();
+    flush_and_maybe_scan(PASS, s_hist, hist, st, ticket, cand_capacity, fuse_scan != 0);
+}
+
+__global__ void k_select_scan(int pass, unsigned long long* hist, SelState* st, long long cand_capacity) {
+    scan_and_advance(pass, hist, st, cand_capacity);
+}
+
+__global__ void k_select_init(SelState* st, unsigned long long* hist, unsigned int* ticket,
+                              unsigned long long k, uint32_t mode, uint32_t allow_collect) {
+    for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) hist[b] = 0ull;
+    if (threadIdx.x == 0) {
+        SelState s;
+        memset(&s, 0, sizeof(s));
+        s.k = k; s.k_request = k; s.mode = mode; s.allow_collect = allow_collect; s.tie_chunk = -1;
+        *st = s;
+        *ticket = 0u;
+    }
+}
+
+// ---- tie resolution (EXACT_K with quota < n_equal) ---------------------------------------
+// chunk_ties[c] = number of alive keys == threshold in chunk c
+__global__ void __launch_bounds__(kThreads)
+k_tie_count_full(SegView sv, const float* const* __restrict__ key_ptrs, const uint32_t* __restrict__ old_mask,
+                 const SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties,
+                 int64_t c_begin, int64_t c_end, int vec_ok) {
+    if (!st->need_ties || st->collect) return;
+    __shared__ int s_cnt;
+    const uint32_t thr = st->thr_key;
+    for (int64_t c = c_begin + blockIdx.x; c < c_end; c += gridDim.x) {
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const ChunkInfo ci = chunk_info(sv, c);
+        const float* __restrict__ src = key_ptrs[ci.seg] + ci.elem0;
+        const uint32_t* mchunk = old_mask ? old_mask + c * kWordsPerChunk : nullptr;
+        uint32_t key[16], alive;
+        if (vec_ok && ci.n == kChunk) load_keys<true>(src, mchunk, ci.n, key, alive);
+        else                          load_keys<false>(src, mchunk, ci.n, key, alive);
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cnt += (((alive >> i) & 1u) && key[i] == thr) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+        __syncthreads();
+        if (threadIdx.x == 0) chunk_ties[c] = (uint32_t)s_cnt;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kThreads)
+k_tie_count_cand(const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_pos,
+                 const SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties) {
+    if (!st->need_ties || !st->collect) return;
+    const uint32_t n = st->cand_count, thr = st->thr_key;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
+        if (cand_key[i] == thr) atomicAdd(&chunk_ties[cand_pos[i] >> 12], 1u);
+}
+// One CTA: walk chunk_ties[c_begin, c_end) in order, find where the (quota - tie_offset)-th tie
+// falls, clear the table again.
+__global__ void __launch_bounds__(1024)
+k_tie_scan(SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties, int64_t c_begin, int64_t c_end,
+           unsigned long long tie_offset) {
+    if (!st->need_ties) return;
+    __shared__ unsigned long long s_part[1024];
+    const int tid = threadIdx.x;
+    const int64_t n = c_end - c_begin;
+    const int64_t per = (n + 1023) / 1024;
+    const int64_t lo = c_begin + tid * per;
+    const int64_t hi = lo + per < c_end ? lo + per : c_end;
+    unsigned long long sum = 0;
+    for (int64_t c = lo; c < hi; ++c) sum += chunk_ties[c];
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; ++i) { unsigned long long v = s_part[i]; s_part[i] = run; run += v; }
+    }
+    __syncthreads();
+    const unsigned long long quota = st->quota;
+    // ties still to prune inside this chunk range
+    const long long target = (long long)quota - (long long)tie_offset;
+    unsigned long long before = s_part[tid];
+    const unsigned long long total = s_part[1023] + (tid == 1023 ? sum : 0ull);   // only valid in tid 1023
+    if (target <= 0) {
+        if (tid == 0) { st->tie_chunk = c_begin; st->tie_resid = 0; st->tie_seen = 0; }
+    } else {
+        bool hit = false;
+        for (int64_t c = lo; c < hi; ++c) {
+            const unsigned long long v = chunk_ties[c];
+            if (!hit && v != 0 && before < (unsigned long long)target && (unsigned long long)target <= before + v) {
+                hit = true;
+                st->tie_chunk = c;
+                st->tie_resid = (uint32_t)((unsigned long long)target - before);
+                st->tie_seen = before;
+            }
+            before += v;
+        }
+        if (tid == 1023 && (unsigned long long)target > total) {
+            st->tie_chunk = c_end; st->tie_resid = 0; st->tie_seen = total;   // every local tie pruned
+        }
+    }
+    __syncthreads();
+    for (int64_t c = lo; c < hi; ++c) chunk_ties[c] = 0;
+}
+
+static unsigned int* ticket_ptr(b200p_plan* p) {
+    // the ticket counter lives in the padding at the end of the state block
+    return (unsigned int*)((char*)p->d_state + offsetof(SelState, pad_));
+}
+
+}  // namespace b200p
+
+using namespace b200p;
+
+static int check_key_source(b200p_plan* p, int key_source, const char* who) {
+    const int slot = key_source == B200P_KEY_ABS_W ? B200P_SLOT_W : B200P_SLOT_SCORE;
+    if (key_source != B200P_KEY_ABS_W && key_source != B200P_KEY_SCORE) {
+        set_error(std::string(who) + ": bad key_source"); return B200P_EINVAL;
+    }
+    if (!p->bound[slot]) { set_error(std::string(who) + ": key slot is not bound"); return B200P_ESTATE; }
+    return B200P_OK;
+}
+static inline int key_slot(int key_source) { return key_source == B200P_KEY_ABS_W ? B200P_SLOT_W : B200P_SLOT_SCORE; }
+
+extern "C" int b200p_select_begin(b200p_plan* p, uint64_t k, int mode, int allow_collect, void* stream) {
+    B200P_REQUIRE(p != nullptr, B200P_EINVAL, "select_begin: null plan");
+    B200P_REQUIRE(mode == B200P_MODE_SNIP_STRICT || mode == B200P_MODE_EXACT_K, B200P_EINVAL, "select_begin: bad mode");
+    B200P_CUDA(cudaSetDevice(p->device));
+    k_select_init<<<1, 256, 0, (cudaStream_t)stream>>>(p->d_state, p->d_hist, ticket_ptr(p), k, (uint32_t)mode,
+                                                      allow_collect ? 1u : 0u);
+    B200P_LAUNCH_CHECK("k_select_init");
+    return B200P_OK;
+}
+
+static int launch_pass_full(b200p_plan* p, int pass, int key_source, const uint32_t* d_old_mask,
+                            int64_t c0, int64_t c1, int fuse_scan, cudaStream_t st) {
+    const int slot = key_slot(key_source);
+    const int grid = p->grid_for(c1 - c0, 4);
+    auto keys = p->ptrs<const float>(slot);
+    const int vec = p->vec_ok[slot] ? 1 : 0;
+    SegView sv = p->view();
+    switch (pass) {
+        case 0: k_select_pass_full<0><<<grid, kThreads, 0, st>>>(sv, keys, d_old_mask, p->d_hist, p->d_state, p->d_cand_key,
+                    p->d_cand_pos, ticket_ptr(p), p->cand_capacity, c0, c1, vec, fuse_scan); break;
+        case 1: k_select_pass_full<1><<<grid, kThreads, 0, st>>>(sv, keys, d_old_mask, p->d_hist, p->d_state, p->d_cand_key,
+                    p->d_cand_pos, ticket_ptr(p), p->cand_capacity, c0, c1, vec, fuse_scan); break;
+        default: k_select_pass_full<2><<<grid, kThreads, 0, st>>>(sv, keys, d_old_mask, p->d_hist, p->d_state, p->d_cand_key,
+                    p->d_cand_pos, ticket_ptr(p), p->cand_capacity, c0, c1, vec, fuse_scan); break;
+    }
+    B200P_LAUNCH_CHECK("k_select_pass_full");
+    return B200P_OK;
+}
+static int launch_pass_cand(b200p_plan* p, int pass, int fuse_scan, cudaStream_t st) {
+    int64_t blocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
+    const int grid = p->grid_for(blocks, 2);
+    if (pass == 1) k_select_pass_cand<1><<<grid, kThreads, 0, st>>>(p->d_cand_key, p->d_hist, p->d_state, ticket_ptr(p), p->cand_capacity, fuse_scan);
+    else           k_select_pass_cand<2><<<grid, kThreads, 0, st>>>(p->d_cand_key, p->d_hist, p->d_state, ticket_ptr(p), p->cand_capacity, fuse_scan);
+    B200P_LAUNCH_CHECK("k_select_pass_cand");
+    return B200P_OK;
+}
+
+extern "C" int b200p_select_hist(b200p_plan* p, int pass, int key_source, const uint32_t* d_old_mask,
+                                 int64_t chunk_begin, int64_t chunk_end, void* stream) {
+    B200P_REQUIRE(p != nullptr, B200P_EINVAL, "select_hist: null plan");
+    B200P_REQUIRE(pass >= 0 && pass <= 2, B200P_EINVAL, "select_hist: pass must be 0..2");
+    int rc = check_key_source(p, key_source, "select_hist"); if (rc) return rc;
+    if (chunk_end < 0) chunk_end = p->n_chunks;
+    B200P_REQUIRE(chunk_begin >= 0 && chunk_begin <= chunk_end && chunk_end <= p->n_chunks, B200P_EINVAL, "select_hist: bad chunk range");
+    B200P_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (chunk_end > chunk_begin) { rc = launch_pass_full(p, pass, key_source, d_old_mask, chunk_begin, chunk_end, 0, st); if (rc) return rc; }
+    if (pass >= 1) { rc = launch_pass_cand(p, pass, 0, st); if (rc) return rc; }   // no-op unless collect mode
+    return B200P_OK;
+}
+
+extern "C" int b200p_select_scan(b200p_plan* p, int pass, void* stream) {
+    B200P_REQUIRE(p != nullptr, B200P_EINVAL, "select_scan: null plan");
+    B200P_REQUIRE(pass >= 0 && pass <= 2, B200P_EINVAL, "select_scan: pass must be 0..2");
+    B200P_CUDA(cudaSetDevice(p->device));
+    k_select_scan<<<1, kScanThreads, 0, (cudaStream_t)stream>>>(pass, p->d_hist, p->d_state, p->cand_capacity);
+    B200P_LAUNCH_CHECK("k_select_scan");
+    return B200P_OK;
+}
+
+extern "C" int b200p_select_ties(b200p_plan* p, int key_source, const uint32_t* d_old_mask,
+                                 int64_t chunk_begin, int64_t chunk_end, uint64_t tie_offset, void* stream) {
+    B200P_REQUIRE(p != nullptr, B200P_EINVAL, "select_ties: null plan");
+    int rc = check_key_source(p, key_source, "select_ties"); if (rc) return rc;
+    if (chunk_end < 0) chunk_end = p->n_chunks;
+    B200P_REQUIRE(chunk_begin >= 0 && chunk_begin <= chunk_end && chunk_end <= p->n_chunks, B200P_EINVAL, "select_ties: bad chunk range");
+    B200P_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int slot = key_slot(key_source);
+    if (chunk_end > chunk_begin) {
+        k_tie_count_full<<<p->grid_for(chunk_end - chunk_begin, 4), kThreads, 0, st>>>(p->view(), p->ptrs<const float>(slot),
+            d_old_mask, p->d_state, p->d_chunk_ties, chunk_begin, chunk_end, p->vec_ok[slot] ? 1 : 0);
+        B200P_LAUNCH_CHECK("k_tie_count_full");
+    }
+    int64_t blocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
+    k_tie_count_cand<<<p->grid_for(blocks, 2), kThreads, 0, st>>>(p->d_cand_key, p->d_cand_pos, p->d_state, p->d_chunk_ties);
+    B200P_LAUNCH_CHECK("k_tie_count_cand");
+    k_tie_scan<<<1, 1024, 0, st>>>(p->d_state, p->d_chunk_ties, chunk_begin, chunk_end, (unsigned long long)tie_offset);
+    B200P_LAUNCH_CHECK("k_tie_scan");
+    return B200P_OK;
+}
+
+extern "C" int b200p_select_kth(b200p_plan* p, int key_source, const uint32_t* d_old_mask,
+                                uint64_t k, int mode, void* stream) {
+    B200P_REQUIRE(p != nullptr, B200P_EINVAL, "select_kth: null plan");
+    int rc = check_key_source(p, key_source, "select_kth"); if (rc) return rc;
+    B200P_REQUIRE(k >= 1 && k <= (uint64_t)p->total, B200P_EINVAL, "select_kth: k must be in [1, N]");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = b200p_select_begin(p, k, mode, 1, stream); if (rc) return rc;
+    rc = launch_pass_full(p, 0, key_source, d_old_mask, 0, p->n_chunks, 1, st); if (rc) return rc;
+    rc = launch_pass_full(p, 1, key_source, d_old_mask, 0, p->n_chunks, 1, st); if (rc) return rc;  // gather or histogram
+    rc = launch_pass_cand(p, 1, 1, st); if (rc) return rc;
+    rc = launch_pass_full(p, 2, key_source, d_old_mask, 0, p->n_chunks, 1, st); if (rc) return rc;  // exits at once in collect mode
+    rc = launch_pass_cand(p, 2, 1, st); if (rc) return rc;
+    if (mode == B200P_MODE_EXACT_K) { rc = b200p_select_ties(p, key_source, d_old_mask, 0, p->n_chunks, 0, stream); if (rc) return rc; }
+    return B200P_OK;
+}
+
+extern "C" int b200p_select_result(b200p_plan* p, b200p_select_result_t* h_out, void* stream) {
+    B200P_REQUIRE(p != nullptr && h_out != nullptr, B200P_EINVAL, "select_result: null argument");
+    B200P_CUDA(cudaSetDevice(p->device));
+    SelState s;
+    B200P_CUDA(cudaMemcpyAsync(&s, p->d_state, sizeof(s), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    B200P_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    h_out->k = s.k_request; h_out->n_valid = s.n_valid; h_out->n_less = s.n_less; h_out->n_equal = s.n_equal;
+    h_out->quota = s.quota; h_out->n_kept = s.n_kept; h_out->threshold = s.threshold; h_out->thr_key = s.thr_key;
+    h_out->passes_full = s.collect ? 2u : 3u; h_out->collected = s.collect ? s.cand_count : 0u;
+    return B200P_OK;
+}
