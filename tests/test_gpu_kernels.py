@@ -1,0 +1,350 @@
+"""GPU parity of the pruning kernels against the CPU oracle and the reference goldens.
+Everything goes through the C-ABI (ctypes) — see pruning_for_vision_representation_b200/plan.py."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pruning_oracle as PO
+
+pytestmark = pytest.mark.gpu
+
+from pruning_for_vision_representation_b200 import _lib as L           # noqa: E402
+from pruning_for_vision_representation_b200.plan import ParamPlan, pack_mask_words   # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _seq(z, prefix):
+    out, i = [], 0
+    while f"{prefix}{i}" in z:
+        out.append(z[f"{prefix}{i}"])
+        i += 1
+    return out
+
+
+def to_dev(arrs, misalign=False, dtype=torch.float32):
+    """numpy arrays -> contiguous CUDA tensors; misalign=True places them 4 bytes off a 16-B boundary."""
+    out = []
+    for a in arrs:
+        a = np.asarray(a)
+        t = torch.from_numpy(a.reshape(-1).copy())
+        if misalign:
+            big = torch.empty(t.numel() + 8, dtype=t.dtype, device=DEV)
+            off = 1 if big.data_ptr() % 16 == 0 else 0
+            v = big[off:off + t.numel()]
+            assert v.data_ptr() % 16 != 0
+            v.copy_(t)
+            out.append(v)
+        else:
+            out.append(t.to(DEV))
+    return out
+
+
+def make_plan(arrs, **kw):
+    return ParamPlan([int(np.asarray(a).size) for a in arrs], DEV, **kw)
+
+
+def gpu_masks(plan, mask):
+    return plan.unpack_mask_host(mask)
+
+
+def run_magnitude(plan, k, old_mask=None):
+    new = plan.new_mask()
+    if k == 0:
+        plan.select_begin(0, L.MODE_EXACT_K)
+        plan.emit_masks(L.KEY_ABS_W, L.MODE_EXACT_K, new, old_mask, force=1)
+    else:
+        plan.select_kth(L.KEY_ABS_W, k, L.MODE_EXACT_K, old_mask)
+        plan.emit_masks(L.KEY_ABS_W, L.MODE_EXACT_K, new, old_mask)
+    return new, plan.result()
+
+
+@pytest.mark.parametrize("misalign", [False, True])
+def test_score_accumulate_bit_exact(misalign):
+    rng = np.random.default_rng(1)
+    sizes = [351, 2808, 25728, 670, 4096, 8192 + 4, 1]
+    w = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    plan = make_plan(w)
+    wt = to_dev(w, misalign)
+    st = [torch.full((n,), 7.0, device=DEV) for n in sizes]           # garbage: assign must overwrite
+    plan.bind(L.SLOT_W, wt).bind(L.SLOT_SCORE, st)
+    acc = [None] * len(sizes)
+    for b in range(3):
+        g = [(1e-3 * rng.standard_normal(n)).astype(np.float32) for n in sizes]
+        if b == 1:
+            g[2][5] = np.nan; g[0][3] = np.inf; w[0][3] = 0.0          # inf * 0 = NaN, NaN propagates
+            wt[0][3] = 0.0
+        gt = to_dev(g, misalign)
+        plan.bind(L.SLOT_G, gt)
+        plan.score_accumulate(accumulate=(b > 0))
+        acc = [PO.snip_score_accumulate(a, ww, gg) for a, ww, gg in zip(acc, w, g)]
+        torch.cuda.synchronize()
+        for s, a in zip(st, acc):
+            got = s.cpu().numpy()
+            assert np.array_equal(got, a, equal_nan=True)
+            assert not np.signbit(got[~np.isnan(got)]).any()
+
+
+def test_snip_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "snip_tiny.npz"))
+    w, g, ref = _seq(z, "w"), _seq(z, "g"), _seq(z, "m")
+    plan = make_plan(w)
+    st = [torch.empty(a.size, device=DEV) for a in w]
+    plan.bind(L.SLOT_W, to_dev(w)).bind(L.SLOT_G, to_dev(g)).bind(L.SLOT_SCORE, st)
+    plan.score_accumulate(False)
+    k = PO.snip_k(plan.total, 0.9)
+    plan.select_kth(L.KEY_SCORE, k, L.MODE_SNIP_STRICT)
+    mask = plan.new_mask()
+    plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask)
+    res = plan.result()
+    assert float(np.float32(res["threshold"])) == float(z["threshold"][0])
+    for m, r in zip(gpu_masks(plan, mask), ref):
+        assert np.array_equal(m, r.reshape(-1).astype(bool))
+    assert res["n_kept"] == sum(int(r.sum()) for r in ref)
+
+
+@pytest.mark.parametrize("misalign", [False, True])
+def test_magnitude_golden_iterative(golden_dir, misalign):
+    z = np.load(os.path.join(golden_dir, "magnitude_tiefree.npz"))
+    w = _seq(z, "w")
+    plan = make_plan(w)
+    plan.bind(L.SLOT_W, to_dev(w, misalign))
+    old, n_alive = None, plan.total
+    for r, amount in enumerate(z["amounts"]):
+        k = PO.magnitude_k(float(amount), n_alive)
+        new, res = run_magnitude(plan, k, old)
+        ref = _seq(z, f"m{r}_")
+        got = gpu_masks(plan, new)
+        if res["quota"] == res["n_equal"]:
+            for m, rm in zip(got, ref):
+                assert np.array_equal(m, rm.reshape(-1).astype(bool)), f"round {r}"
+        else:
+            assert PO.masks_equal_modulo_ties(got, ref, w, res["threshold"])
+        assert res["n_valid"] == n_alive and res["n_kept"] == n_alive - k
+        zeros, bits = plan.count_zeros(new, use_weights=True)
+        assert 100.0 * zeros / plan.total == float(z["sparsity"][r])
+        assert bits == res["n_kept"]
+        # continue from the reference's masks (packed on the host)
+        old = torch.from_numpy(pack_mask_words([rm.reshape(-1) for rm in ref], plan.numels).view(np.int32)).to(DEV)
+        n_alive = sum(int(rm.sum()) for rm in ref)
+
+
+def test_magnitude_planted_ties_policy(golden_dir):
+    z = np.load(os.path.join(golden_dir, "magnitude_tiny.npz"))
+    w = _seq(z, "w")
+    plan = make_plan(w)
+    plan.bind(L.SLOT_W, to_dev(w))
+    k = PO.magnitude_k(0.5, plan.total)
+    new, res = run_magnitude(plan, k)
+    exp, info = PO.magnitude_masks(w, None, 0.5)
+    assert (res["n_less"], res["n_equal"], res["quota"]) == (info["n_less"], info["n_equal"], info["quota"])
+    assert res["quota"] < res["n_equal"]                       # the tie path really ran
+    for m, e in zip(gpu_masks(plan, new), exp):
+        assert np.array_equal(m, e.reshape(-1))               # lowest-flat-index-first, bit exact vs oracle
+    assert PO.masks_equal_modulo_ties(gpu_masks(plan, new), _seq(z, "m1_"), w, res["threshold"])
+    assert res["n_kept"] == plan.total - k
+
+
+@pytest.mark.parametrize("cand_capacity", [0, 64])
+@pytest.mark.parametrize("case", ["random", "constant", "few_values", "nan_tail", "denormal"])
+def test_select_edge_cases(case, cand_capacity):
+    rng = np.random.default_rng(3)
+    sizes = [5000, 4096, 12289, 33]
+    if case == "random":
+        w = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    elif case == "constant":
+        w = [np.full(n, -0.25, np.float32) for n in sizes]
+    elif case == "few_values":
+        w = [rng.choice(np.array([0.0, -0.0, 0.5, -0.5, 2.0], np.float32), n) for n in sizes]
+    elif case == "nan_tail":
+        w = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+        w[1][::7] = np.nan
+    else:
+        w = [(rng.standard_normal(n) * 1e-41).astype(np.float32) for n in sizes]
+    plan = make_plan(w, cand_capacity=cand_capacity)
+    plan.bind(L.SLOT_W, to_dev(w))
+    total = plan.total
+    for k in (1, 2, total // 3, total // 2, total - 1, total):
+        new, res = run_magnitude(plan, k)
+        exp, info = PO.magnitude_masks(w, None, int(k))
+        assert (res["n_less"], res["n_equal"], res["quota"]) == (info["n_less"], info["n_equal"], info["quota"]), (case, k)
+        if not np.isnan(info["threshold"]):
+            assert float(np.float32(res["threshold"])) == info["threshold"]
+        for m, e in zip(gpu_masks(plan, new), exp):
+            assert np.array_equal(m, e.reshape(-1)), (case, k)
+        assert res["n_kept"] == total - k
+        if cand_capacity == 64 and case in ("constant", "few_values"):
+            assert res["passes_full"] == 3                    # histogram mode (bucket larger than the buffer)
+
+
+def test_snip_strict_degenerate():
+    """All scores zero -> threshold 0 -> everything pruned (fresh ViT head)."""
+    sizes = [4096 * 2, 100]
+    s = [np.zeros(n, np.float32) for n in sizes]
+    plan = make_plan(s)
+    plan.bind(L.SLOT_SCORE, to_dev(s))
+    plan.select_kth(L.KEY_SCORE, plan.total // 2, L.MODE_SNIP_STRICT)
+    mask = plan.new_mask()
+    plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask)
+    res = plan.result()
+    assert res["threshold"] == 0.0 and res["n_kept"] == 0
+    assert int(mask.count_nonzero()) == 0
+    # forced thresholds of train.py:300-303
+    plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask, force=3, forced_threshold=-1.0)
+    assert plan.result()["n_kept"] == plan.total
+    plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask, force=3, forced_threshold=float("inf"))
+    assert plan.result()["n_kept"] == 0
+
+
+def test_large_random_select_vs_partition():
+    rng = np.random.default_rng(5)
+    sizes = [3_000_000, 1_234_567, 2_359_296]
+    w = [(rng.standard_normal(n) * s).astype(np.float32) for n, s in zip(sizes, (0.02, 0.05, 0.01))]
+    plan = make_plan(w)
+    plan.bind(L.SLOT_W, to_dev(w))
+    flat = np.abs(np.concatenate(w))
+    for sp in (0.5, 0.9, 0.99):
+        k = round(sp * plan.total)
+        new, res = run_magnitude(plan, k)
+        thr = np.partition(flat, k - 1)[k - 1]
+        assert np.float32(res["threshold"]) == thr
+        assert res["n_less"] == int((flat < thr).sum()) and res["n_equal"] == int((flat == thr).sum())
+        assert res["n_kept"] == plan.total - k and res["passes_full"] == 2
+        got = np.concatenate(gpu_masks(plan, new))
+        assert np.array_equal(got[flat != thr], (flat > thr)[flat != thr])
+
+
+def test_mask_roundtrip_apply_and_grads():
+    rng = np.random.default_rng(9)
+    sizes = [4096 * 3, 777, 4100]
+    w = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    masks = [rng.random(n) > 0.7 for n in sizes]
+    plan = make_plan(w)
+    mf = to_dev([m.astype(np.float32) for m in masks])
+    weff = [torch.empty(n, device=DEV) for n in sizes]
+    w16 = [torch.empty(n, device=DEV, dtype=torch.bfloat16) for n in sizes]
+    g = to_dev([np.ones(n, np.float32) for n in sizes])
+    plan.bind(L.SLOT_W, to_dev(w)).bind(L.SLOT_MASKF, mf).bind(L.SLOT_WEFF, weff).bind(L.SLOT_WEFF16, w16).bind(L.SLOT_G, g)
+    packed = plan.new_mask()
+    plan.mask_pack_from_f32(packed)
+    assert np.array_equal(packed.cpu().numpy().view(np.uint32), pack_mask_words(masks, sizes))
+    for t in mf:
+        t.fill_(5.0)
+    plan.mask_unpack_to_f32(packed)
+    plan.apply_mask(packed, L.EMIT_WEFF | L.SGD_EMIT_WEFF16)
+    plan.mask_grads(packed)
+    torch.cuda.synchronize()
+    for i, n in enumerate(sizes):
+        assert np.array_equal(mf[i].cpu().numpy(), masks[i].astype(np.float32))
+        exp = np.where(masks[i], w[i], 0).astype(np.float32)
+        assert np.array_equal(weff[i].cpu().numpy(), exp)
+        assert torch.equal(w16[i].cpu(), torch.from_numpy(exp).to(torch.bfloat16))
+        assert np.array_equal(g[i].cpu().numpy(), masks[i].astype(np.float32))
+    zeros, bits = plan.count_zeros(packed, use_weights=False)
+    assert bits == sum(int(m.sum()) for m in masks) and zeros == plan.total - bits
+
+
+@pytest.mark.parametrize("nesterov", [False, True])
+def test_masked_sgd_vs_oracle(nesterov):
+    rng = np.random.default_rng(13)
+    sizes = [4096 * 2, 1000, 4097]
+    w = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    masks = [rng.random(n) > 0.5 for n in sizes]
+    plan = make_plan(w)
+    wt = to_dev(w)
+    gt = [torch.empty(n, device=DEV) for n in sizes]
+    bt = [torch.zeros(n, device=DEV) for n in sizes]
+    weff = [torch.empty(n, device=DEV) for n in sizes]
+    w16 = [torch.empty(n, device=DEV, dtype=torch.bfloat16) for n in sizes]
+    plan.bind(L.SLOT_W, wt).bind(L.SLOT_G, gt).bind(L.SLOT_BUF, bt).bind(L.SLOT_WEFF, weff).bind(L.SLOT_WEFF16, w16)
+    packed = torch.from_numpy(pack_mask_words(masks, sizes).view(np.int32)).to(DEV)
+    ow, ob = [x.copy() for x in w], [None] * len(sizes)
+    for step in range(4):
+        g = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+        for t, a in zip(gt, g):
+            t.copy_(torch.from_numpy(a))
+        flags = L.SGD_EMIT_WEFF | L.SGD_EMIT_WEFF16 | (L.SGD_NESTEROV if nesterov else 0) | (L.SGD_FIRST_STEP if step == 0 else 0)
+        plan.masked_sgd_step(packed, 0.1, 0.9, 0.0, 1e-4, flags)
+        torch.cuda.synchronize()
+        for i in range(len(sizes)):
+            ow[i], ob[i], oeff = PO.masked_sgd_step(ow[i], g[i], ob[i], masks[i], 0.1, 0.9, 0.0, 1e-4, nesterov, step == 0)
+            np.testing.assert_allclose(wt[i].cpu().numpy(), ow[i], rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(bt[i].cpu().numpy(), ob[i], rtol=2e-6, atol=1e-7)
+            got_eff = weff[i].cpu().numpy()
+            assert np.array_equal(got_eff != 0, masks[i] & (wt[i].cpu().numpy() != 0))     # never re-densifies
+            assert np.array_equal(got_eff[masks[i]], wt[i].cpu().numpy()[masks[i]])
+            assert torch.equal(w16[i].cpu(), weff[i].cpu().to(torch.bfloat16))
+            # pruned entries of weight_orig keep decaying (wd) exactly like the reference
+            assert np.all(np.abs(ow[i][~masks[i]]) <= np.abs(w[i][~masks[i]]) + 1e-7)
+
+
+def test_host_buffer_entry_points(golden_dir):
+    z = np.load(os.path.join(golden_dir, "snip_tiny.npz"))
+    w, g, ref = _seq(z, "w"), _seq(z, "g"), _seq(z, "m")
+    plan = make_plan(w)
+    flat_w = torch.from_numpy(np.concatenate([a.reshape(-1) for a in w])).pin_memory()
+    rng = np.random.default_rng(2)
+    g2 = [(1e-3 * rng.standard_normal(a.shape)).astype(np.float32) for a in w]
+    flat_g = [torch.from_numpy(np.concatenate([a.reshape(-1) for a in gs])).pin_memory() for gs in (g, g2)]
+    out = torch.zeros(plan.mask_words, dtype=torch.int32).pin_memory()
+    # one batch == the reference
+    res = plan.snip_mask_build_host(flat_w, flat_g[:1], PO.snip_k(plan.total, 0.9), out)
+    assert float(np.float32(res["threshold"])) == float(z["threshold"][0])
+    for m, r in zip(plan.unpack_mask_host(out), ref):
+        assert np.array_equal(m, r.reshape(-1).astype(bool))
+    # two batches == the accumulation oracle
+    res = plan.snip_mask_build_host(flat_w, flat_g, PO.snip_k(plan.total, 0.75), out)
+    exp, thr, _ = PO.snip_pruning(w, [g, g2], 0.75)
+    assert float(np.float32(res["threshold"])) == thr
+    for m, e in zip(plan.unpack_mask_host(out), exp):
+        assert np.array_equal(m, e.reshape(-1))
+    # magnitude from host buffers, with an old mask
+    exp1, info1 = PO.magnitude_masks(w, None, 0.3)
+    res = plan.magnitude_mask_build_host(flat_w, info1["k"], out)
+    for m, e in zip(plan.unpack_mask_host(out), exp1):
+        assert np.array_equal(m, e.reshape(-1))
+    old = out.clone().pin_memory()
+    exp2, info2 = PO.magnitude_masks(w, exp1, 0.2)
+    res = plan.magnitude_mask_build_host(flat_w, info2["k"], out, old)
+    for m, e in zip(plan.unpack_mask_host(out), exp2):
+        assert np.array_equal(m, e.reshape(-1))
+    assert res["n_valid"] == info2["n_alive"]
+
+
+def test_resnet18_known_answer(golden_dir):
+    """Config 1: ResNet-18, seed 1, global magnitude 50 % then 20 % of survivors — mask bits
+    identical to the reference's (sha256 over the flat mask), modulo the recorded tied entries."""
+    import torchvision
+    info = json.load(open(os.path.join(golden_dir, "resnet18_magnitude.json")))
+    torch.manual_seed(1)
+    model = torchvision.models.get_model("resnet18", weights=None, num_classes=1000)
+    ws = [m.weight.detach() for m in model.modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))]
+    plan = ParamPlan([t.numel() for t in ws], DEV)
+    assert plan.total == info["N"]
+    plan.bind(L.SLOT_W, [t.reshape(-1).to(DEV) for t in ws])
+
+    def digest(mask, tied_idx, tied_ref):
+        flat = np.concatenate(plan.unpack_mask_host(mask))
+        for i, v in zip(tied_idx, tied_ref):
+            flat[i] = bool(v)
+        h, ptr = hashlib.sha256(), 0
+        for n in plan.numels:
+            h.update(np.packbits(flat[ptr:ptr + n], bitorder="little").tobytes())
+            ptr += n
+        return h.hexdigest()
+
+    m1, r1 = run_magnitude(plan, info["k"])
+    assert float(np.float32(r1["threshold"])) == info["kth_abs"]
+    assert r1["n_less"] == info["n_less_round1"] and r1["n_equal"] == info["n_equal_at_kth"]
+    assert digest(m1, info["tied_flat_index_round1"], info["tied_ref_mask_round1"]) == info["mask_sha256_round1"]
+    zeros, _ = plan.count_zeros(m1)
+    assert 100.0 * zeros / plan.total == info["sparsity_after_0.5"]
+    m2, r2 = run_magnitude(plan, info["k_round2"], m1)
+    assert float(np.float32(r2["threshold"])) == info["kth_abs_round2"]
+    assert digest(m2, info["tied_flat_index_round2"], info["tied_ref_mask_round2"]) == info["mask_sha256_round2"]
+    zeros, _ = plan.count_zeros(m2)
+    assert 100.0 * zeros / plan.total == info["sparsity_after_0.5_then_0.2"]
