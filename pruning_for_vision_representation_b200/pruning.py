@@ -61,6 +61,12 @@ class PruneState:
         self._mf_ptrs = None
         self.maskf = None
 
+    def __deepcopy__(self, memo):
+        return None                    # copies of the model (EMA, deepcopy) rebuild their own state lazily
+
+    def __reduce__(self):
+        return (type(None), ())        # never pickled with the model; checkpoints carry weight_orig / weight_mask
+
     def weights(self):
         """fp32 master weights: weight_orig if the module is reparametrised, else weight."""
         out = []
@@ -135,10 +141,7 @@ def _get_state(model, modules):
         st = PruneState(modules, dev)
         # adopt masks installed by torch.nn.utils.prune (e.g. a loaded reference checkpoint)
         if any("weight_mask" in m._buffers for m in modules):
-            for m in modules:
-                if "weight_mask" not in m._buffers:
-                    prune.identity(m, "weight")
-            st.ensure_mask_buffers()
+            st.ensure_mask_buffers()          # modules without a mask get an (unregistered) all-ones one
             st.mask = st.plan.new_mask()
             st.plan.mask_pack_from_f32(st.mask)
             _, st.n_alive = st.plan.count_zeros(st.mask, use_weights=False)
