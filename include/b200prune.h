@@ -97,6 +97,9 @@ int64_t b200p_plan_total(const b200p_plan* plan);        /* N = sum numel       
 int64_t b200p_plan_num_chunks(const b200p_plan* plan);
 int64_t b200p_plan_mask_words(const b200p_plan* plan);   /* = num_chunks * 128            */
 int64_t b200p_plan_seg_chunk_start(const b200p_plan* plan, int seg); /* first chunk of seg */
+/* flat (segment-concatenated, unpadded) index of the first element of chunk c; c = num_chunks
+ * gives N.  A chunk range [c0,c1) is the contiguous flat range [flat(c0), flat(c1)). */
+int64_t b200p_plan_chunk_flat_start(const b200p_plan* plan, int64_t chunk);
 /* Upload one device pointer per segment for `slot`.  16-byte aligned pointers take the
  * 128-bit vector path; anything else is accepted and runs the scalar path. */
 int  b200p_plan_bind(b200p_plan* plan, int slot, const void* const* h_ptrs, void* stream);
@@ -109,6 +112,11 @@ void* b200p_plan_state_ptr(b200p_plan* plan);
 /* SCORE[t] (=|+=) |W[t] * G[t]|   (accumulate=0 assigns, 1 adds) over chunks [c0,c1) */
 int  b200p_score_accumulate(b200p_plan* plan, int accumulate,
                             int64_t chunk_begin, int64_t chunk_end, void* stream);
+
+/* Multi-GPU score exchange: d_dst[i] = ((d_src[i] + d_src[stride+i]) + ...) over
+ * n_parts partial score slices received from the ranks, summed in rank (= mini-batch) order. */
+int  b200p_sum_parts(int device, float* d_dst, const float* d_src, int n_parts, int64_t part_stride,
+                     int64_t n, void* stream);
 
 /* ---- K2: global k-th smallest (train.py:299-307; prune.py:526-536) ----------------- */
 /* Whole select on one GPU: radix passes + scans, no host sync.  `d_old_mask` (nullable)
@@ -127,6 +135,14 @@ int  b200p_select_scan(b200p_plan* plan, int pass, void* stream);
  * live in lower-numbered chunks owned by other ranks (0 on one GPU). */
 int  b200p_select_ties(b200p_plan* plan, int key_source, const uint32_t* d_old_mask,
                        int64_t chunk_begin, int64_t chunk_end, uint64_t tie_offset, void* stream);
+/* The same in two stages for the parameter-sharded multi-GPU select: `count` writes the number
+ * of tied keys inside [c0,c1) to caller-owned device memory (8 bytes) so that the host side can
+ * all-gather it; `scan` takes the gathered per-rank table and adds the counts of the n_before
+ * lower ranks on the device (no host round trip). */
+int  b200p_select_ties_count(b200p_plan* plan, int key_source, const uint32_t* d_old_mask,
+                             int64_t chunk_begin, int64_t chunk_end, uint64_t* d_local_count, void* stream);
+int  b200p_select_ties_scan(b200p_plan* plan, int64_t chunk_begin, int64_t chunk_end,
+                            const uint64_t* d_counts, int n_before, void* stream);
 /* copy the result block to the host.  Synchronises the stream. */
 int  b200p_select_result(b200p_plan* plan, b200p_select_result_t* h_out, void* stream);
 

@@ -73,6 +73,10 @@ SIGNATURES = {
     "b200p_select_hist": (_I, [_P, _I, _I, _P, _I64, _I64, _P]),
     "b200p_select_scan": (_I, [_P, _I, _P]),
     "b200p_select_ties": (_I, [_P, _I, _P, _I64, _I64, _U64, _P]),
+    "b200p_select_ties_count": (_I, [_P, _I, _P, _I64, _I64, _P, _P]),
+    "b200p_select_ties_scan": (_I, [_P, _I64, _I64, _P, _I, _P]),
+    "b200p_sum_parts": (_I, [_I, _P, _P, _I, _I64, _I64, _P]),
+    "b200p_plan_chunk_flat_start": (_I64, [_P, _I64]),
     "b200p_select_result": (_I, [_P, ctypes.POINTER(SelectResult), _P]),
     "b200p_emit_masks": (_I, [_P, _I, _I, _I, _F, _P, _P, _I, _I64, _I64, _P]),
     "b200p_count_zeros": (_I, [_P, _P, _P, _I, _P]),

@@ -112,6 +112,14 @@ extern "C" int64_t b200p_plan_seg_chunk_start(const b200p_plan* p, int seg) {
     if (!p || seg < 0 || seg > p->n_seg) return -1;
     return p->seg_chunk_start[seg];
 }
+extern "C" int64_t b200p_plan_chunk_flat_start(const b200p_plan* p, int64_t chunk) {
+    if (!p || chunk < 0 || chunk > p->n_chunks) return -1;
+    if (chunk == p->n_chunks) return p->total;
+    // segment that owns the chunk: last t with seg_chunk_start[t] <= chunk
+    int lo = 0, hi = p->n_seg - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (p->seg_chunk_start[mid] <= chunk) lo = mid; else hi = mid - 1; }
+    return p->seg_flat_start[lo] + (chunk - p->seg_chunk_start[lo]) * (int64_t)kChunk;
+}
 extern "C" void* b200p_plan_hist_ptr(b200p_plan* p) { return p ? (void*)p->d_hist : nullptr; }
 extern "C" void* b200p_plan_state_ptr(b200p_plan* p) { return p ? (void*)p->d_state : nullptr; }
 

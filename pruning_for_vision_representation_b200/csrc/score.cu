@@ -51,9 +51,56 @@ k_score_accumulate(SegView sv, const float* const* __restrict__ w_ptrs,
     }
 }
 
+// dst[i] = ((src[0][i] + src[1][i]) + src[2][i]) + ...   part p at src + p * part_stride.
+// Fixed left-to-right order: the multi-GPU score exchange sums the ranks' partial scores in rank
+// (= mini-batch) order on every rank count, so the result does not depend on the collective's
+// reduction topology (SURVEY §7 "cross-GPU-count determinism").
+__global__ void __launch_bounds__(kThreads)
+k_sum_parts(float* __restrict__ dst, const float* __restrict__ src, int n_parts, int64_t part_stride,
+            int64_t n, int vec_ok) {
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * kThreads;
+    int64_t done = 0;
+    if (vec_ok) {
+        const int64_t nvec = n >> 2;
+        for (int64_t v = tid; v < nvec; v += nthreads) {
+            float4 acc = ld_nc_f4(src + 4 * v);
+            for (int p = 1; p < n_parts; ++p) {
+                const float4 x = ld_nc_f4(src + p * part_stride + 4 * v);
+                acc.x = __fadd_rn(acc.x, x.x); acc.y = __fadd_rn(acc.y, x.y);
+                acc.z = __fadd_rn(acc.z, x.z); acc.w = __fadd_rn(acc.w, x.w);
+            }
+            st_f4(dst + 4 * v, acc);
+        }
+        done = nvec << 2;
+    }
+    for (int64_t i = done + tid; i < n; i += nthreads) {
+        float acc = src[i];
+        for (int p = 1; p < n_parts; ++p) acc = __fadd_rn(acc, src[p * part_stride + i]);
+        dst[i] = acc;
+    }
+}
+
 }  // namespace b200p
 
 using namespace b200p;
+
+extern "C" int b200p_sum_parts(int device, float* d_dst, const float* d_src, int n_parts, int64_t part_stride,
+                               int64_t n, void* stream) {
+    B200P_REQUIRE(d_dst != nullptr && d_src != nullptr, B200P_EINVAL, "sum_parts: null argument");
+    B200P_REQUIRE(n_parts >= 1 && n >= 0 && part_stride >= n, B200P_EINVAL, "sum_parts: bad sizes");
+    if (n == 0) return B200P_OK;
+    B200P_CUDA(cudaSetDevice(device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const bool vec = (((uintptr_t)d_dst | (uintptr_t)d_src) & 15u) == 0 && (part_stride & 3) == 0;
+    int64_t blocks = (n / 4 + kThreads - 1) / kThreads;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    if (blocks < 1) blocks = 1;
+    k_sum_parts<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(d_dst, d_src, n_parts, part_stride, n, vec ? 1 : 0);
+    B200P_LAUNCH_CHECK("k_sum_parts");
+    return B200P_OK;
+}
 
 extern "C" int b200p_score_accumulate(b200p_plan* p, int accumulate, int64_t chunk_begin,
                                       int64_t chunk_end, void* stream) {

@@ -331,12 +331,15 @@ k_tie_count_cand(const uint32_t* __restrict__ cand_key, const uint32_t* __restri
 }
 // One CTA: walk chunk_ties[c_begin, c_end) in order, find where the (quota - tie_offset)-th tie
 // falls, clear the table again.
+// d_counts (nullable): per-rank tie counts gathered from all ranks; the ties owned by the
+// n_before lower ranks are added to tie_offset on the device (no host round trip).
 __global__ void __launch_bounds__(1024)
 k_tie_scan(SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties, int64_t c_begin, int64_t c_end,
-           unsigned long long tie_offset) {
+           unsigned long long tie_offset, const unsigned long long* __restrict__ d_counts, int n_before) {
     if (!st->need_ties) return;
     __shared__ unsigned long long s_part[1024];
     const int tid = threadIdx.x;
+    if (d_counts) for (int r = 0; r < n_before; ++r) tie_offset += d_counts[r];
     const int64_t n = c_end - c_begin;
     const int64_t per = (n + 1023) / 1024;
     const int64_t lo = c_begin + tid * per;
@@ -375,6 +378,23 @@ k_tie_scan(SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties, int64_t
     }
     __syncthreads();
     for (int64_t c = lo; c < hi; ++c) chunk_ties[c] = 0;
+}
+
+// One CTA: *out = sum of chunk_ties[c_begin, c_end) (0 when no tie resolution is needed).
+__global__ void __launch_bounds__(1024)
+k_tie_total(const SelState* __restrict__ st, const uint32_t* __restrict__ chunk_ties, int64_t c_begin, int64_t c_end,
+            unsigned long long* __restrict__ out) {
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    unsigned long long sum = 0;
+    if (st->need_ties)
+        for (int64_t c = c_begin + threadIdx.x; c < c_end; c += blockDim.x) sum += chunk_ties[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&s_sum, sum);
+    __syncthreads();
+    if (threadIdx.x == 0) *out = s_sum;
 }
 
 static unsigned int* ticket_ptr(b200p_plan* p) {
@@ -456,14 +476,8 @@ extern "C" int b200p_select_scan(b200p_plan* p, int pass, void* stream) {
     return B200P_OK;
 }
 
-extern "C" int b200p_select_ties(b200p_plan* p, int key_source, const uint32_t* d_old_mask,
-                                 int64_t chunk_begin, int64_t chunk_end, uint64_t tie_offset, void* stream) {
-    B200P_REQUIRE(p != nullptr, B200P_EINVAL, "select_ties: null plan");
-    int rc = check_key_source(p, key_source, "select_ties"); if (rc) return rc;
-    if (chunk_end < 0) chunk_end = p->n_chunks;
-    B200P_REQUIRE(chunk_begin >= 0 && chunk_begin <= chunk_end && chunk_end <= p->n_chunks, B200P_EINVAL, "select_ties: bad chunk range");
-    B200P_CUDA(cudaSetDevice(p->device));
-    cudaStream_t st = (cudaStream_t)stream;
+static int launch_tie_count(b200p_plan* p, int key_source, const uint32_t* d_old_mask,
+                            int64_t chunk_begin, int64_t chunk_end, cudaStream_t st) {
     const int slot = key_slot(key_source);
     if (chunk_end > chunk_begin) {
         k_tie_count_full<<<p->grid_for(chunk_end - chunk_begin, 4), kThreads, 0, st>>>(p->view(), p->ptrs<const float>(slot),
@@ -473,7 +487,51 @@ extern "C" int b200p_select_ties(b200p_plan* p, int key_source, const uint32_t* 
     int64_t blocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
     k_tie_count_cand<<<p->grid_for(blocks, 2), kThreads, 0, st>>>(p->d_cand_key, p->d_cand_pos, p->d_state, p->d_chunk_ties);
     B200P_LAUNCH_CHECK("k_tie_count_cand");
-    k_tie_scan<<<1, 1024, 0, st>>>(p->d_state, p->d_chunk_ties, chunk_begin, chunk_end, (unsigned long long)tie_offset);
+    return B200P_OK;
+}
+
+static int check_tie_args(b200p_plan* p, int key_source, int64_t& chunk_begin, int64_t& chunk_end, const char* who) {
+    if (!p) { set_error(std::string(who) + ": null plan"); return B200P_EINVAL; }
+    int rc = check_key_source(p, key_source, who); if (rc) return rc;
+    if (chunk_end < 0) chunk_end = p->n_chunks;
+    if (!(chunk_begin >= 0 && chunk_begin <= chunk_end && chunk_end <= p->n_chunks)) {
+        set_error(std::string(who) + ": bad chunk range"); return B200P_EINVAL;
+    }
+    return B200P_OK;
+}
+
+extern "C" int b200p_select_ties(b200p_plan* p, int key_source, const uint32_t* d_old_mask,
+                                 int64_t chunk_begin, int64_t chunk_end, uint64_t tie_offset, void* stream) {
+    int rc = check_tie_args(p, key_source, chunk_begin, chunk_end, "select_ties"); if (rc) return rc;
+    B200P_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_tie_count(p, key_source, d_old_mask, chunk_begin, chunk_end, st); if (rc) return rc;
+    k_tie_scan<<<1, 1024, 0, st>>>(p->d_state, p->d_chunk_ties, chunk_begin, chunk_end, (unsigned long long)tie_offset, nullptr, 0);
+    B200P_LAUNCH_CHECK("k_tie_scan");
+    return B200P_OK;
+}
+
+extern "C" int b200p_select_ties_count(b200p_plan* p, int key_source, const uint32_t* d_old_mask,
+                                       int64_t chunk_begin, int64_t chunk_end, uint64_t* d_local_count, void* stream) {
+    int rc = check_tie_args(p, key_source, chunk_begin, chunk_end, "select_ties_count"); if (rc) return rc;
+    B200P_REQUIRE(d_local_count != nullptr, B200P_EINVAL, "select_ties_count: null output");
+    B200P_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_tie_count(p, key_source, d_old_mask, chunk_begin, chunk_end, st); if (rc) return rc;
+    k_tie_total<<<1, 1024, 0, st>>>(p->d_state, p->d_chunk_ties, chunk_begin, chunk_end, (unsigned long long*)d_local_count);
+    B200P_LAUNCH_CHECK("k_tie_total");
+    return B200P_OK;
+}
+
+extern "C" int b200p_select_ties_scan(b200p_plan* p, int64_t chunk_begin, int64_t chunk_end,
+                                      const uint64_t* d_counts, int n_before, void* stream) {
+    B200P_REQUIRE(p != nullptr, B200P_EINVAL, "select_ties_scan: null plan");
+    if (chunk_end < 0) chunk_end = p->n_chunks;
+    B200P_REQUIRE(chunk_begin >= 0 && chunk_begin <= chunk_end && chunk_end <= p->n_chunks, B200P_EINVAL, "select_ties_scan: bad chunk range");
+    B200P_REQUIRE(n_before == 0 || d_counts != nullptr, B200P_EINVAL, "select_ties_scan: null count table");
+    B200P_CUDA(cudaSetDevice(p->device));
+    k_tie_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(p->d_state, p->d_chunk_ties, chunk_begin, chunk_end, 0ull,
+                                                       (const unsigned long long*)d_counts, n_before);
     B200P_LAUNCH_CHECK("k_tie_scan");
     return B200P_OK;
 }

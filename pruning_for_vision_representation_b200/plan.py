@@ -46,6 +46,9 @@ class ParamPlan:
         self.mask_words = int(self.lib.b200p_plan_mask_words(handle))
         self.seg_chunk_start = [int(self.lib.b200p_plan_seg_chunk_start(handle, t))
                                 for t in range(len(self.numels) + 1)]
+        self.seg_flat_start = [0]
+        for n in self.numels:
+            self.seg_flat_start.append(self.seg_flat_start[-1] + n)
         self._bound = {}
         self._counts = torch.zeros(2, dtype=torch.int64, device=self.device)
 
@@ -67,7 +70,9 @@ class ParamPlan:
             pass
 
     # ---- binding ---------------------------------------------------------------------
-    def bind(self, slot, tensors):
+    def pointer_table(self, slot, tensors):
+        """Validated, reusable pointer table for `bind_table` (re-binding a slot every mini-batch
+        without re-validating the tensors)."""
         tensors = list(tensors)
         if len(tensors) != len(self.numels):
             raise B200PruneError(f"bind: expected {len(self.numels)} tensors, got {len(tensors)}")
@@ -78,9 +83,16 @@ class ParamPlan:
             if t.dtype != want or not t.is_contiguous() or t.numel() != n:
                 raise B200PruneError(f"bind: need contiguous {want} tensors with the plan's element counts")
         ptrs = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        return (slot, ptrs, tensors)
+
+    def bind_table(self, table):
+        slot, ptrs, tensors = table
         check(self.lib.b200p_plan_bind(self.handle, slot, ptrs, _stream_ptr(self.device)), "plan_bind")
         self._bound[slot] = tensors       # keep the storage alive
         return self
+
+    def bind(self, slot, tensors):
+        return self.bind_table(self.pointer_table(slot, tensors))
 
     def bound(self, slot):
         return self._bound.get(slot)
@@ -115,6 +127,28 @@ class ParamPlan:
     def select_ties(self, key_source, old_mask=None, chunk_begin=0, chunk_end=-1, tie_offset=0):
         check(self.lib.b200p_select_ties(self.handle, key_source, _ptr(old_mask), chunk_begin, chunk_end,
                                          int(tie_offset), _stream_ptr(self.device)), "select_ties")
+
+    def select_ties_count(self, key_source, old_mask, chunk_begin, chunk_end, out_count):
+        """Ties inside [chunk_begin, chunk_end) -> out_count (int64 device tensor, 1 element)."""
+        check(self.lib.b200p_select_ties_count(self.handle, key_source, _ptr(old_mask), chunk_begin, chunk_end,
+                                               _ptr(out_count), _stream_ptr(self.device)), "select_ties_count")
+
+    def select_ties_scan(self, chunk_begin, chunk_end, counts, n_before):
+        check(self.lib.b200p_select_ties_scan(self.handle, chunk_begin, chunk_end, _ptr(counts), int(n_before),
+                                              _stream_ptr(self.device)), "select_ties_scan")
+
+    def sum_parts(self, dst, src, n_parts, part_stride, n):
+        """dst[i] = ((src[i] + src[stride+i]) + ...): fixed-order sum of the ranks' score slices."""
+        for t in (dst, src):
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise B200PruneError("sum_parts: need contiguous fp32 CUDA tensors (no CPU fallback)")
+        if dst.numel() < n or src.numel() < (n_parts - 1) * part_stride + n:
+            raise B200PruneError("sum_parts: buffers are too small")
+        check(self.lib.b200p_sum_parts(self.index, _ptr(dst), _ptr(src), int(n_parts), int(part_stride), int(n),
+                                       _stream_ptr(self.device)), "sum_parts")
+
+    def chunk_flat_start(self, chunk):
+        return int(self.lib.b200p_plan_chunk_flat_start(self.handle, int(chunk)))
 
     def result(self):
         """Select/emit result block (synchronises the current stream)."""

@@ -120,3 +120,34 @@ def test_lost_background_seed_raises():
     M = -np.ones(12, np.float32)
     with pytest.raises(ValueError, match="background"):
         LO.detect_box(M, 5, [3, 4], (48, 64), [16, 16])
+
+
+def test_torch_port_matches_goldens(golden_dir):
+    """The torch-CPU timing port (bench.py's cpu_baseline / --impl reference legs) reproduces the
+    unmodified reference's outputs."""
+    import torch
+    from oracle import torch_port as TP
+    z = _load(golden_dir, "snip_tiny.npz")
+    w = [torch.from_numpy(a.copy()) for a in _seq(z, "w")]
+    g = [torch.from_numpy(a.copy()) for a in _seq(z, "g")]
+    masks, thr = TP.snip_mask_build(w, [g], 0.9)
+    assert thr == float(z["threshold"][0])
+    for m, r in zip(masks, _seq(z, "m")):
+        assert np.array_equal(m.numpy().astype(bool), r.astype(bool))
+    assert TP.sparsity_percent(w, masks) == float(z["sparsity"][0])
+    # multi-batch extension agrees with the numpy oracle
+    g2 = [torch.from_numpy((a * 0.5 + 1e-4).astype(np.float32)) for a in _seq(z, "g")]
+    masks2, thr2 = TP.snip_mask_build(w, [g, g2], 0.7)
+    exp, ethr, _ = PO.snip_pruning([t.numpy() for t in w], [[t.numpy() for t in g], [t.numpy() for t in g2]], 0.7)
+    assert thr2 == ethr
+    for m, e in zip(masks2, exp):
+        assert np.array_equal(m.numpy().astype(bool), e)
+    # magnitude, iterative, tie-free fixture: bit-exact with the reference
+    z = _load(golden_dir, "magnitude_tiefree.npz")
+    w = [torch.from_numpy(a.copy()) for a in _seq(z, "w")]
+    masks = None
+    for r, amount in enumerate(z["amounts"]):
+        masks, k = TP.magnitude_mask_build(w, masks, float(amount))
+        ref = _seq(z, f"m{r}_")
+        for m, rm in zip(masks, ref):
+            assert np.array_equal(m.numpy().astype(bool), rm.astype(bool)), f"round {r}"
