@@ -103,6 +103,15 @@ int64_t b200p_plan_chunk_flat_start(const b200p_plan* plan, int64_t chunk);
 /* Upload one device pointer per segment for `slot`.  16-byte aligned pointers take the
  * 128-bit vector path; anything else is accepted and runs the scalar path. */
 int  b200p_plan_bind(b200p_plan* plan, int slot, const void* const* h_ptrs, void* stream);
+/* Reusable pointer table: the same per-segment pointers expanded once into a device-resident
+ * per-chunk table.  Binding it to a slot is a host-side swap (no launch, no copy), which is what
+ * a loop over mini-batches wants (one table per gradient set).  `slot` fixes the element size.
+ * The table must outlive every launch that uses it. */
+typedef struct b200p_ptrtable b200p_ptrtable;
+int  b200p_ptrtable_create(b200p_plan* plan, int slot, const void* const* h_ptrs, void* stream,
+                           b200p_ptrtable** out);
+int  b200p_ptrtable_destroy(b200p_ptrtable* table);
+int  b200p_plan_bind_table(b200p_plan* plan, int slot, const b200p_ptrtable* table);
 /* device address of the 4096-bin uint64 histogram and of the select state, so that the
  * host side can run NCCL collectives on them between stages */
 void* b200p_plan_hist_ptr(b200p_plan* plan);

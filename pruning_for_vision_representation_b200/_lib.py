@@ -65,6 +65,9 @@ SIGNATURES = {
     "b200p_plan_mask_words": (_I64, [_P]),
     "b200p_plan_seg_chunk_start": (_I64, [_P, _I]),
     "b200p_plan_bind": (_I, [_P, _I, ctypes.POINTER(_P), _P]),
+    "b200p_ptrtable_create": (_I, [_P, _I, ctypes.POINTER(_P), _P, ctypes.POINTER(_P)]),
+    "b200p_ptrtable_destroy": (_I, [_P]),
+    "b200p_plan_bind_table": (_I, [_P, _I, _P]),
     "b200p_plan_hist_ptr": (_P, [_P]),
     "b200p_plan_state_ptr": (_P, [_P]),
     "b200p_score_accumulate": (_I, [_P, _I, _I64, _I64, _P]),

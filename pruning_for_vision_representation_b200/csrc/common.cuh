@@ -42,27 +42,15 @@ __host__ __device__ __forceinline__ float key_to_float(uint32_t key) {
 #endif
 }
 
-// device-side view of the segment / chunk tables
-struct SegView {
-    const int32_t* chunk_seg;        // [n_chunks]  segment of each chunk
-    const int64_t* seg_chunk_start;  // [n_seg + 1] first chunk of each segment
-    const int64_t* seg_numel;        // [n_seg]
-};
+// Per-chunk tables.  A kernel never walks segment tables: for chunk c it reads the number of valid
+// elements chunk_n[c] and, per slot it touches, the address of the chunk's first element
+// tab[c] — independent loads that are issued one iteration ahead (ChunkCursor), so the
+// grid-stride loop has no dependent pointer chase in front of its data loads.
+typedef void* const* ChunkTab;          // [n_chunks] device pointers, one table per slot
 
-struct ChunkInfo {
-    int     seg;     // segment index
-    int64_t elem0;   // first element of the chunk inside its segment
-    int     n;       // valid elements in the chunk (1..kChunk)
-};
-
-__device__ __forceinline__ ChunkInfo chunk_info(const SegView& sv, int64_t c) {
-    ChunkInfo ci;
-    ci.seg = sv.chunk_seg[c];
-    int64_t lc = c - sv.seg_chunk_start[ci.seg];
-    ci.elem0 = lc * kChunk;
-    int64_t rem = sv.seg_numel[ci.seg] - ci.elem0;
-    ci.n = rem < kChunk ? (int)rem : kChunk;
-    return ci;
+template <typename T>
+__device__ __forceinline__ T* chunk_ptr(ChunkTab tab, int64_t c) {
+    return reinterpret_cast<T*>(__ldg(reinterpret_cast<const unsigned long long*>(tab) + c));
 }
 
 // 128-bit streaming loads / stores.  Read-only streams go through the non-coherent path
@@ -141,10 +129,11 @@ struct b200p_plan {
     std::vector<int64_t> seg_chunk_start;   // n_seg + 1
     std::vector<int64_t> seg_flat_start;    // n_seg + 1
     // device tables
-    int32_t* d_chunk_seg = nullptr;
-    int64_t* d_seg_chunk_start = nullptr;
-    int64_t* d_seg_numel = nullptr;
-    void**   d_ptrs[B200P_NUM_SLOTS] = {nullptr};
+    int32_t* d_chunk_seg = nullptr;         // [n_chunks] segment of each chunk (bind kernel only)
+    int32_t* d_chunk_n = nullptr;           // [n_chunks] valid elements of each chunk (1..kChunk)
+    int64_t* d_chunk_elem0 = nullptr;       // [n_chunks] first element of the chunk inside its segment
+    void**   d_tab_own[B200P_NUM_SLOTS] = {nullptr};   // plan-owned per-chunk pointer tables
+    void**   d_tab[B200P_NUM_SLOTS] = {nullptr};       // table currently bound to each slot
     bool     bound[B200P_NUM_SLOTS] = {false};
     bool     vec_ok[B200P_NUM_SLOTS] = {false};
     // workspace
@@ -156,19 +145,23 @@ struct b200p_plan {
     // lazily created arena for the host-buffer entry points
     float* arena_w = nullptr; float* arena_g[2] = {nullptr, nullptr}; float* arena_score = nullptr;
     uint32_t* arena_mask = nullptr; uint32_t* arena_old_mask = nullptr;
+    struct b200p_ptrtable* arena_gtab[2] = {nullptr, nullptr};
     cudaStream_t arena_streams[2] = {nullptr, nullptr};
     cudaEvent_t  arena_events[4] = {nullptr, nullptr, nullptr, nullptr};
 
-    b200p::SegView view() const {
-        b200p::SegView sv; sv.chunk_seg = d_chunk_seg; sv.seg_chunk_start = d_seg_chunk_start;
-        sv.seg_numel = d_seg_numel; return sv;
-    }
-    template <typename T> T* const* ptrs(int slot) const { return (T* const*)d_ptrs[slot]; }
+    template <typename T = void> b200p::ChunkTab tab(int slot) const { return (b200p::ChunkTab)d_tab[slot]; }
     int grid_for(int64_t chunks, int ctas_per_sm) const {
         int64_t g = (int64_t)num_sms * ctas_per_sm;
         if (g > chunks) g = chunks;
         return g < 1 ? 1 : (int)g;
     }
+};
+
+// reusable per-chunk pointer table (b200p_ptrtable_create); binding it is a host-side swap
+struct b200p_ptrtable {
+    b200p_plan* plan = nullptr;
+    void** d_tab = nullptr;
+    bool vec_ok = false;
 };
 
 namespace b200p {

@@ -10,10 +10,11 @@
 namespace b200p {
 
 struct EmitArgs {
-    const float* const* key_ptrs;    // |w| or score source
-    const float* const* w_ptrs;      // weights (for WEFF output), may equal key_ptrs
-    float* const* maskf_ptrs;        // optional fp32 mask output
-    float* const* weff_ptrs;         // optional masked weight output
+    const int32_t* chunk_n;
+    ChunkTab key_tab;                // |w| or score source
+    ChunkTab w_tab;                  // weights (for WEFF output), may equal key_tab
+    ChunkTab maskf_tab;              // optional fp32 mask output
+    ChunkTab weff_tab;               // optional masked weight output
     const uint32_t* old_mask;        // nullable
     uint32_t* new_mask;
     SelState* st;
@@ -35,7 +36,7 @@ __device__ __forceinline__ bool keep_decision(float x, int mode, int force, floa
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_emit_masks(SegView sv, EmitArgs a, int64_t c_begin, int64_t c_end) {
+k_emit_masks(EmitArgs a, int64_t c_begin, int64_t c_end) {
     __shared__ unsigned long long s_kept;
     if (threadIdx.x == 0) s_kept = 0;
     __syncthreads();
@@ -49,23 +50,31 @@ k_emit_masks(SegView sv, EmitArgs a, int64_t c_begin, int64_t c_end) {
         if (a.mode == B200P_MODE_EXACT_K) { need_ties = a.st->need_ties; tie_chunk = a.st->tie_chunk; tie_resid = a.st->tie_resid; }
     }
     unsigned long long kept = 0;
+    const bool want_mf = a.outputs & B200P_EMIT_MASKF, want_wf = a.outputs & B200P_EMIT_WEFF;
 
-    for (int64_t c = c_begin + blockIdx.x; c < c_end; c += gridDim.x) {
-        const ChunkInfo ci = chunk_info(sv, c);
-        const float* __restrict__ src = a.key_ptrs[ci.seg] + ci.elem0;
+    int64_t c = c_begin + blockIdx.x;
+    const float* src = nullptr; int n = 0;
+    if (c < c_end) { src = chunk_ptr<const float>(a.key_tab, c); n = __ldg(a.chunk_n + c); }
+    for (; c < c_end; ) {
+        const int64_t cn = c + gridDim.x;
+        const float* srcn = nullptr; int nn = 0;
+        if (cn < c_end) { srcn = chunk_ptr<const float>(a.key_tab, cn); nn = __ldg(a.chunk_n + cn); }
         const uint32_t* mold = a.old_mask ? a.old_mask + c * kWordsPerChunk : nullptr;
         uint32_t* mnew = a.new_mask + c * kWordsPerChunk;
-        float* mf = (a.outputs & B200P_EMIT_MASKF) ? a.maskf_ptrs[ci.seg] + ci.elem0 : nullptr;
-        float* wf = (a.outputs & B200P_EMIT_WEFF) ? a.weff_ptrs[ci.seg] + ci.elem0 : nullptr;
-        const float* wsrc = wf ? a.w_ptrs[ci.seg] + ci.elem0 : nullptr;
+        float* mf = want_mf ? chunk_ptr<float>(a.maskf_tab, c) : nullptr;
+        float* wf = want_wf ? chunk_ptr<float>(a.weff_tab, c) : nullptr;
+        const float* wsrc = want_wf ? chunk_ptr<const float>(a.w_tab, c) : nullptr;
         // ties: pruned everywhere unless the quota runs out at/before this chunk
         const bool ties_pruned = !need_ties || tie_chunk < 0 || c < tie_chunk;
 
-        if (a.vec_ok && ci.n == kChunk) {
+        if (a.vec_ok && n == kChunk) {
+            float4 vv[kVecPerThread];
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) vv[j] = ld_nc_f4(src + 4 * (j * kThreads + tid));
 #pragma unroll
             for (int j = 0; j < kVecPerThread; ++j) {
                 const int e = 4 * (j * kThreads + tid);
-                const float4 v = ld_nc_f4(src + e);
+                const float4 v = vv[j];
                 uint32_t oldn = 0xFu;
                 if (mold) oldn = nibble_of(__ldg(mold + vec_word_index(j)));
                 uint32_t nib = 0;
@@ -95,7 +104,7 @@ k_emit_masks(SegView sv, EmitArgs a, int64_t c_begin, int64_t c_end) {
                 const int e = wd * 32 + lane;
                 bool keep = false;
                 float x = 0.f;
-                if (e < ci.n) {
+                if (e < n) {
                     x = src[e];
                     keep = keep_decision(x, a.mode, a.force, thr_f, thr_key, ties_pruned);
                     if (mold) keep = keep && ((__ldg(mold + wd) >> lane) & 1u);
@@ -117,7 +126,7 @@ k_emit_masks(SegView sv, EmitArgs a, int64_t c_begin, int64_t c_end) {
                 for (int wd = 0; wd < kWordsPerChunk && left > 0; ++wd) {
                     const int e = wd * 32 + tid;
                     bool tie = false;
-                    if (e < ci.n) {
+                    if (e < n) {
                         tie = key_of(src[e]) == thr_key;
                         if (mold) tie = tie && ((mold[wd] >> tid) & 1u);
                     }
@@ -133,6 +142,7 @@ k_emit_masks(SegView sv, EmitArgs a, int64_t c_begin, int64_t c_end) {
             }
             __syncthreads();
         }
+        c = cn; src = srcn; n = nn;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xFFFFFFFFu, kept, o);
@@ -144,7 +154,7 @@ k_emit_masks(SegView sv, EmitArgs a, int64_t c_begin, int64_t c_end) {
 // ---- K5: zeros of the effective weight ---------------------------------------------------
 // out[0] += #(bit == 0 || w == 0)   out[1] += #(bit == 1)
 __global__ void __launch_bounds__(kThreads)
-k_count_zeros(SegView sv, const float* const* __restrict__ w_ptrs, const uint32_t* __restrict__ mask,
+k_count_zeros(const int32_t* __restrict__ chunk_n, ChunkTab w_tab, const uint32_t* __restrict__ mask,
               unsigned long long* __restrict__ out, int64_t n_chunks, int vec_ok, int use_weights) {
     __shared__ unsigned long long s_z, s_b;
     if (threadIdx.x == 0) { s_z = 0; s_b = 0; }
@@ -152,7 +162,7 @@ k_count_zeros(SegView sv, const float* const* __restrict__ w_ptrs, const uint32_
     const int tid = threadIdx.x;
     unsigned long long zeros = 0, bits = 0;
     for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        const ChunkInfo ci = chunk_info(sv, c);
+        const int n = __ldg(chunk_n + c);
         const uint32_t* m = mask ? mask + c * kWordsPerChunk : nullptr;
         if (!use_weights) {
             // packed-only fast path: zeros = n - popcount
@@ -160,11 +170,11 @@ k_count_zeros(SegView sv, const float* const* __restrict__ w_ptrs, const uint32_
                 const uint32_t w = m ? __ldg(m + tid) : 0u;
                 bits += __popc(w);
             }
-            if (tid == 0) zeros += ci.n;     // corrected below by subtracting the bits
+            if (tid == 0) zeros += n;        // corrected below by subtracting the bits
             continue;
         }
-        const float* __restrict__ w = w_ptrs[ci.seg] + ci.elem0;
-        if (vec_ok && ci.n == kChunk) {
+        const float* __restrict__ w = chunk_ptr<const float>(w_tab, c);
+        if (vec_ok && n == kChunk) {
 #pragma unroll
             for (int j = 0; j < kVecPerThread; ++j) {
                 const float4 v = ld_nc_f4(w + 4 * (j * kThreads + tid));
@@ -175,7 +185,7 @@ k_count_zeros(SegView sv, const float* const* __restrict__ w_ptrs, const uint32_
                          ((nib & 4u) == 0 || v.z == 0.f) + ((nib & 8u) == 0 || v.w == 0.f);
             }
         } else {
-            for (int e = tid; e < ci.n; e += kThreads) {
+            for (int e = tid; e < n; e += kThreads) {
                 uint32_t bit = 1u;
                 if (m) bit = (__ldg(m + (e >> 5)) >> (e & 31)) & 1u;
                 bits += bit;
@@ -199,17 +209,16 @@ k_count_zeros(SegView sv, const float* const* __restrict__ w_ptrs, const uint32_
 // DIR 2: WEFF = bit ? W : 0 (and/or bf16).   DIR 3: G = bit ? G : 0.
 template <int DIR>
 __global__ void __launch_bounds__(kThreads)
-k_mask_convert(SegView sv, float* const* __restrict__ f_ptrs, const float* const* __restrict__ w_ptrs,
-               __nv_bfloat16* const* __restrict__ h_ptrs, uint32_t* __restrict__ mask, int64_t n_chunks,
-               int vec_ok, int outputs) {
+k_mask_convert(const int32_t* __restrict__ chunk_n, ChunkTab f_tab, ChunkTab w_tab, ChunkTab h_tab,
+               uint32_t* __restrict__ mask, int64_t n_chunks, int vec_ok, int outputs) {
     const int tid = threadIdx.x;
     for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        const ChunkInfo ci = chunk_info(sv, c);
+        const int n = __ldg(chunk_n + c);
         uint32_t* m = mask + c * kWordsPerChunk;
-        float* f = f_ptrs ? f_ptrs[ci.seg] + ci.elem0 : nullptr;
-        const float* w = w_ptrs ? w_ptrs[ci.seg] + ci.elem0 : nullptr;
-        __nv_bfloat16* h = h_ptrs ? h_ptrs[ci.seg] + ci.elem0 : nullptr;
-        if (vec_ok && ci.n == kChunk) {
+        float* f = f_tab ? chunk_ptr<float>(f_tab, c) : nullptr;
+        const float* w = w_tab ? chunk_ptr<const float>(w_tab, c) : nullptr;
+        __nv_bfloat16* h = h_tab ? chunk_ptr<__nv_bfloat16>(h_tab, c) : nullptr;
+        if (vec_ok && n == kChunk) {
 #pragma unroll
             for (int j = 0; j < kVecPerThread; ++j) {
                 const int e = 4 * (j * kThreads + tid);
@@ -244,10 +253,10 @@ k_mask_convert(SegView sv, float* const* __restrict__ f_ptrs, const float* const
             for (int wd = warp; wd < kWordsPerChunk; wd += kThreads / 32) {
                 const int e = wd * 32 + lane;
                 if (DIR == 0) {
-                    const bool on = e < ci.n && f[e] != 0.f;
+                    const bool on = e < n && f[e] != 0.f;
                     const uint32_t word = __ballot_sync(0xFFFFFFFFu, on);
                     if (lane == 0) m[wd] = word;
-                } else if (e < ci.n) {
+                } else if (e < n) {
                     const bool on = (__ldg(m + wd) >> lane) & 1u;
                     if (DIR == 1) f[e] = on ? 1.f : 0.f;
                     else if (DIR == 2) {
@@ -283,17 +292,18 @@ extern "C" int b200p_emit_masks(b200p_plan* p, int key_source, int mode, int for
     B200P_CUDA(cudaMemsetAsync(&p->d_state->n_kept, 0, sizeof(unsigned long long), st));
     if (chunk_begin == chunk_end) return B200P_OK;
     EmitArgs a;
-    a.key_ptrs = p->ptrs<const float>(kslot);
-    a.w_ptrs = p->ptrs<const float>(B200P_SLOT_W);
-    a.maskf_ptrs = p->ptrs<float>(B200P_SLOT_MASKF);
-    a.weff_ptrs = p->ptrs<float>(B200P_SLOT_WEFF);
+    a.chunk_n = p->d_chunk_n;
+    a.key_tab = p->tab(kslot);
+    a.w_tab = p->tab(B200P_SLOT_W);
+    a.maskf_tab = p->tab(B200P_SLOT_MASKF);
+    a.weff_tab = p->tab(B200P_SLOT_WEFF);
     a.old_mask = d_old_mask; a.new_mask = d_new_mask; a.st = p->d_state;
     a.mode = mode; a.force = force; a.forced_threshold = forced_threshold; a.outputs = outputs;
     bool vec = p->vec_ok[kslot];
     if (outputs & B200P_EMIT_MASKF) vec = vec && p->vec_ok[B200P_SLOT_MASKF];
     if (outputs & B200P_EMIT_WEFF) vec = vec && p->vec_ok[B200P_SLOT_WEFF] && p->vec_ok[B200P_SLOT_W];
     a.vec_ok = vec ? 1 : 0;
-    k_emit_masks<<<p->grid_for(chunk_end - chunk_begin, 4), kThreads, 0, st>>>(p->view(), a, chunk_begin, chunk_end);
+    k_emit_masks<<<p->grid_for(chunk_end - chunk_begin, 4), kThreads, 0, st>>>(a, chunk_begin, chunk_end);
     B200P_LAUNCH_CHECK("k_emit_masks");
     return B200P_OK;
 }
@@ -305,7 +315,7 @@ extern "C" int b200p_count_zeros(b200p_plan* p, const uint32_t* d_mask, uint64_t
     B200P_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     B200P_CUDA(cudaMemsetAsync(d_out, 0, 2 * sizeof(uint64_t), st));
-    k_count_zeros<<<p->grid_for(p->n_chunks, 4), kThreads, 0, st>>>(p->view(), p->ptrs<const float>(B200P_SLOT_W), d_mask,
+    k_count_zeros<<<p->grid_for(p->n_chunks, 4), kThreads, 0, st>>>(p->d_chunk_n, p->tab(B200P_SLOT_W), d_mask,
         (unsigned long long*)d_out, p->n_chunks, p->vec_ok[B200P_SLOT_W] ? 1 : 0, use_weights);
     B200P_LAUNCH_CHECK("k_count_zeros");
     return B200P_OK;
@@ -315,7 +325,7 @@ extern "C" int b200p_mask_pack_from_f32(b200p_plan* p, uint32_t* d_mask, void* s
     B200P_REQUIRE(p != nullptr && d_mask != nullptr, B200P_EINVAL, "mask_pack: null argument");
     B200P_REQUIRE(p->bound[B200P_SLOT_MASKF], B200P_ESTATE, "mask_pack: MASKF slot is not bound");
     B200P_CUDA(cudaSetDevice(p->device));
-    k_mask_convert<0><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->view(), p->ptrs<float>(B200P_SLOT_MASKF),
+    k_mask_convert<0><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->d_chunk_n, p->tab(B200P_SLOT_MASKF),
         nullptr, nullptr, d_mask, p->n_chunks, p->vec_ok[B200P_SLOT_MASKF] ? 1 : 0, 0);
     B200P_LAUNCH_CHECK("k_mask_convert<0>");
     return B200P_OK;
@@ -324,7 +334,7 @@ extern "C" int b200p_mask_unpack_to_f32(b200p_plan* p, const uint32_t* d_mask, v
     B200P_REQUIRE(p != nullptr && d_mask != nullptr, B200P_EINVAL, "mask_unpack: null argument");
     B200P_REQUIRE(p->bound[B200P_SLOT_MASKF], B200P_ESTATE, "mask_unpack: MASKF slot is not bound");
     B200P_CUDA(cudaSetDevice(p->device));
-    k_mask_convert<1><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->view(), p->ptrs<float>(B200P_SLOT_MASKF),
+    k_mask_convert<1><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->d_chunk_n, p->tab(B200P_SLOT_MASKF),
         nullptr, nullptr, const_cast<uint32_t*>(d_mask), p->n_chunks, p->vec_ok[B200P_SLOT_MASKF] ? 1 : 0, 0);
     B200P_LAUNCH_CHECK("k_mask_convert<1>");
     return B200P_OK;
@@ -338,9 +348,9 @@ extern "C" int b200p_apply_mask(b200p_plan* p, const uint32_t* d_mask, int outpu
     if (want16) B200P_REQUIRE(p->bound[B200P_SLOT_WEFF16], B200P_ESTATE, "apply_mask: WEFF16 slot is not bound");
     B200P_CUDA(cudaSetDevice(p->device));
     bool vec = p->vec_ok[B200P_SLOT_W] && (!want32 || p->vec_ok[B200P_SLOT_WEFF]) && (!want16 || p->vec_ok[B200P_SLOT_WEFF16]);
-    k_mask_convert<2><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->view(),
-        want32 ? p->ptrs<float>(B200P_SLOT_WEFF) : nullptr, p->ptrs<const float>(B200P_SLOT_W),
-        want16 ? p->ptrs<__nv_bfloat16>(B200P_SLOT_WEFF16) : nullptr, const_cast<uint32_t*>(d_mask), p->n_chunks,
+    k_mask_convert<2><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->d_chunk_n,
+        want32 ? p->tab(B200P_SLOT_WEFF) : nullptr, p->tab(B200P_SLOT_W),
+        want16 ? p->tab(B200P_SLOT_WEFF16) : nullptr, const_cast<uint32_t*>(d_mask), p->n_chunks,
         vec ? 1 : 0, want32 ? B200P_EMIT_WEFF : 0);
     B200P_LAUNCH_CHECK("k_mask_convert<2>");
     return B200P_OK;
@@ -349,7 +359,7 @@ extern "C" int b200p_mask_grads(b200p_plan* p, const uint32_t* d_mask, void* str
     B200P_REQUIRE(p != nullptr && d_mask != nullptr, B200P_EINVAL, "mask_grads: null argument");
     B200P_REQUIRE(p->bound[B200P_SLOT_G], B200P_ESTATE, "mask_grads: G slot is not bound");
     B200P_CUDA(cudaSetDevice(p->device));
-    k_mask_convert<3><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->view(), p->ptrs<float>(B200P_SLOT_G),
+    k_mask_convert<3><<<p->grid_for(p->n_chunks, 4), kThreads, 0, (cudaStream_t)stream>>>(p->d_chunk_n, p->tab(B200P_SLOT_G),
         nullptr, nullptr, const_cast<uint32_t*>(d_mask), p->n_chunks, p->vec_ok[B200P_SLOT_G] ? 1 : 0, 0);
     B200P_LAUNCH_CHECK("k_mask_convert<3>");
     return B200P_OK;

@@ -18,6 +18,15 @@ static int ensure_arena(b200p_plan* p, bool need_grads) {
         for (int i = 0; i < 2; ++i) if (!p->arena_g[i]) B200P_CUDA(cudaMalloc(&p->arena_g[i], nbytes));
         if (!p->arena_score) B200P_CUDA(cudaMalloc(&p->arena_score, nbytes));
     }
+    if (need_grads) {
+        for (int i = 0; i < 2; ++i) if (!p->arena_gtab[i]) {
+            std::vector<const void*> ptrs(p->n_seg);
+            for (int t = 0; t < p->n_seg; ++t) ptrs[t] = p->arena_g[i] + p->seg_flat_start[t];
+            int rc = b200p_ptrtable_create(p, B200P_SLOT_G, ptrs.data(), nullptr, &p->arena_gtab[i]);
+            if (rc) return rc;
+        }
+        B200P_CUDA(cudaStreamSynchronize(nullptr));
+    }
     for (int i = 0; i < 2; ++i) if (!p->arena_streams[i]) B200P_CUDA(cudaStreamCreateWithFlags(&p->arena_streams[i], cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) if (!p->arena_events[i]) B200P_CUDA(cudaEventCreateWithFlags(&p->arena_events[i], cudaEventDisableTiming));
     return B200P_OK;
@@ -51,7 +60,7 @@ extern "C" int b200p_snip_mask_build_host(b200p_plan* p, const float* h_w, const
         B200P_CUDA(cudaMemcpyAsync(p->arena_g[i], h_g[b], nbytes, cudaMemcpyHostToDevice, copy));
         B200P_CUDA(cudaEventRecord(ev_copied[i], copy));
         B200P_CUDA(cudaStreamWaitEvent(comp, ev_copied[i], 0));
-        rc = bind_flat(p, B200P_SLOT_G, p->arena_g[i], comp); if (rc) return rc;
+        rc = b200p_plan_bind_table(p, B200P_SLOT_G, p->arena_gtab[i]); if (rc) return rc;
         rc = b200p_score_accumulate(p, b > 0, 0, -1, comp); if (rc) return rc;
         B200P_CUDA(cudaEventRecord(ev_consumed[i], comp));
     }

@@ -63,18 +63,23 @@ extern "C" int b200p_plan_create(int device, int n_segments, const int64_t* h_nu
     if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaGetDeviceProperties"); }
     p->num_sms = prop.multiProcessorCount;
 
-    std::vector<int32_t> chunk_seg(chunks);
+    std::vector<int32_t> chunk_seg(chunks), chunk_n(chunks);
+    std::vector<int64_t> chunk_elem0(chunks);
     for (int t = 0; t < n_segments; ++t)
-        for (int64_t c = p->seg_chunk_start[t]; c < p->seg_chunk_start[t + 1]; ++c) chunk_seg[c] = t;
+        for (int64_t c = p->seg_chunk_start[t]; c < p->seg_chunk_start[t + 1]; ++c) {
+            const int64_t e0 = (c - p->seg_chunk_start[t]) * (int64_t)kChunk;
+            const int64_t rem = h_numel[t] - e0;
+            chunk_seg[c] = t; chunk_elem0[c] = e0; chunk_n[c] = rem < kChunk ? (int32_t)rem : kChunk;
+        }
 
 #define TRY(call) do { e = (call); if (e != cudaSuccess) { b200p_plan_destroy(p); return cuda_fail(e, #call); } } while (0)
     TRY(cudaMalloc(&p->d_chunk_seg, chunks * sizeof(int32_t)));
-    TRY(cudaMalloc(&p->d_seg_chunk_start, (n_segments + 1) * sizeof(int64_t)));
-    TRY(cudaMalloc(&p->d_seg_numel, n_segments * sizeof(int64_t)));
+    TRY(cudaMalloc(&p->d_chunk_n, chunks * sizeof(int32_t)));
+    TRY(cudaMalloc(&p->d_chunk_elem0, chunks * sizeof(int64_t)));
     TRY(cudaMemcpy(p->d_chunk_seg, chunk_seg.data(), chunks * sizeof(int32_t), cudaMemcpyHostToDevice));
-    TRY(cudaMemcpy(p->d_seg_chunk_start, p->seg_chunk_start.data(), (n_segments + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
-    TRY(cudaMemcpy(p->d_seg_numel, p->numel.data(), n_segments * sizeof(int64_t), cudaMemcpyHostToDevice));
-    for (int s = 0; s < B200P_NUM_SLOTS; ++s) TRY(cudaMalloc(&p->d_ptrs[s], n_segments * sizeof(void*)));
+    TRY(cudaMemcpy(p->d_chunk_n, chunk_n.data(), chunks * sizeof(int32_t), cudaMemcpyHostToDevice));
+    TRY(cudaMemcpy(p->d_chunk_elem0, chunk_elem0.data(), chunks * sizeof(int64_t), cudaMemcpyHostToDevice));
+    for (int s = 0; s < B200P_NUM_SLOTS; ++s) TRY(cudaMalloc(&p->d_tab_own[s], chunks * sizeof(void*)));
     TRY(cudaMalloc(&p->d_hist, kHistBins * sizeof(unsigned long long)));
     TRY(cudaMalloc(&p->d_state, sizeof(SelState)));
     TRY(cudaMalloc(&p->d_cand_key, cand_capacity * sizeof(uint32_t)));
@@ -92,10 +97,11 @@ extern "C" int b200p_plan_create(int device, int n_segments, const int64_t* h_nu
 extern "C" int b200p_plan_destroy(b200p_plan* p) {
     if (!p) return B200P_OK;
     cudaSetDevice(p->device);
-    cudaFree(p->d_chunk_seg); cudaFree(p->d_seg_chunk_start); cudaFree(p->d_seg_numel);
-    for (int s = 0; s < B200P_NUM_SLOTS; ++s) cudaFree(p->d_ptrs[s]);
+    cudaFree(p->d_chunk_seg); cudaFree(p->d_chunk_n); cudaFree(p->d_chunk_elem0);
+    for (int s = 0; s < B200P_NUM_SLOTS; ++s) cudaFree(p->d_tab_own[s]);
     cudaFree(p->d_hist); cudaFree(p->d_state); cudaFree(p->d_cand_key); cudaFree(p->d_cand_pos);
     cudaFree(p->d_chunk_ties);
+    for (int i = 0; i < 2; ++i) if (p->arena_gtab[i]) { b200p_ptrtable_destroy(p->arena_gtab[i]); p->arena_gtab[i] = nullptr; }
     cudaFree(p->arena_w); cudaFree(p->arena_g[0]); cudaFree(p->arena_g[1]); cudaFree(p->arena_score);
     cudaFree(p->arena_mask); cudaFree(p->arena_old_mask);
     for (int i = 0; i < 2; ++i) if (p->arena_streams[i]) cudaStreamDestroy(p->arena_streams[i]);
@@ -124,10 +130,42 @@ extern "C" void* b200p_plan_hist_ptr(b200p_plan* p) { return p ? (void*)p->d_his
 extern "C" void* b200p_plan_state_ptr(b200p_plan* p) { return p ? (void*)p->d_state : nullptr; }
 
 namespace b200p {
-// pointer tables travel as kernel arguments (no staging buffer, no host sync): 256 per launch
+// Segment pointers travel as kernel arguments (no staging buffer, no host sync), 256 per launch;
+// the kernel expands them into the per-chunk table: tab[c] = seg_ptr[chunk_seg[c]] + elem0[c]*size.
 struct PtrPack { void* p[256]; };
-__global__ void k_set_ptrs(void** dst, PtrPack pack, int n) {
-    if ((int)threadIdx.x < n) dst[threadIdx.x] = pack.p[threadIdx.x];
+__global__ void k_fill_chunk_ptrs(void** __restrict__ tab, const int32_t* __restrict__ chunk_seg,
+                                  const int64_t* __restrict__ chunk_elem0, PtrPack pack, int seg0, int nseg,
+                                  int elem_size, int64_t n_chunks) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const int t = chunk_seg[c] - seg0;
+    if (t < 0 || t >= nseg) return;
+    tab[c] = (char*)pack.p[t] + chunk_elem0[c] * elem_size;
+}
+
+static int slot_elem_size(int slot) { return slot == B200P_SLOT_WEFF16 ? 2 : 4; }
+
+static int fill_table(b200p_plan* p, void** d_tab, const void* const* h_ptrs, int elem_size, cudaStream_t st, bool* vec_out) {
+    bool vec = true;
+    for (int t0 = 0; t0 < p->n_seg; t0 += 256) {
+        PtrPack pack;
+        const int n = p->n_seg - t0 < 256 ? p->n_seg - t0 : 256;
+        for (int i = 0; i < n; ++i) {
+            if (h_ptrs[t0 + i] == nullptr) { set_error("bind: null segment pointer"); return B200P_EINVAL; }
+            pack.p[i] = const_cast<void*>(h_ptrs[t0 + i]);
+            if ((uintptr_t)h_ptrs[t0 + i] & 15u) vec = false;
+        }
+        // only the chunks of segments [t0, t0+n) are touched by this launch
+        const int64_t c0 = p->seg_chunk_start[t0], c1 = p->seg_chunk_start[t0 + n];
+        const int threads = 256;
+        const int blocks = (int)((c1 - c0 + threads - 1) / threads);
+        k_fill_chunk_ptrs<<<blocks, threads, 0, st>>>(d_tab + c0, p->d_chunk_seg + c0, p->d_chunk_elem0 + c0, pack, t0, n,
+                                                     elem_size, c1 - c0);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "k_fill_chunk_ptrs");
+    }
+    *vec_out = vec;
+    return B200P_OK;
 }
 }  // namespace b200p
 
@@ -135,20 +173,51 @@ extern "C" int b200p_plan_bind(b200p_plan* p, int slot, const void* const* h_ptr
     B200P_REQUIRE(p != nullptr && h_ptrs != nullptr, B200P_EINVAL, "plan_bind: null argument");
     B200P_REQUIRE(slot >= 0 && slot < B200P_NUM_SLOTS, B200P_EINVAL, "plan_bind: bad slot");
     B200P_CUDA(cudaSetDevice(p->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    bool vec = true;
-    for (int t0 = 0; t0 < p->n_seg; t0 += 256) {
-        PtrPack pack;
-        const int n = p->n_seg - t0 < 256 ? p->n_seg - t0 : 256;
-        for (int i = 0; i < n; ++i) {
-            B200P_REQUIRE(h_ptrs[t0 + i] != nullptr, B200P_EINVAL, "plan_bind: null segment pointer");
-            pack.p[i] = const_cast<void*>(h_ptrs[t0 + i]);
-            if ((uintptr_t)h_ptrs[t0 + i] & 15u) vec = false;
-        }
-        k_set_ptrs<<<1, 256, 0, st>>>(p->d_ptrs[slot] + t0, pack, n);
-        B200P_LAUNCH_CHECK("k_set_ptrs");
-    }
+    bool vec = false;
+    int rc = fill_table(p, p->d_tab_own[slot], h_ptrs, slot_elem_size(slot), (cudaStream_t)stream, &vec);
+    if (rc) return rc;
+    p->d_tab[slot] = p->d_tab_own[slot];
     p->bound[slot] = true;
     p->vec_ok[slot] = vec;
+    return B200P_OK;
+}
+
+extern "C" int b200p_ptrtable_create(b200p_plan* p, int slot, const void* const* h_ptrs, void* stream,
+                                     b200p_ptrtable** out) {
+    B200P_REQUIRE(p != nullptr && h_ptrs != nullptr && out != nullptr, B200P_EINVAL, "ptrtable_create: null argument");
+    B200P_REQUIRE(slot >= 0 && slot < B200P_NUM_SLOTS, B200P_EINVAL, "ptrtable_create: bad slot");
+    *out = nullptr;
+    B200P_CUDA(cudaSetDevice(p->device));
+    b200p_ptrtable* t = new (std::nothrow) b200p_ptrtable();
+    B200P_REQUIRE(t != nullptr, B200P_ENOMEM, "ptrtable_create: out of host memory");
+    t->plan = p;
+    cudaError_t e = cudaMalloc(&t->d_tab, p->n_chunks * sizeof(void*));
+    if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(ptrtable)"); }
+    int rc = fill_table(p, t->d_tab, h_ptrs, slot_elem_size(slot), (cudaStream_t)stream, &t->vec_ok);
+    if (rc) { cudaFree(t->d_tab); delete t; return rc; }
+    *out = t;
+    return B200P_OK;
+}
+
+extern "C" int b200p_ptrtable_destroy(b200p_ptrtable* t) {
+    if (!t) return B200P_OK;
+    if (t->plan) {
+        cudaSetDevice(t->plan->device);
+        for (int s = 0; s < B200P_NUM_SLOTS; ++s)
+            if (t->plan->d_tab[s] == t->d_tab) { t->plan->d_tab[s] = nullptr; t->plan->bound[s] = false; }
+    }
+    cudaFree(t->d_tab);
+    cudaGetLastError();
+    delete t;
+    return B200P_OK;
+}
+
+extern "C" int b200p_plan_bind_table(b200p_plan* p, int slot, const b200p_ptrtable* t) {
+    B200P_REQUIRE(p != nullptr && t != nullptr, B200P_EINVAL, "plan_bind_table: null argument");
+    B200P_REQUIRE(slot >= 0 && slot < B200P_NUM_SLOTS, B200P_EINVAL, "plan_bind_table: bad slot");
+    B200P_REQUIRE(t->plan == p, B200P_EINVAL, "plan_bind_table: table belongs to another plan");
+    p->d_tab[slot] = t->d_tab;          // host-side swap: no launch, takes effect for the next launch
+    p->bound[slot] = true;
+    p->vec_ok[slot] = t->vec_ok;
     return B200P_OK;
 }

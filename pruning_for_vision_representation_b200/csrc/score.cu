@@ -9,16 +9,25 @@ namespace b200p {
 
 template <bool ACCUMULATE, bool VEC>
 __global__ void __launch_bounds__(kThreads)
-k_score_accumulate(SegView sv, const float* const* __restrict__ w_ptrs,
-                   const float* const* __restrict__ g_ptrs, float* const* __restrict__ s_ptrs,
+k_score_accumulate(const int32_t* __restrict__ chunk_n, ChunkTab w_tab, ChunkTab g_tab, ChunkTab s_tab,
                    int64_t c_begin, int64_t c_end) {
     const int tid = threadIdx.x;
-    for (int64_t c = c_begin + blockIdx.x; c < c_end; c += gridDim.x) {
-        const ChunkInfo ci = chunk_info(sv, c);
-        const float* __restrict__ w = w_ptrs[ci.seg] + ci.elem0;
-        const float* __restrict__ g = g_ptrs[ci.seg] + ci.elem0;
-        float* __restrict__ s = s_ptrs[ci.seg] + ci.elem0;
-        if (VEC && ci.n == kChunk) {
+    int64_t c = c_begin + blockIdx.x;
+    if (c >= c_end) return;
+    const float* w = chunk_ptr<const float>(w_tab, c);
+    const float* g = chunk_ptr<const float>(g_tab, c);
+    float* s = chunk_ptr<float>(s_tab, c);
+    int n = __ldg(chunk_n + c);
+    while (true) {
+        // next chunk's addresses are fetched while this chunk streams
+        const int64_t cn = c + gridDim.x;
+        const bool more = cn < c_end;
+        const float* wn = nullptr; const float* gn = nullptr; float* sn = nullptr; int nn = 0;
+        if (more) {
+            wn = chunk_ptr<const float>(w_tab, cn); gn = chunk_ptr<const float>(g_tab, cn);
+            sn = chunk_ptr<float>(s_tab, cn); nn = __ldg(chunk_n + cn);
+        }
+        if (VEC && n == kChunk) {
             float4 wv[kVecPerThread], gv[kVecPerThread], sv4[kVecPerThread];
 #pragma unroll
             for (int j = 0; j < kVecPerThread; ++j) {
@@ -42,12 +51,14 @@ k_score_accumulate(SegView sv, const float* const* __restrict__ w_ptrs,
                 st_f4(s + e, r);
             }
         } else {
-            for (int e = tid; e < ci.n; e += kThreads) {
+            for (int e = tid; e < n; e += kThreads) {
                 float r = fabsf(__fmul_rn(w[e], g[e]));
                 if (ACCUMULATE) r = __fadd_rn(s[e], r);
                 s[e] = r;
             }
         }
+        if (!more) break;
+        c = cn; w = wn; g = gn; s = sn; n = nn;
     }
 }
 
@@ -115,16 +126,14 @@ extern "C" int b200p_score_accumulate(b200p_plan* p, int accumulate, int64_t chu
     const bool vec = p->vec_ok[B200P_SLOT_W] && p->vec_ok[B200P_SLOT_G] && p->vec_ok[B200P_SLOT_SCORE];
     const int grid = p->grid_for(chunk_end - chunk_begin, 4);
     cudaStream_t st = (cudaStream_t)stream;
-    auto w = p->ptrs<const float>(B200P_SLOT_W);
-    auto g = p->ptrs<const float>(B200P_SLOT_G);
-    auto s = p->ptrs<float>(B200P_SLOT_SCORE);
-    SegView sv = p->view();
+    ChunkTab w = p->tab(B200P_SLOT_W), g = p->tab(B200P_SLOT_G), s = p->tab(B200P_SLOT_SCORE);
+    const int32_t* cn = p->d_chunk_n;
     if (accumulate) {
-        if (vec) k_score_accumulate<true, true><<<grid, kThreads, 0, st>>>(sv, w, g, s, chunk_begin, chunk_end);
-        else     k_score_accumulate<true, false><<<grid, kThreads, 0, st>>>(sv, w, g, s, chunk_begin, chunk_end);
+        if (vec) k_score_accumulate<true, true><<<grid, kThreads, 0, st>>>(cn, w, g, s, chunk_begin, chunk_end);
+        else     k_score_accumulate<true, false><<<grid, kThreads, 0, st>>>(cn, w, g, s, chunk_begin, chunk_end);
     } else {
-        if (vec) k_score_accumulate<false, true><<<grid, kThreads, 0, st>>>(sv, w, g, s, chunk_begin, chunk_end);
-        else     k_score_accumulate<false, false><<<grid, kThreads, 0, st>>>(sv, w, g, s, chunk_begin, chunk_end);
+        if (vec) k_score_accumulate<false, true><<<grid, kThreads, 0, st>>>(cn, w, g, s, chunk_begin, chunk_end);
+        else     k_score_accumulate<false, false><<<grid, kThreads, 0, st>>>(cn, w, g, s, chunk_begin, chunk_end);
     }
     B200P_LAUNCH_CHECK("k_score_accumulate");
     return B200P_OK;

@@ -32,22 +32,44 @@ __device__ __forceinline__ int slot_element(int i) {
     return VEC ? 4 * ((i >> 2) * kThreads + threadIdx.x) + (i & 3) : i * kThreads + threadIdx.x;
 }
 
-// Loads the 16 keys this thread owns and a 16-bit "alive" bitmap (valid element, old mask set).
-template <bool VEC, bool ABS_ONLY = true>
-__device__ __forceinline__ void load_keys(const float* __restrict__ src, const uint32_t* __restrict__ mask_chunk,
-                                          int n, uint32_t (&key)[16], uint32_t& alive) {
-    alive = 0;
-    if (VEC) {
+// Raw registers of one chunk (vector path): 4 float4 + the 16-bit alive bitmap.  Loaded one
+// iteration ahead of its use so that the histogram / compare phase of the current chunk overlaps
+// the loads of the next one.
+struct ChunkRegs {
+    float4 v[kVecPerThread];
+    uint32_t alive;
+    bool vec;          // false: partial or unaligned chunk, handled by the scalar path on demand
+};
+
+__device__ __forceinline__ void prefetch_chunk(const float* __restrict__ src, const uint32_t* __restrict__ mask_chunk,
+                                               int n, int vec_ok, ChunkRegs& r) {
+    r.vec = vec_ok && n == kChunk;
+    r.alive = 0xFFFFu;
+    if (r.vec) {
+#pragma unroll
+        for (int j = 0; j < kVecPerThread; ++j) r.v[j] = ld_nc_f4(src + 4 * (j * kThreads + threadIdx.x));
+        if (mask_chunk) {
+            r.alive = 0;
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j)
+                r.alive |= nibble_of(__ldg(mask_chunk + vec_word_index(j))) << (4 * j);
+        }
+    }
+}
+
+// 16 keys + alive bitmap of this thread for the chunk held in `r` (or loaded here, scalar path)
+__device__ __forceinline__ void chunk_keys(const ChunkRegs& r, const float* __restrict__ src,
+                                           const uint32_t* __restrict__ mask_chunk, int n,
+                                           uint32_t (&key)[16], uint32_t& alive) {
+    if (r.vec) {
 #pragma unroll
         for (int j = 0; j < kVecPerThread; ++j) {
-            const float4 v = ld_nc_f4(src + 4 * (j * kThreads + threadIdx.x));
-            key[4 * j + 0] = key_of(v.x); key[4 * j + 1] = key_of(v.y);
-            key[4 * j + 2] = key_of(v.z); key[4 * j + 3] = key_of(v.w);
-            uint32_t nib = 0xFu;
-            if (mask_chunk) nib = nibble_of(__ldg(mask_chunk + vec_word_index(j)));
-            alive |= nib << (4 * j);
+            key[4 * j + 0] = key_of(r.v[j].x); key[4 * j + 1] = key_of(r.v[j].y);
+            key[4 * j + 2] = key_of(r.v[j].z); key[4 * j + 3] = key_of(r.v[j].w);
         }
+        alive = r.alive;
     } else {
+        alive = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int e = i * kThreads + threadIdx.x;
@@ -149,131 +171,143 @@ __device__ void scan_and_advance(int pass, unsigned long long* __restrict__ hist
     }
 }
 
-// flush the CTA histogram and, if this is the last CTA, run the scan
-__device__ __forceinline__ void flush_and_maybe_scan(int pass, const uint32_t* s_hist,
-                                                     unsigned long long* hist, SelState* st,
-                                                     unsigned int* ticket, long long cand_capacity,
-                                                     bool fuse_scan) {
-    const int bins = digit_bins(pass);
-    for (int b = threadIdx.x; b < bins; b += kThreads) {
-        const uint32_t v = s_hist[b];
-        if (v) atomicAdd(hist + b, (unsigned long long)v);
-    }
-    if (!fuse_scan) return;
-    __shared__ unsigned int s_ticket;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
-    __syncthreads();
-    if (s_ticket == gridDim.x - 1) {
-        __threadfence();
-        scan_and_advance(pass, hist, st, cand_capacity);
-        if (threadIdx.x == 0) *ticket = 0u;
-    }
+// ---- select state initialisation ----------------------------------------------------------
+__device__ __forceinline__ void init_state(SelState* st, unsigned long long k, uint32_t mode, uint32_t allow_collect) {
+    SelState s;
+    memset(&s, 0, sizeof(s));
+    s.k = k; s.k_request = k; s.mode = mode; s.allow_collect = allow_collect; s.tie_chunk = -1;
+    *st = s;
 }
+
+struct PassArgs {
+    const int32_t* chunk_n;
+    ChunkTab key_tab;
+    const uint32_t* old_mask;
+    unsigned long long* hist;
+    SelState* st;
+    uint32_t* cand_key;
+    uint32_t* cand_pos;
+    unsigned int* ticket;
+    long long cand_capacity;
+    int64_t c_begin, c_end;
+    int vec_ok, fuse_scan;
+    // fused initialisation (pass 0 of b200p_select_kth): the last CTA resets the state before its scan
+    int fuse_init;
+    unsigned long long k;
+    uint32_t mode, allow_collect;
+};
 
 // ---- full-data pass --------------------------------------------------------------------
 // PASS 0: histogram digit 0 of every alive key.
-// PASS 1: keys whose digit 0 matches the chosen bucket: gather (collect mode) or histogram.
-// PASS 2: (histogram mode only) keys matching 24 fixed bits: histogram digit 2.
+// PASS 1: keys whose digit 0 matches the chosen bucket are histogrammed by digit 1 and, in collect
+//         mode, appended to the candidate buffer as (key, position) in the same sweep.
+// PASS 2: histogram digit 2 of the keys matching the 24 fixed bits — over the candidate buffer in
+//         collect mode, over the full data otherwise.
 template <int PASS>
-__global__ void __launch_bounds__(kThreads)
-k_select_pass_full(SegView sv, const float* const* __restrict__ key_ptrs, const uint32_t* __restrict__ old_mask,
-                   unsigned long long* __restrict__ hist, SelState* __restrict__ st,
-                   uint32_t* __restrict__ cand_key, uint32_t* __restrict__ cand_pos, unsigned int* __restrict__ ticket,
-                   long long cand_capacity, int64_t c_begin, int64_t c_end, int vec_ok, int fuse_scan) {
+__global__ void __launch_bounds__(kThreads, 3)
+k_select_pass(PassArgs a) {
     __shared__ uint32_t s_hist[kHistBins];
+    SelState* __restrict__ st = a.st;
     uint32_t prefix = 0, collect = 0;
-    if (PASS > 0) {
-        prefix = st->prefix; collect = st->collect;
-        if (PASS == 2 && collect) return;            // candidates carry passes 1 and 2
-    }
-    const bool do_hist = !(PASS == 1 && collect);
-    if (do_hist) {
-        for (int b = threadIdx.x; b < kHistBins; b += kThreads) s_hist[b] = 0;
-        __syncthreads();
-    }
-    const uint32_t pmask = prefix_mask_before(PASS);
-    const int lane = threadIdx.x & 31;
-
-    for (int64_t c = c_begin + blockIdx.x; c < c_end; c += gridDim.x) {
-        const ChunkInfo ci = chunk_info(sv, c);
-        const float* __restrict__ src = key_ptrs[ci.seg] + ci.elem0;
-        const uint32_t* mchunk = old_mask ? old_mask + c * kWordsPerChunk : nullptr;
-        uint32_t key[16], alive;
-        const bool vec = vec_ok && ci.n == kChunk;
-        if (vec) load_keys<true>(src, mchunk, ci.n, key, alive);
-        else     load_keys<false>(src, mchunk, ci.n, key, alive);
-
-        if (PASS == 0) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if ((alive >> i) & 1u) atomicAdd(&s_hist[key[i] >> 19], 1u);
-        } else {
-            uint32_t match = 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (((alive >> i) & 1u) && ((key[i] & pmask) == prefix)) match |= 1u << i;
-            if (do_hist) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if ((match >> i) & 1u) atomicAdd(&s_hist[digit_of(key[i], PASS)], 1u);
-            } else {
-                // warp-aggregated append of (key, position) pairs
-                const int cnt = __popc(match);
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const int warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                if (warp_total > 0) {
-                    uint32_t base = 0;
-                    if (lane == 31) base = atomicAdd(&st->cand_count, (uint32_t)warp_total);
-                    base = __shfl_sync(0xFFFFFFFFu, base, 31);
-                    uint32_t off = base + (uint32_t)(incl - cnt);
-                    const uint32_t pos0 = (uint32_t)(c * kChunk);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if ((match >> i) & 1u) {
-                            if ((long long)off < cand_capacity) {
-                                cand_key[off] = key[i];
-                                cand_pos[off] = pos0 + (uint32_t)(vec ? slot_element<true>(i) : slot_element<false>(i));
-                            }
-                            ++off;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    if (do_hist) {
-        __syncthreads();
-        flush_and_maybe_scan(PASS, s_hist, hist, st, ticket, cand_capacity, fuse_scan != 0);
-    }
-}
-
-// ---- candidate passes (collect mode) ---------------------------------------------------
-template <int PASS>
-__global__ void __launch_bounds__(kThreads)
-k_select_pass_cand(const uint32_t* __restrict__ cand_key, unsigned long long* __restrict__ hist,
-                   SelState* __restrict__ st, unsigned int* __restrict__ ticket, long long cand_capacity,
-                   int fuse_scan) {
-    __shared__ uint32_t s_hist[kHistBins];
-    if (!st->collect) return;
-    const uint32_t n = st->cand_count;
-    const uint32_t prefix = st->prefix;
-    const uint32_t pmask = prefix_mask_before(PASS);
+    if (PASS > 0) { prefix = st->prefix; collect = st->collect; }
     const int bins = digit_bins(PASS);
     for (int b = threadIdx.x; b < bins; b += kThreads) s_hist[b] = 0;
     __syncthreads();
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-        const uint32_t key = cand_key[i];
-        if ((key & pmask) == prefix) atomicAdd(&s_hist[digit_of(key, PASS)], 1u);
+    const uint32_t pmask = prefix_mask_before(PASS);
+    const int lane = threadIdx.x & 31;
+
+    if (PASS == 2 && collect) {
+        const uint32_t n = st->cand_count;
+        for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+            const uint32_t key = a.cand_key[i];
+            if ((key & pmask) == prefix) atomicAdd(&s_hist[key & 0x7Fu], 1u);
+        }
+    } else {
+        int64_t c = a.c_begin + blockIdx.x;
+        if (c < a.c_end) {
+            const float* src = chunk_ptr<const float>(a.key_tab, c);
+            int n = __ldg(a.chunk_n + c);
+            ChunkRegs cur;
+            prefetch_chunk(src, a.old_mask ? a.old_mask + c * kWordsPerChunk : nullptr, n, a.vec_ok, cur);
+            while (true) {
+                const int64_t cn = c + gridDim.x;
+                const bool more = cn < a.c_end;
+                const float* srcn = nullptr; int nn = 0;
+                ChunkRegs nxt; nxt.vec = false; nxt.alive = 0;
+                if (more) {
+                    srcn = chunk_ptr<const float>(a.key_tab, cn);
+                    nn = __ldg(a.chunk_n + cn);
+                    prefetch_chunk(srcn, a.old_mask ? a.old_mask + cn * kWordsPerChunk : nullptr, nn, a.vec_ok, nxt);
+                }
+                uint32_t key[16], alive;
+                chunk_keys(cur, src, a.old_mask ? a.old_mask + c * kWordsPerChunk : nullptr, n, key, alive);
+                if (PASS == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if ((alive >> i) & 1u) atomicAdd(&s_hist[key[i] >> 19], 1u);
+                } else {
+                    uint32_t match = 0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (((alive >> i) & 1u) && ((key[i] & pmask) == prefix)) match |= 1u << i;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if ((match >> i) & 1u) atomicAdd(&s_hist[digit_of(key[i], PASS)], 1u);
+                    if (PASS == 1 && collect) {
+                        // warp-aggregated append of (key, position) pairs
+                        const int cnt = __popc(match);
+                        int incl = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        const int warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                        if (warp_total > 0) {
+                            uint32_t base = 0;
+                            if (lane == 31) base = atomicAdd(&st->cand_count, (uint32_t)warp_total);
+                            base = __shfl_sync(0xFFFFFFFFu, base, 31);
+                            uint32_t off = base + (uint32_t)(incl - cnt);
+                            const uint32_t pos0 = (uint32_t)(c * kChunk);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                if ((match >> i) & 1u) {
+                                    if ((long long)off < a.cand_capacity) {
+                                        a.cand_key[off] = key[i];
+                                        a.cand_pos[off] = pos0 + (uint32_t)(cur.vec ? slot_element<true>(i) : slot_element<false>(i));
+                                    }
+                                    ++off;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (!more) break;
+                c = cn; src = srcn; n = nn; cur = nxt;
+            }
+        }
     }
     __syncthreads();
-    flush_and_maybe_scan(PASS, s_hist, hist, st, ticket, cand_capacity, fuse_scan != 0);
+    // flush the CTA histogram; the last CTA to finish scans it and advances the select state
+    for (int b = threadIdx.x; b < bins; b += kThreads) {
+        const uint32_t v = s_hist[b];
+        if (v) atomicAdd(a.hist + b, (unsigned long long)v);
+    }
+    if (!a.fuse_scan) return;
+    __shared__ unsigned int s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1) {
+        __threadfence();
+        if (PASS == 0 && a.fuse_init) {
+            if (threadIdx.x == 0) init_state(st, a.k, a.mode, a.allow_collect);
+            __syncthreads();
+        }
+        scan_and_advance(PASS, a.hist, st, a.cand_capacity);
+        if (threadIdx.x == 0) *a.ticket = 0u;
+    }
 }
 
 __global__ void k_select_scan(int pass, unsigned long long* hist, SelState* st, long long cand_capacity) {
@@ -284,32 +318,37 @@ __global__ void k_select_init(SelState* st, unsigned long long* hist, unsigned i
                               unsigned long long k, uint32_t mode, uint32_t allow_collect) {
     for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) hist[b] = 0ull;
     if (threadIdx.x == 0) {
-        SelState s;
-        memset(&s, 0, sizeof(s));
-        s.k = k; s.k_request = k; s.mode = mode; s.allow_collect = allow_collect; s.tie_chunk = -1;
-        *st = s;
+        init_state(st, k, mode, allow_collect);
         *ticket = 0u;
     }
 }
 
 // ---- tie resolution (EXACT_K with quota < n_equal) ---------------------------------------
-// chunk_ties[c] = number of alive keys == threshold in chunk c
+// chunk_ties[c] = number of alive keys == threshold in chunk c.  Collect mode: every tie is in the
+// candidate buffer (one atomic per tied candidate into a zeroed table); otherwise re-stream the keys.
 __global__ void __launch_bounds__(kThreads)
-k_tie_count_full(SegView sv, const float* const* __restrict__ key_ptrs, const uint32_t* __restrict__ old_mask,
-                 const SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties,
-                 int64_t c_begin, int64_t c_end, int vec_ok) {
-    if (!st->need_ties || st->collect) return;
-    __shared__ int s_cnt;
+k_tie_count(const int32_t* __restrict__ chunk_n, ChunkTab key_tab, const uint32_t* __restrict__ old_mask,
+            const SelState* __restrict__ st, const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_pos,
+            uint32_t* __restrict__ chunk_ties, int64_t c_begin, int64_t c_end, int vec_ok) {
+    if (!st->need_ties) return;
     const uint32_t thr = st->thr_key;
+    if (st->collect) {
+        const uint32_t n = st->cand_count;
+        for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
+            if (cand_key[i] == thr) atomicAdd(&chunk_ties[cand_pos[i] >> 12], 1u);
+        return;
+    }
+    __shared__ int s_cnt;
     for (int64_t c = c_begin + blockIdx.x; c < c_end; c += gridDim.x) {
         if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
-        const ChunkInfo ci = chunk_info(sv, c);
-        const float* __restrict__ src = key_ptrs[ci.seg] + ci.elem0;
+        const float* src = chunk_ptr<const float>(key_tab, c);
+        const int n = __ldg(chunk_n + c);
         const uint32_t* mchunk = old_mask ? old_mask + c * kWordsPerChunk : nullptr;
+        ChunkRegs r;
+        prefetch_chunk(src, mchunk, n, vec_ok, r);
         uint32_t key[16], alive;
-        if (vec_ok && ci.n == kChunk) load_keys<true>(src, mchunk, ci.n, key, alive);
-        else                          load_keys<false>(src, mchunk, ci.n, key, alive);
+        chunk_keys(r, src, mchunk, n, key, alive);
         int cnt = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) cnt += (((alive >> i) & 1u) && key[i] == thr) ? 1 : 0;
@@ -320,14 +359,6 @@ k_tie_count_full(SegView sv, const float* const* __restrict__ key_ptrs, const ui
         if (threadIdx.x == 0) chunk_ties[c] = (uint32_t)s_cnt;
         __syncthreads();
     }
-}
-__global__ void __launch_bounds__(kThreads)
-k_tie_count_cand(const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_pos,
-                 const SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties) {
-    if (!st->need_ties || !st->collect) return;
-    const uint32_t n = st->cand_count, thr = st->thr_key;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
-        if (cand_key[i] == thr) atomicAdd(&chunk_ties[cand_pos[i] >> 12], 1u);
 }
 // One CTA: walk chunk_ties[c_begin, c_end) in order, find where the (quota - tie_offset)-th tie
 // falls, clear the table again.
@@ -426,30 +457,32 @@ extern "C" int b200p_select_begin(b200p_plan* p, uint64_t k, int mode, int allow
     return B200P_OK;
 }
 
-static int launch_pass_full(b200p_plan* p, int pass, int key_source, const uint32_t* d_old_mask,
-                            int64_t c0, int64_t c1, int fuse_scan, cudaStream_t st) {
-    const int slot = key_slot(key_source);
-    const int grid = p->grid_for(c1 - c0, 4);
-    auto keys = p->ptrs<const float>(slot);
-    const int vec = p->vec_ok[slot] ? 1 : 0;
-    SegView sv = p->view();
-    switch (pass) {
-        case 0: k_select_pass_full<0><<<grid, kThreads, 0, st>>>(sv, keys, d_old_mask, p->d_hist, p->d_state, p->d_cand_key,
-                    p->d_cand_pos, ticket_ptr(p), p->cand_capacity, c0, c1, vec, fuse_scan); break;
-        case 1: k_select_pass_full<1><<<grid, kThreads, 0, st>>>(sv, keys, d_old_mask, p->d_hist, p->d_state, p->d_cand_key,
-                    p->d_cand_pos, ticket_ptr(p), p->cand_capacity, c0, c1, vec, fuse_scan); break;
-        default: k_select_pass_full<2><<<grid, kThreads, 0, st>>>(sv, keys, d_old_mask, p->d_hist, p->d_state, p->d_cand_key,
-                    p->d_cand_pos, ticket_ptr(p), p->cand_capacity, c0, c1, vec, fuse_scan); break;
+// grid of a pass: enough CTAs for the chunk range and, for pass 2 / ties, for the candidate buffer
+static int pass_grid(b200p_plan* p, int64_t chunks, bool cand_too, int ctas_per_sm = 3) {
+    int64_t work = chunks;
+    if (cand_too) {
+        const int64_t blocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
+        if (blocks > work) work = blocks;
     }
-    B200P_LAUNCH_CHECK("k_select_pass_full");
-    return B200P_OK;
+    return p->grid_for(work, ctas_per_sm);
 }
-static int launch_pass_cand(b200p_plan* p, int pass, int fuse_scan, cudaStream_t st) {
-    int64_t blocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
-    const int grid = p->grid_for(blocks, 2);
-    if (pass == 1) k_select_pass_cand<1><<<grid, kThreads, 0, st>>>(p->d_cand_key, p->d_hist, p->d_state, ticket_ptr(p), p->cand_capacity, fuse_scan);
-    else           k_select_pass_cand<2><<<grid, kThreads, 0, st>>>(p->d_cand_key, p->d_hist, p->d_state, ticket_ptr(p), p->cand_capacity, fuse_scan);
-    B200P_LAUNCH_CHECK("k_select_pass_cand");
+
+static int launch_pass(b200p_plan* p, int pass, int key_source, const uint32_t* d_old_mask,
+                       int64_t c0, int64_t c1, int fuse_scan, int fuse_init, uint64_t k, int mode, int allow_collect,
+                       cudaStream_t st) {
+    const int slot = key_slot(key_source);
+    PassArgs a;
+    a.chunk_n = p->d_chunk_n; a.key_tab = p->tab(slot); a.old_mask = d_old_mask; a.hist = p->d_hist; a.st = p->d_state;
+    a.cand_key = p->d_cand_key; a.cand_pos = p->d_cand_pos; a.ticket = ticket_ptr(p); a.cand_capacity = p->cand_capacity;
+    a.c_begin = c0; a.c_end = c1; a.vec_ok = p->vec_ok[slot] ? 1 : 0; a.fuse_scan = fuse_scan;
+    a.fuse_init = fuse_init; a.k = k; a.mode = (uint32_t)mode; a.allow_collect = allow_collect ? 1u : 0u;
+    const int grid = pass_grid(p, c1 - c0, pass == 2, pass == 0 ? 4 : 3);
+    switch (pass) {
+        case 0: k_select_pass<0><<<grid, kThreads, 0, st>>>(a); break;
+        case 1: k_select_pass<1><<<grid, kThreads, 0, st>>>(a); break;
+        default: k_select_pass<2><<<grid, kThreads, 0, st>>>(a); break;
+    }
+    B200P_LAUNCH_CHECK("k_select_pass");
     return B200P_OK;
 }
 
@@ -461,9 +494,9 @@ extern "C" int b200p_select_hist(b200p_plan* p, int pass, int key_source, const 
     if (chunk_end < 0) chunk_end = p->n_chunks;
     B200P_REQUIRE(chunk_begin >= 0 && chunk_begin <= chunk_end && chunk_end <= p->n_chunks, B200P_EINVAL, "select_hist: bad chunk range");
     B200P_CUDA(cudaSetDevice(p->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    if (chunk_end > chunk_begin) { rc = launch_pass_full(p, pass, key_source, d_old_mask, chunk_begin, chunk_end, 0, st); if (rc) return rc; }
-    if (pass >= 1) { rc = launch_pass_cand(p, pass, 0, st); if (rc) return rc; }   // no-op unless collect mode
+    // pass 2 always launches: in collect mode it histograms this rank's candidate buffer
+    if (chunk_end > chunk_begin || pass == 2)
+        return launch_pass(p, pass, key_source, d_old_mask, chunk_begin, chunk_end, 0, 0, 0, 0, 0, (cudaStream_t)stream);
     return B200P_OK;
 }
 
@@ -479,14 +512,9 @@ extern "C" int b200p_select_scan(b200p_plan* p, int pass, void* stream) {
 static int launch_tie_count(b200p_plan* p, int key_source, const uint32_t* d_old_mask,
                             int64_t chunk_begin, int64_t chunk_end, cudaStream_t st) {
     const int slot = key_slot(key_source);
-    if (chunk_end > chunk_begin) {
-        k_tie_count_full<<<p->grid_for(chunk_end - chunk_begin, 4), kThreads, 0, st>>>(p->view(), p->ptrs<const float>(slot),
-            d_old_mask, p->d_state, p->d_chunk_ties, chunk_begin, chunk_end, p->vec_ok[slot] ? 1 : 0);
-        B200P_LAUNCH_CHECK("k_tie_count_full");
-    }
-    int64_t blocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
-    k_tie_count_cand<<<p->grid_for(blocks, 2), kThreads, 0, st>>>(p->d_cand_key, p->d_cand_pos, p->d_state, p->d_chunk_ties);
-    B200P_LAUNCH_CHECK("k_tie_count_cand");
+    k_tie_count<<<pass_grid(p, chunk_end - chunk_begin, true), kThreads, 0, st>>>(p->d_chunk_n, p->tab(slot), d_old_mask,
+        p->d_state, p->d_cand_key, p->d_cand_pos, p->d_chunk_ties, chunk_begin, chunk_end, p->vec_ok[slot] ? 1 : 0);
+    B200P_LAUNCH_CHECK("k_tie_count");
     return B200P_OK;
 }
 
@@ -541,13 +569,15 @@ extern "C" int b200p_select_kth(b200p_plan* p, int key_source, const uint32_t* d
     B200P_REQUIRE(p != nullptr, B200P_EINVAL, "select_kth: null plan");
     int rc = check_key_source(p, key_source, "select_kth"); if (rc) return rc;
     B200P_REQUIRE(k >= 1 && k <= (uint64_t)p->total, B200P_EINVAL, "select_kth: k must be in [1, N]");
+    B200P_REQUIRE(mode == B200P_MODE_SNIP_STRICT || mode == B200P_MODE_EXACT_K, B200P_EINVAL, "select_kth: bad mode");
+    B200P_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
-    rc = b200p_select_begin(p, k, mode, 1, stream); if (rc) return rc;
-    rc = launch_pass_full(p, 0, key_source, d_old_mask, 0, p->n_chunks, 1, st); if (rc) return rc;
-    rc = launch_pass_full(p, 1, key_source, d_old_mask, 0, p->n_chunks, 1, st); if (rc) return rc;  // gather or histogram
-    rc = launch_pass_cand(p, 1, 1, st); if (rc) return rc;
-    rc = launch_pass_full(p, 2, key_source, d_old_mask, 0, p->n_chunks, 1, st); if (rc) return rc;  // exits at once in collect mode
-    rc = launch_pass_cand(p, 2, 1, st); if (rc) return rc;
+    // Three launches, no host round trip: the state reset rides in pass 0's last CTA (the global
+    // histogram and the ticket are left zeroed by every completed scan), every pass ends with the
+    // last-CTA scan.  Pass 2 runs on the candidates gathered by pass 1 unless the bucket overflowed.
+    rc = launch_pass(p, 0, key_source, d_old_mask, 0, p->n_chunks, 1, 1, k, mode, 1, st); if (rc) return rc;
+    rc = launch_pass(p, 1, key_source, d_old_mask, 0, p->n_chunks, 1, 0, 0, 0, 0, st); if (rc) return rc;
+    rc = launch_pass(p, 2, key_source, d_old_mask, 0, p->n_chunks, 1, 0, 0, 0, 0, st); if (rc) return rc;
     if (mode == B200P_MODE_EXACT_K) { rc = b200p_select_ties(p, key_source, d_old_mask, 0, p->n_chunks, 0, stream); if (rc) return rc; }
     return B200P_OK;
 }

@@ -14,8 +14,8 @@
 namespace b200p {
 
 struct SgdArgs {
-    float* const* w_ptrs; const float* const* g_ptrs; float* const* buf_ptrs;
-    float* const* weff_ptrs; __nv_bfloat16* const* weff16_ptrs;
+    const int32_t* chunk_n;
+    ChunkTab w_tab, g_tab, buf_tab, weff_tab, weff16_tab;
     const uint32_t* mask;      // nullable: dense SGD
     float lr, momentum, one_minus_damp, wd;
     int flags, vec_ok;
@@ -37,19 +37,20 @@ __device__ __forceinline__ void sgd_elem(float& w, float g, float& buf, bool on,
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_masked_sgd(SegView sv, SgdArgs a, int64_t n_chunks) {
+k_masked_sgd(SgdArgs a, int64_t n_chunks) {
     const int tid = threadIdx.x;
     const bool use_buf = a.momentum != 0.f;
     const bool read_buf = use_buf && !(a.flags & B200P_SGD_FIRST_STEP);
+    const bool want32 = a.flags & B200P_SGD_EMIT_WEFF, want16 = a.flags & B200P_SGD_EMIT_WEFF16;
     for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        const ChunkInfo ci = chunk_info(sv, c);
-        float* __restrict__ w = a.w_ptrs[ci.seg] + ci.elem0;
-        const float* __restrict__ g = a.g_ptrs[ci.seg] + ci.elem0;
-        float* __restrict__ buf = use_buf ? a.buf_ptrs[ci.seg] + ci.elem0 : nullptr;
-        float* __restrict__ we = (a.flags & B200P_SGD_EMIT_WEFF) ? a.weff_ptrs[ci.seg] + ci.elem0 : nullptr;
-        __nv_bfloat16* __restrict__ wh = (a.flags & B200P_SGD_EMIT_WEFF16) ? a.weff16_ptrs[ci.seg] + ci.elem0 : nullptr;
+        const int n = __ldg(a.chunk_n + c);
+        float* __restrict__ w = chunk_ptr<float>(a.w_tab, c);
+        const float* __restrict__ g = chunk_ptr<const float>(a.g_tab, c);
+        float* __restrict__ buf = use_buf ? chunk_ptr<float>(a.buf_tab, c) : nullptr;
+        float* __restrict__ we = want32 ? chunk_ptr<float>(a.weff_tab, c) : nullptr;
+        __nv_bfloat16* __restrict__ wh = want16 ? chunk_ptr<__nv_bfloat16>(a.weff16_tab, c) : nullptr;
         const uint32_t* m = a.mask ? a.mask + c * kWordsPerChunk : nullptr;
-        if (a.vec_ok && ci.n == kChunk) {
+        if (a.vec_ok && n == kChunk) {
             float4 wv[kVecPerThread], gv[kVecPerThread], bv[kVecPerThread];
             uint32_t nib[kVecPerThread];
 #pragma unroll
@@ -78,7 +79,7 @@ k_masked_sgd(SegView sv, SgdArgs a, int64_t n_chunks) {
                 }
             }
         } else {
-            for (int e = tid; e < ci.n; e += kThreads) {
+            for (int e = tid; e < n; e += kThreads) {
                 const bool on = m ? ((__ldg(m + (e >> 5)) >> (e & 31)) & 1u) : true;
                 float wv = w[e], bv = read_buf ? buf[e] : 0.f, o;
                 sgd_elem(wv, g[e], bv, on, a, o);
@@ -105,16 +106,17 @@ extern "C" int b200p_masked_sgd_step(b200p_plan* p, const uint32_t* d_mask, floa
     if (flags & B200P_SGD_NESTEROV) B200P_REQUIRE(momentum > 0.f && dampening == 0.f, B200P_EINVAL, "masked_sgd_step: nesterov needs momentum > 0 and zero dampening");
     B200P_CUDA(cudaSetDevice(p->device));
     SgdArgs a;
-    a.w_ptrs = p->ptrs<float>(B200P_SLOT_W); a.g_ptrs = p->ptrs<const float>(B200P_SLOT_G);
-    a.buf_ptrs = p->ptrs<float>(B200P_SLOT_BUF); a.weff_ptrs = p->ptrs<float>(B200P_SLOT_WEFF);
-    a.weff16_ptrs = p->ptrs<__nv_bfloat16>(B200P_SLOT_WEFF16);
+    a.chunk_n = p->d_chunk_n;
+    a.w_tab = p->tab(B200P_SLOT_W); a.g_tab = p->tab(B200P_SLOT_G);
+    a.buf_tab = p->tab(B200P_SLOT_BUF); a.weff_tab = p->tab(B200P_SLOT_WEFF);
+    a.weff16_tab = p->tab(B200P_SLOT_WEFF16);
     a.mask = d_mask; a.lr = lr; a.momentum = momentum; a.one_minus_damp = 1.f - dampening; a.wd = weight_decay; a.flags = flags;
     bool vec = p->vec_ok[B200P_SLOT_W] && p->vec_ok[B200P_SLOT_G];
     if (momentum != 0.f) vec = vec && p->vec_ok[B200P_SLOT_BUF];
     if (flags & B200P_SGD_EMIT_WEFF) vec = vec && p->vec_ok[B200P_SLOT_WEFF];
     if (flags & B200P_SGD_EMIT_WEFF16) vec = vec && p->vec_ok[B200P_SLOT_WEFF16];
     a.vec_ok = vec ? 1 : 0;
-    k_masked_sgd<<<p->grid_for(p->n_chunks, 3), kThreads, 0, (cudaStream_t)stream>>>(p->view(), a, p->n_chunks);
+    k_masked_sgd<<<p->grid_for(p->n_chunks, 3), kThreads, 0, (cudaStream_t)stream>>>(a, p->n_chunks);
     B200P_LAUNCH_CHECK("k_masked_sgd");
     return B200P_OK;
 }

@@ -76,7 +76,7 @@ class ShardedMaskBuilder:
             if self.world > 1:
                 dist.all_reduce(self._hist, group=self.group)
             p.select_scan(pass_)
-            launches += 2 if pass_ == 0 else 3
+            launches += 2
         if mode == L.MODE_EXACT_K:
             p.select_ties_count(key_source, old_mask, self.c0, self.c1, self._tie_local)
             if self.world > 1:
@@ -84,7 +84,7 @@ class ShardedMaskBuilder:
             else:
                 self._tie_all.copy_(self._tie_local)
             p.select_ties_scan(self.c0, self.c1, self._tie_all, self.rank)
-            launches += 4
+            launches += 3
         return launches
 
     # ---- emit ---------------------------------------------------------------------------------

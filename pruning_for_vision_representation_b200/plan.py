@@ -70,9 +70,7 @@ class ParamPlan:
             pass
 
     # ---- binding ---------------------------------------------------------------------
-    def pointer_table(self, slot, tensors):
-        """Validated, reusable pointer table for `bind_table` (re-binding a slot every mini-batch
-        without re-validating the tensors)."""
+    def _validate(self, slot, tensors):
         tensors = list(tensors)
         if len(tensors) != len(self.numels):
             raise B200PruneError(f"bind: expected {len(self.numels)} tensors, got {len(tensors)}")
@@ -82,20 +80,30 @@ class ParamPlan:
                 raise B200PruneError("bind: tensor is not on the plan's CUDA device (no CPU fallback)")
             if t.dtype != want or not t.is_contiguous() or t.numel() != n:
                 raise B200PruneError(f"bind: need contiguous {want} tensors with the plan's element counts")
-        ptrs = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
-        return (slot, ptrs, tensors)
+        return tensors, (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    def pointer_table(self, slot, tensors):
+        """Device-resident pointer table for `bind_table`: built once, re-bound with a host-side swap
+        (no launch) — one per gradient set in a loop over mini-batches."""
+        tensors, ptrs = self._validate(slot, tensors)
+        return PtrTable(self, slot, ptrs, tensors)
 
     def bind_table(self, table):
-        slot, ptrs, tensors = table
+        if table.plan is not self:
+            raise B200PruneError("bind_table: table belongs to another plan")
+        check(self.lib.b200p_plan_bind_table(self.handle, table.slot, table.handle), "plan_bind_table")
+        self._bound[table.slot] = table   # keeps the table and its tensors alive
+        return self
+
+    def bind(self, slot, tensors):
+        tensors, ptrs = self._validate(slot, tensors)
         check(self.lib.b200p_plan_bind(self.handle, slot, ptrs, _stream_ptr(self.device)), "plan_bind")
         self._bound[slot] = tensors       # keep the storage alive
         return self
 
-    def bind(self, slot, tensors):
-        return self.bind_table(self.pointer_table(slot, tensors))
-
     def bound(self, slot):
-        return self._bound.get(slot)
+        b = self._bound.get(slot)
+        return b.tensors if isinstance(b, PtrTable) else b
 
     def new_mask(self, fill_ones=False):
         """Packed mask tensor (int32 words, chunk-major layout of include/b200prune.h)."""
@@ -209,6 +217,28 @@ class ParamPlan:
     def unpack_mask_host(self, mask):
         """Packed mask (tensor or ndarray of words) -> list of per-segment bool ndarrays."""
         return unpack_mask_words(np.asarray(mask.cpu() if isinstance(mask, torch.Tensor) else mask), self.numels)
+
+
+class PtrTable:
+    """Handle on a b200p_ptrtable (per-chunk device pointer table of one tensor set)."""
+
+    def __init__(self, plan, slot, ptrs, tensors):
+        self.plan, self.slot, self.tensors = plan, slot, tensors
+        handle = ctypes.c_void_p()
+        check(plan.lib.b200p_ptrtable_create(plan.handle, slot, ptrs, _stream_ptr(plan.device), ctypes.byref(handle)),
+              "ptrtable_create")
+        self.handle = handle
+
+    def close(self):
+        if getattr(self, "handle", None) and getattr(self.plan, "handle", None):
+            self.plan.lib.b200p_ptrtable_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def unpack_mask_words(words, numels):

@@ -79,6 +79,7 @@ def test_snip_pruning_dropin(golden_dir, capsys):
     z = np.load(os.path.join(golden_dir, "snip_tiny.npz"))
     torch.backends.cudnn.allow_tf32 = False          # fp32 convolutions, like the CPU reference run
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(3)                             # same init (incl. biases) as gen_snip_tiny()
     model = TinyNet()
     mods = load_weights(model, _seq(z, "w"))
     model.to(DEV)
