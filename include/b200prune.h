@@ -191,11 +191,13 @@ int  b200p_masked_sgd_step(b200p_plan* plan, const uint32_t* d_mask, float lr, f
 /* Batched LOST over B images that share d.  Image b has n_b = dims[2b]*dims[2b+1] patch
  * keys stored row-major at d_feats + feat_offset[b] (elements), row stride `row_stride`
  * elements (so a qkv buffer can be read in place, main_lost_original.py:251-263).
- * Outputs (device): degree int32 [sum n_b], seed int32 [B], box int32 [B,4]
- * (xmin,ymin,xmax,ymax in pixels, object_discovery.py:120-128), status int32 [B]
+ * Outputs (device): degree int32 [sum n_b] (the call zeroes d_degree[min out_offset, max out_offset
+ * + n_b) first), seed int32 [B], box float [B,4] (xmin,ymin,xmax,ymax in pixels, exact integers when
+ * the scales are integers, object_discovery.py:120-128), status int32 [B]
  * (0 ok, 1 = "The seed is in the background component", object_discovery.py:110-111).
  * d_A (nullable): fp32 Gram matrices, image b at d_A + a_offset[b], n_b x n_b row-major.
- * h_meta is a host array of B records; it is copied to the device by the call. */
+ * h_meta is a host array of B records; it is consumed before the call returns.  At most 4096
+ * patches per image and k_patches <= 1024.  Workspace: b200p_lost_workspace_bytes(). */
 typedef struct b200p_lost_image_t {
     int64_t feat_offset;   /* elements from d_feats                      */
     int64_t a_offset;      /* elements from d_A (ignored if d_A == NULL) */
@@ -213,6 +215,17 @@ int  b200p_lost_batched(int device, const float* d_feats, int64_t row_stride, in
                         float* d_A, int32_t* d_degree, int32_t* d_seed, float* d_box,
                         int32_t* d_status, void* d_workspace, int64_t workspace_bytes,
                         int gram_impl, void* stream);
+
+/* patch_scoring(M, threshold) of object_discovery.py:72-90 on a given n x n matrix (row stride lda):
+ * d_degree[i] = #{j : (i != j ? max(A_ij, 0) : 0) > threshold}; d_sel = patches by ascending degree,
+ * lowest index first among equal degrees (the reference's argsort(-degree, descending) made stable). */
+int  b200p_lost_patch_scoring(int device, const float* d_A, int n, int64_t lda, float threshold,
+                              int32_t* d_degree, int64_t* d_sel, void* stream);
+/* detect_box of object_discovery.py:93-134 on a given correlation vector d_M [dim0*dim1]:
+ * d_box = [xmin,ymin,xmax,ymax] in pixels (img_h / img_w <= 0: no clipping), d_feat_box =
+ * [ymin,xmin,ymax,xmax] in feature cells (max exclusive), d_status = 1 if the seed is background. */
+int  b200p_lost_detect_box(int device, const float* d_M, int dim0, int dim1, int seed, float scale0, float scale1,
+                           int img_h, int img_w, float* d_box, int32_t* d_feat_box, int32_t* d_status, void* stream);
 
 /* ---- host-buffer convenience entry points (the "e2e" path of bench.py) -------------- */
 /* Complete SNIP mask build from HOST buffers: weights h_w [N], B gradient sets h_g[b] [N]

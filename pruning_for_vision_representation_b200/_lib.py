@@ -91,6 +91,8 @@ SIGNATURES = {
     "b200p_lost_workspace_bytes": (_I, [_I, _I64, _I64, ctypes.POINTER(_I64)]),
     "b200p_lost_batched": (_I, [_I, _P, _I64, _I, ctypes.POINTER(LostImage), _I, _I, _P, _P, _P, _P, _P,
                                 _P, _I64, _I, _P]),
+    "b200p_lost_patch_scoring": (_I, [_I, _P, _I, _I64, _F, _P, _P, _P]),
+    "b200p_lost_detect_box": (_I, [_I, _P, _I, _I, _I, _F, _F, _I, _I, _P, _P, _P, _P]),
     "b200p_snip_mask_build_host": (_I, [_P, _P, ctypes.POINTER(_P), _I, _U64, _P, ctypes.POINTER(SelectResult)]),
     "b200p_magnitude_mask_build_host": (_I, [_P, _P, _P, _U64, _P, ctypes.POINTER(SelectResult)]),
 }

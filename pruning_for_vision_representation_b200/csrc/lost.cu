@@ -1,8 +1,485 @@
-// lost.cu — placeholder until the LOST kernels land (K6/K7).
+// lost.cu — LOST object discovery (object_discovery.py:23-134), batched over images.
+//
+//   K6  k_lost_gram_ffma   A_b = F_b F_b^T in fp32 (object_discovery.py:39) with the degree count of
+//                          patch_scoring (:77-87) fused into the epilogue: A is written once and never
+//                          re-read for clone / fill_diagonal / clamp / compare / sum.
+//   K7  k_lost_finish      one CTA per image: seed = argmin degree (:57), the k_patches lowest-degree
+//                          patches with lowest-index-first ties (:60, stable argsort), similars (:61),
+//                          M = sum of the similar rows of A in sorted order (:62), 4-connected component
+//                          of M > 0 that holds the seed (scipy.ndimage.label, :104-107), box (:114-128).
+//   plus the two stand-alone mirrors used by the Python functions patch_scoring() and detect_box().
+//
+// Varlen batching: image b has n_b = dim0*dim1 patches; CTAs are assigned to (image, tile) pairs
+// through a prefix table so one launch covers images of different sizes.
 #include "common.cuh"
+#include <math.h>
+
+namespace b200p {
+
+constexpr int kLostMaxPatches = 4096;     // per image (ViT-S/8 at 480x480 = 3600)
+constexpr int kFinThreads = 512;
+
+struct LostImageDev {
+    long long feat_off, a_off, out_off;
+    int n, dim0, dim1, img_h, img_w;
+    float s0, s1;
+    int tile_base;       // first CTA of this image in the Gram grid
+    int tiles;           // tiles per side
+};
+
+// image records travel as kernel arguments (no pageable-memcpy stream sync, no staging buffer)
+constexpr int kMetaPerLaunch = 64;
+struct MetaPack { LostImageDev m[kMetaPerLaunch]; };
+__global__ void k_lost_set_meta(LostImageDev* __restrict__ dst, MetaPack pack, int n) {
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = pack.m[threadIdx.x];
+}
+
+// ---- K6: fp32 Gram + degree -----------------------------------------------------------------
+constexpr int BM = 128, BK = 16, GT = 256;
+
+__device__ __forceinline__ int find_image(const LostImageDev* __restrict__ meta, int n_images, int cta) {
+    int lo = 0, hi = n_images - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (meta[mid].tile_base <= cta) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// One CTA computes a 128x128 tile of A_b: rows [ti*128, +128) x cols [tj*128, +128).
+// 256 threads, 8x8 accumulators per thread, K in steps of 16 through double-buffered shared memory.
+__global__ void __launch_bounds__(GT)
+k_lost_gram_ffma(const float* __restrict__ feats, long long row_stride, int d,
+                 const LostImageDev* __restrict__ meta, int n_images, float* __restrict__ A_base,
+                 int* __restrict__ degree_base, float threshold, int vec_ok) {
+    __shared__ float As[2][BK][BM + 4];
+    __shared__ float Bs[2][BK][BM + 4];
+    __shared__ int s_rowcnt[BM];
+    const int b = find_image(meta, n_images, blockIdx.x);
+    const LostImageDev im = meta[b];
+    const int local = blockIdx.x - im.tile_base;
+    const int ti = local / im.tiles, tj = local % im.tiles;
+    const int row0 = ti * BM, col0 = tj * BM;
+    const float* __restrict__ F = feats + im.feat_off;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    if (tid < BM) s_rowcnt[tid] = 0;
+
+    float acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+    // loader: thread t handles rows (t>>2) and (t>>2)+64, k-quad (t&3)*4
+    const int lrow = tid >> 2, lk = (tid & 3) * 4;
+    auto load_tile = [&](int base_row, int k0, float (&dst)[BK][BM + 4]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = lrow + 64 * h;
+            const int gr = base_row + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < im.n) {
+                const float* p = F + (long long)gr * row_stride + k0 + lk;
+                if (vec_ok && k0 + lk + 3 < d) v = *reinterpret_cast<const float4*>(p);
+                else {
+                    if (k0 + lk + 0 < d) v.x = p[0];
+                    if (k0 + lk + 1 < d) v.y = p[1];
+                    if (k0 + lk + 2 < d) v.z = p[2];
+                    if (k0 + lk + 3 < d) v.w = p[3];
+                }
+            }
+            dst[lk + 0][r] = v.x; dst[lk + 1][r] = v.y; dst[lk + 2][r] = v.z; dst[lk + 3][r] = v.w;
+        }
+    };
+
+    const int ksteps = (d + BK - 1) / BK;
+    load_tile(row0, 0, As[0]);
+    load_tile(col0, 0, Bs[0]);
+    __syncthreads();
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const int cur = ks & 1;
+        if (ks + 1 < ksteps) {
+            load_tile(row0, (ks + 1) * BK, As[cur ^ 1]);
+            load_tile(col0, (ks + 1) * BK, Bs[cur ^ 1]);
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+
+    // epilogue: write A, count (i != j ? max(A,0) : 0) > threshold per row
+    float* __restrict__ A = A_base + im.a_off;
+    const bool vec_store = (im.n & 3) == 0 && (((uintptr_t)A) & 15u) == 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int lr = (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
+        const int gi = row0 + lr;
+        if (gi >= im.n) continue;
+        int cnt = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int gj0 = col0 + half * 64 + tx * 4;
+            float v[4] = {acc[r][half * 4 + 0], acc[r][half * 4 + 1], acc[r][half * 4 + 2], acc[r][half * 4 + 3]};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int gj = gj0 + q;
+                if (gj < im.n) {
+                    const float e = (gi == gj) ? 0.f : fmaxf(v[q], 0.f);
+                    cnt += (e > threshold) ? 1 : 0;
+                }
+            }
+            if (vec_store && gj0 + 3 < im.n) {
+                *reinterpret_cast<float4*>(A + (long long)gi * im.n + gj0) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (gj0 + q < im.n) A[(long long)gi * im.n + gj0 + q] = v[q];
+            }
+        }
+        if (cnt) atomicAdd(&s_rowcnt[lr], cnt);
+    }
+    __syncthreads();
+    if (tid < BM && row0 + tid < im.n && s_rowcnt[tid]) atomicAdd(degree_base + im.out_off + row0 + tid, s_rowcnt[tid]);
+}
+
+// ---- block helpers ------------------------------------------------------------------------------
+// exclusive scan of one int per thread over the CTA; returns the exclusive prefix, total in *total
+__device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += u; }
+    __syncthreads();                       // s_warp may still be read from a previous call
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nw ? s_warp[lane] : 0, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += u; }
+        if (lane < nw) s_warp[lane] = wi - w;
+        if (lane == nw - 1) s_warp[32] = wi;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[warp] + incl - v;
+}
+
+// Connected component (4-neighbourhood, scipy.ndimage.label's default structure) of `fg` holding
+// `seed`, then its bounding box.  s_comp: one byte per cell.  Returns false if the seed is background.
+__device__ bool component_box(const unsigned char* __restrict__ s_fg, unsigned char* __restrict__ s_comp, int n,
+                              int dim0, int dim1, int seed, int* s_red, int (&box)[4]) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = tid; j < n; j += nt) s_comp[j] = (j == seed && s_fg[j]) ? 1 : 0;
+    __syncthreads();
+    if (!s_fg[seed]) return false;
+    while (true) {
+        int changed = 0;
+        for (int j = tid; j < n; j += nt) {
+            if (s_fg[j] && !s_comp[j]) {
+                const int r = j / dim1, c = j - r * dim1;
+                if ((r > 0 && s_comp[j - dim1]) || (r + 1 < dim0 && s_comp[j + dim1]) ||
+                    (c > 0 && s_comp[j - 1]) || (c + 1 < dim1 && s_comp[j + 1])) { s_comp[j] = 1; changed = 1; }
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    if (tid == 0) { s_red[0] = dim0; s_red[1] = dim1; s_red[2] = -1; s_red[3] = -1; }
+    __syncthreads();
+    int rmin = dim0, cmin = dim1, rmax = -1, cmax = -1;
+    for (int j = tid; j < n; j += nt) {
+        if (s_comp[j]) {
+            const int r = j / dim1, c = j - r * dim1;
+            rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+        }
+    }
+    if (rmax >= 0) { atomicMin(&s_red[0], rmin); atomicMin(&s_red[1], cmin); atomicMax(&s_red[2], rmax); atomicMax(&s_red[3], cmax); }
+    __syncthreads();
+    box[0] = s_red[0]; box[1] = s_red[1]; box[2] = s_red[2]; box[3] = s_red[3];   // ymin, xmin, ymax, xmax (inclusive)
+    return true;
+}
+
+// pred = [s1*xmin, s0*ymin, min(s1*(xmax+1), W), min(s0*(ymax+1), H)]   (object_discovery.py:116-128)
+__device__ __forceinline__ void write_box(float* out, const int (&b)[4], float s0, float s1, int img_h, int img_w) {
+    out[0] = s1 * (float)b[1];
+    out[1] = s0 * (float)b[0];
+    float x1 = s1 * (float)(b[3] + 1), y1 = s0 * (float)(b[2] + 1);
+    if (img_w > 0) x1 = fminf(x1, (float)img_w);
+    if (img_h > 0) y1 = fminf(y1, (float)img_h);
+    out[2] = x1; out[3] = y1;
+}
+
+// ---- K7: seed, seed expansion, box --------------------------------------------------------------
+__global__ void __launch_bounds__(kFinThreads)
+k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A_base, const int* __restrict__ degree_base,
+              int k_patches, int n_max, int* __restrict__ seed_out, float* __restrict__ box_out, int* __restrict__ status_out,
+              float* __restrict__ M_out) {
+    // dynamic shared memory, sized for the largest image of the batch (n_max):
+    //   int deg[n_max] | int hist[n_max+1 (+pad)] | int list[1024] | int sorted[1024] | u8 flag[n_max] | u8 comp[n_max]
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    int* s_deg = reinterpret_cast<int*>(s_dyn);
+    int* s_hist = s_deg + n_max;
+    int* s_list = s_hist + ((n_max + 1 + 3) & ~3);
+    int* s_sorted = s_list + 1024;
+    unsigned char* s_flag = reinterpret_cast<unsigned char*>(s_sorted + 1024);   // foreground of M
+    unsigned char* s_comp = s_flag + n_max;
+    __shared__ int s_warp[33];
+    __shared__ unsigned long long s_best;
+    __shared__ int s_red[4];
+    __shared__ int s_cut[3];
+
+    const LostImageDev im = meta[blockIdx.x];
+    const int n = im.n, tid = threadIdx.x, nt = blockDim.x;
+    const float* __restrict__ A = A_base + im.a_off;
+    const int* __restrict__ deg = degree_base + im.out_off;
+
+    // degrees, seed = lowest degree, lowest index among equals (stable argsort, object_discovery.py:57,88)
+    if (tid == 0) s_best = ~0ull;
+    for (int j = tid; j <= n; j += nt) s_hist[j] = 0;
+    __syncthreads();
+    unsigned long long best = ~0ull;
+    for (int j = tid; j < n; j += nt) {
+        const int dg = deg[j];
+        s_deg[j] = dg;
+        const unsigned long long key = ((unsigned long long)(unsigned)dg << 32) | (unsigned)j;
+        best = key < best ? key : best;
+        atomicAdd(&s_hist[min(dg, n)], 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long u = __shfl_xor_sync(0xFFFFFFFFu, best, o); best = u < best ? u : best; }
+    if ((tid & 31) == 0) atomicMin(&s_best, best);
+    __syncthreads();
+    const int seed = (int)(s_best & 0xFFFFFFFFu);
+
+    // cut-off degree D: the k lowest-degree patches are those with degree < D plus the first
+    // `quota` (by index) of degree == D
+    const int kk = min(k_patches, n);
+    {
+        // scan the degree histogram in slabs of blockDim
+        int carry = 0;
+        if (tid == 0) { s_cut[0] = n + 1; s_cut[1] = 0; }
+        __syncthreads();
+        for (int base = 0; base <= n; base += nt) {
+            const int j = base + tid;
+            const int v = j <= n ? s_hist[j] : 0;
+            int total;
+            const int excl = block_excl_scan(v, s_warp, &total) + carry;
+            if (v > 0 && excl < kk && kk <= excl + v) { s_cut[0] = j; s_cut[1] = kk - excl; }   // unique j
+            carry += total;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    const int D = s_cut[0], quota = s_cut[1];
+    // membership + similars (A[seed, p] > 0 on the unmodified A, object_discovery.py:61)
+    {
+        int carry = 0, n_sim = 0;
+        for (int base = 0; base < n; base += nt) {
+            const int j = base + tid;
+            const int is_eq = (j < n && s_deg[j] == D) ? 1 : 0;
+            int total;
+            const int eq_rank = block_excl_scan(is_eq, s_warp, &total) + carry;
+            carry += total;
+            int sim = 0;
+            if (j < n) {
+                const bool member = s_deg[j] < D || (is_eq && eq_rank < quota);
+                sim = (member && A[(long long)seed * n + j] > 0.0f) ? 1 : 0;
+            }
+            int tot2;
+            const int pos = block_excl_scan(sim, s_warp, &tot2) + n_sim;
+            if (sim && pos < 1024) s_list[pos] = j;
+            n_sim += tot2;
+            __syncthreads();
+        }
+        if (tid == 0) s_cut[2] = min(n_sim, 1024);
+    }
+    __syncthreads();
+    const int n_sim = s_cut[2];
+    // order of the similars = order of `potentials` (ascending degree, index): rank by counting
+    for (int i = tid; i < n_sim; i += nt) {
+        const int p = s_list[i], dp = s_deg[p];
+        int rank = 0;
+        for (int q = 0; q < n_sim; ++q) {
+            const int o = s_list[q], dq = s_deg[o];
+            rank += (dq < dp || (dq == dp && o < p)) ? 1 : 0;
+        }
+        s_sorted[rank] = p;
+    }
+    __syncthreads();
+    // M = sum over similars of A[s, :], rows added in that order (object_discovery.py:62)
+    for (int j = tid; j < n; j += nt) {
+        float m = 0.f;
+        for (int r = 0; r < n_sim; ++r) m = __fadd_rn(m, A[(long long)s_sorted[r] * n + j]);
+        s_flag[j] = m > 0.0f ? 1 : 0;
+        if (M_out) M_out[im.out_off + j] = m;
+    }
+    __syncthreads();
+    int box[4];
+    const bool ok = component_box(s_flag, s_comp, n, im.dim0, im.dim1, seed, s_red, box);
+    if (tid == 0) {
+        seed_out[blockIdx.x] = seed;
+        status_out[blockIdx.x] = ok ? 0 : 1;
+        float* o = box_out + 4 * (long long)blockIdx.x;
+        if (ok) write_box(o, box, im.s0, im.s1, im.img_h, im.img_w);
+        else { o[0] = o[1] = o[2] = o[3] = 0.f; }
+    }
+}
+
+// ---- stand-alone mirrors -------------------------------------------------------------------------
+// degree of a given matrix (patch_scoring, object_discovery.py:72-90): one warp per row
+__global__ void __launch_bounds__(256)
+k_lost_degree(const float* __restrict__ A, int n, long long lda, float threshold, int* __restrict__ degree) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = threadIdx.x & 31;
+    int cnt = 0;
+    for (int j = lane; j < n; j += 32) {
+        const float v = A[(long long)row * lda + j];
+        const float e = (j == row) ? 0.f : fmaxf(v, 0.f);     // fill_diagonal_(0); A[A < 0] = 0
+        cnt += (e > threshold) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if (lane == 0) degree[row] = cnt;
+}
+// sel[rank] = i where rank = #{j : (deg_j, j) < (deg_i, i)}: stable ascending-degree order
+__global__ void __launch_bounds__(256)
+k_lost_rank_by_degree(const int* __restrict__ degree, int n, long long* __restrict__ sel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int di = degree[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) { const int dj = __ldg(degree + j); rank += (dj < di || (dj == di && j < i)) ? 1 : 0; }
+    sel[rank] = i;
+}
+__global__ void __launch_bounds__(kFinThreads)
+k_lost_detect_box(const float* __restrict__ M, int n, int dim0, int dim1, int seed, float s0, float s1,
+                  int img_h, int img_w, float* __restrict__ box_out, int* __restrict__ feat_box_out, int* __restrict__ status_out) {
+    __shared__ unsigned char s_fg[kLostMaxPatches];
+    __shared__ unsigned char s_comp[kLostMaxPatches];
+    __shared__ int s_red[4];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) s_fg[j] = M[j] > 0.0f ? 1 : 0;
+    __syncthreads();
+    int box[4];
+    const bool ok = component_box(s_fg, s_comp, n, dim0, dim1, seed, s_red, box);
+    if (threadIdx.x == 0) {
+        status_out[0] = ok ? 0 : 1;
+        if (ok) {
+            write_box(box_out, box, s0, s1, img_h, img_w);
+            feat_box_out[0] = box[0]; feat_box_out[1] = box[1]; feat_box_out[2] = box[2] + 1; feat_box_out[3] = box[3] + 1;
+        }
+    }
+}
+
+}  // namespace b200p
+
 using namespace b200p;
-extern "C" int b200p_lost_workspace_bytes(int, int64_t, int64_t, int64_t* out) { if (out) *out = 0; return B200P_OK; }
-extern "C" int b200p_lost_batched(int, const float*, int64_t, int, const b200p_lost_image_t*, int, int, float*, int32_t*,
-                                  int32_t*, float*, int32_t*, void*, int64_t, int, void*) {
-    set_error("lost_batched: not implemented yet"); return B200P_ESTATE;
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int b200p_lost_workspace_bytes(int n_images, int64_t total_patches, int64_t total_a, int64_t* out) {
+    B200P_REQUIRE(out != nullptr && n_images >= 0 && total_patches >= 0 && total_a >= 0, B200P_EINVAL, "lost_workspace_bytes: bad argument");
+    (void)total_patches;
+    *out = (int64_t)(align_up((size_t)n_images * sizeof(LostImageDev), 256) + align_up((size_t)total_a * sizeof(float), 256) + 256);
+    return B200P_OK;
+}
+
+extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_stride, int d,
+                                  const b200p_lost_image_t* h_meta, int n_images, int k_patches,
+                                  float* d_A, int32_t* d_degree, int32_t* d_seed, float* d_box,
+                                  int32_t* d_status, void* d_workspace, int64_t workspace_bytes,
+                                  int gram_impl, void* stream) {
+    B200P_REQUIRE(d_feats && h_meta && d_degree && d_seed && d_box && d_status && d_workspace, B200P_EINVAL, "lost_batched: null argument");
+    B200P_REQUIRE(n_images >= 1 && d >= 1 && row_stride >= d && k_patches >= 1, B200P_EINVAL, "lost_batched: bad sizes");
+    B200P_REQUIRE(gram_impl == B200P_LOST_GRAM_FFMA || gram_impl == B200P_LOST_GRAM_TC, B200P_EINVAL, "lost_batched: bad gram_impl");
+    B200P_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<LostImageDev> meta(n_images);
+    long long tile_base = 0, total_a = 0, total_patches = 0, deg_lo = -1, deg_hi = 0;
+    int n_max = 0;
+    B200P_REQUIRE(k_patches <= 1024, B200P_EINVAL, "lost_batched: k_patches must be <= 1024");
+    bool vec = (((uintptr_t)d_feats) & 15u) == 0 && (row_stride & 3) == 0;
+    for (int b = 0; b < n_images; ++b) {
+        const b200p_lost_image_t& h = h_meta[b];
+        const long long n = (long long)h.dim0 * h.dim1;
+        B200P_REQUIRE(h.dim0 >= 1 && h.dim1 >= 1 && n <= kLostMaxPatches, B200P_EINVAL, "lost_batched: dims must give 1..4096 patches");
+        B200P_REQUIRE(h.feat_offset >= 0 && h.out_offset >= 0 && h.a_offset >= 0, B200P_EINVAL, "lost_batched: negative offset");
+        LostImageDev& m = meta[b];
+        m.feat_off = h.feat_offset; m.out_off = h.out_offset; m.n = (int)n; m.dim0 = h.dim0; m.dim1 = h.dim1;
+        m.img_h = h.img_h; m.img_w = h.img_w; m.s0 = h.scale0; m.s1 = h.scale1;
+        m.a_off = d_A ? h.a_offset : total_a;
+        m.tiles = (int)((n + BM - 1) / BM);
+        m.tile_base = (int)tile_base;
+        tile_base += (long long)m.tiles * m.tiles;
+        total_a += n * n;
+        total_patches += n;
+        if (h.feat_offset & 3) vec = false;
+        if (deg_lo < 0 || h.out_offset < deg_lo) deg_lo = h.out_offset;
+        if (h.out_offset + n > deg_hi) deg_hi = h.out_offset + n;
+        if (n > n_max) n_max = (int)n;
+    }
+    B200P_REQUIRE(tile_base < (1ll << 31), B200P_EINVAL, "lost_batched: too many tiles in one call");
+    const size_t meta_bytes = align_up((size_t)n_images * sizeof(LostImageDev), 256);
+    const size_t need = meta_bytes + (d_A ? 0 : align_up((size_t)total_a * sizeof(float), 256));
+    B200P_REQUIRE((size_t)workspace_bytes >= need, B200P_EINVAL, "lost_batched: workspace too small (see b200p_lost_workspace_bytes)");
+    LostImageDev* d_meta = (LostImageDev*)d_workspace;
+    float* A_base = d_A ? d_A : (float*)((char*)d_workspace + meta_bytes);
+    for (int b0 = 0; b0 < n_images; b0 += kMetaPerLaunch) {
+        MetaPack pack;
+        const int nb = n_images - b0 < kMetaPerLaunch ? n_images - b0 : kMetaPerLaunch;
+        for (int i = 0; i < nb; ++i) pack.m[i] = meta[b0 + i];
+        k_lost_set_meta<<<1, kMetaPerLaunch, 0, st>>>(d_meta + b0, pack, nb);
+        B200P_LAUNCH_CHECK("k_lost_set_meta");
+    }
+    // the call owns d_degree[min out_offset, max out_offset + n): cleared in one go
+    B200P_CUDA(cudaMemsetAsync(d_degree + deg_lo, 0, (size_t)(deg_hi - deg_lo) * sizeof(int32_t), st));
+    // gram_impl TC (tcgen05 3xTF32) is not built yet: both values run the fp32 FFMA kernel
+    k_lost_gram_ffma<<<(int)tile_base, GT, 0, st>>>(d_feats, (long long)row_stride, d, d_meta, n_images, A_base, d_degree,
+                                                   0.0f, vec ? 1 : 0);
+    B200P_LAUNCH_CHECK("k_lost_gram_ffma");
+    n_max = (n_max + 15) & ~15;
+    const size_t fin_smem = (size_t)n_max * 4 + (size_t)((n_max + 1 + 3) & ~3) * 4 + 2 * 1024 * 4 + 2 * (size_t)n_max;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set = true;
+    }
+    k_lost_finish<<<n_images, kFinThreads, fin_smem, st>>>(d_meta, A_base, d_degree, k_patches, n_max, d_seed, d_box, d_status, nullptr);
+    B200P_LAUNCH_CHECK("k_lost_finish");
+    return B200P_OK;
+}
+
+extern "C" int b200p_lost_patch_scoring(int device, const float* d_A, int n, int64_t lda, float threshold,
+                                        int32_t* d_degree, int64_t* d_sel, void* stream) {
+    B200P_REQUIRE(d_A && d_degree && d_sel && n >= 1 && lda >= n, B200P_EINVAL, "lost_patch_scoring: bad argument");
+    B200P_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    k_lost_degree<<<(n + 7) / 8, 256, 0, st>>>(d_A, n, (long long)lda, threshold, d_degree);
+    B200P_LAUNCH_CHECK("k_lost_degree");
+    k_lost_rank_by_degree<<<(n + 255) / 256, 256, 0, st>>>(d_degree, n, (long long*)d_sel);
+    B200P_LAUNCH_CHECK("k_lost_rank_by_degree");
+    return B200P_OK;
+}
+
+extern "C" int b200p_lost_detect_box(int device, const float* d_M, int dim0, int dim1, int seed, float scale0, float scale1,
+                                     int img_h, int img_w, float* d_box, int32_t* d_feat_box, int32_t* d_status, void* stream) {
+    B200P_REQUIRE(d_M && d_box && d_feat_box && d_status, B200P_EINVAL, "lost_detect_box: null argument");
+    const long long n = (long long)dim0 * dim1;
+    B200P_REQUIRE(dim0 >= 1 && dim1 >= 1 && n <= kLostMaxPatches, B200P_EINVAL, "lost_detect_box: dims must give 1..4096 patches");
+    B200P_REQUIRE(seed >= 0 && seed < n, B200P_EINVAL, "lost_detect_box: seed out of range");
+    B200P_CUDA(cudaSetDevice(device));
+    k_lost_detect_box<<<1, kFinThreads, 0, (cudaStream_t)stream>>>(d_M, (int)n, dim0, dim1, seed, scale0, scale1, img_h, img_w,
+                                                                  d_box, d_feat_box, d_status);
+    B200P_LAUNCH_CHECK("k_lost_detect_box");
+    return B200P_OK;
 }
