@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-lost", action="store_true", help="skip the LOST images/s leg")
     ap.add_argument("--no-clocks", action="store_true", help="skip the clock sampler and its keep-busy loops (ncu runs)")
     return ap.parse_args()
 
@@ -365,6 +366,10 @@ def run_b200(args):
                    "ms_per_step": e2e_ms, "steps": args.e2e_steps,
                    "api": "ShardedMaskBuilder.snip_mask_build_host (pinned host buffers in, packed mask out)"}
 
+    lost = None
+    if not args.no_lost:
+        lost = lost_leg(args, dev, world, rank, dist)
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, ms, sample, cores = cpu_reference_run(2, 1, numels)
@@ -390,13 +395,93 @@ def run_b200(args):
                          "launches_timed": len(acc_ms),
                          "step_algorithmic_GBps": (n_total * STEP_BYTES_PER_PARAM / (ms_per_step * 1e-3) / 1e9
                                                    if world == 1 else None)},
-            "e2e": e2e, "cpu_baseline": cpu_base, "gpu_launches": n_launches, "clocks": clk,
+            "e2e": e2e, "cpu_baseline": cpu_base, "gpu_launches": n_launches, "clocks": clk, "lost": lost,
             "result": {"threshold": res["threshold"], "n_less": res["n_less"], "n_equal": res["n_equal"],
                        "n_kept": res["n_kept"], "passes_full": res["passes_full"]},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+LOST_N, LOST_D, LOST_DIMS, LOST_B = 900, 384, [30, 30], 256
+LOST_FLOP_PER_IMAGE = 2.0 * LOST_N * LOST_N * LOST_D          # 622 080 000
+
+
+def lost_leg(args, dev, world, rank, dist):
+    """LOST ViT-S/16 images/s (BASELINE.json configs[2]): synthetic patch keys randn(B, 900, 384), seed 0
+    (+ rank), dims 30x30, scales 16, image 480x480, k_patches 100.  Images shard over ranks, no collective.
+    value = images/s with the keys resident in HBM; e2e = keys in pinned host memory -> boxes on the host."""
+    import numpy as np
+    import torch
+    from pruning_for_vision_representation_b200 import object_discovery as OD
+    g = torch.Generator().manual_seed(rank)
+    feats_host = torch.randn(LOST_B, LOST_N, LOST_D, generator=g).pin_memory()
+    feats = feats_host.to(dev)
+    size = (3, 480, 480)
+    run = lambda f: OD.lost_batched(f, LOST_DIMS, [16, 16], size, k_patches=100)
+    for _ in range(3):
+        out = run(feats)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    steps = max(5, min(50, args.steps))
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        out = run(feats)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    # e2e: pinned host keys in, boxes / seeds / status back on the host
+    box_h = torch.empty(LOST_B, 4).pin_memory(); seed_h = torch.empty(LOST_B, dtype=torch.int32).pin_memory()
+    st_h = torch.empty(LOST_B, dtype=torch.int32).pin_memory()
+    def e2e_once():
+        f = feats_host.to(dev, non_blocking=True)
+        o = run(f)
+        box_h.copy_(o["box"], non_blocking=True); seed_h.copy_(o["seed"], non_blocking=True); st_h.copy_(o["status"], non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_once()
+    tt = time.perf_counter()
+    for _ in range(3):
+        e2e_once()
+    e2e_ms = (time.perf_counter() - tt) / 3 * 1e3
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    peak_tf32 = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak_tf32 = float(json.load(f)["bf16_tflops"]) / 2.0
+    except Exception:
+        peak_tf32 = 1590.0 / 2.0
+    img_s = world * LOST_B / (ms * 1e-3)
+    achieved = img_s / world * LOST_FLOP_PER_IMAGE / 1e12
+    leg = {"metric": "LOST ViT-S/16 images/sec", "value": img_s, "unit": "images/s", "ms_per_step": ms, "steps": steps,
+           "config": {"workload": f"LOST on synthetic patch keys randn({LOST_B},{LOST_N},{LOST_D}) per GPU, dims 30x30, "
+                                  "k_patches 100, keys -> Gram -> degree -> seed -> expansion -> box; ViT forward excluded",
+                      "l2": f"{LOST_B} Gram matrices = {LOST_B * LOST_N * LOST_N * 4 >> 20} MiB written per step (> L2)"},
+           "roofline": {"bound": "tensor", "kernel": "k_lost_gram_ffma (fp32 CUDA-core Gram; tcgen05 3xTF32 path not built yet)",
+                        "achieved": achieved, "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32,
+                        "traffic": None, "peak_source": "0.5 x measured bf16 burst (nominal tf32:bf16 ratio; no measured tf32 peak)"},
+           "e2e": {"value": world * LOST_B / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": LOST_B * LOST_N * LOST_D * 4, "d2h_bytes_per_step": LOST_B * (16 + 4 + 4)},
+           "gpu_launches_per_step": 2 + (LOST_B + 63) // 64 + 0,
+           "seed0_box0": [int(out["seed"][0].item()), out["box"][0].tolist()]}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import lost_oracle as LO
+        n_img = 24
+        fs = feats_host[:n_img].numpy()
+        LO.lost(fs[0], LOST_DIMS, [16, 16], size, 100)
+        tt = time.perf_counter()
+        for i in range(n_img):
+            LO.lost(fs[i], LOST_DIMS, [16, 16], size, 100)
+        dt = time.perf_counter() - tt
+        leg["cpu_baseline"] = {"value": n_img / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"{n_img} of the same images through oracle/lost_oracle.lost (numpy BLAS Gram + python flood fill)"}
+    return leg
 
 
 def ncu_traffic():
