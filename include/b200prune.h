@@ -112,6 +112,11 @@ int  b200p_ptrtable_create(b200p_plan* plan, int slot, const void* const* h_ptrs
                            b200p_ptrtable** out);
 int  b200p_ptrtable_destroy(b200p_ptrtable* table);
 int  b200p_plan_bind_table(b200p_plan* plan, int slot, const b200p_ptrtable* table);
+/* options */
+#define B200P_OPT_SELECT_IMPL   1
+#define B200P_SELECT_SAMPLED    0   /* default: 1/64 sample -> bracket -> one full pass -> candidates; exact fallback on a miss */
+#define B200P_SELECT_EXACT      1   /* 3-pass MSD radix select over the full data */
+int  b200p_plan_set_option(b200p_plan* plan, int option, int64_t value);
 /* device address of the 4096-bin uint64 histogram and of the select state, so that the
  * host side can run NCCL collectives on them between stages */
 void* b200p_plan_hist_ptr(b200p_plan* plan);

@@ -20,6 +20,8 @@ KEY_ABS_W, KEY_SCORE = 0, 1
 EMIT_MASKF, EMIT_WEFF = 1, 2
 SGD_NESTEROV, SGD_FIRST_STEP, SGD_EMIT_WEFF, SGD_EMIT_WEFF16 = 1, 2, 4, 8
 LOST_GRAM_FFMA, LOST_GRAM_TC = 0, 1
+OPT_SELECT_IMPL = 1
+SELECT_SAMPLED, SELECT_EXACT = 0, 1
 
 
 class B200PruneError(RuntimeError):
@@ -68,6 +70,7 @@ SIGNATURES = {
     "b200p_ptrtable_create": (_I, [_P, _I, ctypes.POINTER(_P), _P, ctypes.POINTER(_P)]),
     "b200p_ptrtable_destroy": (_I, [_P]),
     "b200p_plan_bind_table": (_I, [_P, _I, _P]),
+    "b200p_plan_set_option": (_I, [_P, _I, _I64]),
     "b200p_plan_hist_ptr": (_P, [_P]),
     "b200p_plan_state_ptr": (_P, [_P]),
     "b200p_score_accumulate": (_I, [_P, _I, _I64, _I64, _P]),

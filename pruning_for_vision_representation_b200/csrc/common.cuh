@@ -16,6 +16,7 @@ constexpr int kThreads = 256;                    // threads per CTA of the strea
 constexpr int kVecPerThread = kChunk / (4 * kThreads);   // float4 per thread per chunk = 4
 constexpr int kWordsPerChunk = B200P_WORDS_PER_CHUNK;
 constexpr int kHistBins = 4096;                  // 12-bit digits
+constexpr int kHistExtra = 8;                    // scalar counters behind the bins: [0] alive keys (sample pass), [1] keys below the bracket
 constexpr uint32_t kNanKey = 0x7FFFFFFFu;        // every NaN sorts last (torch.sort semantics)
 
 // digit layout of the 31-bit key: pass 0 -> bits 30..19, pass 1 -> bits 18..7, pass 2 -> bits 6..0
@@ -111,6 +112,12 @@ struct SelState {
     uint32_t tie_resid;              // ties to prune inside tie_chunk
     uint32_t need_ties;              // EXACT_K and quota < n_equal
     uint32_t passes_full;            // full-data passes executed
+    // sampled (bracketed) select
+    uint32_t sample_ok;              // the sample pass produced a usable bracket
+    uint32_t miss;                   // the k-th key was not inside the bracket (or it overflowed): exact fallback ran
+    uint32_t lo_bucket, hi_bucket;   // bracket in units of the 12-bit digit (inclusive)
+    uint32_t win_lo;                 // first key of the 1024-key window chosen by the bracket pass
+    uint32_t pad2_;
     uint32_t pad_[2];
 };
 
@@ -125,6 +132,8 @@ struct b200p_plan {
     int64_t n_chunks = 0;
     int64_t cand_capacity = 0;
     int num_sms = 148;
+    int coop_ctas_per_sm = 0;      // co-resident CTAs of the cooperative finish kernel (0: not queried yet)
+    int select_impl = 0;           // 0 sampled (bracketed) select, 1 exact 3-pass radix select
     std::vector<int64_t> numel;
     std::vector<int64_t> seg_chunk_start;   // n_seg + 1
     std::vector<int64_t> seg_flat_start;    // n_seg + 1

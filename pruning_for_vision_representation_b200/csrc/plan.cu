@@ -80,12 +80,12 @@ extern "C" int b200p_plan_create(int device, int n_segments, const int64_t* h_nu
     TRY(cudaMemcpy(p->d_chunk_n, chunk_n.data(), chunks * sizeof(int32_t), cudaMemcpyHostToDevice));
     TRY(cudaMemcpy(p->d_chunk_elem0, chunk_elem0.data(), chunks * sizeof(int64_t), cudaMemcpyHostToDevice));
     for (int s = 0; s < B200P_NUM_SLOTS; ++s) TRY(cudaMalloc(&p->d_tab_own[s], chunks * sizeof(void*)));
-    TRY(cudaMalloc(&p->d_hist, kHistBins * sizeof(unsigned long long)));
+    TRY(cudaMalloc(&p->d_hist, (kHistBins + kHistExtra) * sizeof(unsigned long long)));
     TRY(cudaMalloc(&p->d_state, sizeof(SelState)));
     TRY(cudaMalloc(&p->d_cand_key, cand_capacity * sizeof(uint32_t)));
     TRY(cudaMalloc(&p->d_cand_pos, cand_capacity * sizeof(uint32_t)));
     TRY(cudaMalloc(&p->d_chunk_ties, chunks * sizeof(uint32_t)));
-    TRY(cudaMemset(p->d_hist, 0, kHistBins * sizeof(unsigned long long)));
+    TRY(cudaMemset(p->d_hist, 0, (kHistBins + kHistExtra) * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_state, 0, sizeof(SelState)));
     TRY(cudaMemset(p->d_chunk_ties, 0, chunks * sizeof(uint32_t)));
     TRY(cudaDeviceSynchronize());
@@ -125,6 +125,16 @@ extern "C" int64_t b200p_plan_chunk_flat_start(const b200p_plan* p, int64_t chun
     int lo = 0, hi = p->n_seg - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (p->seg_chunk_start[mid] <= chunk) lo = mid; else hi = mid - 1; }
     return p->seg_flat_start[lo] + (chunk - p->seg_chunk_start[lo]) * (int64_t)kChunk;
+}
+extern "C" int b200p_plan_set_option(b200p_plan* p, int option, int64_t value) {
+    B200P_REQUIRE(p != nullptr, B200P_EINVAL, "plan_set_option: null plan");
+    if (option == B200P_OPT_SELECT_IMPL) {
+        B200P_REQUIRE(value == B200P_SELECT_SAMPLED || value == B200P_SELECT_EXACT, B200P_EINVAL, "plan_set_option: bad select implementation");
+        p->select_impl = (int)value;
+        return B200P_OK;
+    }
+    set_error("plan_set_option: unknown option");
+    return B200P_EINVAL;
 }
 extern "C" void* b200p_plan_hist_ptr(b200p_plan* p) { return p ? (void*)p->d_hist : nullptr; }
 extern "C" void* b200p_plan_state_ptr(b200p_plan* p) { return p ? (void*)p->d_state : nullptr; }

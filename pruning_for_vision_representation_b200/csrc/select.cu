@@ -18,6 +18,7 @@
 // separately) exist so that a parameter-sharded multi-GPU select can all-reduce the
 // histogram between them.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace b200p {
 
@@ -171,11 +172,35 @@ __device__ void scan_and_advance(int pass, unsigned long long* __restrict__ hist
     }
 }
 
+// ---- candidate append with per-warp staging -------------------------------------------------
+// A global atomic on the one shared counter per warp per chunk serialises in L2 (tens of thousands
+// of same-address atomics per sweep).  Each warp stages its matches in shared memory and reserves
+// global space once per ~200 candidates instead.
+constexpr int kStage = 256;                       // staged candidates per warp
+struct CandStage {
+    uint32_t key[kThreads / 32][kStage];
+    uint32_t pos[kThreads / 32][kStage];
+};
+
+__device__ __forceinline__ void stage_flush(CandStage& sg, int warp, int lane, int n, SelState* st,
+                                            uint32_t* __restrict__ cand_key, uint32_t* __restrict__ cand_pos, long long cap) {
+    if (n <= 0) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&st->cand_count, (uint32_t)n);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    for (int i = lane; i < n; i += 32) {
+        if ((long long)(base + i) < cap) { cand_key[base + i] = sg.key[warp][i]; cand_pos[base + i] = sg.pos[warp][i]; }
+    }
+    __syncwarp();
+}
+
 // ---- select state initialisation ----------------------------------------------------------
-__device__ __forceinline__ void init_state(SelState* st, unsigned long long k, uint32_t mode, uint32_t allow_collect) {
+__device__ __forceinline__ void init_state(SelState* st, unsigned long long k, uint32_t mode, uint32_t allow_collect,
+                                           uint32_t miss = 0u) {
     SelState s;
     memset(&s, 0, sizeof(s));
     s.k = k; s.k_request = k; s.mode = mode; s.allow_collect = allow_collect; s.tie_chunk = -1;
+    s.miss = miss;           // never transiently cleared: other CTAs of the finish kernel may be reading it
     *st = s;
 }
 
@@ -197,6 +222,116 @@ struct PassArgs {
     uint32_t mode, allow_collect;
 };
 
+// ---- slim sweep used by exact pass 1 and by the bracket pass of the sampled select ------------
+__device__ __forceinline__ float sel16(const float4 (&v)[kVecPerThread], int i) {
+    const int j = i >> 2, q = i & 3;
+    const float4 t = j == 0 ? v[0] : j == 1 ? v[1] : j == 2 ? v[2] : v[3];
+    return q == 0 ? t.x : q == 1 ? t.y : q == 2 ? t.z : t.w;
+}
+
+// one matching key: fine histogram + staged append (order inside the buffer is irrelevant)
+__device__ __forceinline__ void sweep_take(uint32_t key, uint32_t pos, uint32_t base, int fine_shift,
+                                           uint32_t* __restrict__ s_hist, CandStage& sg, int* __restrict__ s_wcount,
+                                           SelState* st, uint32_t* __restrict__ cand_key, uint32_t* __restrict__ cand_pos,
+                                           long long cap, bool collect) {
+    atomicAdd(&s_hist[(key - base) >> fine_shift], 1u);
+    if (!collect) return;
+    const int warp = threadIdx.x >> 5;
+    const int off = atomicAdd(&s_wcount[warp], 1);
+    if (off < kStage) { sg.key[warp][off] = key; sg.pos[warp][off] = pos; }
+    else {
+        const uint32_t g = atomicAdd(&st->cand_count, 1u);
+        if ((long long)g < cap) { cand_key[g] = key; cand_pos[g] = pos; }
+    }
+}
+
+// Sweeps chunks [c_begin, c_end): keys in [base, base + span) are "inside".  Returns this thread's
+// count of alive keys below `base`.  CANON: canonicalise NaN keys (only needed when the range
+// reaches the inf/NaN buckets).
+template <bool CANON>
+__device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint32_t base, uint32_t span, int fine_shift,
+                                                         bool collect, uint32_t* __restrict__ s_hist, CandStage& sg,
+                                                         int* __restrict__ s_wcount) {
+    SelState* __restrict__ st = a.st;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long below = 0;
+    int64_t c = a.c_begin + blockIdx.x;
+    if (c >= a.c_end) return 0;
+    const float* src = chunk_ptr<const float>(a.key_tab, c);
+    int n = __ldg(a.chunk_n + c);
+    ChunkRegs cur;
+    prefetch_chunk(src, a.old_mask ? a.old_mask + c * kWordsPerChunk : nullptr, n, a.vec_ok, cur);
+    while (true) {
+        const int64_t cn = c + gridDim.x;
+        const bool more = cn < a.c_end;
+        const float* srcn = nullptr; int nn = 0;
+        ChunkRegs nxt; nxt.vec = false; nxt.alive = 0;
+        if (more) {
+            srcn = chunk_ptr<const float>(a.key_tab, cn);
+            nn = __ldg(a.chunk_n + cn);
+            prefetch_chunk(srcn, a.old_mask ? a.old_mask + cn * kWordsPerChunk : nullptr, nn, a.vec_ok, nxt);
+        }
+        const uint32_t pos0 = (uint32_t)(c * kChunk);
+        if (cur.vec) {
+            uint32_t lt = 0, in = 0;
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) {
+                const float f[4] = {cur.v[j].x, cur.v[j].y, cur.v[j].z, cur.v[j].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t k = CANON ? key_of(f[q]) : (__float_as_uint(f[q]) & 0x7FFFFFFFu);
+                    const uint32_t d = k - base;
+                    lt |= (k < base ? 1u : 0u) << (4 * j + q);
+                    in |= (d < span ? 1u : 0u) << (4 * j + q);
+                }
+            }
+            below += __popc(lt & cur.alive);
+            uint32_t match = in & cur.alive;
+            while (match) {                           // divergent, rare
+                const int i = __ffs(match) - 1;
+                match &= match - 1;
+                const float x = sel16(cur.v, i);
+                const uint32_t k = CANON ? key_of(x) : (__float_as_uint(x) & 0x7FFFFFFFu);
+                sweep_take(k, pos0 + (uint32_t)slot_element<true>(i), base, fine_shift, s_hist, sg, s_wcount, st,
+                           a.cand_key, a.cand_pos, a.cand_capacity, collect);
+            }
+        } else {
+            // partial or unaligned chunk: element-wise
+            const uint32_t* mchunk = a.old_mask ? a.old_mask + c * kWordsPerChunk : nullptr;
+            for (int e = threadIdx.x; e < n; e += kThreads) {
+                if (mchunk && !((__ldg(mchunk + (e >> 5)) >> (e & 31)) & 1u)) continue;
+                const uint32_t k = key_of(src[e]);
+                if (k < base) ++below;
+                else if (k - base < span)
+                    sweep_take(k, pos0 + (uint32_t)e, base, fine_shift, s_hist, sg, s_wcount, st, a.cand_key, a.cand_pos,
+                               a.cand_capacity, collect);
+            }
+        }
+        __syncwarp();
+        if (collect) {
+            // Broadcast lane 0's view of the fill level: under independent thread scheduling a lane may
+            // run ahead into the next chunk and bump the counter before a slower lane has read it, and a
+            // non-uniform decision here would leave the warp split across different barriers.
+            const int filled = __shfl_sync(0xFFFFFFFFu, s_wcount[warp], 0);
+            if (filled >= kStage / 2) {
+                __syncwarp();
+                stage_flush(sg, warp, lane, filled < kStage ? filled : kStage, st, a.cand_key, a.cand_pos, a.cand_capacity);
+                if (lane == 0) s_wcount[warp] = 0;
+                __syncwarp();
+            }
+        }
+        if (!more) break;
+        c = cn; src = srcn; n = nn; cur = nxt;
+    }
+    __syncwarp();
+    if (collect) {
+        const int filled = __shfl_sync(0xFFFFFFFFu, s_wcount[warp], 0);
+        stage_flush(sg, warp, lane, filled < kStage ? filled : kStage, st, a.cand_key, a.cand_pos, a.cand_capacity);
+        if (lane == 0) s_wcount[warp] = 0;
+    }
+    return below;
+}
+
 // ---- full-data pass --------------------------------------------------------------------
 // PASS 0: histogram digit 0 of every alive key.
 // PASS 1: keys whose digit 0 matches the chosen bucket are histogrammed by digit 1 and, in collect
@@ -204,9 +339,7 @@ struct PassArgs {
 // PASS 2: histogram digit 2 of the keys matching the 24 fixed bits — over the candidate buffer in
 //         collect mode, over the full data otherwise.
 template <int PASS>
-__global__ void __launch_bounds__(kThreads, 3)
-k_select_pass(PassArgs a) {
-    __shared__ uint32_t s_hist[kHistBins];
+__device__ __forceinline__ void pass_body(const PassArgs& a, uint32_t* __restrict__ s_hist, CandStage* sg, int* s_wcount) {
     SelState* __restrict__ st = a.st;
     uint32_t prefix = 0, collect = 0;
     if (PASS > 0) { prefix = st->prefix; collect = st->collect; }
@@ -216,7 +349,13 @@ k_select_pass(PassArgs a) {
     const uint32_t pmask = prefix_mask_before(PASS);
     const int lane = threadIdx.x & 31;
 
-    if (PASS == 2 && collect) {
+    if (PASS == 1) {
+        // keys of the chosen 12-bit bucket: histogram of their next 12 bits, plus the candidate append
+        if (threadIdx.x < kThreads / 32) s_wcount[threadIdx.x] = 0;
+        __syncthreads();
+        if ((prefix >> 19) >= 0xFF0u) sweep_loop<true>(a, prefix, 1u << 19, 7, collect != 0, s_hist, *sg, s_wcount);
+        else                          sweep_loop<false>(a, prefix, 1u << 19, 7, collect != 0, s_hist, *sg, s_wcount);
+    } else if (PASS == 2 && collect) {
         const uint32_t n = st->cand_count;
         for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
             const uint32_t key = a.cand_key[i];
@@ -246,41 +385,9 @@ k_select_pass(PassArgs a) {
                     for (int i = 0; i < 16; ++i)
                         if ((alive >> i) & 1u) atomicAdd(&s_hist[key[i] >> 19], 1u);
                 } else {
-                    uint32_t match = 0;
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (((alive >> i) & 1u) && ((key[i] & pmask) == prefix)) match |= 1u << i;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if ((match >> i) & 1u) atomicAdd(&s_hist[digit_of(key[i], PASS)], 1u);
-                    if (PASS == 1 && collect) {
-                        // warp-aggregated append of (key, position) pairs
-                        const int cnt = __popc(match);
-                        int incl = cnt;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                            if (lane >= o) incl += v;
-                        }
-                        const int warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                        if (warp_total > 0) {
-                            uint32_t base = 0;
-                            if (lane == 31) base = atomicAdd(&st->cand_count, (uint32_t)warp_total);
-                            base = __shfl_sync(0xFFFFFFFFu, base, 31);
-                            uint32_t off = base + (uint32_t)(incl - cnt);
-                            const uint32_t pos0 = (uint32_t)(c * kChunk);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                if ((match >> i) & 1u) {
-                                    if ((long long)off < a.cand_capacity) {
-                                        a.cand_key[off] = key[i];
-                                        a.cand_pos[off] = pos0 + (uint32_t)(cur.vec ? slot_element<true>(i) : slot_element<false>(i));
-                                    }
-                                    ++off;
-                                }
-                            }
-                        }
-                    }
+                        if (((alive >> i) & 1u) && ((key[i] & pmask) == prefix)) atomicAdd(&s_hist[digit_of(key[i], PASS)], 1u);
                 }
                 if (!more) break;
                 c = cn; src = srcn; n = nn; cur = nxt;
@@ -288,24 +395,40 @@ k_select_pass(PassArgs a) {
         }
     }
     __syncthreads();
-    // flush the CTA histogram; the last CTA to finish scans it and advances the select state
+    // flush the CTA histogram: one global atomic per non-empty bin
     for (int b = threadIdx.x; b < bins; b += kThreads) {
         const uint32_t v = s_hist[b];
         if (v) atomicAdd(a.hist + b, (unsigned long long)v);
     }
-    if (!a.fuse_scan) return;
+}
+
+// true in exactly one CTA: the last one to arrive (all other CTAs' global writes are visible to it)
+__device__ __forceinline__ bool last_cta_arrives(unsigned int* ticket) {
     __shared__ unsigned int s_ticket;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
     __syncthreads();
-    if (s_ticket == gridDim.x - 1) {
-        __threadfence();
+    const bool last = s_ticket == gridDim.x - 1;
+    if (last) __threadfence();
+    return last;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kThreads, 3)
+k_select_pass(PassArgs a) {
+    __shared__ uint32_t s_hist[kHistBins];
+    __shared__ CandStage s_stage;
+    __shared__ int s_wcount[kThreads / 32];
+    pass_body<PASS>(a, s_hist, &s_stage, s_wcount);
+    if (!a.fuse_scan) return;
+    // the last CTA to finish scans the global histogram and advances the select state
+    if (last_cta_arrives(a.ticket)) {
         if (PASS == 0 && a.fuse_init) {
-            if (threadIdx.x == 0) init_state(st, a.k, a.mode, a.allow_collect);
+            if (threadIdx.x == 0) init_state(a.st, a.k, a.mode, a.allow_collect);
             __syncthreads();
         }
-        scan_and_advance(PASS, a.hist, st, a.cand_capacity);
+        scan_and_advance(PASS, a.hist, a.st, a.cand_capacity);
         if (threadIdx.x == 0) *a.ticket = 0u;
     }
 }
@@ -316,7 +439,7 @@ __global__ void k_select_scan(int pass, unsigned long long* hist, SelState* st, 
 
 __global__ void k_select_init(SelState* st, unsigned long long* hist, unsigned int* ticket,
                               unsigned long long k, uint32_t mode, uint32_t allow_collect) {
-    for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) hist[b] = 0ull;
+    for (int b = threadIdx.x; b < kHistBins + kHistExtra; b += blockDim.x) hist[b] = 0ull;
     if (threadIdx.x == 0) {
         init_state(st, k, mode, allow_collect);
         *ticket = 0u;
@@ -326,10 +449,10 @@ __global__ void k_select_init(SelState* st, unsigned long long* hist, unsigned i
 // ---- tie resolution (EXACT_K with quota < n_equal) ---------------------------------------
 // chunk_ties[c] = number of alive keys == threshold in chunk c.  Collect mode: every tie is in the
 // candidate buffer (one atomic per tied candidate into a zeroed table); otherwise re-stream the keys.
-__global__ void __launch_bounds__(kThreads)
-k_tie_count(const int32_t* __restrict__ chunk_n, ChunkTab key_tab, const uint32_t* __restrict__ old_mask,
-            const SelState* __restrict__ st, const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_pos,
-            uint32_t* __restrict__ chunk_ties, int64_t c_begin, int64_t c_end, int vec_ok) {
+__device__ void tie_count_body(const int32_t* __restrict__ chunk_n, ChunkTab key_tab, const uint32_t* __restrict__ old_mask,
+                               const SelState* __restrict__ st, const uint32_t* __restrict__ cand_key,
+                               const uint32_t* __restrict__ cand_pos, uint32_t* __restrict__ chunk_ties,
+                               int64_t c_begin, int64_t c_end, int vec_ok) {
     if (!st->need_ties) return;
     const uint32_t thr = st->thr_key;
     if (st->collect) {
@@ -360,37 +483,47 @@ k_tie_count(const int32_t* __restrict__ chunk_n, ChunkTab key_tab, const uint32_
         __syncthreads();
     }
 }
-// One CTA: walk chunk_ties[c_begin, c_end) in order, find where the (quota - tie_offset)-th tie
-// falls, clear the table again.
+__global__ void __launch_bounds__(kThreads)
+k_tie_count(const int32_t* __restrict__ chunk_n, ChunkTab key_tab, const uint32_t* __restrict__ old_mask,
+            const SelState* __restrict__ st, const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_pos,
+            uint32_t* __restrict__ chunk_ties, int64_t c_begin, int64_t c_end, int vec_ok) {
+    tie_count_body(chunk_n, key_tab, old_mask, st, cand_key, cand_pos, chunk_ties, c_begin, c_end, vec_ok);
+}
+// One CTA (any size up to 1024 threads): walk chunk_ties[c_begin, c_end) in order, find where the
+// (quota - tie_offset)-th tie falls, clear the table again.
 // d_counts (nullable): per-rank tie counts gathered from all ranks; the ties owned by the
 // n_before lower ranks are added to tie_offset on the device (no host round trip).
-__global__ void __launch_bounds__(1024)
-k_tie_scan(SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties, int64_t c_begin, int64_t c_end,
-           unsigned long long tie_offset, const unsigned long long* __restrict__ d_counts, int n_before) {
+__device__ void tie_scan_body(SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties, int64_t c_begin, int64_t c_end,
+                              unsigned long long tie_offset, const unsigned long long* __restrict__ d_counts, int n_before,
+                              unsigned long long* s_part /* [blockDim.x] */) {
     if (!st->need_ties) return;
-    __shared__ unsigned long long s_part[1024];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
     if (d_counts) for (int r = 0; r < n_before; ++r) tie_offset += d_counts[r];
     const int64_t n = c_end - c_begin;
-    const int64_t per = (n + 1023) / 1024;
-    const int64_t lo = c_begin + tid * per;
+    const int64_t per = (n + nt - 1) / nt;
+    const int64_t lo = c_begin + tid * per < c_end ? c_begin + tid * per : c_end;
     const int64_t hi = lo + per < c_end ? lo + per : c_end;
     unsigned long long sum = 0;
     for (int64_t c = lo; c < hi; ++c) sum += chunk_ties[c];
     s_part[tid] = sum;
     __syncthreads();
+    __shared__ unsigned long long s_tie_total;
     if (tid == 0) {
         unsigned long long run = 0;
-        for (int i = 0; i < 1024; ++i) { unsigned long long v = s_part[i]; s_part[i] = run; run += v; }
+        for (int i = 0; i < nt; ++i) { unsigned long long v = s_part[i]; s_part[i] = run; run += v; }
+        s_tie_total = run;
     }
     __syncthreads();
     const unsigned long long quota = st->quota;
     // ties still to prune inside this chunk range
     const long long target = (long long)quota - (long long)tie_offset;
     unsigned long long before = s_part[tid];
-    const unsigned long long total = s_part[1023] + (tid == 1023 ? sum : 0ull);   // only valid in tid 1023
+    const unsigned long long total = s_tie_total;
+    __syncthreads();
     if (target <= 0) {
         if (tid == 0) { st->tie_chunk = c_begin; st->tie_resid = 0; st->tie_seen = 0; }
+    } else if ((unsigned long long)target > total) {
+        if (tid == 0) { st->tie_chunk = c_end; st->tie_resid = 0; st->tie_seen = total; }   // every local tie pruned
     } else {
         bool hit = false;
         for (int64_t c = lo; c < hi; ++c) {
@@ -403,12 +536,15 @@ k_tie_scan(SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties, int64_t
             }
             before += v;
         }
-        if (tid == 1023 && (unsigned long long)target > total) {
-            st->tie_chunk = c_end; st->tie_resid = 0; st->tie_seen = total;   // every local tie pruned
-        }
     }
     __syncthreads();
     for (int64_t c = lo; c < hi; ++c) chunk_ties[c] = 0;
+}
+__global__ void __launch_bounds__(1024)
+k_tie_scan(SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties, int64_t c_begin, int64_t c_end,
+           unsigned long long tie_offset, const unsigned long long* __restrict__ d_counts, int n_before) {
+    __shared__ unsigned long long s_part[1024];
+    tie_scan_body(st, chunk_ties, c_begin, c_end, tie_offset, d_counts, n_before, s_part);
 }
 
 // One CTA: *out = sum of chunk_ties[c_begin, c_end) (0 when no tie resolution is needed).
@@ -426,6 +562,331 @@ k_tie_total(const SelState* __restrict__ st, const uint32_t* __restrict__ chunk_
     if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&s_sum, sum);
     __syncthreads();
     if (threadIdx.x == 0) *out = s_sum;
+}
+
+// =============================================================================================
+// Sampled (bracketed) select — the default behind b200p_select_kth.
+//
+// The exact radix pass 0 pays one shared-memory atomic per key (2 cycles per lane: ~44 us for the
+// 25.5 M keys of ResNet-50, 2.5x the HBM time).  Only the bucket that holds rank k matters, so:
+//   S  k_select_sample   histogram of a 1/64 sample (and popcount of the old mask): the last CTA turns
+//                        sample rank r = k*S/n_alive +- 4*sqrt(S) into a bracket of 1..8 twelve-bit buckets
+//   A  k_select_bracket  ONE full-data sweep at memory speed: count the keys below the bracket in
+//                        registers, histogram the (few %) keys inside it by their next 12 bits and append
+//                        them to the candidate buffer; the last CTA verifies that rank k falls inside
+//                        (else: miss) and narrows to a 1024-key window
+//   B  k_select_finish   cooperative launch: histogram of the window over the candidates -> exact key,
+//                        tie count and tie scan (EXACT_K).  On a miss (or an unusable sample) the same
+//                        launch runs the exact 3-pass radix select with grid-wide barriers instead, so
+//                        the result never depends on the sample.
+// Three launches, no host round trip, one read of the keys.
+// =============================================================================================
+constexpr int kSampleSlotsPerChunk = 16;  // float4 sampled per 4096-key chunk (1/64 of the keys)
+constexpr int kMaxBracketBuckets = 8;     // 8 * 2^19 keys >> 10 = 4096 fine bins
+constexpr int kFineShift = 10;
+constexpr int kWindow = 1 << kFineShift;
+
+struct SampleArgs {
+    const int32_t* chunk_n;
+    ChunkTab key_tab;
+    const uint32_t* old_mask;
+    unsigned long long* hist;
+    SelState* st;
+    unsigned int* ticket;
+    int64_t n_chunks;
+    int vec_ok;
+    unsigned long long k, n_total;
+    uint32_t mode;
+};
+
+// exclusive prefix of this thread's 16 bins over the CTA (kScanThreads threads) and the grand total
+__device__ __forceinline__ unsigned long long block_prefix16(const unsigned long long (&local)[kBinsPerThread],
+                                                             unsigned long long* s_warp /*[9]*/, unsigned long long& total) {
+    const int tid = threadIdx.x;
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) sum += local[i];
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((tid & 31) >= o) incl += v;
+    }
+    __syncthreads();
+    if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        unsigned long long v = tid < kScanThreads / 32 ? s_warp[tid] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (tid >= o) inc += u;
+        }
+        if (tid < kScanThreads / 32) s_warp[tid] = inc - v;
+        if (tid == kScanThreads / 32 - 1) s_warp[8] = inc;
+    }
+    __syncthreads();
+    total = s_warp[8];
+    return s_warp[tid >> 5] + (incl - sum);
+}
+
+__device__ __forceinline__ void clear_hist(unsigned long long* hist) {
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) hist[threadIdx.x * kBinsPerThread + i] = 0ull;
+    if (threadIdx.x < kHistExtra) hist[kHistBins + threadIdx.x] = 0ull;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_select_sample(SampleArgs a) {
+    __shared__ uint32_t s_hist[kHistBins];
+    __shared__ unsigned long long s_warp[9];
+    __shared__ unsigned long long s_alive;
+    __shared__ uint32_t s_bkt[2];
+    for (int b = threadIdx.x; b < kHistBins; b += kThreads) s_hist[b] = 0;
+    if (threadIdx.x == 0) s_alive = 0;
+    __syncthreads();
+    const int64_t gtid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nthreads = (int64_t)gridDim.x * kThreads;
+    if (a.old_mask) {
+        unsigned long long cnt = 0;
+        const int64_t words = a.n_chunks * kWordsPerChunk;
+        for (int64_t w = gtid; w < words; w += nthreads) cnt += __popc(__ldg(a.old_mask + w));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_alive, cnt);
+    }
+    // sample slot s = (chunk, i), i < 16: elements 256*i + 4*phase .. +3 (one float4 out of 64), the
+    // phase varying with chunk and i.  Four slots per thread are in flight at once: table loads,
+    // then data loads, then the shared-memory atomics.
+    const int64_t slots = a.n_chunks * kSampleSlotsPerChunk;
+    for (int64_t s0 = gtid; s0 < slots; s0 += 4 * nthreads) {
+        int n[4], e0[4]; const float* src[4]; int64_t cc[4]; bool on[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t sl = s0 + u * nthreads;
+            on[u] = sl < slots;
+            cc[u] = on[u] ? (sl >> 4) : 0;
+            const int i = (int)(sl & 15);
+            e0[u] = 256 * i + 4 * (int)((cc[u] + 5 * i) & 63);
+            n[u] = __ldg(a.chunk_n + cc[u]);
+            src[u] = chunk_ptr<const float>(a.key_tab, cc[u]);
+        }
+        float v[4][4]; uint32_t alive[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            on[u] = on[u] && e0[u] < n[u];
+            alive[u] = 0xFu;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[u][q] = 0.f;
+            if (on[u]) {
+                if (a.vec_ok && e0[u] + 3 < n[u]) {
+                    const float4 t = ld_nc_f4(src[u] + e0[u]);
+                    v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w;
+                } else {
+                    for (int q = 0; q < 4; ++q) if (e0[u] + q < n[u]) v[u][q] = src[u][e0[u] + q];
+                }
+                if (a.old_mask) alive[u] = (__ldg(a.old_mask + cc[u] * kWordsPerChunk + (e0[u] >> 5)) >> (e0[u] & 31)) & 0xFu;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!on[u]) continue;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (((alive[u] >> q) & 1u) && e0[u] + q < n[u]) atomicAdd(&s_hist[key_of(v[u][q]) >> 19], 1u);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kHistBins; b += kThreads) {
+        const uint32_t v = s_hist[b];
+        if (v) atomicAdd(a.hist + b, (unsigned long long)v);
+    }
+    if (threadIdx.x == 0 && s_alive) atomicAdd(a.hist + kHistBins + 0, s_alive);
+    if (!last_cta_arrives(a.ticket)) return;
+
+    // ---- last CTA: bracket from the sample histogram
+    SelState* st = a.st;
+    unsigned long long local[kBinsPerThread];
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) local[i] = ((volatile unsigned long long*)a.hist)[threadIdx.x * kBinsPerThread + i];
+    unsigned long long S;
+    unsigned long long running = block_prefix16(local, s_warp, S);
+    const unsigned long long n_alive = a.old_mask ? ((volatile unsigned long long*)a.hist)[kHistBins + 0] : a.n_total;
+    if (threadIdx.x == 0) { s_bkt[0] = 0xFFFFFFFFu; s_bkt[1] = 0xFFFFFFFFu; init_state(st, a.k, a.mode, 1u); st->n_valid = n_alive; }
+    __syncthreads();
+    bool usable = S >= 1024 && a.k >= 1 && a.k <= n_alive;
+    unsigned long long r_lo = 1, r_hi = 1;
+    if (usable) {
+        // sample rank of the population's k-th key: hypergeometric, sigma <= sqrt(S)/2; margin = 8 sigma_max + 2
+        const unsigned long long r = (unsigned long long)(((__uint128_t)a.k * S + n_alive - 1) / n_alive);
+        // 8 sigma of the hypergeometric rank, sigma^2 <= S q (1-q), plus slack for tiny tails
+        const double q = (double)a.k / (double)n_alive;
+        const unsigned long long m = (unsigned long long)ceil(8.0 * sqrt((double)S * q * (1.0 - q))) + 16ull;
+        r_lo = r > m ? r - m : 1ull;  if (r_lo < 1) r_lo = 1;
+        r_hi = r + m < S ? r + m : S; if (r_hi < 1) r_hi = 1;
+#pragma unroll
+        for (int i = 0; i < kBinsPerThread; ++i) {
+            const unsigned long long v = local[i];
+            if (v != 0 && running < r_lo && r_lo <= running + v) s_bkt[0] = threadIdx.x * kBinsPerThread + i;
+            if (v != 0 && running < r_hi && r_hi <= running + v) s_bkt[1] = threadIdx.x * kBinsPerThread + i;
+            running += v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t lo = s_bkt[0], hi = s_bkt[1];
+        const bool ok = usable && lo != 0xFFFFFFFFu && hi != 0xFFFFFFFFu && hi >= lo && hi - lo < (uint32_t)kMaxBracketBuckets &&
+                        hi < 0xFF0u;      // the sweep does not canonicalise NaN keys: stay below the inf/NaN buckets
+        st->sample_ok = ok ? 1u : 0u;
+        st->miss = ok ? 0u : 1u;
+        st->lo_bucket = lo; st->hi_bucket = hi;
+        *a.ticket = 0u;
+    }
+    clear_hist(a.hist);
+}
+
+// ---- A: one sweep: count below the bracket, fine histogram + collect inside it -----------------
+// The hot loop is issue-bound if written naively (16 keys per thread per chunk): it is kept to one
+// AND, one subtract and two compares per key, builds 16-bit "below" / "inside" masks, applies the
+// alive bitmap once per thread, and leaves everything that concerns the ~1 % matching keys (fine
+// histogram, staging, position) to a divergent slow path that extracts the key by index.
+__global__ void __launch_bounds__(kThreads, 3)
+k_select_bracket(PassArgs a) {
+    __shared__ uint32_t s_hist[kHistBins];
+    __shared__ unsigned long long s_warp[9];
+    __shared__ unsigned long long s_below;
+    __shared__ CandStage s_stage;
+    __shared__ int s_wcount[kThreads / 32];
+    SelState* __restrict__ st = a.st;
+    if (!st->sample_ok) return;                      // the finish kernel runs the exact select instead
+    const uint32_t lo_b = st->lo_bucket, hi_b = st->hi_bucket;
+    const uint32_t base = lo_b << 19, span = (hi_b - lo_b + 1) << 19;
+    for (int b = threadIdx.x; b < kHistBins; b += kThreads) s_hist[b] = 0;
+    if (threadIdx.x == 0) s_below = 0;
+    if (threadIdx.x < kThreads / 32) s_wcount[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long below = sweep_loop<false>(a, base, span, kFineShift, true, s_hist, s_stage, s_wcount);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xFFFFFFFFu, below, o);
+    if ((threadIdx.x & 31) == 0 && below) atomicAdd(&s_below, below);
+    __syncthreads();
+    for (int b = threadIdx.x; b < kHistBins; b += kThreads) {
+        const uint32_t v = s_hist[b];
+        if (v) atomicAdd(a.hist + b, (unsigned long long)v);
+    }
+    if (threadIdx.x == 0 && s_below) atomicAdd(a.hist + kHistBins + 1, s_below);
+    if (!last_cta_arrives(a.ticket)) return;
+
+    // ---- last CTA: verify that rank k is inside the bracket, narrow to a 1024-key window
+    unsigned long long local[kBinsPerThread];
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) local[i] = ((volatile unsigned long long*)a.hist)[threadIdx.x * kBinsPerThread + i];
+    unsigned long long total_in;
+    unsigned long long running = block_prefix16(local, s_warp, total_in);
+    const unsigned long long n_below = ((volatile unsigned long long*)a.hist)[kHistBins + 1];
+    const unsigned long long k = st->k;
+    __syncthreads();
+    const bool inside = k > n_below && k <= n_below + total_in && total_in <= (unsigned long long)a.cand_capacity;
+    if (!inside) {
+        if (threadIdx.x == 0) { st->miss = 1u; st->collect = 0u; st->cand_count = 0u; }
+    } else {
+        const unsigned long long kk = k - n_below;
+#pragma unroll
+        for (int i = 0; i < kBinsPerThread; ++i) {
+            const unsigned long long v = local[i];
+            if (v != 0 && running < kk && kk <= running + v) {
+                st->n_less = n_below + running;
+                st->k = kk - running;
+                st->bucket_count = v;
+                st->win_lo = base + ((uint32_t)(threadIdx.x * kBinsPerThread + i) << kFineShift);
+                st->collect = 1u;
+                st->passes_full = 1u;
+            }
+            running += v;
+        }
+    }
+    if (threadIdx.x == 0) *a.ticket = 0u;
+    clear_hist(a.hist);
+}
+
+// ---- B: finish (cooperative launch) ----------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier() { cooperative_groups::this_grid().sync(); }
+
+__global__ void __launch_bounds__(kThreads, 3)
+k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks) {
+    __shared__ uint32_t s_hist[kHistBins];
+    __shared__ CandStage s_stage;
+    __shared__ int s_wcount[kThreads / 32];
+    __shared__ unsigned long long s_part[kThreads];
+    __shared__ unsigned long long s_warp[9];
+    SelState* __restrict__ st = a.st;
+    const bool exact = st->miss != 0u;               // written by the previous kernel: uniform over the grid
+    if (exact) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) init_state(st, a.k, a.mode, a.allow_collect, 1u);
+        grid_barrier();
+        pass_body<0>(a, s_hist, &s_stage, s_wcount); grid_barrier();
+        if (blockIdx.x == 0) scan_and_advance(0, a.hist, st, a.cand_capacity);
+        grid_barrier();
+        pass_body<1>(a, s_hist, &s_stage, s_wcount); grid_barrier();
+        if (blockIdx.x == 0) scan_and_advance(1, a.hist, st, a.cand_capacity);
+        grid_barrier();
+        pass_body<2>(a, s_hist, &s_stage, s_wcount); grid_barrier();
+        if (blockIdx.x == 0) {
+            scan_and_advance(2, a.hist, st, a.cand_capacity);
+            if (threadIdx.x == 0) st->passes_full = st->collect ? 3u : 4u;
+        }
+        grid_barrier();
+    } else {
+        // window pass over the candidates: exact key among the 1024 keys of the window
+        for (int b = threadIdx.x; b < kWindow; b += kThreads) s_hist[b] = 0;
+        __syncthreads();
+        const uint32_t n = st->cand_count, win_lo = st->win_lo;
+        for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+            const uint32_t d = a.cand_key[i] - win_lo;
+            if (d < (uint32_t)kWindow) atomicAdd(&s_hist[d], 1u);
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < kWindow; b += kThreads) {
+            const uint32_t v = s_hist[b];
+            if (v) atomicAdd(a.hist + b, (unsigned long long)v);
+        }
+        grid_barrier();
+        if (blockIdx.x == 0) {
+            unsigned long long local[kBinsPerThread];
+#pragma unroll
+            for (int i = 0; i < kBinsPerThread; ++i) {
+                const int b = threadIdx.x * kBinsPerThread + i;
+                local[i] = b < kWindow ? ((volatile unsigned long long*)a.hist)[b] : 0ull;
+            }
+            unsigned long long total;
+            unsigned long long running = block_prefix16(local, s_warp, total);
+            const unsigned long long k = st->k;
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < kBinsPerThread; ++i) {
+                const unsigned long long v = local[i];
+                if (v != 0 && running < k && k <= running + v) {
+                    const uint32_t key = win_lo + (uint32_t)(threadIdx.x * kBinsPerThread + i);
+                    st->n_less += running;
+                    st->k = k - running;
+                    st->prefix = key; st->thr_key = key; st->threshold = key_to_float(key);
+                    st->n_equal = v; st->quota = k - running;
+                    st->need_ties = (st->mode == B200P_MODE_EXACT_K && (k - running) < v) ? 1u : 0u;
+                    st->tie_chunk = -1; st->tie_resid = 0; st->tie_seen = 0;
+                }
+                running += v;
+            }
+            __syncthreads();
+            clear_hist(a.hist);
+        }
+        grid_barrier();
+    }
+    // ties (EXACT_K with quota < n_equal): per-chunk counts, then the ordered scan
+    if (a.mode == B200P_MODE_EXACT_K && st->need_ties) {
+        tie_count_body(a.chunk_n, a.key_tab, a.old_mask, st, a.cand_key, a.cand_pos, chunk_ties, 0, n_chunks, a.vec_ok);
+        grid_barrier();
+        if (blockIdx.x == 0) tie_scan_body(st, chunk_ties, 0, n_chunks, 0ull, nullptr, 0, s_part);
+    }
 }
 
 static unsigned int* ticket_ptr(b200p_plan* p) {
@@ -467,15 +928,14 @@ static int pass_grid(b200p_plan* p, int64_t chunks, bool cand_too, int ctas_per_
     return p->grid_for(work, ctas_per_sm);
 }
 
+static void fill_pass_args(b200p_plan* p, PassArgs& a, int key_source, const uint32_t* d_old_mask, int64_t c0, int64_t c1,
+                           int fuse_scan, int fuse_init, uint64_t k, int mode, int allow_collect);
+
 static int launch_pass(b200p_plan* p, int pass, int key_source, const uint32_t* d_old_mask,
                        int64_t c0, int64_t c1, int fuse_scan, int fuse_init, uint64_t k, int mode, int allow_collect,
                        cudaStream_t st) {
-    const int slot = key_slot(key_source);
     PassArgs a;
-    a.chunk_n = p->d_chunk_n; a.key_tab = p->tab(slot); a.old_mask = d_old_mask; a.hist = p->d_hist; a.st = p->d_state;
-    a.cand_key = p->d_cand_key; a.cand_pos = p->d_cand_pos; a.ticket = ticket_ptr(p); a.cand_capacity = p->cand_capacity;
-    a.c_begin = c0; a.c_end = c1; a.vec_ok = p->vec_ok[slot] ? 1 : 0; a.fuse_scan = fuse_scan;
-    a.fuse_init = fuse_init; a.k = k; a.mode = (uint32_t)mode; a.allow_collect = allow_collect ? 1u : 0u;
+    fill_pass_args(p, a, key_source, d_old_mask, c0, c1, fuse_scan, fuse_init, k, mode, allow_collect);
     const int grid = pass_grid(p, c1 - c0, pass == 2, pass == 0 ? 4 : 3);
     switch (pass) {
         case 0: k_select_pass<0><<<grid, kThreads, 0, st>>>(a); break;
@@ -564,6 +1024,61 @@ extern "C" int b200p_select_ties_scan(b200p_plan* p, int64_t chunk_begin, int64_
     return B200P_OK;
 }
 
+static void fill_pass_args(b200p_plan* p, PassArgs& a, int key_source, const uint32_t* d_old_mask, int64_t c0, int64_t c1,
+                           int fuse_scan, int fuse_init, uint64_t k, int mode, int allow_collect) {
+    const int slot = key_slot(key_source);
+    a.chunk_n = p->d_chunk_n; a.key_tab = p->tab(slot); a.old_mask = d_old_mask; a.hist = p->d_hist; a.st = p->d_state;
+    a.cand_key = p->d_cand_key; a.cand_pos = p->d_cand_pos; a.ticket = ticket_ptr(p); a.cand_capacity = p->cand_capacity;
+    a.c_begin = c0; a.c_end = c1; a.vec_ok = p->vec_ok[slot] ? 1 : 0; a.fuse_scan = fuse_scan;
+    a.fuse_init = fuse_init; a.k = k; a.mode = (uint32_t)mode; a.allow_collect = allow_collect ? 1u : 0u;
+}
+
+static int select_kth_exact(b200p_plan* p, int key_source, const uint32_t* d_old_mask, uint64_t k, int mode, cudaStream_t st) {
+    // Three launches, no host round trip: the state reset rides in pass 0's last CTA (the global
+    // histogram and the ticket are left zeroed by every completed scan), every pass ends with the
+    // last-CTA scan.  Pass 2 runs on the candidates gathered by pass 1 unless the bucket overflowed.
+    int rc = launch_pass(p, 0, key_source, d_old_mask, 0, p->n_chunks, 1, 1, k, mode, 1, st); if (rc) return rc;
+    rc = launch_pass(p, 1, key_source, d_old_mask, 0, p->n_chunks, 1, 0, 0, 0, 0, st); if (rc) return rc;
+    rc = launch_pass(p, 2, key_source, d_old_mask, 0, p->n_chunks, 1, 0, 0, 0, 0, st); if (rc) return rc;
+    if (mode == B200P_MODE_EXACT_K) { rc = b200p_select_ties(p, key_source, d_old_mask, 0, p->n_chunks, 0, (void*)st); if (rc) return rc; }
+    return B200P_OK;
+}
+
+static int select_kth_sampled(b200p_plan* p, int key_source, const uint32_t* d_old_mask, uint64_t k, int mode, cudaStream_t st) {
+    const int slot = key_slot(key_source);
+    if (p->coop_ctas_per_sm == 0) {
+        int coop = 0, occ = 0;
+        B200P_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+        if (coop) B200P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select_finish, kThreads, 0));
+        p->coop_ctas_per_sm = occ > 0 ? (occ > 3 ? 3 : occ) : -1;
+    }
+    if (p->coop_ctas_per_sm < 0) return select_kth_exact(p, key_source, d_old_mask, k, mode, st);   // no cooperative launch
+    // S: 1/16 sample
+    SampleArgs sa;
+    sa.chunk_n = p->d_chunk_n; sa.key_tab = p->tab(slot); sa.old_mask = d_old_mask; sa.hist = p->d_hist; sa.st = p->d_state;
+    sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.vec_ok = p->vec_ok[slot] ? 1 : 0;
+    sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)mode;
+    const int64_t sblocks = (p->n_chunks * kSampleSlotsPerChunk + 4 * kThreads - 1) / (4 * kThreads);
+    k_select_sample<<<p->grid_for(sblocks, 1), kThreads, 0, st>>>(sa);
+    B200P_LAUNCH_CHECK("k_select_sample");
+    // A: bracket sweep
+    PassArgs a;
+    fill_pass_args(p, a, key_source, d_old_mask, 0, p->n_chunks, 1, 0, k, mode, 1);
+    k_select_bracket<<<p->grid_for(p->n_chunks, 3), kThreads, 0, st>>>(a);
+    B200P_LAUNCH_CHECK("k_select_bracket");
+    // B: finish (cooperative: grid-wide barriers between its phases)
+    int64_t work = p->n_chunks;
+    const int64_t cblocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
+    if (cblocks > work) work = cblocks;
+    // one CTA per SM: the phases between the grid-wide barriers are tiny, the barriers are not
+    int grid = p->num_sms;
+    if (work < grid) grid = (int)(work < 1 ? 1 : work);
+    uint32_t* ties = p->d_chunk_ties; int64_t n_chunks = p->n_chunks;
+    void* args[] = {(void*)&a, (void*)&ties, (void*)&n_chunks};
+    B200P_CUDA(cudaLaunchCooperativeKernel((const void*)k_select_finish, dim3(grid), dim3(kThreads), args, 0, st));
+    return B200P_OK;
+}
+
 extern "C" int b200p_select_kth(b200p_plan* p, int key_source, const uint32_t* d_old_mask,
                                 uint64_t k, int mode, void* stream) {
     B200P_REQUIRE(p != nullptr, B200P_EINVAL, "select_kth: null plan");
@@ -571,15 +1086,8 @@ extern "C" int b200p_select_kth(b200p_plan* p, int key_source, const uint32_t* d
     B200P_REQUIRE(k >= 1 && k <= (uint64_t)p->total, B200P_EINVAL, "select_kth: k must be in [1, N]");
     B200P_REQUIRE(mode == B200P_MODE_SNIP_STRICT || mode == B200P_MODE_EXACT_K, B200P_EINVAL, "select_kth: bad mode");
     B200P_CUDA(cudaSetDevice(p->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    // Three launches, no host round trip: the state reset rides in pass 0's last CTA (the global
-    // histogram and the ticket are left zeroed by every completed scan), every pass ends with the
-    // last-CTA scan.  Pass 2 runs on the candidates gathered by pass 1 unless the bucket overflowed.
-    rc = launch_pass(p, 0, key_source, d_old_mask, 0, p->n_chunks, 1, 1, k, mode, 1, st); if (rc) return rc;
-    rc = launch_pass(p, 1, key_source, d_old_mask, 0, p->n_chunks, 1, 0, 0, 0, 0, st); if (rc) return rc;
-    rc = launch_pass(p, 2, key_source, d_old_mask, 0, p->n_chunks, 1, 0, 0, 0, 0, st); if (rc) return rc;
-    if (mode == B200P_MODE_EXACT_K) { rc = b200p_select_ties(p, key_source, d_old_mask, 0, p->n_chunks, 0, stream); if (rc) return rc; }
-    return B200P_OK;
+    if (p->select_impl == B200P_SELECT_EXACT) return select_kth_exact(p, key_source, d_old_mask, k, mode, (cudaStream_t)stream);
+    return select_kth_sampled(p, key_source, d_old_mask, k, mode, (cudaStream_t)stream);
 }
 
 extern "C" int b200p_select_result(b200p_plan* p, b200p_select_result_t* h_out, void* stream) {
@@ -590,6 +1098,6 @@ extern "C" int b200p_select_result(b200p_plan* p, b200p_select_result_t* h_out, 
     B200P_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     h_out->k = s.k_request; h_out->n_valid = s.n_valid; h_out->n_less = s.n_less; h_out->n_equal = s.n_equal;
     h_out->quota = s.quota; h_out->n_kept = s.n_kept; h_out->threshold = s.threshold; h_out->thr_key = s.thr_key;
-    h_out->passes_full = s.collect ? 2u : 3u; h_out->collected = s.collect ? s.cand_count : 0u;
+    h_out->passes_full = s.passes_full ? s.passes_full : (s.collect ? 2u : 3u); h_out->collected = s.collect ? s.cand_count : 0u;
     return B200P_OK;
 }

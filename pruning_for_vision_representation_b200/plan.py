@@ -58,6 +58,13 @@ class ParamPlan:
         plan = cls([t.numel() for t in tensors], tensors[0].device, cand_capacity)
         return plan
 
+    def set_select_impl(self, impl):
+        """'sampled' (default: 1/16 sample -> bracket -> one sweep, exact fallback on a miss) or 'exact'
+        (3-pass radix select).  Both return identical results."""
+        value = {"sampled": _lib.SELECT_SAMPLED, "exact": _lib.SELECT_EXACT}[impl]
+        check(self.lib.b200p_plan_set_option(self.handle, _lib.OPT_SELECT_IMPL, value), "plan_set_option")
+        return self
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.b200p_plan_destroy(self.handle)
