@@ -175,24 +175,8 @@ __device__ void scan_and_advance(int pass, unsigned long long* __restrict__ hist
 // ---- candidate append with per-warp staging -------------------------------------------------
 // A global atomic on the one shared counter per warp per chunk serialises in L2 (tens of thousands
 // of same-address atomics per sweep).  Each warp stages its matches in shared memory and reserves
-// global space once per ~200 candidates instead.
+// global space once per ~128 candidates instead (sweep_loop below).
 constexpr int kStage = 256;                       // staged candidates per warp
-struct CandStage {
-    uint32_t key[kThreads / 32][kStage];
-    uint32_t pos[kThreads / 32][kStage];
-};
-
-__device__ __forceinline__ void stage_flush(CandStage& sg, int warp, int lane, int n, SelState* st,
-                                            uint32_t* __restrict__ cand_key, uint32_t* __restrict__ cand_pos, long long cap) {
-    if (n <= 0) return;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&st->cand_count, (uint32_t)n);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    for (int i = lane; i < n; i += 32) {
-        if ((long long)(base + i) < cap) { cand_key[base + i] = sg.key[warp][i]; cand_pos[base + i] = sg.pos[warp][i]; }
-    }
-    __syncwarp();
-}
 
 // ---- select state initialisation ----------------------------------------------------------
 __device__ __forceinline__ void init_state(SelState* st, unsigned long long k, uint32_t mode, uint32_t allow_collect,
@@ -229,105 +213,130 @@ __device__ __forceinline__ float sel16(const float4 (&v)[kVecPerThread], int i) 
     return q == 0 ? t.x : q == 1 ? t.y : q == 2 ? t.z : t.w;
 }
 
-// one matching key: fine histogram + staged append (order inside the buffer is irrelevant)
-__device__ __forceinline__ void sweep_take(uint32_t key, uint32_t pos, uint32_t base, int fine_shift,
-                                           uint32_t* __restrict__ s_hist, CandStage& sg, int* __restrict__ s_wcount,
-                                           SelState* st, uint32_t* __restrict__ cand_key, uint32_t* __restrict__ cand_pos,
-                                           long long cap, bool collect) {
-    atomicAdd(&s_hist[(key - base) >> fine_shift], 1u);
-    if (!collect) return;
-    const int warp = threadIdx.x >> 5;
-    const int off = atomicAdd(&s_wcount[warp], 1);
-    if (off < kStage) { sg.key[warp][off] = key; sg.pos[warp][off] = pos; }
-    else {
-        const uint32_t g = atomicAdd(&st->cand_count, 1u);
-        if ((long long)g < cap) { cand_key[g] = key; cand_pos[g] = pos; }
-    }
-}
-
-// Sweeps chunks [c_begin, c_end): keys in [base, base + span) are "inside".  Returns this thread's
-// count of alive keys below `base`.  CANON: canonicalise NaN keys (only needed when the range
-// reaches the inf/NaN buckets).
-template <bool CANON>
+// Sweeps chunks [c_begin, c_end): alive keys in [base, base + span) are "inside": they are counted in
+// the fine histogram s_hist[(key - base) >> fine_shift] and (collect) appended to the candidate
+// buffer through a per-warp staging area.  Returns this thread's count of alive keys below `base`.
+// canon: the range reaches the inf/NaN buckets, keys must be canonicalised: element-wise path.
+// Two chunks are loaded per iteration (128 B in flight per thread, 4 CTAs per SM) so that the sweep
+// is bound by HBM and not by the latency of one 64-byte load per thread.
 __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint32_t base, uint32_t span, int fine_shift,
-                                                         bool collect, uint32_t* __restrict__ s_hist, CandStage& sg,
-                                                         int* __restrict__ s_wcount) {
+                                                         bool collect, bool canon, uint32_t* __restrict__ s_hist) {
+    __shared__ uint32_t sg_key[kThreads / 32][kStage];
+    __shared__ uint32_t sg_pos[kThreads / 32][kStage];
+    __shared__ int s_wcount[kThreads / 32];
     SelState* __restrict__ st = a.st;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_wcount[warp] = 0;
+    __syncwarp();
     unsigned long long below = 0;
-    int64_t c = a.c_begin + blockIdx.x;
-    if (c >= a.c_end) return 0;
-    const float* src = chunk_ptr<const float>(a.key_tab, c);
-    int n = __ldg(a.chunk_n + c);
-    ChunkRegs cur;
-    prefetch_chunk(src, a.old_mask ? a.old_mask + c * kWordsPerChunk : nullptr, n, a.vec_ok, cur);
-    while (true) {
-        const int64_t cn = c + gridDim.x;
-        const bool more = cn < a.c_end;
-        const float* srcn = nullptr; int nn = 0;
-        ChunkRegs nxt; nxt.vec = false; nxt.alive = 0;
-        if (more) {
-            srcn = chunk_ptr<const float>(a.key_tab, cn);
-            nn = __ldg(a.chunk_n + cn);
-            prefetch_chunk(srcn, a.old_mask ? a.old_mask + cn * kWordsPerChunk : nullptr, nn, a.vec_ok, nxt);
+
+    // one matching key: fine histogram + staged append (order inside the buffer is irrelevant)
+    auto take = [&](uint32_t key, uint32_t pos) {
+        atomicAdd(&s_hist[(key - base) >> fine_shift], 1u);
+        if (!collect) return;
+        const int off = atomicAdd(&s_wcount[warp], 1);
+        if (off < kStage) { sg_key[warp][off] = key; sg_pos[warp][off] = pos; }
+        else {
+            const uint32_t g = atomicAdd(&st->cand_count, 1u);
+            if ((long long)g < a.cand_capacity) { a.cand_key[g] = key; a.cand_pos[g] = pos; }
         }
-        const uint32_t pos0 = (uint32_t)(c * kChunk);
-        if (cur.vec) {
-            uint32_t lt = 0, in = 0;
+    };
+    auto flush = [&](int n) {
+        if (n <= 0) return;
+        uint32_t gbase = 0;
+        if (lane == 0) gbase = atomicAdd(&st->cand_count, (uint32_t)n);
+        gbase = __shfl_sync(0xFFFFFFFFu, gbase, 0);
+        for (int i = lane; i < n; i += 32)
+            if ((long long)(gbase + i) < a.cand_capacity) { a.cand_key[gbase + i] = sg_key[warp][i]; a.cand_pos[gbase + i] = sg_pos[warp][i]; }
+        __syncwarp();
+        if (lane == 0) s_wcount[warp] = 0;
+        __syncwarp();
+    };
+    // vector chunk held in registers.  Per key: AND, two subtracts, two funnel shifts that push the sign
+    // bits of (k - base) and (k - base - span) into two 16-bit masks (first key ends up in bit 15).
+    // k >= base  =>  k - base < 2^31, so the sign of (k - base - span) is the unsigned compare; keys
+    // below `base` are removed from the inside-mask afterwards.
+    auto do_vec = [&](const float4 (&v)[kVecPerThread], uint32_t alive_rev, uint32_t pos0) {
+        uint32_t lt = 0, in = 0;
 #pragma unroll
-            for (int j = 0; j < kVecPerThread; ++j) {
-                const float f[4] = {cur.v[j].x, cur.v[j].y, cur.v[j].z, cur.v[j].w};
+        for (int j = 0; j < kVecPerThread; ++j) {
+            const float f[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t k = CANON ? key_of(f[q]) : (__float_as_uint(f[q]) & 0x7FFFFFFFu);
-                    const uint32_t d = k - base;
-                    lt |= (k < base ? 1u : 0u) << (4 * j + q);
-                    in |= (d < span ? 1u : 0u) << (4 * j + q);
-                }
-            }
-            below += __popc(lt & cur.alive);
-            uint32_t match = in & cur.alive;
-            while (match) {                           // divergent, rare
-                const int i = __ffs(match) - 1;
-                match &= match - 1;
-                const float x = sel16(cur.v, i);
-                const uint32_t k = CANON ? key_of(x) : (__float_as_uint(x) & 0x7FFFFFFFu);
-                sweep_take(k, pos0 + (uint32_t)slot_element<true>(i), base, fine_shift, s_hist, sg, s_wcount, st,
-                           a.cand_key, a.cand_pos, a.cand_capacity, collect);
-            }
-        } else {
-            // partial or unaligned chunk: element-wise
-            const uint32_t* mchunk = a.old_mask ? a.old_mask + c * kWordsPerChunk : nullptr;
-            for (int e = threadIdx.x; e < n; e += kThreads) {
-                if (mchunk && !((__ldg(mchunk + (e >> 5)) >> (e & 31)) & 1u)) continue;
-                const uint32_t k = key_of(src[e]);
-                if (k < base) ++below;
-                else if (k - base < span)
-                    sweep_take(k, pos0 + (uint32_t)e, base, fine_shift, s_hist, sg, s_wcount, st, a.cand_key, a.cand_pos,
-                               a.cand_capacity, collect);
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t d = (__float_as_uint(f[q]) & 0x7FFFFFFFu) - base;
+                lt = __funnelshift_l(d, lt, 1);
+                in = __funnelshift_l(d - span, in, 1);
             }
         }
+        lt &= alive_rev;
+        below += __popc(lt);
+        uint32_t match = in & ~lt & alive_rev;
+        while (match) {                               // divergent, rare (~1-2 % of the keys)
+            const int bit = __ffs(match) - 1;
+            match &= match - 1;
+            const int i = 15 - bit;                   // processing order of the key
+            take(__float_as_uint(sel16(v, i)) & 0x7FFFFFFFu, pos0 + (uint32_t)slot_element<true>(i));
+        }
+    };
+    // partial, unaligned or canonicalised chunk: element-wise
+    auto do_scalar = [&](const float* __restrict__ src, const uint32_t* __restrict__ mchunk, int n, uint32_t pos0) {
+        for (int e = threadIdx.x; e < n; e += kThreads) {
+            if (mchunk && !((__ldg(mchunk + (e >> 5)) >> (e & 31)) & 1u)) continue;
+            const uint32_t k = key_of(src[e]);
+            if (k < base) ++below;
+            else if (k - base < span) take(k, pos0 + (uint32_t)e);
+        }
+    };
+    // alive bitmap in do_vec's bit order (key i -> bit 15 - i)
+    auto load_alive = [&](const uint32_t* __restrict__ mchunk) {
+        uint32_t alive = 0xFFFFu;
+        if (mchunk) {
+            alive = 0;
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) alive |= nibble_of(__ldg(mchunk + vec_word_index(j))) << (4 * j);
+            alive = __brev(alive) >> 16;
+        }
+        return alive;
+    };
+
+    const bool vec_ok = a.vec_ok && !canon;
+    for (int64_t c0 = a.c_begin + blockIdx.x; c0 < a.c_end; c0 += 2 * (int64_t)gridDim.x) {
+        const int64_t c1 = c0 + gridDim.x;
+        const bool has1 = c1 < a.c_end;
+        const float* src0 = chunk_ptr<const float>(a.key_tab, c0);
+        const int n0 = __ldg(a.chunk_n + c0);
+        const float* src1 = has1 ? chunk_ptr<const float>(a.key_tab, c1) : nullptr;
+        const int n1 = has1 ? __ldg(a.chunk_n + c1) : 0;
+        const uint32_t* m0 = a.old_mask ? a.old_mask + c0 * kWordsPerChunk : nullptr;
+        const uint32_t* m1 = (a.old_mask && has1) ? a.old_mask + c1 * kWordsPerChunk : nullptr;
+        const bool vec0 = vec_ok && n0 == kChunk, vec1 = has1 && vec_ok && n1 == kChunk;
+        float4 v0[kVecPerThread], v1[kVecPerThread];
+        uint32_t al0 = 0xFFFFu, al1 = 0xFFFFu;
+        if (vec0) {
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) v0[j] = ld_nc_f4(src0 + 4 * (j * kThreads + threadIdx.x));
+            al0 = load_alive(m0);
+        }
+        if (vec1) {
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) v1[j] = ld_nc_f4(src1 + 4 * (j * kThreads + threadIdx.x));
+            al1 = load_alive(m1);
+        }
+        if (vec0) do_vec(v0, al0, (uint32_t)(c0 * kChunk)); else do_scalar(src0, m0, n0, (uint32_t)(c0 * kChunk));
+        if (has1) { if (vec1) do_vec(v1, al1, (uint32_t)(c1 * kChunk)); else do_scalar(src1, m1, n1, (uint32_t)(c1 * kChunk)); }
         __syncwarp();
         if (collect) {
             // Broadcast lane 0's view of the fill level: under independent thread scheduling a lane may
             // run ahead into the next chunk and bump the counter before a slower lane has read it, and a
             // non-uniform decision here would leave the warp split across different barriers.
             const int filled = __shfl_sync(0xFFFFFFFFu, s_wcount[warp], 0);
-            if (filled >= kStage / 2) {
-                __syncwarp();
-                stage_flush(sg, warp, lane, filled < kStage ? filled : kStage, st, a.cand_key, a.cand_pos, a.cand_capacity);
-                if (lane == 0) s_wcount[warp] = 0;
-                __syncwarp();
-            }
+            if (filled >= kStage / 2) flush(filled < kStage ? filled : kStage);
         }
-        if (!more) break;
-        c = cn; src = srcn; n = nn; cur = nxt;
     }
     __syncwarp();
     if (collect) {
         const int filled = __shfl_sync(0xFFFFFFFFu, s_wcount[warp], 0);
-        stage_flush(sg, warp, lane, filled < kStage ? filled : kStage, st, a.cand_key, a.cand_pos, a.cand_capacity);
-        if (lane == 0) s_wcount[warp] = 0;
+        flush(filled < kStage ? filled : kStage);
     }
     return below;
 }
@@ -339,7 +348,7 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
 // PASS 2: histogram digit 2 of the keys matching the 24 fixed bits — over the candidate buffer in
 //         collect mode, over the full data otherwise.
 template <int PASS>
-__device__ __forceinline__ void pass_body(const PassArgs& a, uint32_t* __restrict__ s_hist, CandStage* sg, int* s_wcount) {
+__device__ __forceinline__ void pass_body(const PassArgs& a, uint32_t* __restrict__ s_hist) {
     SelState* __restrict__ st = a.st;
     uint32_t prefix = 0, collect = 0;
     if (PASS > 0) { prefix = st->prefix; collect = st->collect; }
@@ -351,10 +360,7 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, uint32_t* __restric
 
     if (PASS == 1) {
         // keys of the chosen 12-bit bucket: histogram of their next 12 bits, plus the candidate append
-        if (threadIdx.x < kThreads / 32) s_wcount[threadIdx.x] = 0;
-        __syncthreads();
-        if ((prefix >> 19) >= 0xFF0u) sweep_loop<true>(a, prefix, 1u << 19, 7, collect != 0, s_hist, *sg, s_wcount);
-        else                          sweep_loop<false>(a, prefix, 1u << 19, 7, collect != 0, s_hist, *sg, s_wcount);
+        sweep_loop(a, prefix, 1u << 19, 7, collect != 0, (prefix >> 19) >= 0xFF0u, s_hist);
     } else if (PASS == 2 && collect) {
         const uint32_t n = st->cand_count;
         for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
@@ -418,9 +424,7 @@ template <int PASS>
 __global__ void __launch_bounds__(kThreads, 3)
 k_select_pass(PassArgs a) {
     __shared__ uint32_t s_hist[kHistBins];
-    __shared__ CandStage s_stage;
-    __shared__ int s_wcount[kThreads / 32];
-    pass_body<PASS>(a, s_hist, &s_stage, s_wcount);
+    pass_body<PASS>(a, s_hist);
     if (!a.fuse_scan) return;
     // the last CTA to finish scans the global histogram and advances the select state
     if (last_cta_arrives(a.ticket)) {
@@ -750,22 +754,19 @@ k_select_sample(SampleArgs a) {
 // AND, one subtract and two compares per key, builds 16-bit "below" / "inside" masks, applies the
 // alive bitmap once per thread, and leaves everything that concerns the ~1 % matching keys (fine
 // histogram, staging, position) to a divergent slow path that extracts the key by index.
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 k_select_bracket(PassArgs a) {
     __shared__ uint32_t s_hist[kHistBins];
     __shared__ unsigned long long s_warp[9];
     __shared__ unsigned long long s_below;
-    __shared__ CandStage s_stage;
-    __shared__ int s_wcount[kThreads / 32];
     SelState* __restrict__ st = a.st;
     if (!st->sample_ok) return;                      // the finish kernel runs the exact select instead
     const uint32_t lo_b = st->lo_bucket, hi_b = st->hi_bucket;
     const uint32_t base = lo_b << 19, span = (hi_b - lo_b + 1) << 19;
     for (int b = threadIdx.x; b < kHistBins; b += kThreads) s_hist[b] = 0;
     if (threadIdx.x == 0) s_below = 0;
-    if (threadIdx.x < kThreads / 32) s_wcount[threadIdx.x] = 0;
     __syncthreads();
-    unsigned long long below = sweep_loop<false>(a, base, span, kFineShift, true, s_hist, s_stage, s_wcount);
+    unsigned long long below = sweep_loop(a, base, span, kFineShift, true, false, s_hist);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xFFFFFFFFu, below, o);
     if ((threadIdx.x & 31) == 0 && below) atomicAdd(&s_below, below);
@@ -815,8 +816,6 @@ __device__ __forceinline__ void grid_barrier() { cooperative_groups::this_grid()
 __global__ void __launch_bounds__(kThreads, 3)
 k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks) {
     __shared__ uint32_t s_hist[kHistBins];
-    __shared__ CandStage s_stage;
-    __shared__ int s_wcount[kThreads / 32];
     __shared__ unsigned long long s_part[kThreads];
     __shared__ unsigned long long s_warp[9];
     SelState* __restrict__ st = a.st;
@@ -824,13 +823,13 @@ k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks)
     if (exact) {
         if (blockIdx.x == 0 && threadIdx.x == 0) init_state(st, a.k, a.mode, a.allow_collect, 1u);
         grid_barrier();
-        pass_body<0>(a, s_hist, &s_stage, s_wcount); grid_barrier();
+        pass_body<0>(a, s_hist); grid_barrier();
         if (blockIdx.x == 0) scan_and_advance(0, a.hist, st, a.cand_capacity);
         grid_barrier();
-        pass_body<1>(a, s_hist, &s_stage, s_wcount); grid_barrier();
+        pass_body<1>(a, s_hist); grid_barrier();
         if (blockIdx.x == 0) scan_and_advance(1, a.hist, st, a.cand_capacity);
         grid_barrier();
-        pass_body<2>(a, s_hist, &s_stage, s_wcount); grid_barrier();
+        pass_body<2>(a, s_hist); grid_barrier();
         if (blockIdx.x == 0) {
             scan_and_advance(2, a.hist, st, a.cand_capacity);
             if (threadIdx.x == 0) st->passes_full = st->collect ? 3u : 4u;
@@ -841,9 +840,16 @@ k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks)
         for (int b = threadIdx.x; b < kWindow; b += kThreads) s_hist[b] = 0;
         __syncthreads();
         const uint32_t n = st->cand_count, win_lo = st->win_lo;
-        for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-            const uint32_t d = a.cand_key[i] - win_lo;
-            if (d < (uint32_t)kWindow) atomicAdd(&s_hist[d], 1u);
+        const uint32_t stride = gridDim.x * kThreads;
+        for (uint32_t i0 = blockIdx.x * kThreads + threadIdx.x; i0 < n; i0 += 8 * stride) {
+            uint32_t kk[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) kk[u] = i0 + u * stride < n ? __ldg(a.cand_key + i0 + u * stride) : 0xFFFFFFFFu;   // independent loads
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t d = kk[u] - win_lo;
+                if (i0 + u * stride < n && d < (uint32_t)kWindow) atomicAdd(&s_hist[d], 1u);
+            }
         }
         __syncthreads();
         for (int b = threadIdx.x; b < kWindow; b += kThreads) {
@@ -1064,7 +1070,7 @@ static int select_kth_sampled(b200p_plan* p, int key_source, const uint32_t* d_o
     // A: bracket sweep
     PassArgs a;
     fill_pass_args(p, a, key_source, d_old_mask, 0, p->n_chunks, 1, 0, k, mode, 1);
-    k_select_bracket<<<p->grid_for(p->n_chunks, 3), kThreads, 0, st>>>(a);
+    k_select_bracket<<<p->grid_for((p->n_chunks + 1) / 2, 4), kThreads, 0, st>>>(a);
     B200P_LAUNCH_CHECK("k_select_bracket");
     // B: finish (cooperative: grid-wide barriers between its phases)
     int64_t work = p->n_chunks;
