@@ -91,7 +91,7 @@ SIGNATURES = {
     "b200p_apply_mask": (_I, [_P, _P, _I, _P]),
     "b200p_mask_grads": (_I, [_P, _P, _P]),
     "b200p_masked_sgd_step": (_I, [_P, _P, _F, _F, _F, _F, _I, _P]),
-    "b200p_lost_workspace_bytes": (_I, [_I, _I64, _I64, ctypes.POINTER(_I64)]),
+    "b200p_lost_workspace_bytes": (_I, [_I, _I64, _I64, _I, _I, ctypes.POINTER(_I64)]),
     "b200p_lost_batched": (_I, [_I, _P, _I64, _I, ctypes.POINTER(LostImage), _I, _I, _P, _P, _P, _P, _P,
                                 _P, _I64, _I, _P]),
     "b200p_lost_patch_scoring": (_I, [_I, _P, _I, _I64, _F, _P, _P, _P]),

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200prune.so")
-SOURCES = ["plan.cu", "score.cu", "select.cu", "emit.cu", "sgd.cu", "lost.cu", "host.cu"]
+SOURCES = ["plan.cu", "score.cu", "select.cu", "emit.cu", "sgd.cu", "lost.cu", "lost_tc.cu", "host.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",

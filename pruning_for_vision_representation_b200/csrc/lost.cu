@@ -12,20 +12,13 @@
 // Varlen batching: image b has n_b = dim0*dim1 patches; CTAs are assigned to (image, tile) pairs
 // through a prefix table so one launch covers images of different sizes.
 #include "common.cuh"
+#include "lost_common.cuh"
 #include <math.h>
 
 namespace b200p {
 
 constexpr int kLostMaxPatches = 4096;     // per image (ViT-S/8 at 480x480 = 3600)
 constexpr int kFinThreads = 512;
-
-struct LostImageDev {
-    long long feat_off, a_off, out_off;
-    int n, dim0, dim1, img_h, img_w;
-    float s0, s1;
-    int tile_base;       // first CTA of this image in the Gram grid
-    int tiles;           // tiles per side
-};
 
 // image records travel as kernel arguments (no pageable-memcpy stream sync, no staging buffer)
 constexpr int kMetaPerLaunch = 64;
@@ -36,15 +29,6 @@ __global__ void k_lost_set_meta(LostImageDev* __restrict__ dst, MetaPack pack, i
 
 // ---- K6: fp32 Gram + degree -----------------------------------------------------------------
 constexpr int BM = 128, BK = 16, GT = 256;
-
-__device__ __forceinline__ int find_image(const LostImageDev* __restrict__ meta, int n_images, int cta) {
-    int lo = 0, hi = n_images - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (meta[mid].tile_base <= cta) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
 
 // One CTA computes a 128x128 tile of A_b: rows [ti*128, +128) x cols [tj*128, +128).
 // 256 threads, 8x8 accumulators per thread, K in steps of 16 through double-buffered shared memory.
@@ -387,10 +371,11 @@ using namespace b200p;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-extern "C" int b200p_lost_workspace_bytes(int n_images, int64_t total_patches, int64_t total_a, int64_t* out) {
-    B200P_REQUIRE(out != nullptr && n_images >= 0 && total_patches >= 0 && total_a >= 0, B200P_EINVAL, "lost_workspace_bytes: bad argument");
-    (void)total_patches;
-    *out = (int64_t)(align_up((size_t)n_images * sizeof(LostImageDev), 256) + align_up((size_t)total_a * sizeof(float), 256) + 256);
+extern "C" int b200p_lost_workspace_bytes(int n_images, int64_t total_patches, int64_t total_a, int d, int gram_impl, int64_t* out) {
+    B200P_REQUIRE(out != nullptr && n_images >= 0 && total_patches >= 0 && total_a >= 0 && d >= 1, B200P_EINVAL, "lost_workspace_bytes: bad argument");
+    size_t bytes = align_up((size_t)n_images * sizeof(LostImageDev), 256) + align_up((size_t)total_a * sizeof(float), 256) + 256;
+    if (gram_impl == B200P_LOST_GRAM_TC) bytes += align_up(lost_tc_workspace_bytes(total_patches, d), 256);
+    *out = (int64_t)bytes;
     return B200P_OK;
 }
 
@@ -420,6 +405,7 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
         m.a_off = d_A ? h.a_offset : total_a;
         m.tiles = (int)((n + BM - 1) / BM);
         m.tile_base = (int)tile_base;
+        m.row_base = (int)total_patches; m.pad_ = 0;
         tile_base += (long long)m.tiles * m.tiles;
         total_a += n * n;
         total_patches += n;
@@ -430,7 +416,9 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     }
     B200P_REQUIRE(tile_base < (1ll << 31), B200P_EINVAL, "lost_batched: too many tiles in one call");
     const size_t meta_bytes = align_up((size_t)n_images * sizeof(LostImageDev), 256);
-    const size_t need = meta_bytes + (d_A ? 0 : align_up((size_t)total_a * sizeof(float), 256));
+    const size_t a_bytes = d_A ? 0 : align_up((size_t)total_a * sizeof(float), 256);
+    const size_t tc_bytes = gram_impl == B200P_LOST_GRAM_TC ? align_up(lost_tc_workspace_bytes(total_patches, d), 256) : 0;
+    const size_t need = meta_bytes + a_bytes + tc_bytes;
     B200P_REQUIRE((size_t)workspace_bytes >= need, B200P_EINVAL, "lost_batched: workspace too small (see b200p_lost_workspace_bytes)");
     LostImageDev* d_meta = (LostImageDev*)d_workspace;
     float* A_base = d_A ? d_A : (float*)((char*)d_workspace + meta_bytes);
@@ -443,10 +431,16 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     }
     // the call owns d_degree[min out_offset, max out_offset + n): cleared in one go
     B200P_CUDA(cudaMemsetAsync(d_degree + deg_lo, 0, (size_t)(deg_hi - deg_lo) * sizeof(int32_t), st));
-    // gram_impl TC (tcgen05 3xTF32) is not built yet: both values run the fp32 FFMA kernel
-    k_lost_gram_ffma<<<(int)tile_base, GT, 0, st>>>(d_feats, (long long)row_stride, d, d_meta, n_images, A_base, d_degree,
-                                                   0.0f, vec ? 1 : 0);
-    B200P_LAUNCH_CHECK("k_lost_gram_ffma");
+    if (gram_impl == B200P_LOST_GRAM_TC) {
+        void* tc_ws = (char*)d_workspace + meta_bytes + a_bytes;
+        int rc = lost_gram_tc(d_feats, (long long)row_stride, d, d_meta, meta, total_patches, n_max, A_base, d_degree, tc_ws, tc_bytes,
+                              vec ? 1 : 0, st);
+        if (rc) return rc;
+    } else {
+        k_lost_gram_ffma<<<(int)tile_base, GT, 0, st>>>(d_feats, (long long)row_stride, d, d_meta, n_images, A_base, d_degree,
+                                                       0.0f, vec ? 1 : 0);
+        B200P_LAUNCH_CHECK("k_lost_gram_ffma");
+    }
     n_max = (n_max + 15) & ~15;
     const size_t fin_smem = (size_t)n_max * 4 + (size_t)((n_max + 1 + 3) & ~3) * 4 + 2 * 1024 * 4 + 2 * (size_t)n_max;
     static bool attr_set = false;

@@ -1,0 +1,34 @@
+// lost_common.cuh — image records shared by the LOST kernels (lost.cu, lost_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+
+namespace b200p {
+
+struct LostImageDev {
+    long long feat_off, a_off, out_off;
+    int n, dim0, dim1, img_h, img_w;
+    float s0, s1;
+    int tile_base;       // first CTA of this image in the Gram grid
+    int tiles;           // 128-wide tiles per side
+    int row_base;        // first row of this image in the stacked hi/lo operand arrays
+    int pad_;
+};
+
+__device__ __forceinline__ int find_image(const LostImageDev* __restrict__ meta, int n_images, int cta) {
+    int lo = 0, hi = n_images - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (meta[mid].tile_base <= cta) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// tensor-core Gram (lost_tc.cu)
+size_t lost_tc_workspace_bytes(long long total_patches, int d);
+int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
+                 const std::vector<LostImageDev>& meta, long long total_patches, int n_max, float* A_base,
+                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st);
+
+}  // namespace b200p

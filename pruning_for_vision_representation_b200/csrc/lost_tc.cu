@@ -1,0 +1,322 @@
+// lost_tc.cu — K6 on the 5th-generation tensor cores: batched Gram matrix A_b = F_b F_b^T
+// (object_discovery.py:39) as a TMA -> tcgen05.mma (kind::tf32) -> TMEM pipeline with fp32-grade
+// accuracy from the 3xTF32 split, and the degree count of patch_scoring (:77-87) fused into the
+// TMEM epilogue.
+//
+//   k_lost_split_tf32   F -> (F_hi, F_lo):  hi = tf32(f) (round to nearest), lo = tf32(f - hi).
+//                       hi + lo carries 21+ mantissa bits; A = hi.hi^T + hi.lo^T + lo.hi^T drops only
+//                       the lo.lo^T term (~2^-22 relative to |f_i||f_j|), well inside the 1e-5 bar.
+//                       Rows of all images are stacked; K is zero-padded to a multiple of 32.
+//   k_lost_gram_tc      one CTA per 128x128 tile of one image, 192 threads, warp-specialised:
+//                         warp 0 (one lane): TMA producer — per 32-wide K slab four bulk tensor loads
+//                                  (A_hi, A_lo, B_hi, B_lo; 128 rows x 128 B, SWIZZLE_128B) into a
+//                                  3-stage shared-memory ring, completion on mbarriers
+//                         warp 1 (one lane): MMA issuer — per slab 4 k-steps x 3 tcgen05.mma
+//                                  (hi.hi, hi.lo, lo.hi), M=128 N=128 K=8, fp32 accumulator in 128
+//                                  TMEM columns; tcgen05.commit frees the stage / signals the epilogue
+//                         warps 2-5: epilogue — tcgen05.ld (32 lanes x 32 columns per warp and step),
+//                                  each thread owns one row: writes it to A and counts
+//                                  (i != j ? max(A_ij, 0) : 0) > threshold, one atomic per row.
+// Rows past an image's last patch read the next image's rows (or TMA zero fill at the very end):
+// their products are computed and discarded by the epilogue's bounds checks.
+#include "common.cuh"
+#include "lost_common.cuh"
+#include <cuda.h>
+
+namespace b200p {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB: one operand tile of one stage
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 128;
+constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout_type [61,64) with SWIZZLE_128B = 2).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;                       // leading byte offset: 1 (unused by swizzled K-major layouts)
+    d |= (uint64_t)(1024u >> 4) << 32;            // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N, M
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+// ---- split ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// one thread per float4 of the padded row
+__global__ void __launch_bounds__(256)
+k_lost_split_tf32(const float* __restrict__ feats, long long row_stride, int d, int d_pad,
+                  const LostImageDev* __restrict__ meta, float* __restrict__ hi, float* __restrict__ lo, int vec_ok) {
+    const LostImageDev im = meta[blockIdx.y];
+    const int quads = d_pad >> 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)im.n * quads) return;
+    const int row = (int)(idx / quads), k0 = (int)(idx % quads) * 4;
+    const float* p = feats + im.feat_off + (long long)row * row_stride + k0;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec_ok && k0 + 3 < d) v = *reinterpret_cast<const float4*>(p);
+    else {
+        if (k0 + 0 < d) v.x = p[0];
+        if (k0 + 1 < d) v.y = p[1];
+        if (k0 + 2 < d) v.z = p[2];
+        if (k0 + 3 < d) v.w = p[3];
+    }
+    float4 h, l;
+    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+    const long long o = ((long long)im.row_base + row) * d_pad + k0;
+    *reinterpret_cast<float4*>(hi + o) = h;
+    *reinterpret_cast<float4*>(lo + o) = l;
+}
+
+// ---- Gram tile on tcgen05 -------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_lost_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+               const LostImageDev* __restrict__ meta, int n_images, float* __restrict__ A_base,
+               int* __restrict__ degree_base, float threshold, int d_pad) {
+    extern __shared__ uint8_t smem_raw[];
+    // operand tiles need 1024-byte alignment (SWIZZLE_128B atom)
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * TC_STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 1);          // u32 written by tcgen05.alloc
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = find_image(meta, n_images, blockIdx.x);
+    const LostImageDev im = meta[b];
+    const int local = blockIdx.x - im.tile_base;
+    const int ti = local / im.tiles, tj = local % im.tiles;
+    const int row0 = ti * TC_BM, col0 = tj * TC_BN;
+    const int num_kb = d_pad / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_hi); tma_prefetch_desc(&tm_lo);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();                                  // reconverge after the one-lane setup above (.sync.aligned below)
+        // TMEM: 128 columns x 128 lanes of fp32 accumulators; the allocating warp also frees them
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        const int a_row = im.row_base + row0, b_row = im.row_base + col0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % TC_STAGES;
+            const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);                 // slot free (passes at once the first time round)
+            const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+            mbar_expect_tx(full_bar(s), TC_STAGE_BYTES);
+            tma_load_2d(st + 0 * TC_TILE_BYTES, &tm_hi, kb * TC_BK, a_row, full_bar(s));
+            tma_load_2d(st + 1 * TC_TILE_BYTES, &tm_lo, kb * TC_BK, a_row, full_bar(s));
+            tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_hi, kb * TC_BK, b_row, full_bar(s));
+            tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_lo, kb * TC_BK, b_row, full_bar(s));
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % TC_STAGES;
+            const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+            mbar_wait(full_bar(s), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+            const uint64_t a_hi = umma_desc_sw128(st + 0 * TC_TILE_BYTES), a_lo = umma_desc_sw128(st + 1 * TC_TILE_BYTES);
+            const uint64_t b_hi = umma_desc_sw128(st + 2 * TC_TILE_BYTES), b_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k) {
+                const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);        // 32 bytes per K=8 step inside the swizzle atom
+                umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+            umma_commit(empty_bar(s));                         // stage reusable once these MMAs have read it
+        }
+        umma_commit(tmem_full_bar);                            // accumulator complete
+    } else if (warp >= 2) {
+        // ===== epilogue: TMEM -> registers -> A (global) + degree =====
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                                 // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const int gi = row0 + row;
+        float* __restrict__ A = A_base + im.a_off;
+        const bool vec_store = (im.n & 3) == 0 && (((uintptr_t)A) & 15u) == 0;
+        int cnt = 0;
+#pragma unroll 1
+        for (int ch = 0; ch < TC_BN / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (gi < im.n) {
+                const int gj0 = col0 + ch * 32;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int gj = gj0 + c;
+                    if (gj < im.n) {
+                        const float v = __uint_as_float(r[c]);
+                        const float e = (gi == gj) ? 0.f : fmaxf(v, 0.f);
+                        cnt += (e > threshold) ? 1 : 0;
+                    }
+                }
+                float* dst = A + (long long)gi * im.n + gj0;
+                if (vec_store && gj0 + 31 < im.n) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]),
+                                                                          __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) if (gj0 + c < im.n) dst[c] = __uint_as_float(r[c]);
+                }
+            }
+        }
+        if (gi < im.n && cnt) atomicAdd(degree_base + im.out_off + gi, cnt);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, float* base, long long rows, int d_pad) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("lost_batched: cuTensorMapEncodeTiled is not available from the driver"); return B200P_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)d_pad * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("lost_batched: cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")"); return B200P_ECUDA; }
+    return B200P_OK;
+}
+
+size_t lost_tc_workspace_bytes(long long total_patches, int d) {
+    const int d_pad = (d + TC_BK - 1) / TC_BK * TC_BK;
+    return 2 * ((size_t)total_patches * d_pad * sizeof(float) + 1024);
+}
+
+int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
+                 const std::vector<LostImageDev>& meta, long long total_patches, int n_max, float* A_base,
+                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st) {
+    const int n_images = (int)meta.size();
+    const int d_pad = (d + TC_BK - 1) / TC_BK * TC_BK;
+    const size_t arr = ((size_t)total_patches * d_pad * sizeof(float) + 1023) / 1024 * 1024;
+    if (ws_bytes < 2 * arr) { set_error("lost_batched: tensor-core workspace too small"); return B200P_EINVAL; }
+    float* hi = (float*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    float* lo = (float*)((char*)hi + arr);
+    if ((char*)lo + (size_t)total_patches * d_pad * sizeof(float) > (char*)ws + ws_bytes) {
+        set_error("lost_batched: tensor-core workspace too small"); return B200P_EINVAL;
+    }
+    const long long quads = (long long)n_max * (d_pad / 4);
+    dim3 sgrid((unsigned)((quads + 255) / 256), (unsigned)n_images);
+    k_lost_split_tf32<<<sgrid, 256, 0, st>>>(d_feats, row_stride, d, d_pad, d_meta, hi, lo, vec_ok);
+    B200P_LAUNCH_CHECK("k_lost_split_tf32");
+    alignas(64) CUtensorMap tm_hi, tm_lo;
+    int rc = make_map(&tm_hi, hi, total_patches, d_pad); if (rc) return rc;
+    rc = make_map(&tm_lo, lo, total_patches, d_pad); if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    const LostImageDev& last = meta.back();
+    const int grid = last.tile_base + last.tiles * last.tiles;
+    k_lost_gram_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_hi, tm_lo, d_meta, n_images, A_base, d_degree, 0.0f, d_pad);
+    B200P_LAUNCH_CHECK("k_lost_gram_tc");
+    return B200P_OK;
+}
+
+}  // namespace b200p

@@ -43,12 +43,14 @@ class _Batch:
 
     def __init__(self, feats, row_stride, d, metas, dev, want_A, k_patches, gram_impl):
         lib = L.require_cuda()
+        if gram_impl is None:
+            gram_impl = DEFAULT_GRAM_IMPL
         n_images = len(metas)
         arr = (LostImage * n_images)(*metas)
         ns = [m.dim0 * m.dim1 for m in metas]
         total_p, total_a = sum(ns), sum(n * n for n in ns)
         ws_bytes = ctypes.c_int64()
-        check(lib.b200p_lost_workspace_bytes(n_images, total_p, 0 if want_A else total_a, ctypes.byref(ws_bytes)),
+        check(lib.b200p_lost_workspace_bytes(n_images, total_p, 0 if want_A else total_a, int(d), gram_impl, ctypes.byref(ws_bytes)),
               "lost_workspace_bytes")
         self.workspace = torch.empty(int(ws_bytes.value), dtype=torch.uint8, device=dev)
         self.A = torch.empty(total_a, dtype=torch.float32, device=dev) if want_A else None
@@ -75,7 +77,10 @@ def _meta(feat_off, a_off, out_off, dims, scales, init_image_size):
     return m
 
 
-def lost(feats, dims, scales, init_image_size, k_patches=100, gram_impl=L.LOST_GRAM_TC):
+DEFAULT_GRAM_IMPL = L.LOST_GRAM_TC      # TMA + tcgen05 3xTF32; L.LOST_GRAM_FFMA = fp32 CUDA cores
+
+
+def lost(feats, dims, scales, init_image_size, k_patches=100, gram_impl=None):
     """object_discovery.py:23-69.  feats: [1, N, d] fp32 CUDA tensor (any row stride, e.g. the k slice of
     a qkv buffer), dims = [w_featmap, h_featmap] with N = dims[0]*dims[1].
     Returns (pred ndarray[4], A [N,N] tensor, scores [N] tensor = -degree, seed 0-d int64 tensor)."""
@@ -99,7 +104,7 @@ def lost(feats, dims, scales, init_image_size, k_patches=100, gram_impl=L.LOST_G
     return np.asarray(pred), A, scores, seed
 
 
-def lost_batched(feats, dims, scales, init_image_sizes, k_patches=100, return_A=False, gram_impl=L.LOST_GRAM_TC):
+def lost_batched(feats, dims, scales, init_image_sizes, k_patches=100, return_A=False, gram_impl=None):
     """LOST over a batch in one call.  feats: [B, N, d] tensor (shared dims) or a list of [N_b, d]
     tensors with per-image dims / init_image_sizes.  Returns a dict of CUDA tensors:
     box [B,4] (xmin,ymin,xmax,ymax), seed [B], status [B] (1 = seed in background), degree (list of

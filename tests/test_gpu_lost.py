@@ -22,6 +22,16 @@ DEV = torch.device("cuda:0")
 EPS = float(np.finfo(np.float32).eps)
 
 
+@pytest.fixture(params=["tc", "ffma"], autouse=True)
+def gram_impl(request):
+    """Every test runs with both Gram implementations: TMA + tcgen05 3xTF32 and fp32 CUDA cores."""
+    from pruning_for_vision_representation_b200 import _lib as L
+    old = OD.DEFAULT_GRAM_IMPL
+    OD.DEFAULT_GRAM_IMPL = L.LOST_GRAM_TC if request.param == "tc" else L.LOST_GRAM_FFMA
+    yield request.param
+    OD.DEFAULT_GRAM_IMPL = old
+
+
 def _cases(golden_dir):
     z = np.load(os.path.join(golden_dir, "lost_cases.npz"))
     meta = json.load(open(os.path.join(golden_dir, "lost_cases.json")))
