@@ -16,6 +16,9 @@ _LAZY = {
     "MaskedSGD": "masked_sgd",
     "lost": "object_discovery", "patch_scoring": "object_discovery", "detect_box": "object_discovery",
     "lost_batched": "object_discovery",
+    "load_pruned": "checkpoint", "packed_mask_state": "checkpoint", "fp32_masks_from_packed": "checkpoint",
+    "add_pruning_args": "cli", "run_pruning_schedule": "cli",
+    "ShardedMaskBuilder": "distributed",
 }
 
 

@@ -136,6 +136,9 @@ def _get_state(model, modules):
     if dev.type != "cuda":
         raise B200PruneError("the B200 pruning path needs the model on a CUDA device (no CPU fallback)")
     st = getattr(model, "_b200p_state", None)
+    if st is not None and st.maskf is not None and any(
+            "weight_mask" in m._buffers and m._buffers["weight_mask"] is not buf for m, buf in zip(st.modules, st.maskf)):
+        st = None          # torch.nn.utils.prune (or a checkpoint load) replaced the mask buffers underneath: re-adopt
     if st is None or len(st.modules) != len(modules) or any(a is not b for a, b in zip(st.modules, modules)) \
             or st.device != dev:
         st = PruneState(modules, dev)
