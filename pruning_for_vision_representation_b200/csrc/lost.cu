@@ -390,7 +390,7 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     B200P_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<LostImageDev> meta(n_images);
-    long long tile_base = 0, total_a = 0, total_patches = 0, deg_lo = -1, deg_hi = 0;
+    long long tile_base = 0, pair_base = 0, total_a = 0, total_patches = 0, deg_lo = -1, deg_hi = 0;
     int n_max = 0;
     B200P_REQUIRE(k_patches <= 1024, B200P_EINVAL, "lost_batched: k_patches must be <= 1024");
     bool vec = (((uintptr_t)d_feats) & 15u) == 0 && (row_stride & 3) == 0;
@@ -405,7 +405,8 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
         m.a_off = d_A ? h.a_offset : total_a;
         m.tiles = (int)((n + BM - 1) / BM);
         m.tile_base = (int)tile_base;
-        m.row_base = (int)total_patches; m.pad_ = 0;
+        m.row_base = (int)total_patches; m.pair_base = (int)pair_base;
+        pair_base += (long long)m.tiles * (m.tiles + 1) / 2;
         tile_base += (long long)m.tiles * m.tiles;
         total_a += n * n;
         total_patches += n;

@@ -13,7 +13,7 @@ struct LostImageDev {
     int tile_base;       // first CTA of this image in the Gram grid
     int tiles;           // 128-wide tiles per side
     int row_base;        // first row of this image in the stacked hi/lo operand arrays
-    int pad_;
+    int pair_base;       // first tile of this image in the symmetric (ti <= tj) tile list of the tensor-core Gram
 };
 
 __device__ __forceinline__ int find_image(const LostImageDev* __restrict__ meta, int n_images, int cta) {

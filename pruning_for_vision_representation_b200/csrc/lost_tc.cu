@@ -29,7 +29,6 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;                 // 16 KB: one operand tile of one stage
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;                // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_THREADS = 192;
-constexpr int TC_TMEM_COLS = 128;
 constexpr size_t TC_SMEM_BYTES = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -131,39 +130,64 @@ k_lost_split_tf32(const float* __restrict__ feats, long long row_stride, int d, 
     *reinterpret_cast<float4*>(lo + o) = l;
 }
 
-// ---- Gram tile on tcgen05 -------------------------------------------------------------------------
+// ---- Gram on tcgen05: persistent, symmetric, double-buffered accumulator ---------------------------
+// Tile schedule: only the upper-triangular 128x128 tiles (ti <= tj) of every image are computed;
+// an off-diagonal tile is written twice (as is and transposed) and feeds the degree of its rows
+// AND of its columns.  Each CTA (one per SM) walks tiles blockIdx.x, +gridDim.x, ... ; the smem ring
+// and the two TMEM accumulators run across tile boundaries, so the epilogue of tile t overlaps the
+// TMA/MMA main loop of tile t+1.
+struct TileCoord { int img, ti, tj; };
+
+__device__ __forceinline__ int find_image_pairs(const LostImageDev* __restrict__ meta, int n_images, int t) {
+    int lo = 0, hi = n_images - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (meta[mid].pair_base <= t) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ TileCoord decode_tile(const LostImageDev* __restrict__ meta, int n_images, int t) {
+    TileCoord tc;
+    tc.img = find_image_pairs(meta, n_images, t);
+    const int T = meta[tc.img].tiles;
+    int p = t - meta[tc.img].pair_base, ti = 0;
+    while (p >= T - ti) { p -= T - ti; ++ti; }
+    tc.ti = ti; tc.tj = ti + p;
+    return tc;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+constexpr int TC_ACC = 2;                                       // TMEM accumulator buffers
+constexpr int TC_TMEM_COLS2 = TC_ACC * TC_BN;                   // 256 columns
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_lost_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-               const LostImageDev* __restrict__ meta, int n_images, float* __restrict__ A_base,
+               const LostImageDev* __restrict__ meta, int n_images, int n_tiles, float* __restrict__ A_base,
                int* __restrict__ degree_base, float threshold, int d_pad) {
     extern __shared__ uint8_t smem_raw[];
-    // operand tiles need 1024-byte alignment (SWIZZLE_128B atom)
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B atoms need 1024-B alignment
     const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * TC_STAGES);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 1);          // u32 written by tcgen05.alloc
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + TC_ACC + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 2 * TC_ACC);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = find_image(meta, n_images, blockIdx.x);
-    const LostImageDev im = meta[b];
-    const int local = blockIdx.x - im.tile_base;
-    const int ti = local / im.tiles, tj = local % im.tiles;
-    const int row0 = ti * TC_BM, col0 = tj * TC_BN;
     const int num_kb = d_pad / TC_BK;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_hi); tma_prefetch_desc(&tm_lo);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < TC_ACC; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         __syncwarp();                                  // reconverge after the one-lane setup above (.sync.aligned below)
-        // TMEM: 128 columns x 128 lanes of fp32 accumulators; the allocating warp also frees them
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)TC_TMEM_COLS2) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -173,83 +197,118 @@ k_lost_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
-        const int a_row = im.row_base + row0, b_row = im.row_base + col0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % TC_STAGES;
-            const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-            mbar_wait(empty_bar(s), ph ^ 1u);                 // slot free (passes at once the first time round)
-            const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-            mbar_expect_tx(full_bar(s), TC_STAGE_BYTES);
-            tma_load_2d(st + 0 * TC_TILE_BYTES, &tm_hi, kb * TC_BK, a_row, full_bar(s));
-            tma_load_2d(st + 1 * TC_TILE_BYTES, &tm_lo, kb * TC_BK, a_row, full_bar(s));
-            tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_hi, kb * TC_BK, b_row, full_bar(s));
-            tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_lo, kb * TC_BK, b_row, full_bar(s));
+        int it = 0;                                                    // k-block counter across tiles
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(meta, n_images, t);
+            const int a_row = meta[tc.img].row_base + tc.ti * TC_BM, b_row = meta[tc.img].row_base + tc.tj * TC_BN;
+            const bool diag = tc.ti == tc.tj;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);                     // slot free (passes at once the first time round)
+                const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+                mbar_expect_tx(full_bar(s), diag ? 2 * TC_TILE_BYTES : 4 * TC_TILE_BYTES);
+                tma_load_2d(st + 0 * TC_TILE_BYTES, &tm_hi, kb * TC_BK, a_row, full_bar(s));
+                tma_load_2d(st + 1 * TC_TILE_BYTES, &tm_lo, kb * TC_BK, a_row, full_bar(s));
+                if (!diag) {                                             // a diagonal tile multiplies the A tiles by themselves
+                    tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_hi, kb * TC_BK, b_row, full_bar(s));
+                    tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_lo, kb * TC_BK, b_row, full_bar(s));
+                }
+            }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % TC_STAGES;
-            const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-            mbar_wait(full_bar(s), ph);
+        int it = 0, tl = 0;                                            // k-block / local tile counters
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+            const TileCoord tc = decode_tile(meta, n_images, t);
+            const bool diag = tc.ti == tc.tj;
+            const int acc = tl % TC_ACC;
+            const uint32_t acc_ph = (uint32_t)(tl / TC_ACC) & 1u;
+            mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);               // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-            const uint64_t a_hi = umma_desc_sw128(st + 0 * TC_TILE_BYTES), a_lo = umma_desc_sw128(st + 1 * TC_TILE_BYTES);
-            const uint64_t b_hi = umma_desc_sw128(st + 2 * TC_TILE_BYTES), b_lo = umma_desc_sw128(st + 3 * TC_TILE_BYTES);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+                const uint64_t a_hi = umma_desc_sw128(st + 0 * TC_TILE_BYTES), a_lo = umma_desc_sw128(st + 1 * TC_TILE_BYTES);
+                const uint64_t b_hi = diag ? a_hi : umma_desc_sw128(st + 2 * TC_TILE_BYTES);
+                const uint64_t b_lo = diag ? a_lo : umma_desc_sw128(st + 3 * TC_TILE_BYTES);
 #pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k) {
-                const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);        // 32 bytes per K=8 step inside the swizzle atom
-                umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-                umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);    // 32 bytes per K=8 step inside the swizzle atom
+                    umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                    umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+                umma_commit(empty_bar(s));                             // stage reusable once these MMAs have read it
             }
-            umma_commit(empty_bar(s));                         // stage reusable once these MMAs have read it
+            umma_commit(tmem_full_bar(acc));                           // accumulator complete
         }
-        umma_commit(tmem_full_bar);                            // accumulator complete
     } else if (warp >= 2) {
-        // ===== epilogue: TMEM -> registers -> A (global) + degree =====
-        mbar_wait(tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3;                                 // TMEM lane quadrant this warp may access
-        const int row = q * 32 + lane;
-        const int gi = row0 + row;
-        float* __restrict__ A = A_base + im.a_off;
-        const bool vec_store = (im.n & 3) == 0 && (((uintptr_t)A) & 15u) == 0;
-        int cnt = 0;
+        // ===== epilogue: TMEM -> registers -> A (both triangles) + degrees =====
+        const int q = warp & 3;                                         // TMEM lane quadrant this warp may access
+        int tl = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+            const TileCoord tc = decode_tile(meta, n_images, t);
+            const LostImageDev im = meta[tc.img];
+            const int acc = tl % TC_ACC;
+            const uint32_t acc_ph = (uint32_t)(tl / TC_ACC) & 1u;
+            mbar_wait(tmem_full_bar(acc), acc_ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row0 = tc.ti * TC_BM, col0 = tc.tj * TC_BN;
+            const bool mirror = tc.ti != tc.tj;
+            const int gi = row0 + q * 32 + lane;
+            float* __restrict__ A = A_base + im.a_off;
+            int* __restrict__ deg = degree_base + im.out_off;
+            const bool vec_store = (im.n & 3) == 0 && (((uintptr_t)A) & 15u) == 0;
+            int cnt = 0;
 #pragma unroll 1
-        for (int ch = 0; ch < TC_BN / 32; ++ch) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (gi < im.n) {
+            for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + ch * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const int gj0 = col0 + ch * 32;
+                int colcnt = 0;                                          // lane c ends up with the count of column gj0 + c
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                     const int gj = gj0 + c;
-                    if (gj < im.n) {
-                        const float v = __uint_as_float(r[c]);
-                        const float e = (gi == gj) ? 0.f : fmaxf(v, 0.f);
-                        cnt += (e > threshold) ? 1 : 0;
+                    const float v = __uint_as_float(r[c]);
+                    const bool in = gi < im.n && gj < im.n;
+                    const bool pos = in && ((gi == gj) ? 0.f : fmaxf(v, 0.f)) > threshold;
+                    cnt += pos ? 1 : 0;
+                    if (mirror) {
+                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, pos);
+                        if (lane == c) colcnt = __popc(bal);
+                        if (in) A[(long long)gj * im.n + gi] = v;         // transposed: lanes = consecutive addresses
                     }
                 }
-                float* dst = A + (long long)gi * im.n + gj0;
-                if (vec_store && gj0 + 31 < im.n) {
+                if (mirror && colcnt && gj0 + lane < im.n) atomicAdd(deg + gj0 + lane, colcnt);
+                if (gi < im.n) {
+                    float* dst = A + (long long)gi * im.n + gj0;
+                    if (vec_store && gj0 + 31 < im.n) {
 #pragma unroll
-                    for (int c = 0; c < 32; c += 4)
-                        *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]),
-                                                                          __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
-                } else {
+                        for (int c = 0; c < 32; c += 4)
+                            *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]),
+                                                                              __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) if (gj0 + c < im.n) dst[c] = __uint_as_float(r[c]);
+                        for (int c = 0; c < 32; ++c) if (gj0 + c < im.n) dst[c] = __uint_as_float(r[c]);
+                    }
                 }
             }
+            if (gi < im.n && cnt) atomicAdd(deg + gi, cnt);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tmem_empty_bar(acc));                          // 128 arrivals free the accumulator
         }
-        if (gi < im.n && cnt) atomicAdd(degree_base + im.out_off + gi, cnt);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS2) : "memory");
     }
 }
 
@@ -313,8 +372,12 @@ int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostIm
         attr_set = true;
     }
     const LostImageDev& last = meta.back();
-    const int grid = last.tile_base + last.tiles * last.tiles;
-    k_lost_gram_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_hi, tm_lo, d_meta, n_images, A_base, d_degree, 0.0f, d_pad);
+    const int n_tiles = last.pair_base + last.tiles * (last.tiles + 1) / 2;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = n_tiles < sms ? n_tiles : sms;                  // persistent: one CTA per SM
+    k_lost_gram_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_hi, tm_lo, d_meta, n_images, n_tiles, A_base, d_degree, 0.0f, d_pad);
     B200P_LAUNCH_CHECK("k_lost_gram_tc");
     return B200P_OK;
 }
