@@ -10,7 +10,9 @@ One "step" = one complete mask build (score accumulate x 8 -> radix select -> em
 `e2e`   = the same metric through the host-buffer C-ABI entry point
           (b200p_snip_mask_build_host): weights and all gradient sets start in pinned HOST memory,
           the packed mask and the result block come back to the host inside the timed region.
-`roofline` is for the dominant kernel of the step (k_score_accumulate, 7 of ~10 streaming passes).
+`roofline` is for the dominant kernel of the step: k_score_multi (default --score-mode fused: all 8 resident
+          gradient sets folded in one pass, 4*(B+2) B/param) or k_score_accumulate (--score-mode streaming,
+          16 B/param/batch).
 `cpu_baseline` / `--impl reference`: the reference's own torch-CPU operator sequence
           (oracle/torch_port.py) on the box's host cores.
 
@@ -51,6 +53,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lost", action="store_true", help="skip the LOST images/s leg")
+    ap.add_argument("--score-mode", default="fused", choices=["fused", "streaming"],
+                    help="fused: one pass over all resident gradient sets (4*(B+2) B/param); "
+                         "streaming: one accumulate launch per mini-batch (16 B/param/batch)")
     ap.add_argument("--no-clocks", action="store_true", help="skip the clock sampler and its keep-busy loops (ncu runs)")
     return ap.parse_args()
 
@@ -264,15 +269,25 @@ def run_b200(args):
     launches = [0]
     score_events = []
 
+    fused = args.score_mode == "fused"
+
     def step(record):
-        for i, tbl in enumerate(g_tables):
-            plan.bind_table(tbl)                     # host-side table swap, no launch
+        if fused:
             if record:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            plan.score_accumulate(i > 0); launches[0] += 1
+            plan.score_accumulate_multi(g_tables, accumulate=False); launches[0] += 1
             if record:
-                e1.record(); score_events.append((i > 0, e0, e1))
+                e1.record(); score_events.append((True, e0, e1))
+        else:
+            for i, tbl in enumerate(g_tables):
+                plan.bind_table(tbl)                     # host-side table swap, no launch
+                if record:
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                plan.score_accumulate(i > 0); launches[0] += 1
+                if record:
+                    e1.record(); score_events.append((i > 0, e0, e1))
         if world == 1:
             plan.select_kth(L.KEY_SCORE, k, L.MODE_SNIP_STRICT); launches[0] += 3
             plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask); launches[0] += 1
@@ -333,7 +348,13 @@ def run_b200(args):
     acc_ms = [a.elapsed_time(b) for is_acc, a, b in score_events if is_acc]
     kernel_ms = sum(acc_ms) / max(1, len(acc_ms))
     peak, peak_src = peaks()
-    achieved = n_total * SCORE_BYTES_PER_PARAM / (kernel_ms * 1e-3) / 1e9
+    nb_local = len(my_batches)
+    # algorithmic bytes per launch of the dominant kernel: fused pass reads w and nb_local
+    # gradient sets and writes the score once; the streaming pass reads w, g, acc and writes acc
+    kernel_bytes = n_total * (4.0 * (nb_local + 2) if fused else SCORE_BYTES_PER_PARAM)
+    kernel_name = (f"k_score_multi<ACCUMULATE=0,B={nb_local}>" if fused else "k_score_accumulate<ACCUMULATE=1,VEC=1>")
+    step_bytes_per_param = (4.0 * (N_BATCHES + 2) if fused else 16.0 * N_BATCHES) + 8.125
+    achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9
     ms_per_step = elapsed_ms / args.steps
     value = n_total / (ms_per_step * 1e-3) / 1e9
 
@@ -385,15 +406,19 @@ def run_b200(args):
             "config": {"workload": f"{MODEL} SNIP mask build, target sparsity {TARGET_SPARSITY}, {N_BATCHES} mini-batches "
                                    f"of synthetic gradients (1e-3*randn) accumulated, N={n_total} params in {len(numels)} tensors, "
                                    f"k={k}", "weights": wsrc,
+                       "score_mode": ("fused: all resident gradient sets folded in one pass, bit-identical to per-batch accumulation"
+                                      if fused else "streaming: one accumulate launch per mini-batch"),
                        "l2": f"inputs larger than L2: {N_BATCHES // world} gradient sets x {n_total * 4 >> 20} MiB streamed per step",
                        "parallelism": "1 GPU" if world == 1 else f"batches split over {world} ranks, NCCL all-to-all score exchange + "
                                       "rank-order sum, parameter-sharded radix select with histogram all-reduce"},
-            "roofline": {"bound": "hbm", "kernel": "k_score_accumulate<ACCUMULATE=1,VEC=1>", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(fused),
                          "peak_source": peak_src, "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": n_total * SCORE_BYTES_PER_PARAM,
+                         "algorithmic_bytes_per_launch": kernel_bytes,
+                         "algorithmic_bytes_per_param": kernel_bytes / n_total,
                          "launches_timed": len(acc_ms),
-                         "step_algorithmic_GBps": (n_total * STEP_BYTES_PER_PARAM / (ms_per_step * 1e-3) / 1e9
+                         "step_algorithmic_bytes_per_param": step_bytes_per_param,
+                         "step_algorithmic_GBps": (n_total * step_bytes_per_param / (ms_per_step * 1e-3) / 1e9
                                                    if world == 1 else None)},
             "e2e": e2e, "cpu_baseline": cpu_base, "gpu_launches": n_launches, "clocks": clk, "lost": lost,
             "result": {"threshold": res["threshold"], "n_less": res["n_less"], "n_equal": res["n_equal"],
@@ -487,13 +512,13 @@ def lost_leg(args, dev, world, rank, dist):
     return leg
 
 
-def ncu_traffic():
+def ncu_traffic(fused=True):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/roofline_traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get("k_score_accumulate_traffic_bytes")
+            return json.load(f).get("k_score_multi_traffic_bytes" if fused else "k_score_accumulate_traffic_bytes")
     except Exception:
         return None
 

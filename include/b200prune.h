@@ -127,6 +127,12 @@ void* b200p_plan_state_ptr(b200p_plan* plan);
 int  b200p_score_accumulate(b200p_plan* plan, int accumulate,
                             int64_t chunk_begin, int64_t chunk_end, void* stream);
 
+/* The same over n_sets gradient sets in ONE pass (groups of 8 per launch): SCORE (=|+=) sum_b |W*G_b|,
+ * added in table order — bit-identical to n_sets calls of b200p_score_accumulate, but W is read once and
+ * SCORE touched once: 4*(n_sets+2) B/param instead of 16*n_sets.  g_tables: b200p_ptrtable_create(slot G). */
+int  b200p_score_accumulate_multi(b200p_plan* plan, const b200p_ptrtable* const* g_tables, int n_sets, int accumulate,
+                                  int64_t chunk_begin, int64_t chunk_end, void* stream);
+
 /* Multi-GPU score exchange: d_dst[i] = ((d_src[i] + d_src[stride+i]) + ...) over
  * n_parts partial score slices received from the ranks, summed in rank (= mini-batch) order. */
 int  b200p_sum_parts(int device, float* d_dst, const float* d_src, int n_parts, int64_t part_stride,

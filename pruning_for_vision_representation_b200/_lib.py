@@ -74,6 +74,7 @@ SIGNATURES = {
     "b200p_plan_hist_ptr": (_P, [_P]),
     "b200p_plan_state_ptr": (_P, [_P]),
     "b200p_score_accumulate": (_I, [_P, _I, _I64, _I64, _P]),
+    "b200p_score_accumulate_multi": (_I, [_P, ctypes.POINTER(_P), _I, _I, _I64, _I64, _P]),
     "b200p_select_kth": (_I, [_P, _I, _P, _U64, _I, _P]),
     "b200p_select_begin": (_I, [_P, _U64, _I, _I, _P]),
     "b200p_select_hist": (_I, [_P, _I, _I, _P, _I64, _I64, _P]),

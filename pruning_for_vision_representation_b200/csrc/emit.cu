@@ -51,6 +51,10 @@ k_emit_masks(EmitArgs a, int64_t c_begin, int64_t c_end) {
     }
     unsigned long long kept = 0;
     const bool want_mf = a.outputs & B200P_EMIT_MASKF, want_wf = a.outputs & B200P_EMIT_WEFF;
+    // keep-decision variant, uniform over the launch: 0 strict float compare, 1 integer key compare
+    // against a finite threshold (no NaN canonicalisation needed), 2 generic (forced all/none, NaN threshold)
+    const int variant = (a.force == 3 || (a.force == 0 && a.mode == B200P_MODE_SNIP_STRICT)) ? 0
+                      : (a.force == 0 && thr_key <= 0x7F800000u) ? 1 : 2;
 
     int64_t c = c_begin + blockIdx.x;
     const float* src = nullptr; int n = 0;
@@ -78,10 +82,18 @@ k_emit_masks(EmitArgs a, int64_t c_begin, int64_t c_end) {
                 uint32_t oldn = 0xFu;
                 if (mold) oldn = nibble_of(__ldg(mold + vec_word_index(j)));
                 uint32_t nib = 0;
-                nib |= keep_decision(v.x, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 1u : 0u;
-                nib |= keep_decision(v.y, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 2u : 0u;
-                nib |= keep_decision(v.z, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 4u : 0u;
-                nib |= keep_decision(v.w, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 8u : 0u;
+                if (variant == 0) {              // strict float compare (SNIP / forced threshold); NaN -> pruned
+                    nib = (v.x > thr_f ? 1u : 0u) | (v.y > thr_f ? 2u : 0u) | (v.z > thr_f ? 4u : 0u) | (v.w > thr_f ? 8u : 0u);
+                } else if (variant == 1) {       // integer key compare, finite threshold: raw |x| bits order like the keys
+                    const int cmp = ties_pruned ? (int)thr_key : (int)thr_key - 1;
+                    nib = ((int)(__float_as_uint(v.x) & 0x7FFFFFFFu) > cmp ? 1u : 0u) | ((int)(__float_as_uint(v.y) & 0x7FFFFFFFu) > cmp ? 2u : 0u) |
+                          ((int)(__float_as_uint(v.z) & 0x7FFFFFFFu) > cmp ? 4u : 0u) | ((int)(__float_as_uint(v.w) & 0x7FFFFFFFu) > cmp ? 8u : 0u);
+                } else {
+                    nib |= keep_decision(v.x, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 1u : 0u;
+                    nib |= keep_decision(v.y, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 2u : 0u;
+                    nib |= keep_decision(v.z, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 4u : 0u;
+                    nib |= keep_decision(v.w, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 8u : 0u;
+                }
                 nib &= oldn;
                 const uint32_t word = gather_nibbles(nib);
                 if ((tid & 7) == 0) { mnew[vec_word_index(j)] = word; kept += __popc(word); }

@@ -62,6 +62,58 @@ k_score_accumulate(const int32_t* __restrict__ chunk_n, ChunkTab w_tab, ChunkTab
     }
 }
 
+// Multi-batch form: SCORE (=|+=) |W*G_0| + |W*G_1| + ... + |W*G_{B-1}|, added left to right, which is
+// bit-identical to B successive k_score_accumulate launches but reads W once and touches SCORE once:
+// 4*(B+2) B/param (+4 when accumulating) instead of 16*B.  The B200's 180 GB make it free to keep the
+// gradient sets of all SNIP mini-batches resident (102 MB each for ResNet-50) and fold them in one pass.
+constexpr int kMaxSets = 8;
+struct GradTabs { ChunkTab t[kMaxSets]; };
+
+template <bool ACCUMULATE, int B>
+__global__ void __launch_bounds__(kThreads)
+k_score_multi(const int32_t* __restrict__ chunk_n, ChunkTab w_tab, GradTabs g_tabs, ChunkTab s_tab,
+              int64_t c_begin, int64_t c_end, int vec_ok) {
+    const int tid = threadIdx.x;
+    for (int64_t c = c_begin + blockIdx.x; c < c_end; c += gridDim.x) {
+        const int n = __ldg(chunk_n + c);
+        const float* __restrict__ w = chunk_ptr<const float>(w_tab, c);
+        float* __restrict__ s = chunk_ptr<float>(s_tab, c);
+        const float* g[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) g[b] = chunk_ptr<const float>(g_tabs.t[b], c);
+        if (vec_ok && n == kChunk) {
+#pragma unroll 2
+            for (int j = 0; j < kVecPerThread; ++j) {
+                const int e = 4 * (j * kThreads + tid);
+                const float4 wv = ld_nc_f4(w + e);
+                float4 gv[B];
+#pragma unroll
+                for (int b = 0; b < B; ++b) gv[b] = ld_nc_f4(g[b] + e);
+                float4 r;
+                if (ACCUMULATE) r = ld_f4(s + e);
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    const float4 t = make_float4(fabsf(__fmul_rn(wv.x, gv[b].x)), fabsf(__fmul_rn(wv.y, gv[b].y)),
+                                                 fabsf(__fmul_rn(wv.z, gv[b].z)), fabsf(__fmul_rn(wv.w, gv[b].w)));
+                    if (b == 0 && !ACCUMULATE) r = t;
+                    else { r.x = __fadd_rn(r.x, t.x); r.y = __fadd_rn(r.y, t.y); r.z = __fadd_rn(r.z, t.z); r.w = __fadd_rn(r.w, t.w); }
+                }
+                st_f4(s + e, r);
+            }
+        } else {
+            for (int e = tid; e < n; e += kThreads) {
+                float r = ACCUMULATE ? s[e] : 0.f;
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    const float t = fabsf(__fmul_rn(w[e], g[b][e]));
+                    r = (b == 0 && !ACCUMULATE) ? t : __fadd_rn(r, t);
+                }
+                s[e] = r;
+            }
+        }
+    }
+}
+
 // dst[i] = ((src[0][i] + src[1][i]) + src[2][i]) + ...   part p at src + p * part_stride.
 // Fixed left-to-right order: the multi-GPU score exchange sums the ranks' partial scores in rank
 // (= mini-batch) order on every rank count, so the result does not depend on the collective's
@@ -95,6 +147,48 @@ k_sum_parts(float* __restrict__ dst, const float* __restrict__ src, int n_parts,
 }  // namespace b200p
 
 using namespace b200p;
+
+template <bool ACC>
+static void launch_multi(int nb, int grid, cudaStream_t st, const int32_t* cn, ChunkTab w, const GradTabs& g, ChunkTab s,
+                         int64_t c0, int64_t c1, int vec) {
+    switch (nb) {
+        case 1: k_score_multi<ACC, 1><<<grid, kThreads, 0, st>>>(cn, w, g, s, c0, c1, vec); break;
+        case 2: k_score_multi<ACC, 2><<<grid, kThreads, 0, st>>>(cn, w, g, s, c0, c1, vec); break;
+        case 3: k_score_multi<ACC, 3><<<grid, kThreads, 0, st>>>(cn, w, g, s, c0, c1, vec); break;
+        case 4: k_score_multi<ACC, 4><<<grid, kThreads, 0, st>>>(cn, w, g, s, c0, c1, vec); break;
+        case 5: k_score_multi<ACC, 5><<<grid, kThreads, 0, st>>>(cn, w, g, s, c0, c1, vec); break;
+        case 6: k_score_multi<ACC, 6><<<grid, kThreads, 0, st>>>(cn, w, g, s, c0, c1, vec); break;
+        case 7: k_score_multi<ACC, 7><<<grid, kThreads, 0, st>>>(cn, w, g, s, c0, c1, vec); break;
+        default: k_score_multi<ACC, 8><<<grid, kThreads, 0, st>>>(cn, w, g, s, c0, c1, vec); break;
+    }
+}
+
+extern "C" int b200p_score_accumulate_multi(b200p_plan* p, const b200p_ptrtable* const* g_tables, int n_sets, int accumulate,
+                                            int64_t chunk_begin, int64_t chunk_end, void* stream) {
+    B200P_REQUIRE(p != nullptr && g_tables != nullptr, B200P_EINVAL, "score_accumulate_multi: null argument");
+    B200P_REQUIRE(n_sets >= 1, B200P_EINVAL, "score_accumulate_multi: need at least one gradient set");
+    B200P_REQUIRE(p->bound[B200P_SLOT_W] && p->bound[B200P_SLOT_SCORE], B200P_ESTATE, "score_accumulate_multi: W and SCORE slots must be bound");
+    if (chunk_end < 0) chunk_end = p->n_chunks;
+    B200P_REQUIRE(chunk_begin >= 0 && chunk_begin <= chunk_end && chunk_end <= p->n_chunks, B200P_EINVAL, "score_accumulate_multi: bad chunk range");
+    bool vec = p->vec_ok[B200P_SLOT_W] && p->vec_ok[B200P_SLOT_SCORE];
+    for (int i = 0; i < n_sets; ++i) {
+        B200P_REQUIRE(g_tables[i] != nullptr && g_tables[i]->plan == p, B200P_EINVAL, "score_accumulate_multi: table belongs to another plan");
+        vec = vec && g_tables[i]->vec_ok;
+    }
+    if (chunk_begin == chunk_end) return B200P_OK;
+    B200P_CUDA(cudaSetDevice(p->device));
+    const int grid = p->grid_for(chunk_end - chunk_begin, 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i0 = 0; i0 < n_sets; i0 += kMaxSets) {          // groups of up to 8 sets per launch
+        const int nb = n_sets - i0 < kMaxSets ? n_sets - i0 : kMaxSets;
+        GradTabs g;
+        for (int b = 0; b < kMaxSets; ++b) g.t[b] = (ChunkTab)g_tables[i0 + (b < nb ? b : 0)]->d_tab;
+        if (accumulate || i0 > 0) launch_multi<true>(nb, grid, st, p->d_chunk_n, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE), chunk_begin, chunk_end, vec ? 1 : 0);
+        else                      launch_multi<false>(nb, grid, st, p->d_chunk_n, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE), chunk_begin, chunk_end, vec ? 1 : 0);
+        B200P_LAUNCH_CHECK("k_score_multi");
+    }
+    return B200P_OK;
+}
 
 extern "C" int b200p_sum_parts(int device, float* d_dst, const float* d_src, int n_parts, int64_t part_stride,
                                int64_t n, void* stream) {

@@ -124,6 +124,18 @@ class ParamPlan:
         check(self.lib.b200p_score_accumulate(self.handle, 1 if accumulate else 0, chunk_begin, chunk_end,
                                               _stream_ptr(self.device)), "score_accumulate")
 
+    def score_accumulate_multi(self, tables, accumulate=False, chunk_begin=0, chunk_end=-1):
+        """SCORE (=|+=) sum_b |W * G_b| over the gradient sets in `tables` (PtrTables of slot G) in one pass,
+        added in list order: bit-identical to len(tables) score_accumulate calls."""
+        tables = list(tables)
+        for t in tables:
+            if t.plan is not self or t.slot != SLOT_G:
+                raise B200PruneError("score_accumulate_multi: need pointer tables of this plan's G slot")
+        arr = (ctypes.c_void_p * len(tables))(*[t.handle for t in tables])
+        check(self.lib.b200p_score_accumulate_multi(self.handle, arr, len(tables), 1 if accumulate else 0, chunk_begin,
+                                                    chunk_end, _stream_ptr(self.device)), "score_accumulate_multi")
+        self._multi_keepalive = tables
+
     def select_kth(self, key_source, k, mode, old_mask=None):
         check(self.lib.b200p_select_kth(self.handle, key_source, _ptr(old_mask), int(k), mode,
                                         _stream_ptr(self.device)), "select_kth")

@@ -188,7 +188,7 @@ def snip_pruning(model, data_loader, device, criterion, target_sparsity=0.9, num
     modules = [m for _, m in prunable_modules(model) if hasattr(m, "weight")]
     data_iter = iter(data_loader)
     st = None
-    scores = None
+    stashed = []                         # gradient sets of all mini-batches stay resident (B x N x 4 bytes)
     for b in range(num_batches):
         images, targets = next(data_iter)
         images = images.to(device)
@@ -203,13 +203,21 @@ def snip_pruning(model, data_loader, device, criterion, target_sparsity=0.9, num
             if not modules:
                 raise RuntimeError("torch.cat(): expected a non-empty list of Tensors")   # train.py:294
             st = _get_state(model, modules)
-            scores = [torch.empty(m.weight.numel(), dtype=torch.float32, device=st.device) for m in modules]
-            st.plan.bind(L.SLOT_SCORE, scores)
-        # |w| uses the weight the forward saw: the masked one if the module is already pruned
-        st.plan.bind(L.SLOT_W, [_flat(m.weight.detach()) for m in modules])
-        st._w_ptrs = None
-        st.plan.bind(L.SLOT_G, [_flat(_grad_of(m)) for m in modules])
-        st.plan.score_accumulate(accumulate=(b > 0))
+        grads = [_flat(_grad_of(m)) for m in modules]
+        if num_batches > 1:
+            for m in modules:            # take the tensors over: the next backward allocates fresh ones, no copy
+                _grad_param(m).grad = None
+        stashed.append(grads)
+    scores = [torch.empty(m.weight.numel(), dtype=torch.float32, device=st.device) for m in modules]
+    st.plan.bind(L.SLOT_SCORE, scores)
+    # |w| uses the weight the forward saw: the masked one if the module is already pruned
+    st.plan.bind(L.SLOT_W, [_flat(m.weight.detach()) for m in modules])
+    st._w_ptrs = None
+    # one fused pass: score = sum_b |w * g_b|, added in batch order (bit-identical to per-batch accumulation)
+    st.plan.score_accumulate_multi([st.plan.pointer_table(L.SLOT_G, g) for g in stashed], accumulate=False)
+    if num_batches > 1:
+        for m, g in zip(modules, stashed[-1]):
+            _grad_param(m).grad = g.view_as(_grad_param(m))      # leave .grad populated like the reference does
     plan = st.plan
     n = plan.total
     k = int(n * target_sparsity)                                 # train.py:299
@@ -239,10 +247,15 @@ def snip_pruning(model, data_loader, device, criterion, target_sparsity=0.9, num
     return model
 
 
-def _grad_of(m):
+def _grad_param(m):
     p = m._parameters.get("weight_orig", None)
     if p is None:
         p = m._parameters.get("weight", None)
+    return p
+
+
+def _grad_of(m):
+    p = _grad_param(m)
     return None if p is None else p.grad
 
 

@@ -101,6 +101,42 @@ def test_score_accumulate_bit_exact(misalign):
             assert not np.signbit(got[~np.isnan(got)]).any()
 
 
+@pytest.mark.parametrize("misalign", [False, True])
+def test_score_multi_is_bit_identical_to_sequential(misalign):
+    """One fused pass over B gradient sets == B successive accumulate launches, bit for bit."""
+    rng = np.random.default_rng(7)
+    sizes = [351, 2808, 25728, 4096 * 2, 8192 + 4, 1]
+    w = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    plan = make_plan(w)
+    plan.bind(L.SLOT_W, to_dev(w, misalign))
+    for n_sets in (1, 2, 3, 5, 8, 11):
+        grads = [[(1e-3 * rng.standard_normal(n)).astype(np.float32) for n in sizes] for _ in range(n_sets)]
+        gdev = [to_dev(g, misalign) for g in grads]
+        seq = [torch.full((n,), 3.0, device=DEV) for n in sizes]
+        plan.bind(L.SLOT_SCORE, seq)
+        for b in range(n_sets):
+            plan.bind(L.SLOT_G, gdev[b]); plan.score_accumulate(b > 0)
+        fused = [torch.full((n,), -7.0, device=DEV) for n in sizes]
+        plan.bind(L.SLOT_SCORE, fused)
+        tables = [plan.pointer_table(L.SLOT_G, g) for g in gdev]
+        plan.score_accumulate_multi(tables, accumulate=False)
+        for a, b_ in zip(seq, fused):
+            assert torch.equal(a, b_), n_sets
+        # accumulate=True continues an existing score
+        m = min(2, n_sets)
+        plan.score_accumulate_multi(tables[:m], accumulate=True)
+        plan.bind(L.SLOT_SCORE, seq)
+        for b in range(m):
+            plan.bind(L.SLOT_G, gdev[b]); plan.score_accumulate(True)
+        for a, b_ in zip(seq, fused):
+            assert torch.equal(a, b_), n_sets
+        acc = [None] * len(sizes)
+        for g in grads + grads[:m]:
+            acc = [PO.snip_score_accumulate(x, ww, gg) for x, ww, gg in zip(acc, w, g)]
+        for a, e in zip(fused, acc):
+            assert np.array_equal(a.cpu().numpy(), e)
+
+
 def test_snip_golden(golden_dir):
     z = np.load(os.path.join(golden_dir, "snip_tiny.npz"))
     w, g, ref = _seq(z, "w"), _seq(z, "g"), _seq(z, "m")
