@@ -75,25 +75,33 @@ k_emit_masks(EmitArgs a, int64_t c_begin, int64_t c_end) {
             float4 vv[kVecPerThread];
 #pragma unroll
             for (int j = 0; j < kVecPerThread; ++j) vv[j] = ld_nc_f4(src + 4 * (j * kThreads + tid));
+            // keep bits of this thread's 16 keys, one variant-specific loop (the variant is launch-uniform)
+            uint32_t nibs[kVecPerThread];
+            if (variant == 0) {                  // strict float compare (SNIP / forced threshold); NaN -> pruned
+#pragma unroll
+                for (int j = 0; j < kVecPerThread; ++j)
+                    nibs[j] = (vv[j].x > thr_f ? 1u : 0u) | (vv[j].y > thr_f ? 2u : 0u) | (vv[j].z > thr_f ? 4u : 0u) | (vv[j].w > thr_f ? 8u : 0u);
+            } else if (variant == 1) {           // integer key compare, finite threshold: raw |x| bits order like the keys
+                const int cmp = ties_pruned ? (int)thr_key : (int)thr_key - 1;
+#pragma unroll
+                for (int j = 0; j < kVecPerThread; ++j)
+                    nibs[j] = ((int)(__float_as_uint(vv[j].x) & 0x7FFFFFFFu) > cmp ? 1u : 0u) | ((int)(__float_as_uint(vv[j].y) & 0x7FFFFFFFu) > cmp ? 2u : 0u) |
+                              ((int)(__float_as_uint(vv[j].z) & 0x7FFFFFFFu) > cmp ? 4u : 0u) | ((int)(__float_as_uint(vv[j].w) & 0x7FFFFFFFu) > cmp ? 8u : 0u);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kVecPerThread; ++j)
+                    nibs[j] = (keep_decision(vv[j].x, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 1u : 0u) |
+                              (keep_decision(vv[j].y, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 2u : 0u) |
+                              (keep_decision(vv[j].z, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 4u : 0u) |
+                              (keep_decision(vv[j].w, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 8u : 0u);
+            }
 #pragma unroll
             for (int j = 0; j < kVecPerThread; ++j) {
                 const int e = 4 * (j * kThreads + tid);
                 const float4 v = vv[j];
                 uint32_t oldn = 0xFu;
                 if (mold) oldn = nibble_of(__ldg(mold + vec_word_index(j)));
-                uint32_t nib = 0;
-                if (variant == 0) {              // strict float compare (SNIP / forced threshold); NaN -> pruned
-                    nib = (v.x > thr_f ? 1u : 0u) | (v.y > thr_f ? 2u : 0u) | (v.z > thr_f ? 4u : 0u) | (v.w > thr_f ? 8u : 0u);
-                } else if (variant == 1) {       // integer key compare, finite threshold: raw |x| bits order like the keys
-                    const int cmp = ties_pruned ? (int)thr_key : (int)thr_key - 1;
-                    nib = ((int)(__float_as_uint(v.x) & 0x7FFFFFFFu) > cmp ? 1u : 0u) | ((int)(__float_as_uint(v.y) & 0x7FFFFFFFu) > cmp ? 2u : 0u) |
-                          ((int)(__float_as_uint(v.z) & 0x7FFFFFFFu) > cmp ? 4u : 0u) | ((int)(__float_as_uint(v.w) & 0x7FFFFFFFu) > cmp ? 8u : 0u);
-                } else {
-                    nib |= keep_decision(v.x, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 1u : 0u;
-                    nib |= keep_decision(v.y, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 2u : 0u;
-                    nib |= keep_decision(v.z, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 4u : 0u;
-                    nib |= keep_decision(v.w, a.mode, a.force, thr_f, thr_key, ties_pruned) ? 8u : 0u;
-                }
+                uint32_t nib = nibs[j];
                 nib &= oldn;
                 const uint32_t word = gather_nibbles(nib);
                 if ((tid & 7) == 0) { mnew[vec_word_index(j)] = word; kept += __popc(word); }
