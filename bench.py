@@ -16,11 +16,14 @@ One "step" = one complete mask build (score accumulate x 8 -> radix select -> em
 `cpu_baseline` / `--impl reference`: the reference's own torch-CPU operator sequence
           (oracle/torch_port.py) on the box's host cores.
 
-N > 1 (launched under torchrun): the 8 mini-batches are split contiguously across ranks (strong
-scaling of one mask build): local accumulate -> NCCL all-to-all of score slices summed
-in rank order on the owner -> parameter-sharded select with a histogram all-reduce per radix pass
--> every rank emits its slice of the packed mask -> all-reduce of the mask words.  Timing is the
-max over ranks of CUDA-event time.
+N > 1 (launched under torchrun), default --dist-mode replicas: mask builds are independent units (one
+per model replica / sparsity level), so every rank builds the mask of its own replica from its own 8
+gradient sets with no data-path collective (weak scaling); value = N mask builds / max-over-ranks time.
+--dist-mode sharded runs ONE mask build over the ranks (SURVEY §8e, strong scaling): local accumulate
+-> NCCL all-to-all of score slices summed in rank order on the owner -> parameter-sharded select with
+a histogram all-reduce per radix pass -> every rank emits its slice of the packed mask -> all-reduce of
+the mask words.  For ResNet-50 that exchange (~100 MB per GPU) costs more than the whole single-GPU
+build (0.26 ms), see DESIGN.md §4.  Timing is the max over ranks of CUDA-event time.
 """
 import argparse
 import json
@@ -53,6 +56,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lost", action="store_true", help="skip the LOST images/s leg")
+    ap.add_argument("--dist-mode", default="replicas", choices=["replicas", "sharded"],
+                    help="N > 1: replicas = every rank builds the mask of its own model replica from its own 8 gradient "
+                         "sets (independent units, no collective, weak scaling); sharded = ONE mask build split over the "
+                         "ranks (batches shard the scores, parameters shard the select; NCCL exchange; strong scaling)")
     ap.add_argument("--score-mode", default="fused", choices=["fused", "streaming"],
                     help="fused: one pass over all resident gradient sets (4*(B+2) B/param); "
                          "streaming: one accumulate launch per mini-batch (16 B/param/batch)")
@@ -217,7 +224,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "mask-build Gparams/s (score+global top-k)", "value": val,
         "unit": "Gparams/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{MODEL} SNIP {TARGET_SPARSITY} sparsity, {N_BATCHES} mini-batches of synthetic "
                                "gradients, score accumulate + full sort threshold + mask (CPU, torch ops)"},
@@ -225,7 +232,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "Gparams/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    GUARD.emit(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -245,13 +252,18 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     numels = model_numels()
     n_total = sum(numels)
     k = int(n_total * TARGET_SPARSITY)                      # train.py:299
-    assert N_BATCHES % world == 0, "mini-batches must split evenly across ranks"
-    my_batches = list(range(rank * N_BATCHES // world, (rank + 1) * N_BATCHES // world))
+    sharded = world > 1 and args.dist_mode == "sharded"
+    if sharded:
+        assert N_BATCHES % world == 0, "mini-batches must split evenly across ranks"
+        my_batches = list(range(rank * N_BATCHES // world, (rank + 1) * N_BATCHES // world))
+    else:
+        my_batches = [b + 1000 * rank for b in range(N_BATCHES)]     # every rank: its own full set of 8 gradient sets
 
     w_flat_cpu, wsrc = make_weights_cpu(numels)
     w_flat = w_flat_cpu.to(dev)
@@ -262,7 +274,7 @@ def run_b200(args):
     g_tables = [plan.pointer_table(L.SLOT_G, split_views(g, numels)) for g in g_flat]
     mask = plan.new_mask()
 
-    if world > 1:
+    if sharded:
         from pruning_for_vision_representation_b200.distributed import ShardedMaskBuilder
         builder = ShardedMaskBuilder(plan, dist.group.WORLD)
 
@@ -288,7 +300,7 @@ def run_b200(args):
                 plan.score_accumulate(i > 0); launches[0] += 1
                 if record:
                     e1.record(); score_events.append((i > 0, e0, e1))
-        if world == 1:
+        if not sharded:
             plan.select_kth(L.KEY_SCORE, k, L.MODE_SNIP_STRICT); launches[0] += 3
             plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask); launches[0] += 1
         else:
@@ -356,7 +368,8 @@ def run_b200(args):
     step_bytes_per_param = (4.0 * (N_BATCHES + 2) if fused else 16.0 * N_BATCHES) + 8.125
     achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9
     ms_per_step = elapsed_ms / args.steps
-    value = n_total / (ms_per_step * 1e-3) / 1e9
+    units = 1 if sharded else world                      # mask builds completed per step over all ranks
+    value = units * n_total / (ms_per_step * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C-ABI (rank-local; N = 1 headline) -----------------------
     e2e = None
@@ -365,7 +378,7 @@ def run_b200(args):
         w_host = w_flat_cpu.pin_memory()
         g_host = [g.cpu().pin_memory() for g in g_flat]
         mask_host = torch.empty(plan.mask_words, dtype=torch.int32).pin_memory()
-        if world == 1:
+        if not sharded:
             for _ in range(1):
                 plan.snip_mask_build_host(w_host, g_host, k, mask_host)
             sync_all()
@@ -374,9 +387,13 @@ def run_b200(args):
                 r2 = plan.snip_mask_build_host(w_host, g_host, k, mask_host)    # synchronises
             e2e_s = (time.perf_counter() - tt) / args.e2e_steps
             assert torch.equal(mask_host, mask.cpu()), "host-buffer path and resident path disagree"
-            e2e = {"value": n_total / e2e_s / 1e9, "unit": "Gparams/s",
-                   "h2d_bytes_per_step": (1 + nb) * n_total * 4,
-                   "d2h_bytes_per_step": plan.mask_words * 4 + 64,
+            if world > 1:
+                t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_s = float(t.item())
+            e2e = {"value": world * n_total / e2e_s / 1e9, "unit": "Gparams/s",
+                   "h2d_bytes_per_step": world * (1 + nb) * n_total * 4,
+                   "d2h_bytes_per_step": world * (plan.mask_words * 4 + 64),
                    "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
                    "api": "b200p_snip_mask_build_host (pinned host buffers in, packed mask out)"}
         else:
@@ -401,7 +418,7 @@ def run_b200(args):
         line = {
             "metric": "mask-build Gparams/s (score+global top-k)", "value": value, "unit": "Gparams/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{MODEL} SNIP mask build, target sparsity {TARGET_SPARSITY}, {N_BATCHES} mini-batches "
                                    f"of synthetic gradients (1e-3*randn) accumulated, N={n_total} params in {len(numels)} tensors, "
@@ -409,8 +426,11 @@ def run_b200(args):
                        "score_mode": ("fused: all resident gradient sets folded in one pass, bit-identical to per-batch accumulation"
                                       if fused else "streaming: one accumulate launch per mini-batch"),
                        "l2": f"inputs larger than L2: {N_BATCHES // world} gradient sets x {n_total * 4 >> 20} MiB streamed per step",
-                       "parallelism": "1 GPU" if world == 1 else f"batches split over {world} ranks, NCCL all-to-all score exchange + "
-                                      "rank-order sum, parameter-sharded radix select with histogram all-reduce"},
+                       "parallelism": ("1 GPU" if world == 1 else
+                                       f"batches split over {world} ranks, NCCL all-to-all score exchange + rank-order sum, "
+                                       "parameter-sharded radix select with histogram all-reduce (one mask build, strong scaling)" if sharded
+                                       else f"{world} independent mask builds, one model replica with its own 8 gradient sets per "
+                                            "rank, no data-path collective (weak scaling); --dist-mode sharded runs the NCCL path")},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(fused),
                          "peak_source": peak_src, "kernel_ms": kernel_ms,
@@ -424,7 +444,7 @@ def run_b200(args):
             "result": {"threshold": res["threshold"], "n_less": res["n_less"], "n_equal": res["n_equal"],
                        "n_kept": res["n_kept"], "passes_full": res["passes_full"]},
         }
-        print(json.dumps(line), flush=True)
+        GUARD.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -523,7 +543,28 @@ def ncu_traffic(fused=True):
         return None
 
 
+class StdoutGuard:
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; stdout carries only
+    the one JSON line the driver parses."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(text, flush=True)
+        os.dup2(2, 1)
+
+
+GUARD = None
+
+
 def main():
+    global GUARD
+    GUARD = StdoutGuard()
     args = parse()
     if args.impl == "reference":
         run_reference(args)
