@@ -162,3 +162,17 @@ def test_lost_batched_uniform_tensor_and_random_features():
         if np.array_equal(deg, (-escores).astype(np.int32)):
             assert seed[i] == eseed and box[i].tolist() == [float(v) for v in epred], i
     assert int(seed[0]) == 269 and box[0].tolist() == [416.0, 96.0, 480.0, 160.0]      # SURVEY §4 known answer
+
+
+def test_driver_discover_matches_single_image_lost(golden_dir):
+    from pruning_for_vision_representation_b200 import lost_driver as D
+    z, meta = _cases(golden_dir)
+    names = list(meta)
+    keys = [torch.from_numpy(z[f"{n}_feats"]).to(DEV) for n in names]
+    preds = D.discover(names, keys, [meta[n]["dims"] for n in names], [tuple(meta[n]["init_image_size"]) for n in names],
+                       patch_size=16, k_patches=100, max_batch=3)
+    for n in names:
+        if meta[n]["k_patches"] == 100:
+            assert preds[n].tolist() == meta[n]["pred"], n
+    gts = {n: np.array([meta[n]["pred"]]) for n in names if meta[n]["k_patches"] == 100}
+    assert D.corloc(preds, gts)[0] == 100.0
