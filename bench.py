@@ -301,8 +301,7 @@ def run_b200(args):
                 if record:
                     e1.record(); score_events.append((i > 0, e0, e1))
         if not sharded:
-            plan.select_kth(L.KEY_SCORE, k, L.MODE_SNIP_STRICT); launches[0] += 3
-            plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask); launches[0] += 1
+            plan.mask_build(L.KEY_SCORE, k, L.MODE_SNIP_STRICT, mask); launches[0] += 4      # sample, sweep, finish, emit
         else:
             launches[0] += builder.snip_select_emit(s_flat, k, mask)
 

@@ -177,6 +177,12 @@ int  b200p_emit_masks(b200p_plan* plan, int key_source, int mode, int force,
                       float forced_threshold, const uint32_t* d_old_mask, uint32_t* d_new_mask,
                       int outputs, int64_t chunk_begin, int64_t chunk_end, void* stream);
 
+/* Select + emit in one call (k-th smallest of the alive keys, then the packed mask).  Same result as
+ * b200p_select_kth followed by b200p_emit_masks; the select's sweep writes a provisional mask directly into
+ * d_new_mask and the emit only patches the ~2 % of keys near the threshold instead of re-reading all keys. */
+int  b200p_mask_build(b200p_plan* plan, int key_source, const uint32_t* d_old_mask, uint64_t k, int mode,
+                      uint32_t* d_new_mask, void* stream);
+
 /* ---- K5: sparsity (train.py:347-369) ------------------------------------------------ */
 /* d_out[0] = # elements with (mask bit == 0 or W == 0)  (d_mask nullable -> counts W == 0),
  * d_out[1] = # mask bits set.  d_out is 2 x uint64 device memory, zeroed by the call. */

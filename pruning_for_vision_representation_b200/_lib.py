@@ -86,6 +86,7 @@ SIGNATURES = {
     "b200p_plan_chunk_flat_start": (_I64, [_P, _I64]),
     "b200p_select_result": (_I, [_P, ctypes.POINTER(SelectResult), _P]),
     "b200p_emit_masks": (_I, [_P, _I, _I, _I, _F, _P, _P, _I, _I64, _I64, _P]),
+    "b200p_mask_build": (_I, [_P, _I, _P, _U64, _I, _P, _P]),
     "b200p_count_zeros": (_I, [_P, _P, _P, _I, _P]),
     "b200p_mask_pack_from_f32": (_I, [_P, _P, _P]),
     "b200p_mask_unpack_to_f32": (_I, [_P, _P, _P]),

@@ -117,7 +117,7 @@ struct SelState {
     uint32_t miss;                   // the k-th key was not inside the bracket (or it overflowed): exact fallback ran
     uint32_t lo_bucket, hi_bucket;   // bracket in units of the 12-bit digit (inclusive)
     uint32_t win_lo;                 // first key of the 1024-key window chosen by the bracket pass
-    uint32_t pad2_;
+    uint32_t prov_ok;                // the provisional mask (bits: alive && key >= bracket base) and the candidate list are valid
     uint32_t pad_[2];
 };
 
@@ -151,6 +151,10 @@ struct b200p_plan {
     uint32_t* d_cand_key = nullptr;         // cand_capacity
     uint32_t* d_cand_pos = nullptr;         // cand_capacity   (chunk * kChunk + element)
     uint32_t* d_chunk_ties = nullptr;       // n_chunks
+    uint32_t* d_prov = nullptr;             // n_chunks * 128 words: provisional packed mask written by the select sweep
+    // emit-by-patch: valid for the emit that directly follows b200p_select_kth with the same arguments
+    uint32_t* prov_target = nullptr;        // where the sweep writes the provisional mask (nullptr: d_prov)
+    bool prov_armed = false; int prov_key_source = -1; int prov_mode = -1; const uint32_t* prov_old_mask = nullptr;
     // lazily created arena for the host-buffer entry points
     float* arena_w = nullptr; float* arena_g[2] = {nullptr, nullptr}; float* arena_score = nullptr;
     uint32_t* arena_mask = nullptr; uint32_t* arena_old_mask = nullptr;

@@ -23,6 +23,8 @@ struct EmitArgs {
     float forced_threshold;
     int outputs;                     // B200P_EMIT_*
     int vec_ok;
+    // emit-by-patch: when the select left a valid provisional mask in `prov`, only the candidates are patched
+    int patch; uint32_t* prov; const uint32_t* cand_key; const uint32_t* cand_pos; int64_t n_chunks;
 };
 
 // keep decision for one element
@@ -35,9 +37,63 @@ __device__ __forceinline__ bool keep_decision(float x, int mode, int force, floa
     return key > thr_key || (key == thr_key && !ties_pruned);
 }
 
+// ---- K3': emit by patching ---------------------------------------------------------------------------
+// The select's sweep already wrote a provisional mask (alive && key >= bracket base) and gathered every
+// key inside the bracket with its position.  Once the threshold is known only those candidates can still
+// change: clear the bits of the ones that are pruned.  ~2 % of the keys are touched instead of re-reading
+// all of them (4.125 B/param -> ~0.3 B/param).  Ties of the chunk where the EXACT_K quota runs out are
+// dropped in element order by one warp, exactly like the full emit does.
+__device__ void emit_patch_body(const int32_t* __restrict__ chunk_n, ChunkTab key_tab, const uint32_t* __restrict__ old_mask,
+                                SelState* __restrict__ st, const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_pos,
+                                uint32_t* __restrict__ prov, int mode, int64_t n_chunks) {
+    const uint32_t n = st->cand_count, thr_key = st->thr_key;
+    const bool strict = mode == B200P_MODE_SNIP_STRICT;
+    const uint32_t need_ties = strict ? 0u : st->need_ties;
+    const long long tie_chunk = st->tie_chunk;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const uint32_t key = __ldg(cand_key + i), pos = __ldg(cand_pos + i);
+        const long long c = pos >> 12;
+        bool prune;
+        if (strict) prune = key <= thr_key;                           // keep = score > threshold (train.py:316)
+        else {
+            const bool ties_pruned = !need_ties || tie_chunk < 0 || c < tie_chunk;
+            prune = key < thr_key || (key == thr_key && ties_pruned);
+        }
+        if (prune) atomicAnd(prov + (size_t)c * kWordsPerChunk + ((pos & 4095u) >> 5), ~(1u << (pos & 31u)));
+    }
+    if (blockIdx.x != 0) return;
+    if (threadIdx.x == 0) st->n_kept = st->n_valid - st->n_less - (strict ? st->n_equal : st->quota);
+    if (need_ties && tie_chunk >= 0 && tie_chunk < n_chunks && threadIdx.x < 32) {
+        // first tie_resid tied + alive keys of this chunk, in element order
+        const int lane = threadIdx.x;
+        const float* __restrict__ src = chunk_ptr<const float>(key_tab, tie_chunk);
+        const int cn = __ldg(chunk_n + tie_chunk);
+        const uint32_t* mold = old_mask ? old_mask + tie_chunk * kWordsPerChunk : nullptr;
+        uint32_t left = st->tie_resid;
+        for (int wd = 0; wd < kWordsPerChunk && left > 0; ++wd) {
+            const int e = wd * 32 + lane;
+            bool tie = false;
+            if (e < cn) {
+                tie = key_of(src[e]) == thr_key;
+                if (mold) tie = tie && ((mold[wd] >> lane) & 1u);
+            }
+            const uint32_t tmask = __ballot_sync(0xFFFFFFFFu, tie);
+            if (tmask == 0) continue;
+            const uint32_t rank = __popc(tmask & ((1u << lane) - 1u));
+            const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, tie && rank < left);
+            if (lane == 0) atomicAnd(prov + (size_t)tie_chunk * kWordsPerChunk + wd, ~dmask);
+            left -= __popc(dmask);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_emit_masks(EmitArgs a, int64_t c_begin, int64_t c_end) {
     __shared__ unsigned long long s_kept;
+    if (a.patch && a.st->prov_ok) {
+        emit_patch_body(a.chunk_n, a.key_tab, a.old_mask, a.st, a.cand_key, a.cand_pos, a.prov, a.mode, a.n_chunks);
+        return;
+    }
     if (threadIdx.x == 0) s_kept = 0;
     __syncthreads();
     const int tid = threadIdx.x;
@@ -311,7 +367,16 @@ extern "C" int b200p_emit_masks(b200p_plan* p, int key_source, int mode, int for
     cudaStream_t st = (cudaStream_t)stream;
     B200P_CUDA(cudaMemsetAsync(&p->d_state->n_kept, 0, sizeof(unsigned long long), st));
     if (chunk_begin == chunk_end) return B200P_OK;
+    // emit-by-patch: directly after b200p_select_kth with the same key source / mode / old mask, over the whole
+    // parameter set and without fused fp32 outputs.  Whether the provisional mask is valid is only known on the
+    // device (the select may have fallen back to histogram mode), so the full pass is still launched and exits at
+    // once when the patch has done the job.
+    const bool patch = p->prov_armed && force == 0 && outputs == 0 && chunk_begin == 0 && chunk_end == p->n_chunks &&
+                       p->prov_key_source == key_source && p->prov_mode == mode && p->prov_old_mask == d_old_mask;
+    uint32_t* prov = p->prov_target ? p->prov_target : p->d_prov;
+    p->prov_armed = false; p->prov_target = nullptr;
     EmitArgs a;
+    a.patch = patch ? 1 : 0; a.prov = prov; a.cand_key = p->d_cand_key; a.cand_pos = p->d_cand_pos; a.n_chunks = p->n_chunks;
     a.chunk_n = p->d_chunk_n;
     a.key_tab = p->tab(kslot);
     a.w_tab = p->tab(B200P_SLOT_W);
@@ -323,8 +388,12 @@ extern "C" int b200p_emit_masks(b200p_plan* p, int key_source, int mode, int for
     if (outputs & B200P_EMIT_MASKF) vec = vec && p->vec_ok[B200P_SLOT_MASKF];
     if (outputs & B200P_EMIT_WEFF) vec = vec && p->vec_ok[B200P_SLOT_WEFF] && p->vec_ok[B200P_SLOT_W];
     a.vec_ok = vec ? 1 : 0;
+    if (patch && prov == d_new_mask) a.new_mask = d_new_mask;           // the sweep wrote straight into the destination
+    else if (patch) a.new_mask = prov;                                     // full-pass fallback and patch both work on `prov`
     k_emit_masks<<<p->grid_for(chunk_end - chunk_begin, 4), kThreads, 0, st>>>(a, chunk_begin, chunk_end);
     B200P_LAUNCH_CHECK("k_emit_masks");
+    if (patch && prov != d_new_mask)
+        B200P_CUDA(cudaMemcpyAsync(d_new_mask, prov, (size_t)p->n_chunks * kWordsPerChunk * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     return B200P_OK;
 }
 
@@ -383,4 +452,15 @@ extern "C" int b200p_mask_grads(b200p_plan* p, const uint32_t* d_mask, void* str
         nullptr, nullptr, const_cast<uint32_t*>(d_mask), p->n_chunks, p->vec_ok[B200P_SLOT_G] ? 1 : 0, 0);
     B200P_LAUNCH_CHECK("k_mask_convert<3>");
     return B200P_OK;
+}
+
+// select + emit in one call: the sweep writes the provisional mask straight into d_new_mask, the emit patches it
+extern "C" int b200p_mask_build(b200p_plan* p, int key_source, const uint32_t* d_old_mask, uint64_t k, int mode,
+                                uint32_t* d_new_mask, void* stream) {
+    B200P_REQUIRE(p != nullptr && d_new_mask != nullptr, B200P_EINVAL, "mask_build: null argument");
+    B200P_REQUIRE(d_new_mask != d_old_mask, B200P_EINVAL, "mask_build: the new mask must not alias the old one");
+    p->prov_target = d_new_mask;
+    int rc = b200p_select_kth(p, key_source, d_old_mask, k, mode, stream);
+    if (rc) { p->prov_target = nullptr; return rc; }
+    return b200p_emit_masks(p, key_source, mode, 0, 0.f, d_old_mask, d_new_mask, 0, 0, -1, stream);
 }

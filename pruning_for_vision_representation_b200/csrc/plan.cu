@@ -85,6 +85,7 @@ extern "C" int b200p_plan_create(int device, int n_segments, const int64_t* h_nu
     TRY(cudaMalloc(&p->d_cand_key, cand_capacity * sizeof(uint32_t)));
     TRY(cudaMalloc(&p->d_cand_pos, cand_capacity * sizeof(uint32_t)));
     TRY(cudaMalloc(&p->d_chunk_ties, chunks * sizeof(uint32_t)));
+    TRY(cudaMalloc(&p->d_prov, chunks * kWordsPerChunk * sizeof(uint32_t)));
     TRY(cudaMemset(p->d_hist, 0, (kHistBins + kHistExtra) * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_state, 0, sizeof(SelState)));
     TRY(cudaMemset(p->d_chunk_ties, 0, chunks * sizeof(uint32_t)));
@@ -100,7 +101,7 @@ extern "C" int b200p_plan_destroy(b200p_plan* p) {
     cudaFree(p->d_chunk_seg); cudaFree(p->d_chunk_n); cudaFree(p->d_chunk_elem0);
     for (int s = 0; s < B200P_NUM_SLOTS; ++s) cudaFree(p->d_tab_own[s]);
     cudaFree(p->d_hist); cudaFree(p->d_state); cudaFree(p->d_cand_key); cudaFree(p->d_cand_pos);
-    cudaFree(p->d_chunk_ties);
+    cudaFree(p->d_chunk_ties); cudaFree(p->d_prov);
     for (int i = 0; i < 2; ++i) if (p->arena_gtab[i]) { b200p_ptrtable_destroy(p->arena_gtab[i]); p->arena_gtab[i] = nullptr; }
     cudaFree(p->arena_w); cudaFree(p->arena_g[0]); cudaFree(p->arena_g[1]); cudaFree(p->arena_score);
     cudaFree(p->arena_mask); cudaFree(p->arena_old_mask);

@@ -198,6 +198,7 @@ struct PassArgs {
     uint32_t* cand_pos;
     unsigned int* ticket;
     long long cand_capacity;
+    uint32_t* prov;          // nullable: provisional packed mask (alive && key >= base) written by the sweep
     int64_t c_begin, c_end;
     int vec_ok, fuse_scan;
     // fused initialisation (pass 0 of b200p_select_kth): the last CTA resets the state before its scan
@@ -229,6 +230,7 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
     if (lane == 0) s_wcount[warp] = 0;
     __syncwarp();
     unsigned long long below = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->prov_ok = (a.prov != nullptr && collect) ? 1u : 0u;
 
     // one matching key: fine histogram + staged append (order inside the buffer is irrelevant)
     auto take = [&](uint32_t key, uint32_t pos) {
@@ -270,6 +272,18 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
         }
         lt &= alive_rev;
         below += __popc(lt);
+        if (a.prov) {
+            // provisional mask: alive keys at or above the bracket base stay set; the emit only patches the
+            // candidates afterwards instead of re-reading every key
+            const uint32_t keep = alive_rev & ~lt;
+            uint32_t* pw = a.prov + (size_t)(pos0 >> 12) * kWordsPerChunk;
+#pragma unroll
+            for (int j = 0; j < kVecPerThread; ++j) {
+                const uint32_t nib = __brev((keep >> (12 - 4 * j)) & 0xFu) >> 28;       // key 4j+q sits at bit 15-(4j+q)
+                const uint32_t word = gather_nibbles(nib);
+                if ((threadIdx.x & 7) == 0) pw[vec_word_index(j)] = word;
+            }
+        }
         uint32_t match = in & ~lt & alive_rev;
         while (match) {                               // divergent, rare (~1-2 % of the keys)
             const int bit = __ffs(match) - 1;
@@ -280,11 +294,20 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
     };
     // partial, unaligned or canonicalised chunk: element-wise
     auto do_scalar = [&](const float* __restrict__ src, const uint32_t* __restrict__ mchunk, int n, uint32_t pos0) {
-        for (int e = threadIdx.x; e < n; e += kThreads) {
-            if (mchunk && !((__ldg(mchunk + (e >> 5)) >> (e & 31)) & 1u)) continue;
-            const uint32_t k = key_of(src[e]);
-            if (k < base) ++below;
-            else if (k - base < span) take(k, pos0 + (uint32_t)e);
+        uint32_t* pw = a.prov ? a.prov + (size_t)(pos0 >> 12) * kWordsPerChunk : nullptr;
+        for (int it = 0; it < kChunk / kThreads; ++it) {                  // warp-uniform trip count: one mask word per warp and step
+            const int e = it * kThreads + threadIdx.x;
+            bool alive = e < n;
+            if (alive && mchunk) alive = (__ldg(mchunk + (e >> 5)) >> (e & 31)) & 1u;
+            const uint32_t k = alive ? key_of(src[e]) : 0u;
+            if (pw) {
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, alive && k >= base);
+                if (lane == 0) pw[e >> 5] = word;
+            }
+            if (alive) {
+                if (k < base) ++below;
+                else if (k - base < span) take(k, pos0 + (uint32_t)e);
+            }
         }
     };
     // alive bitmap in do_vec's bit order (key i -> bit 15 - i)
@@ -789,7 +812,7 @@ k_select_bracket(PassArgs a) {
     __syncthreads();
     const bool inside = k > n_below && k <= n_below + total_in && total_in <= (unsigned long long)a.cand_capacity;
     if (!inside) {
-        if (threadIdx.x == 0) { st->miss = 1u; st->collect = 0u; st->cand_count = 0u; }
+        if (threadIdx.x == 0) { st->miss = 1u; st->collect = 0u; st->cand_count = 0u; st->prov_ok = 0u; }
     } else {
         const unsigned long long kk = k - n_below;
 #pragma unroll
@@ -918,6 +941,7 @@ extern "C" int b200p_select_begin(b200p_plan* p, uint64_t k, int mode, int allow
     B200P_REQUIRE(p != nullptr, B200P_EINVAL, "select_begin: null plan");
     B200P_REQUIRE(mode == B200P_MODE_SNIP_STRICT || mode == B200P_MODE_EXACT_K, B200P_EINVAL, "select_begin: bad mode");
     B200P_CUDA(cudaSetDevice(p->device));
+    p->prov_armed = false;
     k_select_init<<<1, 256, 0, (cudaStream_t)stream>>>(p->d_state, p->d_hist, ticket_ptr(p), k, (uint32_t)mode,
                                                       allow_collect ? 1u : 0u);
     B200P_LAUNCH_CHECK("k_select_init");
@@ -935,13 +959,13 @@ static int pass_grid(b200p_plan* p, int64_t chunks, bool cand_too, int ctas_per_
 }
 
 static void fill_pass_args(b200p_plan* p, PassArgs& a, int key_source, const uint32_t* d_old_mask, int64_t c0, int64_t c1,
-                           int fuse_scan, int fuse_init, uint64_t k, int mode, int allow_collect);
+                           int fuse_scan, int fuse_init, uint64_t k, int mode, int allow_collect, bool with_prov = false);
 
 static int launch_pass(b200p_plan* p, int pass, int key_source, const uint32_t* d_old_mask,
                        int64_t c0, int64_t c1, int fuse_scan, int fuse_init, uint64_t k, int mode, int allow_collect,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool with_prov = false) {
     PassArgs a;
-    fill_pass_args(p, a, key_source, d_old_mask, c0, c1, fuse_scan, fuse_init, k, mode, allow_collect);
+    fill_pass_args(p, a, key_source, d_old_mask, c0, c1, fuse_scan, fuse_init, k, mode, allow_collect, with_prov);
     const int grid = pass_grid(p, c1 - c0, pass == 2, pass == 0 ? 4 : 3);
     switch (pass) {
         case 0: k_select_pass<0><<<grid, kThreads, 0, st>>>(a); break;
@@ -1031,8 +1055,9 @@ extern "C" int b200p_select_ties_scan(b200p_plan* p, int64_t chunk_begin, int64_
 }
 
 static void fill_pass_args(b200p_plan* p, PassArgs& a, int key_source, const uint32_t* d_old_mask, int64_t c0, int64_t c1,
-                           int fuse_scan, int fuse_init, uint64_t k, int mode, int allow_collect) {
+                           int fuse_scan, int fuse_init, uint64_t k, int mode, int allow_collect, bool with_prov) {
     const int slot = key_slot(key_source);
+    a.prov = with_prov ? (p->prov_target ? p->prov_target : p->d_prov) : nullptr;
     a.chunk_n = p->d_chunk_n; a.key_tab = p->tab(slot); a.old_mask = d_old_mask; a.hist = p->d_hist; a.st = p->d_state;
     a.cand_key = p->d_cand_key; a.cand_pos = p->d_cand_pos; a.ticket = ticket_ptr(p); a.cand_capacity = p->cand_capacity;
     a.c_begin = c0; a.c_end = c1; a.vec_ok = p->vec_ok[slot] ? 1 : 0; a.fuse_scan = fuse_scan;
@@ -1044,7 +1069,7 @@ static int select_kth_exact(b200p_plan* p, int key_source, const uint32_t* d_old
     // histogram and the ticket are left zeroed by every completed scan), every pass ends with the
     // last-CTA scan.  Pass 2 runs on the candidates gathered by pass 1 unless the bucket overflowed.
     int rc = launch_pass(p, 0, key_source, d_old_mask, 0, p->n_chunks, 1, 1, k, mode, 1, st); if (rc) return rc;
-    rc = launch_pass(p, 1, key_source, d_old_mask, 0, p->n_chunks, 1, 0, 0, 0, 0, st); if (rc) return rc;
+    rc = launch_pass(p, 1, key_source, d_old_mask, 0, p->n_chunks, 1, 0, 0, 0, 0, st, true); if (rc) return rc;
     rc = launch_pass(p, 2, key_source, d_old_mask, 0, p->n_chunks, 1, 0, 0, 0, 0, st); if (rc) return rc;
     if (mode == B200P_MODE_EXACT_K) { rc = b200p_select_ties(p, key_source, d_old_mask, 0, p->n_chunks, 0, (void*)st); if (rc) return rc; }
     return B200P_OK;
@@ -1069,7 +1094,7 @@ static int select_kth_sampled(b200p_plan* p, int key_source, const uint32_t* d_o
     B200P_LAUNCH_CHECK("k_select_sample");
     // A: bracket sweep
     PassArgs a;
-    fill_pass_args(p, a, key_source, d_old_mask, 0, p->n_chunks, 1, 0, k, mode, 1);
+    fill_pass_args(p, a, key_source, d_old_mask, 0, p->n_chunks, 1, 0, k, mode, 1, true);
     k_select_bracket<<<p->grid_for((p->n_chunks + 1) / 2, 4), kThreads, 0, st>>>(a);
     B200P_LAUNCH_CHECK("k_select_bracket");
     // B: finish (cooperative: grid-wide barriers between its phases)
@@ -1092,6 +1117,8 @@ extern "C" int b200p_select_kth(b200p_plan* p, int key_source, const uint32_t* d
     B200P_REQUIRE(k >= 1 && k <= (uint64_t)p->total, B200P_EINVAL, "select_kth: k must be in [1, N]");
     B200P_REQUIRE(mode == B200P_MODE_SNIP_STRICT || mode == B200P_MODE_EXACT_K, B200P_EINVAL, "select_kth: bad mode");
     B200P_CUDA(cudaSetDevice(p->device));
+    // the emit that follows with the same arguments can patch the provisional mask instead of re-reading the keys
+    p->prov_armed = true; p->prov_key_source = key_source; p->prov_mode = mode; p->prov_old_mask = d_old_mask;
     if (p->select_impl == B200P_SELECT_EXACT) return select_kth_exact(p, key_source, d_old_mask, k, mode, (cudaStream_t)stream);
     return select_kth_sampled(p, key_source, d_old_mask, k, mode, (cudaStream_t)stream);
 }

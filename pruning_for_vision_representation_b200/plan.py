@@ -189,6 +189,11 @@ class ParamPlan:
                                         _ptr(old_mask), _ptr(new_mask), outputs, chunk_begin, chunk_end,
                                         _stream_ptr(self.device)), "emit_masks")
 
+    def mask_build(self, key_source, k, mode, new_mask, old_mask=None):
+        """select_kth + emit_masks in one call (the sweep writes the provisional mask straight into new_mask)."""
+        check(self.lib.b200p_mask_build(self.handle, key_source, _ptr(old_mask), int(k), mode, _ptr(new_mask),
+                                        _stream_ptr(self.device)), "mask_build")
+
     def count_zeros(self, mask=None, use_weights=True):
         """(zeros of the effective weight, kept bits) as Python ints (one host sync)."""
         check(self.lib.b200p_count_zeros(self.handle, _ptr(mask), _ptr(self._counts), 1 if use_weights else 0,

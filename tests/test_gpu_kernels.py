@@ -268,6 +268,41 @@ def test_large_random_select_vs_partition():
         assert np.array_equal(got[flat != thr], (flat > thr)[flat != thr])
 
 
+def test_mask_build_equals_select_plus_emit():
+    """b200p_mask_build (sweep writes the provisional mask into the destination, emit patches it) gives the
+    same packed words and result block as select_kth + emit_masks, with and without an old mask, with ties."""
+    rng = np.random.default_rng(21)
+    sizes = [700_001, 4096 * 50, 123_457, 33]
+    w = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    for a in w:
+        idx = rng.choice(a.size, size=a.size // 6, replace=False)
+        a[idx] = np.float32(0.3)                                           # a big tied set around the 20-30 % quantile
+    plan = make_plan(w)
+    plan.bind(L.SLOT_W, to_dev(w))
+    sc = to_dev([np.abs(a) * np.float32(1e-3) for a in w])
+    plan.bind(L.SLOT_SCORE, sc)
+    old = None
+    n_alive = plan.total
+    for amount in (0.25, 0.2, 0.5):
+        k = PO.magnitude_k(amount, n_alive)
+        m1 = plan.new_mask(); plan.select_kth(L.KEY_ABS_W, k, L.MODE_EXACT_K, old); plan.emit_masks(L.KEY_ABS_W, L.MODE_EXACT_K, m1, old)
+        r1 = plan.result()
+        m2 = plan.new_mask(); plan.mask_build(L.KEY_ABS_W, k, L.MODE_EXACT_K, m2, old)
+        r2 = plan.result()
+        assert torch.equal(m1, m2) and r1 == r2
+        assert r1["n_kept"] == n_alive - k and int(m1.view(torch.int32).cpu().numpy().view(np.uint32).astype(np.uint64).sum()) >= 0
+        zeros, bits = plan.count_zeros(m1, use_weights=False)
+        assert bits == n_alive - k
+        old, n_alive = m1, n_alive - k
+    k = int(plan.total * 0.9)
+    m1 = plan.new_mask(); plan.select_kth(L.KEY_SCORE, k, L.MODE_SNIP_STRICT); plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, m1)
+    r1 = plan.result()
+    m2 = plan.new_mask(); plan.mask_build(L.KEY_SCORE, k, L.MODE_SNIP_STRICT, m2)
+    assert torch.equal(m1, m2) and r1 == plan.result()
+    flat = np.concatenate([np.abs(a) * np.float32(1e-3) for a in w])
+    assert np.array_equal(np.concatenate(gpu_masks(plan, m1)), flat > np.float32(r1["threshold"]))
+
+
 def test_mask_roundtrip_apply_and_grads():
     rng = np.random.default_rng(9)
     sizes = [4096 * 3, 777, 4100]

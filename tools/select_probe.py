@@ -34,8 +34,9 @@ for impl in ("sampled", "exact"):
     old.copy_(mask)
     t5 = timed(lambda: plan.select_kth(L.KEY_ABS_W, N // 10, L.MODE_EXACT_K, old)); r5 = plan.result()
     def full():
-        plan.select_kth(L.KEY_ABS_W, N // 2, L.MODE_EXACT_K); plan.emit_masks(L.KEY_ABS_W, L.MODE_EXACT_K, mask)
+        plan.mask_build(L.KEY_ABS_W, N // 2, L.MODE_EXACT_K, mask)
     t6 = timed(full)
+    t7 = timed(lambda: plan.mask_build(L.KEY_SCORE, int(N * 0.9), L.MODE_SNIP_STRICT, mask))
     print(f"{model} {impl}: select_score {t1:.1f} us (passes {r1['passes_full']}, cand {r1['collected']}) emit_snip {t2:.1f} | "
           f"select_absw {t3:.1f} (passes {r3['passes_full']}) emit_mag {t4:.1f} | round2 select {t5:.1f} (passes {r5['passes_full']}) | "
-          f"magnitude build {t6:.1f} us = {N / t6 / 1e3:.1f} Gparams/s", flush=True)
+          f"magnitude build {t6:.1f} us = {N / t6 / 1e3:.1f} Gparams/s | snip select+emit {t7:.1f} us", flush=True)
