@@ -171,8 +171,10 @@ def magnitude_pruning(model, prune_amount=0.2):
         plan.select_begin(0, L.MODE_EXACT_K)
         plan.emit_masks(L.KEY_ABS_W, L.MODE_EXACT_K, new_mask, st.mask, force=1, outputs=L.EMIT_MASKF)
     else:
-        plan.select_kth(L.KEY_ABS_W, k, L.MODE_EXACT_K, st.mask)
-        plan.emit_masks(L.KEY_ABS_W, L.MODE_EXACT_K, new_mask, st.mask, outputs=L.EMIT_MASKF)
+        # select + emit-by-patch on the packed mask, then the fp32 `weight_mask` buffers (checkpoint format) are
+        # expanded from it: the keys are read once, not twice
+        plan.mask_build(L.KEY_ABS_W, k, L.MODE_EXACT_K, new_mask, st.mask)
+        plan.mask_unpack_to_f32(new_mask)
     st.mask = new_mask
     st.n_alive -= k
     st.install()
