@@ -21,7 +21,7 @@ constexpr int kLostMaxPatches = 4096;     // per image (ViT-S/8 at 480x480 = 360
 constexpr int kFinThreads = 512;
 
 // image records travel as kernel arguments (no pageable-memcpy stream sync, no staging buffer)
-constexpr int kMetaPerLaunch = 64;
+constexpr int kMetaPerLaunch = 256;
 struct MetaPack { LostImageDev m[kMetaPerLaunch]; };
 __global__ void k_lost_set_meta(LostImageDev* __restrict__ dst, MetaPack pack, int n) {
     if ((int)threadIdx.x < n) dst[threadIdx.x] = pack.m[threadIdx.x];
@@ -303,7 +303,15 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
     // M = sum over similars of A[s, :], rows added in that order (object_discovery.py:62)
     for (int j = tid; j < n; j += nt) {
         float m = 0.f;
-        for (int r = 0; r < n_sim; ++r) m = __fadd_rn(m, A[(long long)s_sorted[r] * n + j]);
+        int r = 0;
+        for (; r + 8 <= n_sim; r += 8) {                       // 8 independent loads in flight, then the ordered adds
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(A + (long long)s_sorted[r + u] * n + j);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) m = __fadd_rn(m, v[u]);
+        }
+        for (; r < n_sim; ++r) m = __fadd_rn(m, __ldg(A + (long long)s_sorted[r] * n + j));
         s_flag[j] = m > 0.0f ? 1 : 0;
         if (M_out) M_out[im.out_off + j] = m;
     }
