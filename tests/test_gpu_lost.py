@@ -176,3 +176,22 @@ def test_driver_discover_matches_single_image_lost(golden_dir):
             assert preds[n].tolist() == meta[n]["pred"], n
     gts = {n: np.array([meta[n]["pred"]]) for n in names if meta[n]["k_patches"] == 100}
     assert D.corloc(preds, gts)[0] == 100.0
+
+
+def test_end_to_end_from_images_with_vit_s16():
+    """images -> ViT-S/16 last-layer qkv -> in-place key view -> batched LOST -> boxes inside the images."""
+    from pruning_for_vision_representation_b200 import lost_driver as D
+    from pruning_for_vision_representation_b200.vit_features import vit_small_16
+    torch.manual_seed(0)
+    vit = vit_small_16().to(DEV).eval()
+    imgs = torch.randn(3, 3, 200, 264, device=DEV)          # padded to 208 x 272 -> 13 x 17 patches
+    qkv, (h, w) = vit.last_qkv(imgs)
+    keys = D.keys_from_qkv(qkv)
+    assert keys.shape == (3, h * w, 384) and not keys.is_contiguous()
+    preds = D.discover(["a", "b", "c"], [keys[i] for i in range(3)], [[h, w]] * 3, [(3, 200, 264)] * 3, patch_size=16)
+    for name in "abc":
+        p = preds[name]
+        assert p is not None and 0 <= p[0] < p[2] <= 264 and 0 <= p[1] < p[3] <= 200
+    # single-image path on the strided view gives the same box
+    pred, A, scores, seed = OD.lost(keys[1:2], [h, w], [16, 16], (3, 200, 264))
+    assert pred.tolist() == preds["b"].tolist()

@@ -34,3 +34,23 @@ def test_save_predictions(tmp_path):
     D.save_predictions(preds, str(tmp_path), (61.94, 1, 1))
     assert pickle.load(open(os.path.join(tmp_path, "preds.pkl"), "rb"))["img1"].tolist() == [1, 2, 3, 4]
     assert open(os.path.join(tmp_path, "results.txt")).read() == "corloc,61.9,,\n"
+
+
+def test_vit_feature_producer_contract():
+    from pruning_for_vision_representation_b200.vit_features import ViTFeatures
+    torch.manual_seed(0)
+    m = ViTFeatures(patch_size=16, dim=48, depth=2, heads=3, img_size=64).eval()
+    img = torch.randn(2, 3, 75, 100)                       # not a multiple of 16: padded to 80 x 112
+    qkv, (h, w) = m.last_qkv(img)
+    assert (h, w) == (5, 7) and qkv.shape == (2, 1 + 35, 3 * 48)
+    keys = D.keys_from_qkv(qkv)
+    assert keys.shape == (2, 35, 48)
+    # the hook contract of main_lost_original.py:222-263: k of the last block, CLS dropped
+    captured = {}
+    hnd = m.blocks[-1].attn.qkv.register_forward_hook(lambda mod, i, o: captured.setdefault("qkv", o))
+    m.last_qkv(img); hnd.remove()
+    B, T = 2, 36
+    q, k, v = captured["qkv"].reshape(B, T, 3, 3, 16).permute(2, 0, 3, 1, 4)
+    assert torch.equal(keys, k.transpose(1, 2).reshape(B, T, -1)[:, 1:, :])
+    # native grid: position embeddings are used as they are
+    assert m.interpolate_pos(4, 4) is m.pos_embed and m.interpolate_pos(5, 7).shape == (1, 36, 48)

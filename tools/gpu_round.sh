@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_lost.py tests/test_gpu_fullsize.py -m gpu -q -x --timeout 90 -k "lost" > gpurun_out/pytest_lost.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_lost.log
-timeout 60 python tools/lost_probe.py 256 5
-timeout 60 python tools/lost_probe.py 256 3 > gpurun_out/plain.log 2>&1 && timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_lost' -c 16 --csv --log-file gpurun_out/launches_lost.csv python tools/lost_probe.py 256 3 > gpurun_out/ncu_list.log 2>&1; echo "ncu rc=$?"
+( time python __graft_entry__.py --smoke ) 2>&1 | tail -6
+( time timeout 600 python -m pytest tests -m gpu -q --timeout 120 ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_gpu.log
+( time python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err ) 2>&1 | tail -4; echo "bench rc=$?"; python -c "
+import json; d=json.loads(open('gpurun_out/bench_n1.json').read().strip().splitlines()[-1]); print({k:(v if not isinstance(v,dict) else '...') for k,v in d.items()}); print(d['roofline']); print(d['e2e']); print(d['cpu_baseline']); print(d['clocks']); print(d['lost']['value'], d['lost']['e2e'], d['lost'].get('cpu_baseline'))"
+( time python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ) 2>&1 | tail -4; cut -c1-400 gpurun_out/bench_ref.json
