@@ -14,6 +14,8 @@ struct LostImageDev {
     int tiles;           // 128-wide tiles per side
     int row_base;        // first row of this image in the stacked hi/lo operand arrays
     int pair_base;       // first tile of this image in the symmetric (ti <= tj) tile list of the tensor-core Gram
+    int pair2_base;      // the same for the 256x256 tiles of the CTA-pair kernel
+    int pad_;
 };
 
 __device__ __forceinline__ int find_image(const LostImageDev* __restrict__ meta, int n_images, int cta) {
@@ -29,6 +31,6 @@ __device__ __forceinline__ int find_image(const LostImageDev* __restrict__ meta,
 size_t lost_tc_workspace_bytes(long long total_patches, int d);
 int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
                  const std::vector<LostImageDev>& meta, long long total_patches, int n_max, float* A_base,
-                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st);
+                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st, bool pair_mode);
 
 }  // namespace b200p

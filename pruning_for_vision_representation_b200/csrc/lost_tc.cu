@@ -312,6 +312,243 @@ k_lost_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
 }
 
+// ---- Gram on tcgen05, CTA pairs (cta_group::2) ----------------------------------------------------
+// The single-CTA kernel above is bound by operand traffic: a 128x128 tile needs 64 KB of hi/lo operands
+// per 768 tensor cycles.  Two CTAs of a cluster (adjacent SMs) compute one 256x256 tile together: CTA r
+// supplies A rows [128r, +128) and the B half [128r, +128) of the tile's columns, the pair's tensor cores
+// read both halves of B, and each CTA accumulates its 128 rows x 256 columns in its own TMEM — the same
+// 64 KB per CTA and k-block now feed twice the flops.  Protocol:
+//   * TMA loads in both CTAs use the .cta_group::2 form and report their bytes to the LEADER's (rank 0) full
+//     barrier, which expects the bytes of both CTAs;
+//   * the leader's elected thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 8) and commits with
+//     .multicast::cluster to the empty / tmem_full barriers of BOTH CTAs;
+//   * the epilogue warps of both CTAs arrive on the leader's tmem_empty barrier (256 arrivals);
+//   * tile schedule: upper-triangular 256x256 tiles, one cluster walks tiles cluster_id, +n_clusters, ...
+constexpr int T2_BM = 128, T2_BN = 256, T2_TILE = 256;           // rows per CTA, columns per tile, tile edge
+constexpr int T2_ACC = 2, T2_TMEM_COLS = T2_ACC * T2_BN;         // 512 columns: all of TMEM
+constexpr int T2_THREADS = 320;                                  // TMA warp, MMA warp, 8 epilogue warps
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;                      // clears the CTA-rank bit of a shared::cluster address (rank 0 of the pair)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {       // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {   // bar: shared::cluster address (possibly the peer's)
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ int find_image_pairs2(const LostImageDev* __restrict__ meta, int n_images, int t) {
+    int lo = 0, hi = n_images - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (meta[mid].pair2_base <= t) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ TileCoord decode_tile2(const LostImageDev* __restrict__ meta, int n_images, int t) {
+    TileCoord tc;
+    tc.img = find_image_pairs2(meta, n_images, t);
+    const int T = (meta[tc.img].n + T2_TILE - 1) / T2_TILE;
+    int p = t - meta[tc.img].pair2_base, ti = 0;
+    while (p >= T - ti) { p -= T - ti; ++ti; }
+    tc.ti = ti; tc.tj = ti + p;
+    return tc;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                const LostImageDev* __restrict__ meta, int n_images, int n_tiles, float* __restrict__ A_base,
+                int* __restrict__ degree_base, float threshold, int d_pad) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + T2_ACC + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 2 * T2_ACC);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                    // 0 = leader of the pair
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int num_kb = d_pad / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_hi); tma_prefetch_desc(&tm_lo);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < T2_ACC; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 2 * (T2_THREADS - 64)); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)T2_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                          // barriers of both CTAs are initialised, TMEM is allocated
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer (both CTAs): own A rows and own half of B, bytes reported to the leader's barrier
+        int it = 0;
+        for (int t = cluster_id; t < n_tiles; t += n_clusters) {
+            const TileCoord tc = decode_tile2(meta, n_images, t);
+            const int a_row = meta[tc.img].row_base + tc.ti * T2_TILE + (int)rank * T2_BM;
+            const int b_row = meta[tc.img].row_base + tc.tj * T2_TILE + (int)rank * T2_BM;
+            const bool diag = tc.ti == tc.tj;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+                const uint32_t lbar = full_bar(s) & kPeerMask;
+                if (rank == 0) mbar_expect_tx(full_bar(s), 2u * (diag ? 2 * TC_TILE_BYTES : 4 * TC_TILE_BYTES));   // bytes of both CTAs
+                tma_load_2d_2sm(st + 0 * TC_TILE_BYTES, &tm_hi, kb * TC_BK, a_row, lbar);
+                tma_load_2d_2sm(st + 1 * TC_TILE_BYTES, &tm_lo, kb * TC_BK, a_row, lbar);
+                if (!diag) {
+                    tma_load_2d_2sm(st + 2 * TC_TILE_BYTES, &tm_hi, kb * TC_BK, b_row, lbar);
+                    tma_load_2d_2sm(st + 3 * TC_TILE_BYTES, &tm_lo, kb * TC_BK, b_row, lbar);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ===== MMA issuer (leader CTA only) =====
+        const uint32_t idesc = umma_idesc_tf32(2 * T2_BM, T2_BN);
+        int it = 0, tl = 0;
+        for (int t = cluster_id; t < n_tiles; t += n_clusters, ++tl) {
+            const TileCoord tc = decode_tile2(meta, n_images, t);
+            const bool diag = tc.ti == tc.tj;
+            const int acc = tl % T2_ACC;
+            const uint32_t acc_ph = (uint32_t)(tl / T2_ACC) & 1u;
+            mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T2_BN);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+                const uint64_t a_hi = umma_desc_sw128(st + 0 * TC_TILE_BYTES), a_lo = umma_desc_sw128(st + 1 * TC_TILE_BYTES);
+                const uint64_t b_hi = diag ? a_hi : umma_desc_sw128(st + 2 * TC_TILE_BYTES);
+                const uint64_t b_lo = diag ? a_lo : umma_desc_sw128(st + 3 * TC_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+                    umma_tf32_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_tf32_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                    umma_tf32_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+                umma_commit_2sm(empty_bar(s));                      // frees the stage in both CTAs
+            }
+            umma_commit_2sm(tmem_full_bar(acc));                    // both epilogues may read their half
+        }
+    } else if (warp >= 2) {
+        // ===== epilogue (both CTAs): rows [256 ti + 128 rank, +128) x 256 columns of the tile =====
+        // 8 warps: TMEM lane quadrant q = warp & 3 (rows), column half hsel (4 chunks of 32 columns each)
+        const int q = warp & 3, hsel = (warp - 2) >> 2;
+        int tl = 0;
+        for (int t = cluster_id; t < n_tiles; t += n_clusters, ++tl) {
+            const TileCoord tc = decode_tile2(meta, n_images, t);
+            const LostImageDev im = meta[tc.img];
+            const int acc = tl % T2_ACC;
+            const uint32_t acc_ph = (uint32_t)(tl / T2_ACC) & 1u;
+            mbar_wait(tmem_full_bar(acc), acc_ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row0 = tc.ti * T2_TILE + (int)rank * T2_BM, col0 = tc.tj * T2_TILE;
+            const bool mirror = tc.ti != tc.tj;                 // a diagonal 256-tile holds both triangles already
+            const int gi = row0 + q * 32 + lane;
+            float* __restrict__ A = A_base + im.a_off;
+            int* __restrict__ deg = degree_base + im.out_off;
+            const bool vec_store = (im.n & 3) == 0 && (((uintptr_t)A) & 15u) == 0;
+            const bool interior = mirror && row0 + T2_BM <= im.n && col0 + T2_BN <= im.n && vec_store;   // no bounds, no diagonal
+            int cnt = 0;
+#pragma unroll 1
+            for (int ch = 4 * hsel; ch < 4 * hsel + 4; ++ch) {
+                const int gj0 = col0 + ch * 32;
+                if (gj0 >= im.n) break;                          // warp-uniform: columns past the image
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_BN + ch * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (interior) {
+                    int colcnt = 0;
+                    float* __restrict__ col = A + (long long)gj0 * im.n + gi;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float v = __uint_as_float(r[c]);
+                        const bool pos = v > threshold && v > 0.f;
+                        cnt += pos ? 1 : 0;
+                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, pos);
+                        if (lane == c) colcnt = __popc(bal);
+                        col[(long long)c * im.n] = v;            // transposed: lanes = consecutive addresses
+                    }
+                    if (colcnt) atomicAdd(deg + gj0 + lane, colcnt);
+                    float* dst = A + (long long)gi * im.n + gj0;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]),
+                                                                          __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+                    continue;
+                }
+                int colcnt = 0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int gj = gj0 + c;
+                    const float v = __uint_as_float(r[c]);
+                    const bool in = gi < im.n && gj < im.n;
+                    const bool pos = in && ((gi == gj) ? 0.f : fmaxf(v, 0.f)) > threshold;
+                    cnt += pos ? 1 : 0;
+                    if (mirror) {
+                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, pos);
+                        if (lane == c) colcnt = __popc(bal);
+                        if (in) A[(long long)gj * im.n + gi] = v;
+                    }
+                }
+                if (mirror && colcnt && gj0 + lane < im.n) atomicAdd(deg + gj0 + lane, colcnt);
+                if (gi < im.n) {
+                    float* dst = A + (long long)gi * im.n + gj0;
+                    if (vec_store && gj0 + 31 < im.n) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4)
+                            *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]),
+                                                                              __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) if (gj0 + c < im.n) dst[c] = __uint_as_float(r[c]);
+                    }
+                }
+            }
+            if (gi < im.n && cnt) atomicAdd(deg + gi, cnt);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_cluster(tmem_empty_bar(acc) & kPeerMask);  // 2 x 256 arrivals on the leader's barrier
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                          // both CTAs are done with TMEM and with each other's barriers
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)T2_TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host ----------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -349,7 +586,7 @@ size_t lost_tc_workspace_bytes(long long total_patches, int d) {
 
 int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
                  const std::vector<LostImageDev>& meta, long long total_patches, int n_max, float* A_base,
-                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st) {
+                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st, bool pair_mode) {
     const int n_images = (int)meta.size();
     const int d_pad = (d + TC_BK - 1) / TC_BK * TC_BK;
     const size_t arr = ((size_t)total_patches * d_pad * sizeof(float) + 1023) / 1024 * 1024;
@@ -377,6 +614,19 @@ int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostIm
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = n_tiles < sms ? n_tiles : sms;                  // persistent: one CTA per SM
+    if (pair_mode) {
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+            attr2_set = true;
+        }
+        const int T2 = (last.n + T2_TILE - 1) / T2_TILE;
+        const int n_tiles2 = last.pair2_base + T2 * (T2 + 1) / 2;
+        int grid2 = 2 * (n_tiles2 < sms / 2 ? n_tiles2 : sms / 2);           // one cluster (CTA pair) per two SMs
+        k_lost_gram_tc2<<<grid2, T2_THREADS, TC_SMEM_BYTES, st>>>(tm_hi, tm_lo, d_meta, n_images, n_tiles2, A_base, d_degree, 0.0f, d_pad);
+        B200P_LAUNCH_CHECK("k_lost_gram_tc2");
+        return B200P_OK;
+    }
     k_lost_gram_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_hi, tm_lo, d_meta, n_images, n_tiles, A_base, d_degree, 0.0f, d_pad);
     B200P_LAUNCH_CHECK("k_lost_gram_tc");
     return B200P_OK;

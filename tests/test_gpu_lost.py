@@ -22,12 +22,13 @@ DEV = torch.device("cuda:0")
 EPS = float(np.finfo(np.float32).eps)
 
 
-@pytest.fixture(params=["tc", "ffma"], autouse=True)
+@pytest.fixture(params=["tc", "tc2", "ffma"], autouse=True)
 def gram_impl(request):
-    """Every test runs with both Gram implementations: TMA + tcgen05 3xTF32 and fp32 CUDA cores."""
+    """Every test runs with all Gram implementations: TMA + tcgen05 3xTF32 on single CTAs, the same on CTA
+    pairs (cta_group::2), and fp32 CUDA cores."""
     from pruning_for_vision_representation_b200 import _lib as L
     old = OD.DEFAULT_GRAM_IMPL
-    OD.DEFAULT_GRAM_IMPL = L.LOST_GRAM_TC if request.param == "tc" else L.LOST_GRAM_FFMA
+    OD.DEFAULT_GRAM_IMPL = {"tc": L.LOST_GRAM_TC, "tc2": L.LOST_GRAM_TC2, "ffma": L.LOST_GRAM_FFMA}[request.param]
     yield request.param
     OD.DEFAULT_GRAM_IMPL = old
 

@@ -2,6 +2,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pruning_for_vision_representation_b200 import object_discovery as OD
+if len(sys.argv) > 3:
+    OD.DEFAULT_GRAM_IMPL = int(sys.argv[3])
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
