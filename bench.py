@@ -503,19 +503,35 @@ def lost_leg(args, dev, world, rank, dist):
         peak_tf32 = 1590.0 / 2.0
     img_s = world * LOST_B / (ms * 1e-3)
     achieved = img_s / world * LOST_FLOP_PER_IMAGE / 1e12
+    # flop the tensor cores execute per image: upper-triangular 256x256 tiles (256 rows each), the last column tile
+    # trimmed to the next multiple of 16 columns, three tf32 MMAs per product (3xTF32)
+    t2 = (LOST_N + 255) // 256
+    last_cols = min(256, (LOST_N - (t2 - 1) * 256 + 15) // 16 * 16)
+    exec_elems = sum(256 * (256 if tj < t2 - 1 else last_cols) for ti in range(t2) for tj in range(ti, t2))
+    exec_flop = 3 * 2 * exec_elems * LOST_D
+    prof = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            prof = json.load(f)
+    except Exception:
+        pass
     leg = {"metric": "LOST ViT-S/16 images/sec", "value": img_s, "unit": "images/s", "ms_per_step": ms, "steps": steps,
            "config": {"workload": f"LOST on synthetic patch keys randn({LOST_B},{LOST_N},{LOST_D}) per GPU, dims 30x30, "
                                   "k_patches 100, keys -> Gram -> degree -> seed -> expansion -> box; ViT forward excluded",
                       "l2": f"{LOST_B} Gram matrices = {LOST_B * LOST_N * LOST_N * 4 >> 20} MiB written per step (> L2)"},
-           "roofline": {"bound": "tensor", "kernel": "k_lost_gram_tc (TMA + tcgen05.mma kind::tf32, 3xTF32 split, TMEM epilogue with fused degree)",
+           "roofline": {"bound": "tensor", "kernel": "k_lost_gram_tc2<direct> (TMA on the caller's keys + tcgen05.mma cta_group::2 kind::tf32, 3xTF32 with "
+                                                     "the lo tiles derived in shared memory, TMEM epilogue with fused degree)",
                         "achieved": achieved, "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32,
-                        "executed_tflops": 3.0 * achieved * (1024.0 * 1024.0) / (LOST_N * LOST_N),
-                        "traffic": None, "peak_source": "0.5 x measured bf16 burst (nominal tf32:bf16 ratio; no measured tf32 peak); "
-                                                        "achieved counts the algorithmic 2*N^2*d flop per image, executed_tflops the 3 MMAs of the "
-                                                        "3xTF32 split on the 1024-padded tiles"},
+                        "executed_tflops": img_s / world * exec_flop / 1e12,
+                        "executed_frac": img_s / world * exec_flop / 1e12 / peak_tf32,
+                        "tensor_pipe_active_pct_ncu": prof.get("k_lost_gram_tc2_tensor_pipe_active_pct"),
+                        "traffic": prof.get("k_lost_gram_tc2_traffic_bytes"),
+                        "peak_source": "0.5 x measured bf16 burst (nominal tf32:bf16 ratio; no measured tf32 peak); achieved counts the "
+                                       "algorithmic 2*N^2*d flop per image over the WHOLE LOST step (Gram + finish + launches); executed_tflops "
+                                       "counts what the tensor cores run: 3 tf32 MMAs per product on the upper-triangular 256-row tiles"},
            "e2e": {"value": world * LOST_B / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": LOST_B * LOST_N * LOST_D * 4, "d2h_bytes_per_step": LOST_B * (16 + 4 + 4)},
-           "gpu_launches_per_step": 3 + (LOST_B + 63) // 64,
+           "gpu_launches_per_step": 3 + (LOST_B + 255) // 256,   # set_meta x ceil(B/256), tile table, Gram, finish (+ 1 memset node)
            "seed0_box0": [int(out["seed"][0].item()), out["box"][0].tolist()]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import lost_oracle as LO

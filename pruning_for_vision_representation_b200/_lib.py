@@ -19,7 +19,7 @@ MODE_SNIP_STRICT, MODE_EXACT_K = 0, 1
 KEY_ABS_W, KEY_SCORE = 0, 1
 EMIT_MASKF, EMIT_WEFF = 1, 2
 SGD_NESTEROV, SGD_FIRST_STEP, SGD_EMIT_WEFF, SGD_EMIT_WEFF16 = 1, 2, 4, 8
-LOST_GRAM_FFMA, LOST_GRAM_TC, LOST_GRAM_TC2 = 0, 1, 2
+LOST_GRAM_FFMA, LOST_GRAM_TC, LOST_GRAM_TC2, LOST_GRAM_TC2D = 0, 1, 2, 3
 OPT_SELECT_IMPL = 1
 SELECT_SAMPLED, SELECT_EXACT = 0, 1
 

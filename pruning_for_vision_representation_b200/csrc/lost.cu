@@ -382,7 +382,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 extern "C" int b200p_lost_workspace_bytes(int n_images, int64_t total_patches, int64_t total_a, int d, int gram_impl, int64_t* out) {
     B200P_REQUIRE(out != nullptr && n_images >= 0 && total_patches >= 0 && total_a >= 0 && d >= 1, B200P_EINVAL, "lost_workspace_bytes: bad argument");
     size_t bytes = align_up((size_t)n_images * sizeof(LostImageDev), 256) + align_up((size_t)total_a * sizeof(float), 256) + 256;
-    if (gram_impl != B200P_LOST_GRAM_FFMA) bytes += align_up(lost_tc_workspace_bytes(total_patches, d), 256);
+    if (gram_impl != B200P_LOST_GRAM_FFMA) bytes += align_up(lost_tc_workspace_bytes(n_images, total_patches, d), 256);
     *out = (int64_t)bytes;
     return B200P_OK;
 }
@@ -394,7 +394,7 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
                                   int gram_impl, void* stream) {
     B200P_REQUIRE(d_feats && h_meta && d_degree && d_seed && d_box && d_status && d_workspace, B200P_EINVAL, "lost_batched: null argument");
     B200P_REQUIRE(n_images >= 1 && d >= 1 && row_stride >= d && k_patches >= 1, B200P_EINVAL, "lost_batched: bad sizes");
-    B200P_REQUIRE(gram_impl == B200P_LOST_GRAM_FFMA || gram_impl == B200P_LOST_GRAM_TC || gram_impl == B200P_LOST_GRAM_TC2, B200P_EINVAL, "lost_batched: bad gram_impl");
+    B200P_REQUIRE(gram_impl >= B200P_LOST_GRAM_FFMA && gram_impl <= B200P_LOST_GRAM_TC2D, B200P_EINVAL, "lost_batched: bad gram_impl");
     B200P_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<LostImageDev> meta(n_images);
@@ -402,6 +402,8 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     int n_max = 0;
     B200P_REQUIRE(k_patches <= 1024, B200P_EINVAL, "lost_batched: k_patches must be <= 1024");
     bool vec = (((uintptr_t)d_feats) & 15u) == 0 && (row_stride & 3) == 0;
+    int tc_mode = gram_impl == B200P_LOST_GRAM_TC ? LOST_TC_SINGLE : LOST_TC_PAIR;
+    if (gram_impl == B200P_LOST_GRAM_TC2D && lost_tc_direct_ok(d_feats, (long long)row_stride, d, h_meta, n_images)) tc_mode = LOST_TC_PAIR_DIRECT;
     for (int b = 0; b < n_images; ++b) {
         const b200p_lost_image_t& h = h_meta[b];
         const long long n = (long long)h.dim0 * h.dim1;
@@ -413,7 +415,8 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
         m.a_off = d_A ? h.a_offset : total_a;
         m.tiles = (int)((n + BM - 1) / BM);
         m.tile_base = (int)tile_base;
-        m.row_base = (int)total_patches; m.pair_base = (int)pair_base;
+        m.row_base = tc_mode == LOST_TC_PAIR_DIRECT ? (int)(h.feat_offset / row_stride) : (int)total_patches;
+        m.pair_base = (int)pair_base;
         pair_base += (long long)m.tiles * (m.tiles + 1) / 2;
         m.pair2_base = (int)pair2_base; m.pad_ = 0;
         { const long long t2 = (n + 255) / 256; pair2_base += t2 * (t2 + 1) / 2; }
@@ -428,7 +431,7 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     B200P_REQUIRE(tile_base < (1ll << 31), B200P_EINVAL, "lost_batched: too many tiles in one call");
     const size_t meta_bytes = align_up((size_t)n_images * sizeof(LostImageDev), 256);
     const size_t a_bytes = d_A ? 0 : align_up((size_t)total_a * sizeof(float), 256);
-    const size_t tc_bytes = gram_impl != B200P_LOST_GRAM_FFMA ? align_up(lost_tc_workspace_bytes(total_patches, d), 256) : 0;
+    const size_t tc_bytes = gram_impl != B200P_LOST_GRAM_FFMA ? align_up(lost_tc_workspace_bytes(n_images, total_patches, d), 256) : 0;
     const size_t need = meta_bytes + a_bytes + tc_bytes;
     B200P_REQUIRE((size_t)workspace_bytes >= need, B200P_EINVAL, "lost_batched: workspace too small (see b200p_lost_workspace_bytes)");
     LostImageDev* d_meta = (LostImageDev*)d_workspace;
@@ -445,7 +448,7 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     if (gram_impl != B200P_LOST_GRAM_FFMA) {
         void* tc_ws = (char*)d_workspace + meta_bytes + a_bytes;
         int rc = lost_gram_tc(d_feats, (long long)row_stride, d, d_meta, meta, total_patches, n_max, A_base, d_degree, tc_ws, tc_bytes,
-                              vec ? 1 : 0, st, gram_impl == B200P_LOST_GRAM_TC2);
+                              vec ? 1 : 0, st, tc_mode);
         if (rc) return rc;
     } else {
         k_lost_gram_ffma<<<(int)tile_base, GT, 0, st>>>(d_feats, (long long)row_stride, d, d_meta, n_images, A_base, d_degree,

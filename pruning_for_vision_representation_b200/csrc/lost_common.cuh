@@ -12,7 +12,7 @@ struct LostImageDev {
     float s0, s1;
     int tile_base;       // first CTA of this image in the Gram grid
     int tiles;           // 128-wide tiles per side
-    int row_base;        // first row of this image in the stacked hi/lo operand arrays
+    int row_base;        // first row of this image in the stacked hi/lo operand arrays (direct mode: in the caller's array)
     int pair_base;       // first tile of this image in the symmetric (ti <= tj) tile list of the tensor-core Gram
     int pair2_base;      // the same for the 256x256 tiles of the CTA-pair kernel
     int pad_;
@@ -28,9 +28,11 @@ __device__ __forceinline__ int find_image(const LostImageDev* __restrict__ meta,
 }
 
 // tensor-core Gram (lost_tc.cu)
-size_t lost_tc_workspace_bytes(long long total_patches, int d);
+enum { LOST_TC_SINGLE = 0, LOST_TC_PAIR = 1, LOST_TC_PAIR_DIRECT = 2 };
+size_t lost_tc_workspace_bytes(int n_images, long long total_patches, int d);
+bool lost_tc_direct_ok(const float* d_feats, long long row_stride, int d, const b200p_lost_image_t* h_meta, int n_images);
 int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
                  const std::vector<LostImageDev>& meta, long long total_patches, int n_max, float* A_base,
-                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st, bool pair_mode);
+                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st, int mode);
 
 }  // namespace b200p

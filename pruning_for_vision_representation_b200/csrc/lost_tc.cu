@@ -17,6 +17,9 @@
 //                         warps 2-5: epilogue — tcgen05.ld (32 lanes x 32 columns per warp and step),
 //                                  each thread owns one row: writes it to A and counts
 //                                  (i != j ? max(A_ij, 0) : 0) > threshold, one atomic per row.
+//   k_lost_gram_tc2<DIRECT>  the production kernel: CTA pairs (cta_group::2, 256x256 tiles, last column tile
+//                       trimmed to a multiple of 16), persistent over a precomputed tile table; DIRECT reads the
+//                       caller's features in place and derives the lo tiles in shared memory (no split kernel).
 // Rows past an image's last patch read the next image's rows (or TMA zero fill at the very end):
 // their products are computed and discarded by the epilogue's bounds checks.
 #include "common.cuh"
@@ -327,6 +330,8 @@ k_lost_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 constexpr int T2_BM = 128, T2_BN = 256, T2_TILE = 256;           // rows per CTA, columns per tile, tile edge
 constexpr int T2_ACC = 2, T2_TMEM_COLS = T2_ACC * T2_BN;         // 512 columns: all of TMEM
 constexpr int T2_THREADS = 320;                                  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int T2_CONV_WARPS = 4;                                 // direct mode: + 4 warps deriving the lo tiles in shared memory
+constexpr int T2_THREADS_DIRECT = T2_THREADS + 32 * T2_CONV_WARPS;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;                      // clears the CTA-rank bit of a shared::cluster address (rank 0 of the pair)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -353,6 +358,37 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {       // arrives
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {   // bar: shared::cluster address (possibly the peer's)
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
 }
+// Arrival with the default semantics (release at CTA scope), the form CUTLASS's ClusterBarrier::arrive(cta_id) uses to
+// hand smem written by transform warps (after fence.proxy.async) to a UMMA issued by the pair's leader.  The
+// release.cluster form above costs a MEMBAR.ALL.GPU per arrival.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+// Same arrival without cluster-scope release of this thread's global stores: for barriers that only order
+// tcgen05 work (the epilogue handing a TMEM accumulator back; tcgen05.fence::before_thread_sync does the
+// ordering).  The release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. every epilogue thread
+// waited for its A stores to reach L2 before freeing the accumulator.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope: the data behind
+    uint32_t done;                                                                  // the barrier was written by the peer CTA too
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// columns the tensor cores compute for column tile tj of an image with n patches: the last tile is
+// trimmed to the next multiple of 16 (the N granularity of cta_group::2), e.g. 144 instead of 256 at n = 900
+__device__ __forceinline__ int tile2_cols(int n, int tj) {
+    const int rest = (n - tj * T2_TILE + 15) & ~15;
+    return rest < T2_BN ? rest : T2_BN;
+}
 
 __device__ __forceinline__ int find_image_pairs2(const LostImageDev* __restrict__ meta, int n_images, int t) {
     int lo = 0, hi = n_images - 1;
@@ -372,19 +408,87 @@ __device__ __forceinline__ TileCoord decode_tile2(const LostImageDev* __restrict
     return tc;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+// One record per 256x256 tile, built by k_lost_tile_table before the Gram kernel: the persistent roles read
+// tile t + n_clusters while they work on tile t, so no role ever waits on the binary search over the image
+// records (ten dependent L2 round trips per tile and role in the first version, ~20 % of the tile time in
+// the TMA producer).
+struct __align__(16) Tile2 {
+    int a_row0, b_row0;        // first operand row of the tile's row / column block (before the rank offset)
+    int info;                  // ncols | share << 9 | diag << 10 | ti << 12 | tj << 16
+    int n;                     // patches of the image
+    long long a_off, out_off;  // the image's offsets into A_base / degree_base
+};
+constexpr int kT2Share = 1 << 9, kT2Diag = 1 << 10;
+
+__global__ void __launch_bounds__(128)
+k_lost_tile_table(const LostImageDev* __restrict__ meta, int n_images, int n_tiles, Tile2* __restrict__ tab) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const TileCoord tc = decode_tile2(meta, n_images, t);
+    const LostImageDev im = meta[tc.img];
+    const int ncols = tile2_cols(im.n, tc.tj);
+    Tile2 e;
+    e.a_row0 = im.row_base + tc.ti * T2_TILE;
+    e.b_row0 = im.row_base + tc.tj * T2_TILE;
+    const bool diag = tc.ti == tc.tj;
+    e.info = ncols | (diag && ncols == T2_BN ? kT2Share : 0) | (diag ? kT2Diag : 0) | (tc.ti << 12) | (tc.tj << 16);
+    e.n = im.n; e.a_off = im.a_off; e.out_off = im.out_off;
+    tab[t] = e;
+}
+__device__ __forceinline__ Tile2 load_tile2(const Tile2* __restrict__ tab, int t, int n_tiles) {
+    Tile2 e;
+    const int4* p = reinterpret_cast<const int4*>(tab + (t < n_tiles ? t : n_tiles - 1));
+    const int4 u = __ldg(p), v = __ldg(p + 1);
+    e.a_row0 = u.x; e.b_row0 = u.y; e.info = u.z; e.n = u.w;
+    e.a_off = ((long long)(unsigned)v.x) | ((long long)v.y << 32);
+    e.out_off = ((long long)(unsigned)v.z) | ((long long)v.w << 32);
+    return e;
+}
+
+// DIRECT = true: the TMA reads the caller's fp32 features in place (one tensor map with the caller's row
+// stride, e.g. the k slice of a qkv buffer) and only the RAW tiles travel; the tensor cores ignore the low 13
+// mantissa bits of an fp32 word fed to kind::tf32, so the raw tile IS the hi operand (hi = x with those
+// bits cleared), and four extra warps derive lo = tf32(x - hi) from the landed tile into a second ring
+// (same swizzled position), publish it to the async proxy and arrive on the leader's conv barrier the MMA
+// issuer waits on.  No split kernel, no hi/lo arrays in HBM, half the L2 -> SM operand traffic.
+//
+// Shared memory (per CTA, 1024-B aligned):
+//   pre-split:  3 stages x [A_hi | A_lo | B_hi | B_lo]                         (16 KB tiles)      192 KB
+//   direct:     4 raw stages x [A_raw | B_raw]  +  2 lo stages x [A_lo | B_lo]                    192 KB
+//               (TMA runs up to four k-blocks ahead; the conversion of k-block i+1 overlaps the MMAs of i)
+//   epilogue:   8 warps x 32 x 32 floats, 16-B XOR swizzle: the row-major copy of A is transposed through
+//               shared memory so that one store instruction writes four full 128-B lines           32 KB
+constexpr int T2_RAW_STAGES = 4, T2_LO_STAGES = 2;
+constexpr int T2_RING_BYTES = TC_STAGES * TC_STAGE_BYTES;        // == (T2_RAW_STAGES + T2_LO_STAGES) * 2 tiles
+constexpr int T2_STAGING_BYTES = 8 * 32 * 32 * 4;
+constexpr size_t T2_SMEM_BYTES = (size_t)T2_RING_BYTES + T2_STAGING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+static_assert(T2_RING_BYTES == (T2_RAW_STAGES + T2_LO_STAGES) * 2 * TC_TILE_BYTES, "ring layouts must have the same size");
+static_assert(T2_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+template <bool DIRECT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DIRECT ? T2_THREADS_DIRECT : T2_THREADS, 1)
 k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                const LostImageDev* __restrict__ meta, int n_images, int n_tiles, float* __restrict__ A_base,
+                const Tile2* __restrict__ tab, int n_tiles, float* __restrict__ A_base,
                 int* __restrict__ degree_base, float threshold, int d_pad) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
-    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + T2_ACC + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 2 * T2_ACC);
+    const uint32_t staging_base = smem_base + T2_RING_BYTES;
+    const uint32_t bar_base = staging_base + T2_STAGING_BYTES;
+    constexpr int NFULL = DIRECT ? T2_RAW_STAGES : TC_STAGES;     // stages the TMA fills
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // [4]
+    auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };                // [4]
+    auto conv_bar = [&](int s) { return bar_base + 8u * (8 + s); };                 // [2] direct: lo tiles ready (leader's copy is used)
+    auto lo_empty_bar = [&](int s) { return bar_base + 8u * (10 + s); };            // [2] direct: MMAs done with the lo stage
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (12 + a); };           // [2]
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (14 + a); };          // [2]
+    const uint32_t tmem_slot = bar_base + 8u * 16;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    // operand tile addresses of k-block `it`
+    auto hi_tiles = [&](int it) { return DIRECT ? smem_base + (uint32_t)(it % T2_RAW_STAGES) * (2 * TC_TILE_BYTES)
+                                                : smem_base + (uint32_t)(it % TC_STAGES) * TC_STAGE_BYTES; };
+    auto lo_tiles = [&](int it) { return DIRECT ? smem_base + (uint32_t)(T2_RAW_STAGES * 2 + (it % T2_LO_STAGES) * 2) * TC_TILE_BYTES
+                                                : smem_base + (uint32_t)(it % TC_STAGES) * TC_STAGE_BYTES + 2 * TC_TILE_BYTES; };
+    // each pair of tiles is [A | B]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();                    // 0 = leader of the pair
@@ -392,9 +496,14 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     const int num_kb = d_pad / TC_BK;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_hi); tma_prefetch_desc(&tm_lo);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < T2_ACC; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 2 * (T2_THREADS - 64)); }
+        tma_prefetch_desc(&tm_hi);
+        if (!DIRECT) tma_prefetch_desc(&tm_lo);
+        for (int s = 0; s < 4; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(conv_bar(s), 2 * T2_CONV_WARPS);          // one arrival per converter warp of both CTAs
+            mbar_init(lo_empty_bar(s), 1);
+        }
+        for (int a = 0; a < T2_ACC; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 2 * 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -408,49 +517,61 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0 && lane == 0) {
-        // ===== TMA producer (both CTAs): own A rows and own half of B, bytes reported to the leader's barrier
+        // ===== TMA producer (both CTAs): own A rows and own half of the tile's B columns
         int it = 0;
+        Tile2 nxt = load_tile2(tab, cluster_id, n_tiles);
         for (int t = cluster_id; t < n_tiles; t += n_clusters) {
-            const TileCoord tc = decode_tile2(meta, n_images, t);
-            const int a_row = meta[tc.img].row_base + tc.ti * T2_TILE + (int)rank * T2_BM;
-            const int b_row = meta[tc.img].row_base + tc.tj * T2_TILE + (int)rank * T2_BM;
-            const bool diag = tc.ti == tc.tj;
+            const Tile2 e = nxt;
+            nxt = load_tile2(tab, t + n_clusters, n_tiles);
+            const int ncols = e.info & 511;
+            const int a_row = e.a_row0 + (int)rank * T2_BM;
+            const int b_row = e.b_row0 + (int)rank * (ncols >> 1);
+            const bool share = (e.info & kT2Share) != 0;           // full diagonal tile: the B halves are the A tiles
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % TC_STAGES;
-                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                const int s = it % NFULL;
+                const uint32_t ph = (uint32_t)(it / NFULL) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u);
-                const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-                const uint32_t lbar = full_bar(s) & kPeerMask;
-                if (rank == 0) mbar_expect_tx(full_bar(s), 2u * (diag ? 2 * TC_TILE_BYTES : 4 * TC_TILE_BYTES));   // bytes of both CTAs
-                tma_load_2d_2sm(st + 0 * TC_TILE_BYTES, &tm_hi, kb * TC_BK, a_row, lbar);
-                tma_load_2d_2sm(st + 1 * TC_TILE_BYTES, &tm_lo, kb * TC_BK, a_row, lbar);
-                if (!diag) {
-                    tma_load_2d_2sm(st + 2 * TC_TILE_BYTES, &tm_hi, kb * TC_BK, b_row, lbar);
-                    tma_load_2d_2sm(st + 3 * TC_TILE_BYTES, &tm_lo, kb * TC_BK, b_row, lbar);
+                const uint32_t hi = hi_tiles(it);
+                if (DIRECT) {                                    // raw tiles only, bytes reported to this CTA's own barrier
+                    mbar_expect_tx(full_bar(s), share ? TC_TILE_BYTES : 2 * TC_TILE_BYTES);
+                    tma_load_2d(hi, &tm_hi, kb * TC_BK, a_row, full_bar(s));
+                    if (!share) tma_load_2d(hi + TC_TILE_BYTES, &tm_hi, kb * TC_BK, b_row, full_bar(s));
+                } else {                                         // bytes of both CTAs reported to the leader's barrier
+                    const uint32_t lo = lo_tiles(it);
+                    const uint32_t lbar = full_bar(s) & kPeerMask;
+                    if (rank == 0) mbar_expect_tx(full_bar(s), 2u * (share ? 2 * TC_TILE_BYTES : 4 * TC_TILE_BYTES));
+                    tma_load_2d_2sm(hi, &tm_hi, kb * TC_BK, a_row, lbar);
+                    tma_load_2d_2sm(lo, &tm_lo, kb * TC_BK, a_row, lbar);
+                    if (!share) {
+                        tma_load_2d_2sm(hi + TC_TILE_BYTES, &tm_hi, kb * TC_BK, b_row, lbar);
+                        tma_load_2d_2sm(lo + TC_TILE_BYTES, &tm_lo, kb * TC_BK, b_row, lbar);
+                    }
                 }
             }
         }
     } else if (warp == 1 && lane == 0 && rank == 0) {
         // ===== MMA issuer (leader CTA only) =====
-        const uint32_t idesc = umma_idesc_tf32(2 * T2_BM, T2_BN);
         int it = 0, tl = 0;
+        Tile2 nxt = load_tile2(tab, cluster_id, n_tiles);
         for (int t = cluster_id; t < n_tiles; t += n_clusters, ++tl) {
-            const TileCoord tc = decode_tile2(meta, n_images, t);
-            const bool diag = tc.ti == tc.tj;
+            const Tile2 e = nxt;
+            nxt = load_tile2(tab, t + n_clusters, n_tiles);
+            const int ncols = e.info & 511;
+            const bool share = (e.info & kT2Share) != 0;
+            const uint32_t idesc = umma_idesc_tf32(2 * T2_BM, ncols);
             const int acc = tl % T2_ACC;
             const uint32_t acc_ph = (uint32_t)(tl / T2_ACC) & 1u;
             mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T2_BN);
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % TC_STAGES;
-                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-                mbar_wait(full_bar(s), ph);
+                if (DIRECT) mbar_wait_cluster(conv_bar(it % T2_LO_STAGES), (uint32_t)(it / T2_LO_STAGES) & 1u);   // raw tiles landed, lo tiles derived, both CTAs
+                else mbar_wait(full_bar(it % TC_STAGES), (uint32_t)(it / TC_STAGES) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-                const uint64_t a_hi = umma_desc_sw128(st + 0 * TC_TILE_BYTES), a_lo = umma_desc_sw128(st + 1 * TC_TILE_BYTES);
-                const uint64_t b_hi = diag ? a_hi : umma_desc_sw128(st + 2 * TC_TILE_BYTES);
-                const uint64_t b_lo = diag ? a_lo : umma_desc_sw128(st + 3 * TC_TILE_BYTES);
+                const uint32_t hi = hi_tiles(it), lo = lo_tiles(it);
+                const uint64_t a_hi = umma_desc_sw128(hi), a_lo = umma_desc_sw128(lo);
+                const uint64_t b_hi = share ? a_hi : umma_desc_sw128(hi + TC_TILE_BYTES);
+                const uint64_t b_lo = share ? a_lo : umma_desc_sw128(lo + TC_TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
                     const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
@@ -458,25 +579,63 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                     umma_tf32_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
                     umma_tf32_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
                 }
-                umma_commit_2sm(empty_bar(s));                      // frees the stage in both CTAs
+                umma_commit_2sm(empty_bar(it % NFULL));             // frees the (raw) stage in both CTAs
+                if (DIRECT) umma_commit_2sm(lo_empty_bar(it % T2_LO_STAGES));
             }
             umma_commit_2sm(tmem_full_bar(acc));                    // both epilogues may read their half
         }
-    } else if (warp >= 2) {
+    } else if (DIRECT && warp >= T2_THREADS / 32) {
+        // ===== lo converter (both CTAs, 4 warps): lo = tf32(x - trunc_tf32(x)) for every raw tile =====
+        const int ct = threadIdx.x - T2_THREADS;                     // 0..127
+        int it = 0;
+        Tile2 nxt = load_tile2(tab, cluster_id, n_tiles);
+        for (int t = cluster_id; t < n_tiles; t += n_clusters) {
+            const bool share = (nxt.info & kT2Share) != 0;
+            nxt = load_tile2(tab, t + n_clusters, n_tiles);
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                mbar_wait(full_bar(it % T2_RAW_STAGES), (uint32_t)(it / T2_RAW_STAGES) & 1u);          // this CTA's raw tiles have landed
+                mbar_wait(lo_empty_bar(it % T2_LO_STAGES), ((uint32_t)(it / T2_LO_STAGES) & 1u) ^ 1u); // the MMAs two k-blocks back are done with the lo stage
+                // plain shared-memory pointers: the compiler batches the eight loads of a tile ahead of the math and the stores
+                const uint4* __restrict__ src = reinterpret_cast<const uint4*>(smem_raw + (hi_tiles(it) - smem_u32(smem_raw))) + ct;
+                uint4* __restrict__ dst = reinterpret_cast<uint4*>(smem_raw + (lo_tiles(it) - smem_u32(smem_raw))) + ct;
+                constexpr int QUADS = TC_TILE_BYTES / (16 * 32 * T2_CONV_WARPS);      // 8 float4 per thread and tile
+#pragma unroll 1
+                for (int tile = 0; tile < (share ? 1 : 2); ++tile) {
+                    uint4 x[QUADS];
+#pragma unroll
+                    for (int j = 0; j < QUADS; ++j) x[j] = src[(tile * QUADS + j) * (32 * T2_CONV_WARPS)];
+#pragma unroll
+                    for (int j = 0; j < QUADS; ++j) {
+                        uint4 l;
+                        l.x = __float_as_uint(to_tf32(__uint_as_float(x[j].x) - __uint_as_float(x[j].x & 0xFFFFE000u)));
+                        l.y = __float_as_uint(to_tf32(__uint_as_float(x[j].y) - __uint_as_float(x[j].y & 0xFFFFE000u)));
+                        l.z = __float_as_uint(to_tf32(__uint_as_float(x[j].z) - __uint_as_float(x[j].z & 0xFFFFE000u)));
+                        l.w = __float_as_uint(to_tf32(__uint_as_float(x[j].w) - __uint_as_float(x[j].w & 0xFFFFE000u)));
+                        dst[(tile * QUADS + j) * (32 * T2_CONV_WARPS)] = l;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor cores
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(conv_bar(it % T2_LO_STAGES) & kPeerMask);
+            }
+        }
+    } else if (warp >= 2 && warp < T2_THREADS / 32) {
         // ===== epilogue (both CTAs): rows [256 ti + 128 rank, +128) x 256 columns of the tile =====
         // 8 warps: TMEM lane quadrant q = warp & 3 (rows), column half hsel (4 chunks of 32 columns each)
         const int q = warp & 3, hsel = (warp - 2) >> 2;
+        const uint32_t stg = staging_base + (uint32_t)(warp - 2) * 4096u;      // this warp's 32x32 transpose buffer
         int tl = 0;
+        Tile2 nxt = load_tile2(tab, cluster_id, n_tiles);
         for (int t = cluster_id; t < n_tiles; t += n_clusters, ++tl) {
-            const TileCoord tc = decode_tile2(meta, n_images, t);
-            const LostImageDev im = meta[tc.img];
+            const Tile2 im = nxt;
+            nxt = load_tile2(tab, t + n_clusters, n_tiles);
             const int acc = tl % T2_ACC;
             const uint32_t acc_ph = (uint32_t)(tl / T2_ACC) & 1u;
             mbar_wait(tmem_full_bar(acc), acc_ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row0 = tc.ti * T2_TILE + (int)rank * T2_BM, col0 = tc.tj * T2_TILE;
-            const bool mirror = tc.ti != tc.tj;                 // a diagonal 256-tile holds both triangles already
-            const int gi = row0 + q * 32 + lane;
+            const int row0 = (im.info >> 12 & 15) * T2_TILE + (int)rank * T2_BM, col0 = (im.info >> 16 & 15) * T2_TILE;
+            const bool mirror = (im.info & kT2Diag) == 0;       // a diagonal 256-tile holds both triangles already
+            const int gi0 = row0 + q * 32, gi = gi0 + lane;
             float* __restrict__ A = A_base + im.a_off;
             int* __restrict__ deg = degree_base + im.out_off;
             const bool vec_store = (im.n & 3) == 0 && (((uintptr_t)A) & 15u) == 0;
@@ -489,6 +648,29 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_BN + ch * 32), r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (vec_store) {
+                    // row-major copy through shared memory: lane i parks its row (8 float4, 16-B groups XOR-swizzled by
+                    // i & 7: conflict-free both ways), then lane l picks up columns 4 (l & 7) .. +3 of rows 4 p + (l >> 3)
+                    // and one store instruction covers four complete 128-B lines of A
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(stg + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) << 4)),
+                                     "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]), "r"(r[4 * g + 3]) : "memory");
+                    __syncwarp();
+                    const int cg = lane & 7, rsub = lane >> 3;
+                    const bool col_in = gj0 + 4 * cg < im.n;         // n % 4 == 0: a group of four columns is in or out as a whole
+#pragma unroll
+                    for (int pth = 0; pth < 8; ++pth) {
+                        const int rr = 4 * pth + rsub;
+                        uint32_t y0, y1, y2, y3;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(y0), "=r"(y1), "=r"(y2), "=r"(y3)
+                                     : "r"(stg + (uint32_t)rr * 128u + (uint32_t)((cg ^ (rr & 7)) << 4)) : "memory");
+                        if (col_in && gi0 + rr < im.n)
+                            *reinterpret_cast<float4*>(A + (long long)(gi0 + rr) * im.n + gj0 + 4 * cg) =
+                                make_float4(__uint_as_float(y0), __uint_as_float(y1), __uint_as_float(y2), __uint_as_float(y3));
+                    }
+                    __syncwarp();                                    // the buffer is rewritten by the next chunk
+                }
                 if (interior) {
                     int colcnt = 0;
                     float* __restrict__ col = A + (long long)gj0 * im.n + gi;
@@ -502,11 +684,6 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                         col[(long long)c * im.n] = v;            // transposed: lanes = consecutive addresses
                     }
                     if (colcnt) atomicAdd(deg + gj0 + lane, colcnt);
-                    float* dst = A + (long long)gi * im.n + gj0;
-#pragma unroll
-                    for (int c = 0; c < 32; c += 4)
-                        *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]),
-                                                                          __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
                     continue;
                 }
                 int colcnt = 0;
@@ -524,22 +701,15 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                     }
                 }
                 if (mirror && colcnt && gj0 + lane < im.n) atomicAdd(deg + gj0 + lane, colcnt);
-                if (gi < im.n) {
+                if (!vec_store && gi < im.n) {          // unaligned A: scalar row stores
                     float* dst = A + (long long)gi * im.n + gj0;
-                    if (vec_store && gj0 + 31 < im.n) {
 #pragma unroll
-                        for (int c = 0; c < 32; c += 4)
-                            *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]),
-                                                                              __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) if (gj0 + c < im.n) dst[c] = __uint_as_float(r[c]);
-                    }
+                    for (int c = 0; c < 32; ++c) if (gj0 + c < im.n) dst[c] = __uint_as_float(r[c]);
                 }
             }
             if (gi < im.n && cnt) atomicAdd(deg + gi, cnt);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive_cluster(tmem_empty_bar(acc) & kPeerMask);  // 2 x 256 arrivals on the leader's barrier
+            mbar_arrive_cluster_relaxed(tmem_empty_bar(acc) & kPeerMask);  // 2 x 256 arrivals on the leader's barrier
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -566,29 +736,77 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap* map, float* base, long long rows, int d_pad) {
+static int make_map(CUtensorMap* map, const float* base, long long rows, int cols, long long row_stride) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("lost_batched: cuTensorMapEncodeTiled is not available from the driver"); return B200P_ECUDA; }
-    cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)d_pad * sizeof(float)};
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("lost_batched: cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")"); return B200P_ECUDA; }
     return B200P_OK;
 }
 
-size_t lost_tc_workspace_bytes(long long total_patches, int d) {
+// upper bound of the 256x256 tile records of a batch: an image of n <= 4096 patches has T = ceil(n / 256) <= 16
+// tile rows and T (T + 1) / 2 <= 8.5 T tiles
+static size_t tile_table_bytes(int n_images, long long total_patches) {
+    return ((size_t)(9 * (total_patches / T2_TILE + n_images)) + 16) * sizeof(Tile2);
+}
+
+size_t lost_tc_workspace_bytes(int n_images, long long total_patches, int d) {
     const int d_pad = (d + TC_BK - 1) / TC_BK * TC_BK;
-    return 2 * ((size_t)total_patches * d_pad * sizeof(float) + 1024);
+    return 2 * ((size_t)total_patches * d_pad * sizeof(float) + 1024) + tile_table_bytes(n_images, total_patches) + 256;
+}
+
+// The caller's features can be read in place by one tensor map when they form a 2-D array with a uniform,
+// 16-byte-granular row stride in which every image starts on a row boundary.
+bool lost_tc_direct_ok(const float* d_feats, long long row_stride, int d, const b200p_lost_image_t* h_meta, int n_images) {
+    if ((((uintptr_t)d_feats) & 15u) != 0 || (row_stride & 3) != 0 || d < TC_BK || row_stride < d) return false;
+    for (int b = 0; b < n_images; ++b) {
+        if (h_meta[b].feat_offset % row_stride != 0) return false;
+        if (h_meta[b].feat_offset / row_stride + (long long)h_meta[b].dim0 * h_meta[b].dim1 >= (1ll << 31)) return false;
+    }
+    return true;
 }
 
 int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
                  const std::vector<LostImageDev>& meta, long long total_patches, int n_max, float* A_base,
-                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st, bool pair_mode) {
+                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st, int mode) {
     const int n_images = (int)meta.size();
     const int d_pad = (d + TC_BK - 1) / TC_BK * TC_BK;
+    const LostImageDev& last = meta.back();
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    alignas(64) CUtensorMap tm_hi, tm_lo;
+    const int T2 = (last.n + T2_TILE - 1) / T2_TILE;
+    const int n_tiles2 = last.pair2_base + T2 * (T2 + 1) / 2;
+    const int grid2 = 2 * (n_tiles2 < sms / 2 ? n_tiles2 : sms / 2);       // one cluster (CTA pair) per two SMs
+    // workspace: [tile table | hi | lo]
+    const size_t tab_bytes = (tile_table_bytes(n_images, total_patches) + 255) / 256 * 256;
+    Tile2* tab = (Tile2*)(((uintptr_t)ws + 15) & ~(uintptr_t)15);
+    if (mode != LOST_TC_SINGLE) {
+        if (ws_bytes < tab_bytes || (size_t)n_tiles2 * sizeof(Tile2) + 16 > tab_bytes) { set_error("lost_batched: tensor-core workspace too small"); return B200P_EINVAL; }
+        k_lost_tile_table<<<(n_tiles2 + 127) / 128, 128, 0, st>>>(d_meta, n_images, n_tiles2, tab);
+        B200P_LAUNCH_CHECK("k_lost_tile_table");
+    }
+    ws = (char*)ws + tab_bytes; ws_bytes -= ws_bytes < tab_bytes ? ws_bytes : tab_bytes;
+    if (mode == LOST_TC_PAIR_DIRECT) {
+        // meta[].row_base holds each image's first row in the caller's array (set by the caller of this function)
+        long long rows = 0;
+        for (const LostImageDev& m : meta) if ((long long)m.row_base + m.n > rows) rows = (long long)m.row_base + m.n;
+        int rc = make_map(&tm_hi, d_feats, rows, d, row_stride); if (rc) return rc;
+        static bool attr3_set = false;
+        if (!attr3_set) {
+            B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
+            attr3_set = true;
+        }
+        k_lost_gram_tc2<true><<<grid2, T2_THREADS_DIRECT, T2_SMEM_BYTES, st>>>(tm_hi, tm_hi, tab, n_tiles2, A_base, d_degree, 0.0f, d_pad);
+        B200P_LAUNCH_CHECK("k_lost_gram_tc2<direct>");
+        return B200P_OK;
+    }
     const size_t arr = ((size_t)total_patches * d_pad * sizeof(float) + 1023) / 1024 * 1024;
     if (ws_bytes < 2 * arr) { set_error("lost_batched: tensor-core workspace too small"); return B200P_EINVAL; }
     float* hi = (float*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
@@ -600,33 +818,25 @@ int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostIm
     dim3 sgrid((unsigned)((quads + 255) / 256), (unsigned)n_images);
     k_lost_split_tf32<<<sgrid, 256, 0, st>>>(d_feats, row_stride, d, d_pad, d_meta, hi, lo, vec_ok);
     B200P_LAUNCH_CHECK("k_lost_split_tf32");
-    alignas(64) CUtensorMap tm_hi, tm_lo;
-    int rc = make_map(&tm_hi, hi, total_patches, d_pad); if (rc) return rc;
-    rc = make_map(&tm_lo, lo, total_patches, d_pad); if (rc) return rc;
+    int rc = make_map(&tm_hi, hi, total_patches, d_pad, d_pad); if (rc) return rc;
+    rc = make_map(&tm_lo, lo, total_patches, d_pad, d_pad); if (rc) return rc;
+    if (mode == LOST_TC_PAIR) {
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
+            attr2_set = true;
+        }
+        k_lost_gram_tc2<false><<<grid2, T2_THREADS, T2_SMEM_BYTES, st>>>(tm_hi, tm_lo, tab, n_tiles2, A_base, d_degree, 0.0f, d_pad);
+        B200P_LAUNCH_CHECK("k_lost_gram_tc2");
+        return B200P_OK;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
         attr_set = true;
     }
-    const LostImageDev& last = meta.back();
     const int n_tiles = last.pair_base + last.tiles * (last.tiles + 1) / 2;
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = n_tiles < sms ? n_tiles : sms;                  // persistent: one CTA per SM
-    if (pair_mode) {
-        static bool attr2_set = false;
-        if (!attr2_set) {
-            B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-            attr2_set = true;
-        }
-        const int T2 = (last.n + T2_TILE - 1) / T2_TILE;
-        const int n_tiles2 = last.pair2_base + T2 * (T2 + 1) / 2;
-        int grid2 = 2 * (n_tiles2 < sms / 2 ? n_tiles2 : sms / 2);           // one cluster (CTA pair) per two SMs
-        k_lost_gram_tc2<<<grid2, T2_THREADS, TC_SMEM_BYTES, st>>>(tm_hi, tm_lo, d_meta, n_images, n_tiles2, A_base, d_degree, 0.0f, d_pad);
-        B200P_LAUNCH_CHECK("k_lost_gram_tc2");
-        return B200P_OK;
-    }
     k_lost_gram_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_hi, tm_lo, d_meta, n_images, n_tiles, A_base, d_degree, 0.0f, d_pad);
     B200P_LAUNCH_CHECK("k_lost_gram_tc");
     return B200P_OK;

@@ -77,7 +77,10 @@ def _meta(feat_off, a_off, out_off, dims, scales, init_image_size):
     return m
 
 
-DEFAULT_GRAM_IMPL = L.LOST_GRAM_TC      # TMA + tcgen05 3xTF32; L.LOST_GRAM_FFMA = fp32 CUDA cores
+# TMA + tcgen05 3xTF32 on CTA pairs, features read in place (falls back to pre-split operands when the
+# layout is not TMA-addressable); L.LOST_GRAM_TC2 / L.LOST_GRAM_TC = pre-split pairs / single CTAs,
+# L.LOST_GRAM_FFMA = fp32 CUDA cores
+DEFAULT_GRAM_IMPL = L.LOST_GRAM_TC2D
 
 
 def lost(feats, dims, scales, init_image_size, k_patches=100, gram_impl=None):

@@ -22,13 +22,14 @@ DEV = torch.device("cuda:0")
 EPS = float(np.finfo(np.float32).eps)
 
 
-@pytest.fixture(params=["tc", "tc2", "ffma"], autouse=True)
+@pytest.fixture(params=["tc", "tc2", "tc2d", "ffma"], autouse=True)
 def gram_impl(request):
     """Every test runs with all Gram implementations: TMA + tcgen05 3xTF32 on single CTAs, the same on CTA
-    pairs (cta_group::2), and fp32 CUDA cores."""
+    pairs (cta_group::2) from pre-split hi/lo arrays, CTA pairs reading the features in place with the lo
+    tiles derived in shared memory (the default), and fp32 CUDA cores."""
     from pruning_for_vision_representation_b200 import _lib as L
     old = OD.DEFAULT_GRAM_IMPL
-    OD.DEFAULT_GRAM_IMPL = {"tc": L.LOST_GRAM_TC, "tc2": L.LOST_GRAM_TC2, "ffma": L.LOST_GRAM_FFMA}[request.param]
+    OD.DEFAULT_GRAM_IMPL = {"tc": L.LOST_GRAM_TC, "tc2": L.LOST_GRAM_TC2, "tc2d": L.LOST_GRAM_TC2D, "ffma": L.LOST_GRAM_FFMA}[request.param]
     yield request.param
     OD.DEFAULT_GRAM_IMPL = old
 
