@@ -60,7 +60,7 @@ def parse():
                     help="N > 1: replicas = every rank builds the mask of its own model replica from its own 8 gradient "
                          "sets (independent units, no collective, weak scaling); sharded = ONE mask build split over the "
                          "ranks (batches shard the scores, parameters shard the select; NCCL exchange; strong scaling)")
-    ap.add_argument("--score-mode", default="fused", choices=["fused", "streaming"],
+    ap.add_argument("--score-mode", default="sweep", choices=["sweep", "fused", "streaming"],
                     help="fused: one pass over all resident gradient sets (4*(B+2) B/param); "
                          "streaming: one accumulate launch per mini-batch (16 B/param/batch)")
     ap.add_argument("--no-clocks", action="store_true", help="skip the clock sampler and its keep-busy loops (ncu runs)")
@@ -281,9 +281,15 @@ def run_b200(args):
     launches = [0]
     score_events = []
 
-    fused = args.score_mode == "fused"
+    sweep = args.score_mode == "sweep" and not sharded      # score pass + bracket sweep in one kernel (b200p_snip_mask_build)
+    fused = args.score_mode == "fused" or (args.score_mode == "sweep" and sharded)
+    if sweep:
+        plan.time_sweep(True)
 
     def step(record):
+        if sweep:
+            plan.snip_mask_build(g_tables, k, mask); launches[0] += 4      # sample, score+sweep, finish, emit
+            return
         if fused:
             if record:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -358,13 +364,19 @@ def run_b200(args):
 
     acc_ms = [a.elapsed_time(b) for is_acc, a, b in score_events if is_acc]
     kernel_ms = sum(acc_ms) / max(1, len(acc_ms))
+    n_timed = len(acc_ms)
+    if sweep:
+        kernel_ms, n_timed = plan.kernel_time_ms()       # CUDA events recorded by the library around k_snip_score_sweep, same stream
     peak, peak_src = peaks()
     nb_local = len(my_batches)
     # algorithmic bytes per launch of the dominant kernel: fused pass reads w and nb_local
     # gradient sets and writes the score once; the streaming pass reads w, g, acc and writes acc
-    kernel_bytes = n_total * (4.0 * (nb_local + 2) if fused else SCORE_BYTES_PER_PARAM)
-    kernel_name = (f"k_score_multi<ACCUMULATE=0,B={nb_local}>" if fused else "k_score_accumulate<ACCUMULATE=1,VEC=1>")
-    step_bytes_per_param = (4.0 * (N_BATCHES + 2) if fused else 16.0 * N_BATCHES) + 8.125
+    kernel_bytes = n_total * (4.0 * (nb_local + 2) + 0.125 if sweep else 4.0 * (nb_local + 2) if fused else SCORE_BYTES_PER_PARAM)
+    kernel_name = (f"k_snip_score_sweep<ACCUMULATE=0,B={nb_local}>" if sweep else
+                   f"k_score_multi<ACCUMULATE=0,B={nb_local}>" if fused else "k_score_accumulate<ACCUMULATE=1,VEC=1>")
+    # whole step: the fused score+sweep never re-reads the scores (no 4 B select read, no 4 B emit read)
+    step_bytes_per_param = (4.0 * (N_BATCHES + 2) + 0.125 if sweep else
+                            (4.0 * (N_BATCHES + 2) if fused else 16.0 * N_BATCHES) + 8.125)
     achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9
     ms_per_step = elapsed_ms / args.steps
     units = 1 if sharded else world                      # mask builds completed per step over all ranks
@@ -422,7 +434,10 @@ def run_b200(args):
             "config": {"workload": f"{MODEL} SNIP mask build, target sparsity {TARGET_SPARSITY}, {N_BATCHES} mini-batches "
                                    f"of synthetic gradients (1e-3*randn) accumulated, N={n_total} params in {len(numels)} tensors, "
                                    f"k={k}", "weights": wsrc,
-                       "score_mode": ("fused: all resident gradient sets folded in one pass, bit-identical to per-batch accumulation"
+                       "score_mode": ("sweep: one pass folds all resident gradient sets into the score (bit-identical to per-batch "
+                                      "accumulation) and classifies it against the sampled bracket; the scores are never read back"
+                                      if sweep else
+                                      "fused: all resident gradient sets folded in one pass, bit-identical to per-batch accumulation"
                                       if fused else "streaming: one accumulate launch per mini-batch"),
                        "l2": f"inputs larger than L2: {N_BATCHES // world} gradient sets x {n_total * 4 >> 20} MiB streamed per step",
                        "parallelism": ("1 GPU" if world == 1 else
@@ -431,11 +446,11 @@ def run_b200(args):
                                        else f"{world} independent mask builds, one model replica with its own 8 gradient sets per "
                                             "rank, no data-path collective (weak scaling); --dist-mode sharded runs the NCCL path")},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(fused),
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_snip_score_sweep" if sweep else "k_score_multi" if fused else "k_score_accumulate"),
                          "peak_source": peak_src, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": kernel_bytes,
                          "algorithmic_bytes_per_param": kernel_bytes / n_total,
-                         "launches_timed": len(acc_ms),
+                         "launches_timed": n_timed,
                          "step_algorithmic_bytes_per_param": step_bytes_per_param,
                          "step_algorithmic_GBps": (n_total * step_bytes_per_param / (ms_per_step * 1e-3) / 1e9
                                                    if world == 1 else None)},
@@ -547,13 +562,13 @@ def lost_leg(args, dev, world, rank, dist):
     return leg
 
 
-def ncu_traffic(fused=True):
+def ncu_traffic(kernel):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/roofline_traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get("k_score_multi_traffic_bytes" if fused else "k_score_accumulate_traffic_bytes")
+            return json.load(f).get(kernel + "_traffic_bytes")
     except Exception:
         return None
 

@@ -116,7 +116,12 @@ int  b200p_plan_bind_table(b200p_plan* plan, int slot, const b200p_ptrtable* tab
 #define B200P_OPT_SELECT_IMPL   1
 #define B200P_SELECT_SAMPLED    0   /* default: 1/64 sample -> bracket -> one full pass -> candidates; exact fallback on a miss */
 #define B200P_SELECT_EXACT      1   /* 3-pass MSD radix select over the full data */
+#define B200P_OPT_TIME_SWEEP    2   /* value 1: record CUDA events around every fused score+sweep kernel of
+                                       b200p_snip_mask_build / b200p_snip_score_select (measurement only) */
 int  b200p_plan_set_option(b200p_plan* plan, int option, int64_t value);
+/* Mean duration (ms) and number of the fused score+sweep launches timed since the option was set or this was last
+ * called; synchronises on the last recorded event.  *out_launches may be 0 (then *out_ms = 0). */
+int  b200p_plan_kernel_time_ms(b200p_plan* plan, double* out_ms, int64_t* out_launches);
 /* device address of the 4096-bin uint64 histogram and of the select state, so that the
  * host side can run NCCL collectives on them between stages */
 void* b200p_plan_hist_ptr(b200p_plan* plan);
@@ -182,6 +187,20 @@ int  b200p_emit_masks(b200p_plan* plan, int key_source, int mode, int force,
  * d_new_mask and the emit only patches the ~2 % of keys near the threshold instead of re-reading all keys. */
 int  b200p_mask_build(b200p_plan* plan, int key_source, const uint32_t* d_old_mask, uint64_t k, int mode,
                       uint32_t* d_new_mask, void* stream);
+
+/* SNIP score + select + emit in one call (train.py:282-317 with the multi-batch score of SURVEY 8c):
+ * SCORE = sum over the n_sets gradient tables of |W * G_b| (written to the SCORE slot, bit-identical to
+ * b200p_score_accumulate_multi), threshold = k-th smallest score, mask = score > threshold (strict).  Same
+ * result as b200p_score_accumulate_multi followed by b200p_mask_build(KEY_SCORE, NULL, k, SNIP_STRICT), but the
+ * pass that writes the scores also classifies them against a bracket obtained from a 1/64 sample, so the scores
+ * are never read back (a bracket miss runs the exact select over the SCORE slot).  W and SCORE must be bound. */
+int  b200p_snip_mask_build(b200p_plan* plan, const b200p_ptrtable* const* g_tables, int n_sets, uint64_t k,
+                           uint32_t* d_new_mask, void* stream);
+/* The score + select half of it (= b200p_score_accumulate_multi + b200p_select_kth(KEY_SCORE, NULL, k, SNIP_STRICT)):
+ * the caller issues its own b200p_emit_masks afterwards (e.g. with an old mask to AND with, or fp32 mask outputs).
+ * d_prov_target: nullable, where the provisional mask of the sweep goes (the d_new_mask of a following plain emit). */
+int  b200p_snip_score_select(b200p_plan* plan, const b200p_ptrtable* const* g_tables, int n_sets, uint64_t k,
+                             uint32_t* d_prov_target, void* stream);
 
 /* ---- K5: sparsity (train.py:347-369) ------------------------------------------------ */
 /* d_out[0] = # elements with (mask bit == 0 or W == 0)  (d_mask nullable -> counts W == 0),

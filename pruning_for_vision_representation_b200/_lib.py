@@ -20,7 +20,7 @@ KEY_ABS_W, KEY_SCORE = 0, 1
 EMIT_MASKF, EMIT_WEFF = 1, 2
 SGD_NESTEROV, SGD_FIRST_STEP, SGD_EMIT_WEFF, SGD_EMIT_WEFF16 = 1, 2, 4, 8
 LOST_GRAM_FFMA, LOST_GRAM_TC, LOST_GRAM_TC2, LOST_GRAM_TC2D = 0, 1, 2, 3
-OPT_SELECT_IMPL = 1
+OPT_SELECT_IMPL, OPT_TIME_SWEEP = 1, 2
 SELECT_SAMPLED, SELECT_EXACT = 0, 1
 
 
@@ -71,6 +71,7 @@ SIGNATURES = {
     "b200p_ptrtable_destroy": (_I, [_P]),
     "b200p_plan_bind_table": (_I, [_P, _I, _P]),
     "b200p_plan_set_option": (_I, [_P, _I, _I64]),
+    "b200p_plan_kernel_time_ms": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),
     "b200p_plan_hist_ptr": (_P, [_P]),
     "b200p_plan_state_ptr": (_P, [_P]),
     "b200p_score_accumulate": (_I, [_P, _I, _I64, _I64, _P]),
@@ -87,6 +88,8 @@ SIGNATURES = {
     "b200p_select_result": (_I, [_P, ctypes.POINTER(SelectResult), _P]),
     "b200p_emit_masks": (_I, [_P, _I, _I, _I, _F, _P, _P, _I, _I64, _I64, _P]),
     "b200p_mask_build": (_I, [_P, _I, _P, _U64, _I, _P, _P]),
+    "b200p_snip_mask_build": (_I, [_P, ctypes.POINTER(_P), _I, _U64, _P, _P]),
+    "b200p_snip_score_select": (_I, [_P, ctypes.POINTER(_P), _I, _U64, _P, _P]),
     "b200p_count_zeros": (_I, [_P, _P, _P, _I, _P]),
     "b200p_mask_pack_from_f32": (_I, [_P, _P, _P]),
     "b200p_mask_unpack_to_f32": (_I, [_P, _P, _P]),

@@ -54,6 +54,10 @@ __device__ __forceinline__ T* chunk_ptr(ChunkTab tab, int64_t c) {
     return reinterpret_cast<T*>(__ldg(reinterpret_cast<const unsigned long long*>(tab) + c));
 }
 
+// up to 8 gradient sets (one per-chunk pointer table each) folded by one score launch
+constexpr int kMaxSets = 8;
+struct GradTabs { ChunkTab t[kMaxSets]; };
+
 // 128-bit streaming loads / stores.  Read-only streams go through the non-coherent path
 // without allocating in L1; read-modify-write streams use plain (coherent) accesses.
 __device__ __forceinline__ float4 ld_nc_f4(const float* p) {
@@ -162,6 +166,13 @@ struct b200p_plan {
     cudaStream_t arena_streams[2] = {nullptr, nullptr};
     cudaEvent_t  arena_events[4] = {nullptr, nullptr, nullptr, nullptr};
 
+    // B200P_OPT_TIME_SWEEP: CUDA events around every k_snip_score_sweep launch (ring of pairs), read back with
+    // b200p_plan_kernel_time_ms — how bench.py times the dominant kernel of the fused sequence on its own stream
+    bool time_sweep = false;
+    std::vector<cudaEvent_t> tev;           // 2 * kTimedPairs events, created on first use
+    int tev_head = 0, tev_pending = 0;      // next pair to record / recorded pairs not yet folded into the sum
+    double tev_sum_ms = 0.0; long long tev_n = 0;
+
     template <typename T = void> b200p::ChunkTab tab(int slot) const { return (b200p::ChunkTab)d_tab[slot]; }
     int grid_for(int64_t chunks, int ctas_per_sm) const {
         int64_t g = (int64_t)num_sms * ctas_per_sm;
@@ -179,6 +190,7 @@ struct b200p_ptrtable {
 
 namespace b200p {
 void set_error(const std::string& msg);
+int  plan_time_mark(b200p_plan* p, int which, cudaStream_t st);
 int  cuda_fail(cudaError_t e, const char* what);
 }  // namespace b200p
 

@@ -107,6 +107,7 @@ extern "C" int b200p_plan_destroy(b200p_plan* p) {
     cudaFree(p->arena_mask); cudaFree(p->arena_old_mask);
     for (int i = 0; i < 2; ++i) if (p->arena_streams[i]) cudaStreamDestroy(p->arena_streams[i]);
     for (int i = 0; i < 4; ++i) if (p->arena_events[i]) cudaEventDestroy(p->arena_events[i]);
+    for (auto& e : p->tev) cudaEventDestroy(e);
     cudaGetLastError();
     delete p;
     return B200P_OK;
@@ -134,8 +135,46 @@ extern "C" int b200p_plan_set_option(b200p_plan* p, int option, int64_t value) {
         p->select_impl = (int)value;
         return B200P_OK;
     }
+    if (option == B200P_OPT_TIME_SWEEP) {
+        p->time_sweep = value != 0;
+        return B200P_OK;
+    }
     set_error("plan_set_option: unknown option");
     return B200P_EINVAL;
+}
+
+namespace b200p {
+constexpr int kTimedPairs = 64;
+static int fold_oldest_pair(b200p_plan* p) {
+    const int idx = ((p->tev_head - p->tev_pending) % kTimedPairs + kTimedPairs) % kTimedPairs;
+    B200P_CUDA(cudaEventSynchronize(p->tev[2 * idx + 1]));
+    float ms = 0.f;
+    B200P_CUDA(cudaEventElapsedTime(&ms, p->tev[2 * idx], p->tev[2 * idx + 1]));
+    p->tev_sum_ms += ms; p->tev_n += 1; p->tev_pending -= 1;
+    return B200P_OK;
+}
+// called by the fused SNIP sequence right before (which = 0) and after (which = 1) the sweep launch
+int plan_time_mark(b200p_plan* p, int which, cudaStream_t st) {
+    if (!p->time_sweep) return B200P_OK;
+    if (p->tev.empty()) {
+        p->tev.resize(2 * kTimedPairs);
+        for (auto& e : p->tev) B200P_CUDA(cudaEventCreate(&e));
+    }
+    if (which == 0 && p->tev_pending == kTimedPairs) { int rc = fold_oldest_pair(p); if (rc) return rc; }
+    B200P_CUDA(cudaEventRecord(p->tev[2 * p->tev_head + which], st));
+    if (which == 1) { p->tev_head = (p->tev_head + 1) % kTimedPairs; p->tev_pending += 1; }
+    return B200P_OK;
+}
+}  // namespace b200p
+
+extern "C" int b200p_plan_kernel_time_ms(b200p_plan* p, double* out_ms, int64_t* out_launches) {
+    B200P_REQUIRE(p != nullptr && out_ms != nullptr && out_launches != nullptr, B200P_EINVAL, "plan_kernel_time_ms: null argument");
+    B200P_CUDA(cudaSetDevice(p->device));
+    while (p->tev_pending > 0) { int rc = fold_oldest_pair(p); if (rc) return rc; }
+    *out_launches = p->tev_n;
+    *out_ms = p->tev_n ? p->tev_sum_ms / (double)p->tev_n : 0.0;
+    p->tev_sum_ms = 0.0; p->tev_n = 0;
+    return B200P_OK;
 }
 extern "C" void* b200p_plan_hist_ptr(b200p_plan* p) { return p ? (void*)p->d_hist : nullptr; }
 extern "C" void* b200p_plan_state_ptr(b200p_plan* p) { return p ? (void*)p->d_state : nullptr; }

@@ -66,9 +66,6 @@ k_score_accumulate(const int32_t* __restrict__ chunk_n, ChunkTab w_tab, ChunkTab
 // bit-identical to B successive k_score_accumulate launches but reads W once and touches SCORE once:
 // 4*(B+2) B/param (+4 when accumulating) instead of 16*B.  The B200's 180 GB make it free to keep the
 // gradient sets of all SNIP mini-batches resident (102 MB each for ResNet-50) and fold them in one pass.
-constexpr int kMaxSets = 8;
-struct GradTabs { ChunkTab t[kMaxSets]; };
-
 template <bool ACCUMULATE, int B>
 __global__ void __launch_bounds__(kThreads)
 k_score_multi(const int32_t* __restrict__ chunk_n, ChunkTab w_tab, GradTabs g_tabs, ChunkTab s_tab,

@@ -258,14 +258,19 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
     // bits of (k - base) and (k - base - span) into two 16-bit masks (first key ends up in bit 15).
     // k >= base  =>  k - base < 2^31, so the sign of (k - base - span) is the unsigned compare; keys
     // below `base` are removed from the inside-mask afterwards.
+    // SNIP_STRICT prunes NaN scores (NaN > thr is false, train.py:316) although they sort last: their provisional bits
+    // must be clear, the patching emit never sees them.  One max per key finds the (rare) threads that hold one.
+    const bool nan_pruned = st->mode == B200P_MODE_SNIP_STRICT;      // the state was initialised by the kernel before this one
     auto do_vec = [&](const float4 (&v)[kVecPerThread], uint32_t alive_rev, uint32_t pos0) {
-        uint32_t lt = 0, in = 0;
+        uint32_t lt = 0, in = 0, mx = 0;
 #pragma unroll
         for (int j = 0; j < kVecPerThread; ++j) {
             const float f[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint32_t d = (__float_as_uint(f[q]) & 0x7FFFFFFFu) - base;
+                const uint32_t key = __float_as_uint(f[q]) & 0x7FFFFFFFu;
+                const uint32_t d = key - base;
+                mx = max(mx, key);
                 lt = __funnelshift_l(d, lt, 1);
                 in = __funnelshift_l(d - span, in, 1);
             }
@@ -275,7 +280,12 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
         if (a.prov) {
             // provisional mask: alive keys at or above the bracket base stay set; the emit only patches the
             // candidates afterwards instead of re-reading every key
-            const uint32_t keep = alive_rev & ~lt;
+            uint32_t keep = alive_rev & ~lt;
+            if (nan_pruned && mx > 0x7F800000u) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if ((__float_as_uint(sel16(v, i)) & 0x7FFFFFFFu) > 0x7F800000u) keep &= ~(1u << (15 - i));
+            }
             uint32_t* pw = a.prov + (size_t)(pos0 >> 12) * kWordsPerChunk;
 #pragma unroll
             for (int j = 0; j < kVecPerThread; ++j) {
@@ -301,7 +311,7 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
             if (alive && mchunk) alive = (__ldg(mchunk + (e >> 5)) >> (e & 31)) & 1u;
             const uint32_t k = alive ? key_of(src[e]) : 0u;
             if (pw) {
-                const uint32_t word = __ballot_sync(0xFFFFFFFFu, alive && k >= base);
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, alive && k >= base && !(nan_pruned && k == kNanKey));
                 if (lane == 0) pw[e >> 5] = word;
             }
             if (alive) {
@@ -624,6 +634,7 @@ struct SampleArgs {
     int vec_ok;
     unsigned long long k, n_total;
     uint32_t mode;
+    uint32_t sigmas;         // bracket half-width in standard deviations of the sample rank (8; 12 for clustered granules)
 };
 
 // exclusive prefix of this thread's 16 bins over the CTA (kScanThreads threads) and the grand total
@@ -662,6 +673,48 @@ __device__ __forceinline__ void clear_hist(unsigned long long* hist) {
 #pragma unroll
     for (int i = 0; i < kBinsPerThread; ++i) hist[threadIdx.x * kBinsPerThread + i] = 0ull;
     if (threadIdx.x < kHistExtra) hist[kHistBins + threadIdx.x] = 0ull;
+}
+
+// last CTA of a sample kernel: bracket of 1..8 buckets around the sample rank of k
+__device__ __forceinline__ void sample_tail(const SampleArgs& a, unsigned long long* s_warp /*[9]*/, uint32_t* s_bkt /*[2]*/) {
+    SelState* st = a.st;
+    unsigned long long local[kBinsPerThread];
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) local[i] = ((volatile unsigned long long*)a.hist)[threadIdx.x * kBinsPerThread + i];
+    unsigned long long S;
+    unsigned long long running = block_prefix16(local, s_warp, S);
+    const unsigned long long n_alive = a.old_mask ? ((volatile unsigned long long*)a.hist)[kHistBins + 0] : a.n_total;
+    if (threadIdx.x == 0) { s_bkt[0] = 0xFFFFFFFFu; s_bkt[1] = 0xFFFFFFFFu; init_state(st, a.k, a.mode, 1u); st->n_valid = n_alive; }
+    __syncthreads();
+    bool usable = S >= 1024 && a.k >= 1 && a.k <= n_alive;
+    unsigned long long r_lo = 1, r_hi = 1;
+    if (usable) {
+        // sample rank of the population's k-th key: hypergeometric, sigma <= sqrt(S)/2; margin = 8 sigma_max + 2
+        const unsigned long long r = (unsigned long long)(((__uint128_t)a.k * S + n_alive - 1) / n_alive);
+        // 8 sigma of the hypergeometric rank, sigma^2 <= S q (1-q), plus slack for tiny tails
+        const double q = (double)a.k / (double)n_alive;
+        const unsigned long long m = (unsigned long long)ceil((double)a.sigmas * sqrt((double)S * q * (1.0 - q))) + 16ull;
+        r_lo = r > m ? r - m : 1ull;  if (r_lo < 1) r_lo = 1;
+        r_hi = r + m < S ? r + m : S; if (r_hi < 1) r_hi = 1;
+#pragma unroll
+        for (int i = 0; i < kBinsPerThread; ++i) {
+            const unsigned long long v = local[i];
+            if (v != 0 && running < r_lo && r_lo <= running + v) s_bkt[0] = threadIdx.x * kBinsPerThread + i;
+            if (v != 0 && running < r_hi && r_hi <= running + v) s_bkt[1] = threadIdx.x * kBinsPerThread + i;
+            running += v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t lo = s_bkt[0], hi = s_bkt[1];
+        const bool ok = usable && lo != 0xFFFFFFFFu && hi != 0xFFFFFFFFu && hi >= lo && hi - lo < (uint32_t)kMaxBracketBuckets &&
+                        hi < 0xFF0u;      // the sweep does not canonicalise NaN keys: stay below the inf/NaN buckets
+        st->sample_ok = ok ? 1u : 0u;
+        st->miss = ok ? 0u : 1u;
+        st->lo_bucket = lo; st->hi_bucket = hi;
+        *a.ticket = 0u;
+    }
+    clear_hist(a.hist);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -730,45 +783,40 @@ k_select_sample(SampleArgs a) {
     }
     if (threadIdx.x == 0 && s_alive) atomicAdd(a.hist + kHistBins + 0, s_alive);
     if (!last_cta_arrives(a.ticket)) return;
+    sample_tail(a, s_warp, s_bkt);
+}
 
-    // ---- last CTA: bracket from the sample histogram
-    SelState* st = a.st;
+// last CTA of a bracket sweep: verify that rank k is inside the bracket, narrow to a 1024-key window
+__device__ __forceinline__ void bracket_tail(const PassArgs& a, uint32_t base, unsigned long long* s_warp /*[9]*/) {
+    SelState* __restrict__ st = a.st;
     unsigned long long local[kBinsPerThread];
 #pragma unroll
     for (int i = 0; i < kBinsPerThread; ++i) local[i] = ((volatile unsigned long long*)a.hist)[threadIdx.x * kBinsPerThread + i];
-    unsigned long long S;
-    unsigned long long running = block_prefix16(local, s_warp, S);
-    const unsigned long long n_alive = a.old_mask ? ((volatile unsigned long long*)a.hist)[kHistBins + 0] : a.n_total;
-    if (threadIdx.x == 0) { s_bkt[0] = 0xFFFFFFFFu; s_bkt[1] = 0xFFFFFFFFu; init_state(st, a.k, a.mode, 1u); st->n_valid = n_alive; }
+    unsigned long long total_in;
+    unsigned long long running = block_prefix16(local, s_warp, total_in);
+    const unsigned long long n_below = ((volatile unsigned long long*)a.hist)[kHistBins + 1];
+    const unsigned long long k = st->k;
     __syncthreads();
-    bool usable = S >= 1024 && a.k >= 1 && a.k <= n_alive;
-    unsigned long long r_lo = 1, r_hi = 1;
-    if (usable) {
-        // sample rank of the population's k-th key: hypergeometric, sigma <= sqrt(S)/2; margin = 8 sigma_max + 2
-        const unsigned long long r = (unsigned long long)(((__uint128_t)a.k * S + n_alive - 1) / n_alive);
-        // 8 sigma of the hypergeometric rank, sigma^2 <= S q (1-q), plus slack for tiny tails
-        const double q = (double)a.k / (double)n_alive;
-        const unsigned long long m = (unsigned long long)ceil(8.0 * sqrt((double)S * q * (1.0 - q))) + 16ull;
-        r_lo = r > m ? r - m : 1ull;  if (r_lo < 1) r_lo = 1;
-        r_hi = r + m < S ? r + m : S; if (r_hi < 1) r_hi = 1;
+    const bool inside = k > n_below && k <= n_below + total_in && total_in <= (unsigned long long)a.cand_capacity;
+    if (!inside) {
+        if (threadIdx.x == 0) { st->miss = 1u; st->collect = 0u; st->cand_count = 0u; st->prov_ok = 0u; }
+    } else {
+        const unsigned long long kk = k - n_below;
 #pragma unroll
         for (int i = 0; i < kBinsPerThread; ++i) {
             const unsigned long long v = local[i];
-            if (v != 0 && running < r_lo && r_lo <= running + v) s_bkt[0] = threadIdx.x * kBinsPerThread + i;
-            if (v != 0 && running < r_hi && r_hi <= running + v) s_bkt[1] = threadIdx.x * kBinsPerThread + i;
+            if (v != 0 && running < kk && kk <= running + v) {
+                st->n_less = n_below + running;
+                st->k = kk - running;
+                st->bucket_count = v;
+                st->win_lo = base + ((uint32_t)(threadIdx.x * kBinsPerThread + i) << kFineShift);
+                st->collect = 1u;
+                st->passes_full = 1u;
+            }
             running += v;
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t lo = s_bkt[0], hi = s_bkt[1];
-        const bool ok = usable && lo != 0xFFFFFFFFu && hi != 0xFFFFFFFFu && hi >= lo && hi - lo < (uint32_t)kMaxBracketBuckets &&
-                        hi < 0xFF0u;      // the sweep does not canonicalise NaN keys: stay below the inf/NaN buckets
-        st->sample_ok = ok ? 1u : 0u;
-        st->miss = ok ? 0u : 1u;
-        st->lo_bucket = lo; st->hi_bucket = hi;
-        *a.ticket = 0u;
-    }
+    if (threadIdx.x == 0) *a.ticket = 0u;
     clear_hist(a.hist);
 }
 
@@ -800,37 +848,230 @@ k_select_bracket(PassArgs a) {
     }
     if (threadIdx.x == 0 && s_below) atomicAdd(a.hist + kHistBins + 1, s_below);
     if (!last_cta_arrives(a.ticket)) return;
+    bracket_tail(a, base, s_warp);
+}
 
-    // ---- last CTA: verify that rank k is inside the bracket, narrow to a 1024-key window
-    unsigned long long local[kBinsPerThread];
+// =============================================================================================
+// Fused SNIP mask build (b200p_snip_mask_build): the score pass IS the sweep.
+//   S' k_snip_sample<ACC,B>       scores of the 1/64 sample positions computed from W and the B gradient sets
+//                                 (same slots, same bracket logic as k_select_sample)
+//   A' k_snip_score_sweep<ACC,B>  SCORE = sum_b |W*G_b| written once (bit-identical to k_score_multi) and, while the
+//                                 16 scores of a thread are still in registers, classified against the bracket:
+//                                 below-count, fine histogram + candidates inside it, provisional mask word.  The
+//                                 separate read of the scores by k_select_bracket (4 B/param and ~40 us of issue-bound
+//                                 sweep for ResNet-50) disappears.
+// then k_select_finish and the patching emit exactly as in the unfused sequence; on a bracket miss the finish kernel
+// runs the exact select over the SCORE slot this kernel has just written.
+// =============================================================================================
+template <bool ACC, int B>
+__device__ __forceinline__ float4 snip_score4(const float* __restrict__ w, const float* const (&g)[B], const float* __restrict__ s, int e) {
+    const float4 wv = ld_nc_f4(w + e);
+    float4 gv[B];
 #pragma unroll
-    for (int i = 0; i < kBinsPerThread; ++i) local[i] = ((volatile unsigned long long*)a.hist)[threadIdx.x * kBinsPerThread + i];
-    unsigned long long total_in;
-    unsigned long long running = block_prefix16(local, s_warp, total_in);
-    const unsigned long long n_below = ((volatile unsigned long long*)a.hist)[kHistBins + 1];
-    const unsigned long long k = st->k;
+    for (int b = 0; b < B; ++b) gv[b] = ld_nc_f4(g[b] + e);
+    float4 r;
+    if (ACC) r = ld_f4(s + e);
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        const float4 t = make_float4(fabsf(__fmul_rn(wv.x, gv[b].x)), fabsf(__fmul_rn(wv.y, gv[b].y)),
+                                     fabsf(__fmul_rn(wv.z, gv[b].z)), fabsf(__fmul_rn(wv.w, gv[b].w)));
+        if (b == 0 && !ACC) r = t;
+        else { r.x = __fadd_rn(r.x, t.x); r.y = __fadd_rn(r.y, t.y); r.z = __fadd_rn(r.z, t.z); r.w = __fadd_rn(r.w, t.w); }
+    }
+    return r;
+}
+template <bool ACC, int B>
+__device__ __forceinline__ float snip_score1(const float* __restrict__ w, const float* const (&g)[B], const float* __restrict__ s, int e) {
+    float r = ACC ? s[e] : 0.f;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        const float t = fabsf(__fmul_rn(w[e], g[b][e]));
+        r = (b == 0 && !ACC) ? t : __fadd_rn(r, t);
+    }
+    return r;
+}
+
+// Sample granules for the fused SNIP path: 8 consecutive keys (one 32-byte DRAM sector per array) instead of the 4 of
+// k_select_sample, 4 granules per chunk (1/128 of the keys).  Every granule costs 1 + B sector reads from B + 1
+// different arrays, so the kernel is bound by the random-access rate of HBM, not by bytes: the first version
+// (16 x 4 keys per chunk) took 33 us for ResNet-50, twice the plain sample.  Neighbouring keys are correlated
+// (same filter), so the bracket margin is 12 sigma instead of 8 (SampleArgs::sigmas).
+constexpr int kSnipGranulesPerChunk = 4;
+template <bool ACC, int B>
+__global__ void __launch_bounds__(kThreads)
+k_snip_sample(SampleArgs a, ChunkTab w_tab, GradTabs g_tabs, ChunkTab s_tab) {
+    __shared__ uint32_t s_hist[kHistBins];
+    __shared__ unsigned long long s_warp[9];
+    __shared__ uint32_t s_bkt[2];
+    for (int b = threadIdx.x; b < kHistBins; b += kThreads) s_hist[b] = 0;
     __syncthreads();
-    const bool inside = k > n_below && k <= n_below + total_in && total_in <= (unsigned long long)a.cand_capacity;
-    if (!inside) {
-        if (threadIdx.x == 0) { st->miss = 1u; st->collect = 0u; st->cand_count = 0u; st->prov_ok = 0u; }
-    } else {
-        const unsigned long long kk = k - n_below;
+    const int64_t gtid = (int64_t)blockIdx.x * kThreads + threadIdx.x, nthreads = (int64_t)gridDim.x * kThreads;
+    const int64_t slots = a.n_chunks * kSnipGranulesPerChunk;
+    for (int64_t sl = gtid; sl < slots; sl += nthreads) {
+        const int64_t c = sl >> 2;
+        const int i = (int)(sl & 3);
+        const int e0 = 1024 * i + 8 * (int)((c * 7 + 5 * i) & 127);
+        const int n = __ldg(a.chunk_n + c);
+        const float* w = chunk_ptr<const float>(w_tab, c);
+        const float* sc = ACC ? chunk_ptr<const float>(s_tab, c) : nullptr;
+        const float* g[B];
 #pragma unroll
-        for (int i = 0; i < kBinsPerThread; ++i) {
-            const unsigned long long v = local[i];
-            if (v != 0 && running < kk && kk <= running + v) {
-                st->n_less = n_below + running;
-                st->k = kk - running;
-                st->bucket_count = v;
-                st->win_lo = base + ((uint32_t)(threadIdx.x * kBinsPerThread + i) << kFineShift);
-                st->collect = 1u;
-                st->passes_full = 1u;
+        for (int b = 0; b < B; ++b) g[b] = chunk_ptr<const float>(g_tabs.t[b], c);
+        if (e0 >= n) continue;
+        float v[8]; int cnt = 0;
+        if (a.vec_ok && e0 + 7 < n) {
+            const float4 t0 = snip_score4<ACC, B>(w, g, sc, e0), t1 = snip_score4<ACC, B>(w, g, sc, e0 + 4);
+            v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w; cnt = 8;
+        } else {
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            for (int q = 0; q < 8 && e0 + q < n; ++q) { v[q] = snip_score1<ACC, B>(w, g, sc, e0 + q); cnt = q + 1; }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q < cnt) atomicAdd(&s_hist[key_of(v[q]) >> 19], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kHistBins; b += kThreads) {
+        const uint32_t v = s_hist[b];
+        if (v) atomicAdd(a.hist + b, (unsigned long long)v);
+    }
+    if (!last_cta_arrives(a.ticket)) return;
+    sample_tail(a, s_warp, s_bkt);
+}
+
+template <bool ACC, int B>
+__global__ void __launch_bounds__(kThreads, 4)
+k_snip_score_sweep(PassArgs a, ChunkTab w_tab, GradTabs g_tabs, int vec_all) {
+    __shared__ uint32_t s_hist[kHistBins];
+    __shared__ uint32_t sg_key[kThreads / 32][kStage];
+    __shared__ uint32_t sg_pos[kThreads / 32][kStage];
+    __shared__ int s_wcount[kThreads / 32];
+    __shared__ unsigned long long s_warp[9];
+    __shared__ unsigned long long s_below;
+    SelState* __restrict__ st = a.st;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool classify = st->sample_ok != 0u;           // written by the sample kernel: uniform over the grid
+    const uint32_t lo_b = st->lo_bucket, hi_b = st->hi_bucket;
+    const uint32_t base = lo_b << 19, span = (hi_b - lo_b + 1) << 19;
+    for (int b = tid; b < kHistBins; b += kThreads) s_hist[b] = 0;
+    if (tid == 0) s_below = 0;
+    if (lane == 0) s_wcount[warp] = 0;
+    if (blockIdx.x == 0 && tid == 0) st->prov_ok = (a.prov != nullptr && classify) ? 1u : 0u;
+    __syncthreads();
+
+    auto take = [&](uint32_t key, uint32_t pos) {
+        atomicAdd(&s_hist[(key - base) >> kFineShift], 1u);
+        const int off = atomicAdd(&s_wcount[warp], 1);
+        if (off < kStage) { sg_key[warp][off] = key; sg_pos[warp][off] = pos; }
+        else {
+            const uint32_t gi = atomicAdd(&st->cand_count, 1u);
+            if ((long long)gi < a.cand_capacity) { a.cand_key[gi] = key; a.cand_pos[gi] = pos; }
+        }
+    };
+    auto flush = [&](int n) {
+        if (n <= 0) return;
+        uint32_t gbase = 0;
+        if (lane == 0) gbase = atomicAdd(&st->cand_count, (uint32_t)n);
+        gbase = __shfl_sync(0xFFFFFFFFu, gbase, 0);
+        for (int i = lane; i < n; i += 32)
+            if ((long long)(gbase + i) < a.cand_capacity) { a.cand_key[gbase + i] = sg_key[warp][i]; a.cand_pos[gbase + i] = sg_pos[warp][i]; }
+        __syncwarp();
+        if (lane == 0) s_wcount[warp] = 0;
+        __syncwarp();
+    };
+
+    unsigned long long below = 0;
+    for (int64_t c = a.c_begin + blockIdx.x; c < a.c_end; c += gridDim.x) {
+        const int n = __ldg(a.chunk_n + c);
+        const float* __restrict__ w = chunk_ptr<const float>(w_tab, c);
+        float* __restrict__ s = chunk_ptr<float>(a.key_tab, c);
+        const float* g[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) g[b] = chunk_ptr<const float>(g_tabs.t[b], c);
+        const uint32_t pos0 = (uint32_t)(c * kChunk);
+        uint32_t* pw = a.prov ? a.prov + (size_t)c * kWordsPerChunk : nullptr;
+        if (vec_all && n == kChunk) {
+#pragma unroll 2
+            for (int j = 0; j < kVecPerThread; ++j) {
+                const int e = 4 * (j * kThreads + tid);
+                const float4 r = snip_score4<ACC, B>(w, g, s, e);
+                st_f4(s + e, r);
+                if (classify) {
+                    // four keys: sign bits of (key - base) and (key - base - span) shifted into 4-bit masks (key q -> bit 3 - q)
+                    const float f[4] = {r.x, r.y, r.z, r.w};
+                    uint32_t lt = 0, in = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t d = (__float_as_uint(f[q]) & 0x7FFFFFFFu) - base;
+                        lt = __funnelshift_l(d, lt, 1);
+                        in = __funnelshift_l(d - span, in, 1);
+                    }
+                    lt &= 0xFu;
+                    below += __popc(lt);
+                    if (pw) {
+                        // NaN scores are pruned (NaN > thr is false, train.py:316): the patching emit never sees them
+                        if (r.x != r.x) lt |= 8u;
+                        if (r.y != r.y) lt |= 4u;
+                        if (r.z != r.z) lt |= 2u;
+                        if (r.w != r.w) lt |= 1u;
+                        const uint32_t word = gather_nibbles(__brev(~lt & 0xFu) >> 28);      // bit q = key q at or above the bracket base
+                        if ((tid & 7) == 0) pw[vec_word_index(j)] = word;
+                    }
+                    uint32_t match = in & ~lt & 0xFu;
+                    while (match) {                           // divergent, rare (~1-2 % of the keys)
+                        const int bit = __ffs(match) - 1;
+                        match &= match - 1;
+                        const int q = 3 - bit;
+                        const float fv = q == 0 ? r.x : q == 1 ? r.y : q == 2 ? r.z : r.w;     // no dynamic indexing: keeps r in registers
+                        take(__float_as_uint(fv) & 0x7FFFFFFFu, pos0 + (uint32_t)(e + q));
+                    }
+                }
             }
-            running += v;
+        } else {
+            for (int it = 0; it < kChunk / kThreads; ++it) {     // warp-uniform trip count: one mask word per warp and step
+                const int e = it * kThreads + tid;
+                const bool valid = e < n;
+                uint32_t k = 0u;
+                if (valid) {
+                    const float r = snip_score1<ACC, B>(w, g, s, e);
+                    s[e] = r;
+                    k = key_of(r);
+                }
+                if (classify) {
+                    if (pw) {
+                        const uint32_t word = __ballot_sync(0xFFFFFFFFu, valid && k >= base && k != kNanKey);
+                        if (lane == 0) pw[e >> 5] = word;
+                    }
+                    if (valid) {
+                        if (k < base) ++below;
+                        else if (k - base < span) take(k, pos0 + (uint32_t)e);
+                    }
+                }
+            }
+        }
+        if (classify) {
+            __syncwarp();
+            const int filled = __shfl_sync(0xFFFFFFFFu, s_wcount[warp], 0);       // uniform decision, see sweep_loop
+            if (filled >= kStage / 2) flush(filled < kStage ? filled : kStage);
         }
     }
-    if (threadIdx.x == 0) *a.ticket = 0u;
-    clear_hist(a.hist);
+    if (!classify) return;                            // the finish kernel runs the exact select over the scores
+    __syncwarp();
+    {
+        const int filled = __shfl_sync(0xFFFFFFFFu, s_wcount[warp], 0);
+        flush(filled < kStage ? filled : kStage);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xFFFFFFFFu, below, o);
+    if (lane == 0 && below) atomicAdd(&s_below, below);
+    __syncthreads();
+    for (int b = tid; b < kHistBins; b += kThreads) {
+        const uint32_t v = s_hist[b];
+        if (v) atomicAdd(a.hist + b, (unsigned long long)v);
+    }
+    if (tid == 0 && s_below) atomicAdd(a.hist + kHistBins + 1, s_below);
+    if (!last_cta_arrives(a.ticket)) return;
+    bracket_tail(a, base, s_warp);
 }
 
 // ---- B: finish (cooperative launch) ----------------------------------------------------------------
@@ -1088,7 +1329,7 @@ static int select_kth_sampled(b200p_plan* p, int key_source, const uint32_t* d_o
     SampleArgs sa;
     sa.chunk_n = p->d_chunk_n; sa.key_tab = p->tab(slot); sa.old_mask = d_old_mask; sa.hist = p->d_hist; sa.st = p->d_state;
     sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.vec_ok = p->vec_ok[slot] ? 1 : 0;
-    sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)mode;
+    sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)mode; sa.sigmas = 8u;
     const int64_t sblocks = (p->n_chunks * kSampleSlotsPerChunk + 4 * kThreads - 1) / (4 * kThreads);
     k_select_sample<<<p->grid_for(sblocks, 1), kThreads, 0, st>>>(sa);
     B200P_LAUNCH_CHECK("k_select_sample");
@@ -1121,6 +1362,103 @@ extern "C" int b200p_select_kth(b200p_plan* p, int key_source, const uint32_t* d
     p->prov_armed = true; p->prov_key_source = key_source; p->prov_mode = mode; p->prov_old_mask = d_old_mask;
     if (p->select_impl == B200P_SELECT_EXACT) return select_kth_exact(p, key_source, d_old_mask, k, mode, (cudaStream_t)stream);
     return select_kth_sampled(p, key_source, d_old_mask, k, mode, (cudaStream_t)stream);
+}
+
+// ---- fused SNIP mask build ------------------------------------------------------------------------
+template <bool ACC>
+static void launch_snip_sample(int nb, int grid, cudaStream_t st, const SampleArgs& sa, ChunkTab w, const GradTabs& g, ChunkTab s) {
+    switch (nb) {
+        case 1: k_snip_sample<ACC, 1><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
+        case 2: k_snip_sample<ACC, 2><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
+        case 3: k_snip_sample<ACC, 3><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
+        case 4: k_snip_sample<ACC, 4><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
+        case 5: k_snip_sample<ACC, 5><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
+        case 6: k_snip_sample<ACC, 6><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
+        case 7: k_snip_sample<ACC, 7><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
+        default: k_snip_sample<ACC, 8><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
+    }
+}
+template <bool ACC>
+static void launch_snip_sweep(int nb, int grid, cudaStream_t st, const PassArgs& a, ChunkTab w, const GradTabs& g, int vec) {
+    switch (nb) {
+        case 1: k_snip_score_sweep<ACC, 1><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
+        case 2: k_snip_score_sweep<ACC, 2><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
+        case 3: k_snip_score_sweep<ACC, 3><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
+        case 4: k_snip_score_sweep<ACC, 4><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
+        case 5: k_snip_score_sweep<ACC, 5><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
+        case 6: k_snip_score_sweep<ACC, 6><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
+        case 7: k_snip_score_sweep<ACC, 7><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
+        default: k_snip_score_sweep<ACC, 8><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
+    }
+}
+
+extern "C" int b200p_snip_score_select(b200p_plan* p, const b200p_ptrtable* const* g_tables, int n_sets, uint64_t k,
+                                       uint32_t* d_prov_target, void* stream) {
+    B200P_REQUIRE(p != nullptr && g_tables != nullptr, B200P_EINVAL, "snip_mask_build: null argument");
+    B200P_REQUIRE(n_sets >= 1, B200P_EINVAL, "snip_mask_build: need at least one gradient set");
+    B200P_REQUIRE(p->bound[B200P_SLOT_W] && p->bound[B200P_SLOT_SCORE], B200P_ESTATE, "snip_mask_build: W and SCORE slots must be bound");
+    B200P_REQUIRE(k >= 1 && k <= (uint64_t)p->total, B200P_EINVAL, "snip_mask_build: k must be in [1, N]");
+    for (int i = 0; i < n_sets; ++i)
+        B200P_REQUIRE(g_tables[i] != nullptr && g_tables[i]->plan == p, B200P_EINVAL, "snip_mask_build: table belongs to another plan");
+    B200P_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->coop_ctas_per_sm == 0) {
+        int coop = 0, occ = 0;
+        B200P_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+        if (coop) B200P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select_finish, kThreads, 0));
+        p->coop_ctas_per_sm = occ > 0 ? (occ > 3 ? 3 : occ) : -1;
+    }
+    // all but the last group of up to 8 sets are plain accumulate launches; the last group is fused with the select
+    const int last0 = ((n_sets - 1) / kMaxSets) * kMaxSets, nb = n_sets - last0;
+    const bool unfused = p->select_impl == B200P_SELECT_EXACT || p->coop_ctas_per_sm < 0;
+    const int n_plain = unfused ? n_sets : last0;
+    if (n_plain > 0) { int rc = b200p_score_accumulate_multi(p, g_tables, n_plain, 0, 0, -1, stream); if (rc) return rc; }
+    if (unfused) {
+        p->prov_target = d_prov_target;
+        return b200p_select_kth(p, B200P_KEY_SCORE, nullptr, k, B200P_MODE_SNIP_STRICT, stream);
+    }
+    const bool acc = last0 > 0;
+    bool vec = p->vec_ok[B200P_SLOT_W] && p->vec_ok[B200P_SLOT_SCORE];
+    GradTabs g;
+    for (int b = 0; b < kMaxSets; ++b) { g.t[b] = (ChunkTab)g_tables[last0 + (b < nb ? b : 0)]->d_tab; if (b < nb) vec = vec && g_tables[last0 + b]->vec_ok; }
+    // an emit that follows with the same arguments patches the provisional mask the sweep writes (into d_prov_target if given)
+    p->prov_target = d_prov_target;
+    p->prov_armed = true; p->prov_key_source = B200P_KEY_SCORE; p->prov_mode = B200P_MODE_SNIP_STRICT; p->prov_old_mask = nullptr;
+    // S': sample
+    SampleArgs sa;
+    sa.chunk_n = p->d_chunk_n; sa.key_tab = p->tab(B200P_SLOT_SCORE); sa.old_mask = nullptr; sa.hist = p->d_hist; sa.st = p->d_state;
+    sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.vec_ok = vec ? 1 : 0;
+    sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)B200P_MODE_SNIP_STRICT; sa.sigmas = 12u;
+    const int64_t sblocks = (p->n_chunks * kSnipGranulesPerChunk + kThreads - 1) / kThreads;      // one granule per thread
+    if (acc) launch_snip_sample<true>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE));
+    else     launch_snip_sample<false>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE));
+    B200P_LAUNCH_CHECK("k_snip_sample");
+    // A': score + sweep
+    PassArgs a;
+    fill_pass_args(p, a, B200P_KEY_SCORE, nullptr, 0, p->n_chunks, 1, 0, k, B200P_MODE_SNIP_STRICT, 1, true);
+    { int rc = plan_time_mark(p, 0, st); if (rc) return rc; }
+    if (acc) launch_snip_sweep<true>(nb, p->grid_for(p->n_chunks, 4), st, a, p->tab(B200P_SLOT_W), g, vec ? 1 : 0);
+    else     launch_snip_sweep<false>(nb, p->grid_for(p->n_chunks, 4), st, a, p->tab(B200P_SLOT_W), g, vec ? 1 : 0);
+    B200P_LAUNCH_CHECK("k_snip_score_sweep");
+    { int rc = plan_time_mark(p, 1, st); if (rc) return rc; }
+    // B: finish
+    int64_t work = p->n_chunks;
+    const int64_t cblocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
+    if (cblocks > work) work = cblocks;
+    int grid = p->num_sms;
+    if (work < grid) grid = (int)(work < 1 ? 1 : work);
+    uint32_t* ties = p->d_chunk_ties; int64_t n_chunks = p->n_chunks;
+    void* args[] = {(void*)&a, (void*)&ties, (void*)&n_chunks};
+    B200P_CUDA(cudaLaunchCooperativeKernel((const void*)k_select_finish, dim3(grid), dim3(kThreads), args, 0, st));
+    return B200P_OK;
+}
+
+extern "C" int b200p_snip_mask_build(b200p_plan* p, const b200p_ptrtable* const* g_tables, int n_sets, uint64_t k,
+                                     uint32_t* d_new_mask, void* stream) {
+    B200P_REQUIRE(d_new_mask != nullptr, B200P_EINVAL, "snip_mask_build: null argument");
+    int rc = b200p_snip_score_select(p, g_tables, n_sets, k, d_new_mask, stream);
+    if (rc) { if (p) p->prov_target = nullptr; return rc; }
+    return b200p_emit_masks(p, B200P_KEY_SCORE, B200P_MODE_SNIP_STRICT, 0, 0.f, nullptr, d_new_mask, 0, 0, -1, stream);
 }
 
 extern "C" int b200p_select_result(b200p_plan* p, b200p_select_result_t* h_out, void* stream) {

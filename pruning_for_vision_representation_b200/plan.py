@@ -136,6 +136,38 @@ class ParamPlan:
                                                     chunk_end, _stream_ptr(self.device)), "score_accumulate_multi")
         self._multi_keepalive = tables
 
+    def time_sweep(self, on=True):
+        """Record CUDA events around every fused score+sweep kernel (measurement only, see kernel_time_ms)."""
+        check(self.lib.b200p_plan_set_option(self.handle, _lib.OPT_TIME_SWEEP, 1 if on else 0), "plan_set_option")
+        return self
+
+    def kernel_time_ms(self):
+        """(mean ms, launches) of the fused score+sweep kernels timed since the last call (synchronises)."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        check(self.lib.b200p_plan_kernel_time_ms(self.handle, ctypes.byref(ms), ctypes.byref(n)), "plan_kernel_time_ms")
+        return float(ms.value), int(n.value)
+
+    def _table_array(self, tables, who):
+        tables = list(tables)
+        for t in tables:
+            if t.plan is not self or t.slot != SLOT_G:
+                raise B200PruneError(f"{who}: need pointer tables of this plan's G slot")
+        self._multi_keepalive = tables
+        return (ctypes.c_void_p * len(tables))(*[t.handle for t in tables]), len(tables)
+
+    def snip_mask_build(self, tables, k, new_mask):
+        """SCORE = sum_b |W * G_b|, threshold = k-th smallest, new_mask = score > threshold, in one fused sequence:
+        the pass that writes the scores also classifies them (b200p_snip_mask_build)."""
+        arr, n = self._table_array(tables, "snip_mask_build")
+        check(self.lib.b200p_snip_mask_build(self.handle, arr, n, int(k), _ptr(new_mask), _stream_ptr(self.device)),
+              "snip_mask_build")
+
+    def snip_score_select(self, tables, k, prov_target=None):
+        """The score + select half of snip_mask_build; follow with emit_masks."""
+        arr, n = self._table_array(tables, "snip_score_select")
+        check(self.lib.b200p_snip_score_select(self.handle, arr, n, int(k), _ptr(prov_target), _stream_ptr(self.device)),
+              "snip_score_select")
+
     def select_kth(self, key_source, k, mode, old_mask=None):
         check(self.lib.b200p_select_kth(self.handle, key_source, _ptr(old_mask), int(k), mode,
                                         _stream_ptr(self.device)), "select_kth")

@@ -215,30 +215,27 @@ def snip_pruning(model, data_loader, device, criterion, target_sparsity=0.9, num
     # |w| uses the weight the forward saw: the masked one if the module is already pruned
     st.plan.bind(L.SLOT_W, [_flat(m.weight.detach()) for m in modules])
     st._w_ptrs = None
-    # one fused pass: score = sum_b |w * g_b|, added in batch order (bit-identical to per-batch accumulation)
-    st.plan.score_accumulate_multi([st.plan.pointer_table(L.SLOT_G, g) for g in stashed], accumulate=False)
-    if num_batches > 1:
-        for m, g in zip(modules, stashed[-1]):
-            _grad_param(m).grad = g.view_as(_grad_param(m))      # leave .grad populated like the reference does
     plan = st.plan
     n = plan.total
     k = int(n * target_sparsity)                                 # train.py:299
+    tables = [plan.pointer_table(L.SLOT_G, g) for g in stashed]
     st.ensure_mask_buffers()
     new_mask = plan.new_mask()
-    if k >= n:                                                   # train.py:300-301
-        threshold = float("inf")
-        plan.select_begin(0, L.MODE_SNIP_STRICT)
-        plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, new_mask, st.mask, force=3, forced_threshold=threshold,
-                        outputs=L.EMIT_MASKF)
-    elif k <= 0:                                                 # train.py:302-303
-        threshold = -1
-        plan.select_begin(0, L.MODE_SNIP_STRICT)
-        plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, new_mask, st.mask, force=3, forced_threshold=-1.0,
-                        outputs=L.EMIT_MASKF)
-    else:
-        plan.select_kth(L.KEY_SCORE, k, L.MODE_SNIP_STRICT)       # dead entries score 0 and count, as in the reference
+    if 0 < k < n:
+        # one fused pass: score = sum_b |w * g_b|, added in batch order (bit-identical to per-batch accumulation),
+        # classified against the sampled bracket while it is written; dead entries score 0 and count, as in the reference
+        plan.snip_score_select(tables, k)
         plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, new_mask, st.mask, outputs=L.EMIT_MASKF)
         threshold = None
+    else:
+        plan.score_accumulate_multi(tables, accumulate=False)
+        threshold = float("inf") if k >= n else -1               # train.py:300-303
+        plan.select_begin(0, L.MODE_SNIP_STRICT)
+        plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, new_mask, st.mask, force=3, forced_threshold=float(threshold),
+                        outputs=L.EMIT_MASKF)
+    if num_batches > 1:
+        for m, g in zip(modules, stashed[-1]):
+            _grad_param(m).grad = g.view_as(_grad_param(m))      # leave .grad populated like the reference does
     res = plan.result()                                          # the reference's `.item()` sync (train.py:307)
     if threshold is None:
         threshold = float(res["threshold"])

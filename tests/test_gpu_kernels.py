@@ -303,6 +303,79 @@ def test_mask_build_equals_select_plus_emit():
     assert np.array_equal(np.concatenate(gpu_masks(plan, m1)), flat > np.float32(r1["threshold"]))
 
 
+@pytest.mark.parametrize("misalign", [False, True])
+@pytest.mark.parametrize("n_sets", [1, 3, 8, 11])
+def test_snip_mask_build_fused_equals_unfused(misalign, n_sets):
+    """b200p_snip_mask_build (the pass that writes the scores classifies them against the sampled bracket) gives the
+    same scores, packed mask and result block as score_accumulate_multi + mask_build, and the oracle's mask."""
+    rng = np.random.default_rng(100 + n_sets)
+    sizes = [700_001, 4096 * 37, 123_457, 33, 4096]
+    w = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    g = [[(1e-3 * rng.standard_normal(n)).astype(np.float32) for n in sizes] for _ in range(n_sets)]
+    g[0][0][17] = np.nan                                                # NaN scores sort last and are pruned
+    w[1][5] = 0.0                                                       # exact zero score
+    plan = make_plan(w)
+    plan.bind(L.SLOT_W, to_dev(w, misalign))
+    tables = [plan.pointer_table(L.SLOT_G, to_dev(gb, misalign)) for gb in g]
+    acc = [None] * len(sizes)
+    for gb in g:
+        acc = [PO.snip_score_accumulate(a, ww, gg) for a, ww, gg in zip(acc, w, gb)]
+    flat = np.concatenate(acc)
+    for sparsity in (0.9, 0.5, 0.01, 0.999):
+        k = PO.snip_k(plan.total, sparsity)
+        s1 = [torch.zeros(n, device=DEV) for n in sizes]
+        plan.bind(L.SLOT_SCORE, s1)
+        plan.score_accumulate_multi(tables)
+        m1 = plan.new_mask(); plan.mask_build(L.KEY_SCORE, k, L.MODE_SNIP_STRICT, m1)
+        r1 = plan.result()
+        s2 = [torch.full((n,), 7.0, device=DEV) for n in sizes]
+        plan.bind(L.SLOT_SCORE, s2)
+        m2 = plan.new_mask(); plan.snip_mask_build(tables, k, m2)
+        r2 = plan.result()
+        for a, b, ref in zip(s1, s2, acc):
+            assert np.array_equal(b.cpu().numpy(), ref, equal_nan=True) and torch.equal(a.isnan(), b.isnan())
+        assert torch.equal(m1, m2)
+        for key in ("k", "n_less", "n_equal", "n_kept", "threshold", "thr_key"):
+            assert r1[key] == r2[key], key
+        thr = np.sort(flat)[k - 1]                                       # train.py:306-307 (NaN sorts last)
+        assert np.float32(r2["threshold"]) == thr
+        assert np.array_equal(np.concatenate(gpu_masks(plan, m2)), flat > thr)          # train.py:316
+        # the two-call form with an old mask and fp32 mask outputs
+        s3 = [torch.zeros(n, device=DEV) for n in sizes]
+        plan.bind(L.SLOT_SCORE, s3)
+        plan.snip_score_select(tables, k)
+        m3 = plan.new_mask(); plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, m3)
+        assert torch.equal(m3, m2)
+
+
+def test_snip_mask_build_fused_degenerate_scores():
+    """Scores the sample cannot bracket (all equal / all zero / a huge tied set at the threshold) take the exact
+    fallback inside the finish kernel, over the scores the fused pass has just written."""
+    rng = np.random.default_rng(5)
+    sizes = [4096 * 9 + 5, 50_000]
+    plan = make_plan([np.zeros(n, np.float32) for n in sizes])
+    cases = []
+    w0 = [np.ones(n, np.float32) for n in sizes]; g0 = [np.full(n, 0.5, np.float32) for n in sizes]; cases.append((w0, g0))    # constant
+    cases.append(([np.zeros(n, np.float32) for n in sizes], g0))                                                                # fresh-ViT case: all zero
+    w2 = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    g2 = [np.where(rng.random(n) < 0.6, 0.0, 1e-3 * rng.standard_normal(n)).astype(np.float32) for n in sizes]               # 60 % exact zeros
+    cases.append((w2, g2))
+    for w, g in cases:
+        plan.bind(L.SLOT_W, to_dev(w))
+        sc = [torch.empty(n, device=DEV) for n in sizes]
+        plan.bind(L.SLOT_SCORE, sc)
+        tables = [plan.pointer_table(L.SLOT_G, to_dev(g))]
+        flat = np.concatenate([PO.snip_score_accumulate(None, ww, gg) for ww, gg in zip(w, g)])
+        for sparsity in (0.5, 0.9):
+            k = PO.snip_k(plan.total, sparsity)
+            m = plan.new_mask(); plan.snip_mask_build(tables, k, m)
+            r = plan.result()
+            thr = np.sort(flat)[k - 1]
+            assert np.float32(r["threshold"]) == thr
+            assert np.array_equal(np.concatenate(gpu_masks(plan, m)), flat > thr)
+            assert np.array_equal(np.concatenate([t.cpu().numpy() for t in sc]), flat)
+
+
 def test_mask_roundtrip_apply_and_grads():
     rng = np.random.default_rng(9)
     sizes = [4096 * 3, 777, 4100]
