@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "lost_common.cuh"
 #include <math.h>
+#include <string.h>
 
 namespace b200p {
 
@@ -25,6 +26,39 @@ constexpr int kMetaPerLaunch = 256;
 struct MetaPack { LostImageDev m[kMetaPerLaunch]; };
 __global__ void k_lost_set_meta(LostImageDev* __restrict__ dst, MetaPack pack, int n) {
     if ((int)threadIdx.x < n) dst[threadIdx.x] = pack.m[threadIdx.x];
+}
+
+// Uniform batches (a [B, N, d] tensor: same dims, offsets in arithmetic progression) need no upload at all: record b
+// is record 0 plus b times a constant step.  (Copying 256 records out of the kernel-parameter bank costs 13 us: the
+// constant cache serialises the thread-dependent addresses.)
+__global__ void k_lost_gen_meta(LostImageDev* __restrict__ dst, LostImageDev first, LostImageDev step, int n) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    LostImageDev m = first;
+    m.feat_off += (long long)b * step.feat_off; m.a_off += (long long)b * step.a_off; m.out_off += (long long)b * step.out_off;
+    m.tile_base += b * step.tile_base; m.row_base += b * step.row_base;
+    m.pair_base += b * step.pair_base; m.pair2_base += b * step.pair2_base;
+    dst[b] = m;
+}
+static bool lost_meta_uniform(const std::vector<LostImageDev>& meta, LostImageDev& step) {
+    if (meta.size() < 2) return false;
+    const LostImageDev& a = meta[0];
+    const LostImageDev& b1 = meta[1];
+    memset(&step, 0, sizeof(step));
+    step.feat_off = b1.feat_off - a.feat_off; step.a_off = b1.a_off - a.a_off; step.out_off = b1.out_off - a.out_off;
+    step.tile_base = b1.tile_base - a.tile_base; step.row_base = b1.row_base - a.row_base;
+    step.pair_base = b1.pair_base - a.pair_base; step.pair2_base = b1.pair2_base - a.pair2_base;
+    for (size_t i = 1; i < meta.size(); ++i) {
+        const LostImageDev& m = meta[i];
+        const long long k = (long long)i;
+        if (m.n != a.n || m.dim0 != a.dim0 || m.dim1 != a.dim1 || m.img_h != a.img_h || m.img_w != a.img_w ||
+            m.s0 != a.s0 || m.s1 != a.s1 || m.tiles != a.tiles) return false;
+        if (m.feat_off != a.feat_off + k * step.feat_off || m.a_off != a.a_off + k * step.a_off ||
+            m.out_off != a.out_off + k * step.out_off || m.tile_base != a.tile_base + k * step.tile_base ||
+            m.row_base != a.row_base + k * step.row_base || m.pair_base != a.pair_base + k * step.pair_base ||
+            m.pair2_base != a.pair2_base + k * step.pair2_base) return false;
+    }
+    return true;
 }
 
 // ---- K6: fp32 Gram + degree -----------------------------------------------------------------
@@ -436,6 +470,11 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     B200P_REQUIRE((size_t)workspace_bytes >= need, B200P_EINVAL, "lost_batched: workspace too small (see b200p_lost_workspace_bytes)");
     LostImageDev* d_meta = (LostImageDev*)d_workspace;
     float* A_base = d_A ? d_A : (float*)((char*)d_workspace + meta_bytes);
+    LostImageDev step;
+    if (lost_meta_uniform(meta, step)) {
+        k_lost_gen_meta<<<(n_images + 255) / 256, 256, 0, st>>>(d_meta, meta[0], step, n_images);
+        B200P_LAUNCH_CHECK("k_lost_gen_meta");
+    } else
     for (int b0 = 0; b0 < n_images; b0 += kMetaPerLaunch) {
         MetaPack pack;
         const int nb = n_images - b0 < kMetaPerLaunch ? n_images - b0 : kMetaPerLaunch;
