@@ -376,6 +376,29 @@ def test_snip_mask_build_fused_degenerate_scores():
             assert np.array_equal(np.concatenate([t.cpu().numpy() for t in sc]), flat)
 
 
+def test_snip_mask_build_fused_repeatable():
+    """Candidate order in the buffer depends on scheduling, the mask, the scores and the result block must not:
+    ten builds of a ResNet-18-sized set, bit-identical every time."""
+    rng = np.random.default_rng(77)
+    sizes = [2_359_296, 1_179_648, 589_824, 147_456, 36_864, 9_408, 512_000 + 3]
+    w = [torch.from_numpy(rng.standard_normal(n).astype(np.float32)).to(DEV) for n in sizes]
+    plan = make_plan([np.empty(n, np.float32) for n in sizes])
+    plan.bind(L.SLOT_W, w)
+    tables = [plan.pointer_table(L.SLOT_G, [torch.from_numpy((1e-3 * rng.standard_normal(n)).astype(np.float32)).to(DEV) for n in sizes])
+              for _ in range(4)]
+    sc = [torch.empty(n, device=DEV) for n in sizes]
+    plan.bind(L.SLOT_SCORE, sc)
+    k = PO.snip_k(plan.total, 0.9)
+    m0 = plan.new_mask(); plan.snip_mask_build(tables, k, m0); r0 = plan.result()
+    s0 = torch.cat(sc).clone()
+    for _ in range(9):
+        for t in sc:
+            t.fill_(-1.0)
+        m = plan.new_mask(); plan.snip_mask_build(tables, k, m)
+        assert torch.equal(m, m0) and plan.result() == r0 and torch.equal(torch.cat(sc), s0)
+    assert r0["n_kept"] == plan.total - r0["n_less"] - r0["n_equal"] and r0["n_less"] + 1 <= k <= r0["n_less"] + r0["n_equal"]
+
+
 def test_mask_roundtrip_apply_and_grads():
     rng = np.random.default_rng(9)
     sizes = [4096 * 3, 777, 4100]
