@@ -372,17 +372,6 @@ __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope: the data behind
-    uint32_t done;                                                                  // the barrier was written by the peer CTA too
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
 // columns the tensor cores compute for column tile tj of an image with n patches: the last tile is
 // trimmed to the next multiple of 16 (the N granularity of cta_group::2), e.g. 144 instead of 256 at n = 900
 __device__ __forceinline__ int tile2_cols(int n, int tj) {
@@ -448,17 +437,17 @@ __device__ __forceinline__ Tile2 load_tile2(const Tile2* __restrict__ tab, int t
 // DIRECT = true: the TMA reads the caller's fp32 features in place (one tensor map with the caller's row
 // stride, e.g. the k slice of a qkv buffer) and only the RAW tiles travel; the tensor cores ignore the low 13
 // mantissa bits of an fp32 word fed to kind::tf32, so the raw tile IS the hi operand (hi = x with those
-// bits cleared), and four extra warps derive lo = tf32(x - hi) from the landed tile into a second ring
+// bits cleared), and four extra warps derive lo = x - hi (exact in fp32) from the landed tile into a second ring
 // (same swizzled position), publish it to the async proxy and arrive on the leader's conv barrier the MMA
 // issuer waits on.  No split kernel, no hi/lo arrays in HBM, half the L2 -> SM operand traffic.
 //
 // Shared memory (per CTA, 1024-B aligned):
 //   pre-split:  3 stages x [A_hi | A_lo | B_hi | B_lo]                         (16 KB tiles)      192 KB
-//   direct:     4 raw stages x [A_raw | B_raw]  +  2 lo stages x [A_lo | B_lo]                    192 KB
-//               (TMA runs up to four k-blocks ahead; the conversion of k-block i+1 overlaps the MMAs of i)
+//   direct:     3 raw stages x [A_raw | B_raw]  +  3 lo stages x [A_lo | B_lo]                    192 KB
+//               (the conversion of k-blocks i+1, i+2 overlaps the MMAs of i; 4 + 2 stages measure the same)
 //   epilogue:   8 warps x 32 x 32 floats, 16-B XOR swizzle: the row-major copy of A is transposed through
 //               shared memory so that one store instruction writes four full 128-B lines           32 KB
-constexpr int T2_RAW_STAGES = 4, T2_LO_STAGES = 2;
+constexpr int T2_RAW_STAGES = 3, T2_LO_STAGES = 3;
 constexpr int T2_RING_BYTES = TC_STAGES * TC_STAGE_BYTES;        // == (T2_RAW_STAGES + T2_LO_STAGES) * 2 tiles
 constexpr int T2_STAGING_BYTES = 8 * 32 * 32 * 4;
 constexpr size_t T2_SMEM_BYTES = (size_t)T2_RING_BYTES + T2_STAGING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
@@ -477,11 +466,11 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     constexpr int NFULL = DIRECT ? T2_RAW_STAGES : TC_STAGES;     // stages the TMA fills
     auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // [4]
     auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };                // [4]
-    auto conv_bar = [&](int s) { return bar_base + 8u * (8 + s); };                 // [2] direct: lo tiles ready (leader's copy is used)
-    auto lo_empty_bar = [&](int s) { return bar_base + 8u * (10 + s); };            // [2] direct: MMAs done with the lo stage
-    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (12 + a); };           // [2]
-    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (14 + a); };          // [2]
-    const uint32_t tmem_slot = bar_base + 8u * 16;
+    auto conv_bar = [&](int s) { return bar_base + 8u * (8 + s); };                 // [4] direct: lo tiles ready (leader's copy is used)
+    auto lo_empty_bar = [&](int s) { return bar_base + 8u * (12 + s); };            // [4] direct: MMAs done with the lo stage
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (16 + a); };           // [2]
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (18 + a); };          // [2]
+    const uint32_t tmem_slot = bar_base + 8u * 20;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     // operand tile addresses of k-block `it`
     auto hi_tiles = [&](int it) { return DIRECT ? smem_base + (uint32_t)(it % T2_RAW_STAGES) * (2 * TC_TILE_BYTES)
@@ -499,7 +488,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         tma_prefetch_desc(&tm_hi);
         if (!DIRECT) tma_prefetch_desc(&tm_lo);
         for (int s = 0; s < 4; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 4; ++s) {
             mbar_init(conv_bar(s), 2 * T2_CONV_WARPS);          // one arrival per converter warp of both CTAs
             mbar_init(lo_empty_bar(s), 1);
         }
@@ -565,7 +554,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T2_BN);
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                if (DIRECT) mbar_wait_cluster(conv_bar(it % T2_LO_STAGES), (uint32_t)(it / T2_LO_STAGES) & 1u);   // raw tiles landed, lo tiles derived, both CTAs
+                if (DIRECT) mbar_wait(conv_bar(it % T2_LO_STAGES), (uint32_t)(it / T2_LO_STAGES) & 1u);    // raw tiles landed, lo tiles derived, in both CTAs   // raw tiles landed, lo tiles derived, both CTAs
                 else mbar_wait(full_bar(it % TC_STAGES), (uint32_t)(it / TC_STAGES) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t hi = hi_tiles(it), lo = lo_tiles(it);
@@ -585,7 +574,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             umma_commit_2sm(tmem_full_bar(acc));                    // both epilogues may read their half
         }
     } else if (DIRECT && warp >= T2_THREADS / 32) {
-        // ===== lo converter (both CTAs, 4 warps): lo = tf32(x - trunc_tf32(x)) for every raw tile =====
+        // ===== lo converter (both CTAs, 4 warps): lo = x - trunc_tf32(x) for every raw tile =====
         const int ct = threadIdx.x - T2_THREADS;                     // 0..127
         int it = 0;
         Tile2 nxt = load_tile2(tab, cluster_id, n_tiles);
@@ -594,7 +583,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             nxt = load_tile2(tab, t + n_clusters, n_tiles);
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 mbar_wait(full_bar(it % T2_RAW_STAGES), (uint32_t)(it / T2_RAW_STAGES) & 1u);          // this CTA's raw tiles have landed
-                mbar_wait(lo_empty_bar(it % T2_LO_STAGES), ((uint32_t)(it / T2_LO_STAGES) & 1u) ^ 1u); // the MMAs two k-blocks back are done with the lo stage
+                mbar_wait(lo_empty_bar(it % T2_LO_STAGES), ((uint32_t)(it / T2_LO_STAGES) & 1u) ^ 1u); // the MMAs three k-blocks back are done with the lo stage
                 // plain shared-memory pointers: the compiler batches the eight loads of a tile ahead of the math and the stores
                 const uint4* __restrict__ src = reinterpret_cast<const uint4*>(smem_raw + (hi_tiles(it) - smem_u32(smem_raw))) + ct;
                 uint4* __restrict__ dst = reinterpret_cast<uint4*>(smem_raw + (lo_tiles(it) - smem_u32(smem_raw))) + ct;
@@ -606,11 +595,14 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                     for (int j = 0; j < QUADS; ++j) x[j] = src[(tile * QUADS + j) * (32 * T2_CONV_WARPS)];
 #pragma unroll
                     for (int j = 0; j < QUADS; ++j) {
+                        // lo = x - trunc_tf32(x), exact in fp32 (13 significant bits); the tensor core truncates it to tf32 itself.
+                        // (Rounding it here - cvt.rna.tf32 is emulated with 3 instructions on sm_100a - made the converter the
+                        // bottleneck: 1370 of the 2110 cycles per k-block; the truncation adds < 2^-20 |a||b| to the Gram error.)
                         uint4 l;
-                        l.x = __float_as_uint(to_tf32(__uint_as_float(x[j].x) - __uint_as_float(x[j].x & 0xFFFFE000u)));
-                        l.y = __float_as_uint(to_tf32(__uint_as_float(x[j].y) - __uint_as_float(x[j].y & 0xFFFFE000u)));
-                        l.z = __float_as_uint(to_tf32(__uint_as_float(x[j].z) - __uint_as_float(x[j].z & 0xFFFFE000u)));
-                        l.w = __float_as_uint(to_tf32(__uint_as_float(x[j].w) - __uint_as_float(x[j].w & 0xFFFFE000u)));
+                        l.x = __float_as_uint(__uint_as_float(x[j].x) - __uint_as_float(x[j].x & 0xFFFFE000u));
+                        l.y = __float_as_uint(__uint_as_float(x[j].y) - __uint_as_float(x[j].y & 0xFFFFE000u));
+                        l.z = __float_as_uint(__uint_as_float(x[j].z) - __uint_as_float(x[j].z & 0xFFFFE000u));
+                        l.w = __float_as_uint(__uint_as_float(x[j].w) - __uint_as_float(x[j].w & 0xFFFFE000u));
                         dst[(tile * QUADS + j) * (32 * T2_CONV_WARPS)] = l;
                     }
                 }
