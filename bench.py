@@ -343,6 +343,8 @@ def run_b200(args):
     keep_busy(0.5)
     launches[0] = 0
     sync_all()
+    if sweep:
+        plan.kernel_time_ms()                 # discard the launches timed during warm-up
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
@@ -359,6 +361,7 @@ def run_b200(args):
         dist.all_reduce(tl)
         n_launches = int(tl.item())
     res = plan.result()
+    sweep_ms, sweep_n = plan.kernel_time_ms() if sweep else (0.0, 0)     # the launches of the timed region only
     keep_busy(0.4)
     clk = clocks.stop() if rank == 0 else None
 
@@ -366,7 +369,7 @@ def run_b200(args):
     kernel_ms = sum(acc_ms) / max(1, len(acc_ms))
     n_timed = len(acc_ms)
     if sweep:
-        kernel_ms, n_timed = plan.kernel_time_ms()       # CUDA events recorded by the library around k_snip_score_sweep, same stream
+        kernel_ms, n_timed = sweep_ms, sweep_n           # CUDA events recorded by the library around k_snip_score_sweep, same stream
     peak, peak_src = peaks()
     nb_local = len(my_batches)
     # algorithmic bytes per launch of the dominant kernel: fused pass reads w and nb_local
