@@ -467,7 +467,6 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // [4]
     auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };                // [4]
     auto conv_bar = [&](int s) { return bar_base + 8u * (8 + s); };                 // [4] direct: lo tiles ready (leader's copy is used)
-    auto lo_empty_bar = [&](int s) { return bar_base + 8u * (12 + s); };            // [4] direct: MMAs done with the lo stage
     auto tmem_full_bar = [&](int a) { return bar_base + 8u * (16 + a); };           // [2]
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (18 + a); };          // [2]
     const uint32_t tmem_slot = bar_base + 8u * 20;
@@ -490,7 +489,6 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         for (int s = 0; s < 4; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 4; ++s) {
             mbar_init(conv_bar(s), 2 * T2_CONV_WARPS);          // one arrival per converter warp of both CTAs
-            mbar_init(lo_empty_bar(s), 1);
         }
         for (int a = 0; a < T2_ACC; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 2 * 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -554,7 +552,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T2_BN);
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                if (DIRECT) mbar_wait(conv_bar(it % T2_LO_STAGES), (uint32_t)(it / T2_LO_STAGES) & 1u);    // raw tiles landed, lo tiles derived, in both CTAs   // raw tiles landed, lo tiles derived, both CTAs
+                if (DIRECT) mbar_wait(conv_bar(it % T2_LO_STAGES), (uint32_t)(it / T2_LO_STAGES) & 1u);    // raw tiles landed, lo tiles derived, in both CTAs
                 else mbar_wait(full_bar(it % TC_STAGES), (uint32_t)(it / TC_STAGES) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t hi = hi_tiles(it), lo = lo_tiles(it);
@@ -568,8 +566,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                     umma_tf32_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
                     umma_tf32_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
                 }
-                umma_commit_2sm(empty_bar(it % NFULL));             // frees the (raw) stage in both CTAs
-                if (DIRECT) umma_commit_2sm(lo_empty_bar(it % T2_LO_STAGES));
+                umma_commit_2sm(empty_bar(it % NFULL));             // frees the stage in both CTAs (direct: raw and lo stage, see below)
             }
             umma_commit_2sm(tmem_full_bar(acc));                    // both epilogues may read their half
         }
@@ -583,7 +580,10 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             nxt = load_tile2(tab, t + n_clusters, n_tiles);
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 mbar_wait(full_bar(it % T2_RAW_STAGES), (uint32_t)(it / T2_RAW_STAGES) & 1u);          // this CTA's raw tiles have landed
-                mbar_wait(lo_empty_bar(it % T2_LO_STAGES), ((uint32_t)(it / T2_LO_STAGES) & 1u) ^ 1u); // the MMAs three k-blocks back are done with the lo stage
+                // the MMAs three k-blocks back are done with the lo stage: the rings have the same length, so the raw stage's
+                // empty barrier says so too (a second tcgen05.commit per k-block for a separate barrier costs ~0.1 ms per call)
+                static_assert(T2_RAW_STAGES == T2_LO_STAGES, "one empty barrier serves the raw and the lo stage of a k-block");
+                mbar_wait(empty_bar(it % T2_LO_STAGES), ((uint32_t)(it / T2_LO_STAGES) & 1u) ^ 1u);
                 // plain shared-memory pointers: the compiler batches the eight loads of a tile ahead of the math and the stores
                 const uint4* __restrict__ src = reinterpret_cast<const uint4*>(smem_raw + (hi_tiles(it) - smem_u32(smem_raw))) + ct;
                 uint4* __restrict__ dst = reinterpret_cast<uint4*>(smem_raw + (lo_tiles(it) - smem_u32(smem_raw))) + ct;
