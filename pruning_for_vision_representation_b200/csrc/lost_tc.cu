@@ -435,11 +435,11 @@ __device__ __forceinline__ Tile2 load_tile2(const Tile2* __restrict__ tab, int t
 }
 
 // DIRECT = true: the TMA reads the caller's fp32 features in place (one tensor map with the caller's row
-// stride, e.g. the k slice of a qkv buffer) and only the RAW tiles travel; the tensor cores ignore the low 13
-// mantissa bits of an fp32 word fed to kind::tf32, so the raw tile IS the hi operand (hi = x with those
-// bits cleared), and four extra warps derive lo = x - hi (exact in fp32) from the landed tile into a second ring
-// (same swizzled position), publish it to the async proxy and arrive on the leader's conv barrier the MMA
-// issuer waits on.  No split kernel, no hi/lo arrays in HBM, half the L2 -> SM operand traffic.
+// stride, e.g. the k slice of a qkv buffer) and only the RAW tiles travel; four extra warps split every landed
+// tile in shared memory the way k_lost_split_tf32 does in HBM - hi = tf32(x) over the raw word, lo = x - hi
+// into a second ring at the same swizzled position - publish both to the async proxy and arrive on the
+// leader's conv barrier the MMA issuer waits on.  No split kernel, no hi/lo arrays in HBM, half the L2 -> SM
+// operand traffic.
 //
 // Shared memory (per CTA, 1024-B aligned):
 //   pre-split:  3 stages x [A_hi | A_lo | B_hi | B_lo]                         (16 KB tiles)      192 KB
@@ -571,7 +571,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             umma_commit_2sm(tmem_full_bar(acc));                    // both epilogues may read their half
         }
     } else if (DIRECT && warp >= T2_THREADS / 32) {
-        // ===== lo converter (both CTAs, 4 warps): lo = x - trunc_tf32(x) for every raw tile =====
+        // ===== converter (both CTAs, 4 warps): raw tile -> (hi in place, lo) =====
         const int ct = threadIdx.x - T2_THREADS;                     // 0..127
         int it = 0;
         Tile2 nxt = load_tile2(tab, cluster_id, n_tiles);
@@ -585,7 +585,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                 static_assert(T2_RAW_STAGES == T2_LO_STAGES, "one empty barrier serves the raw and the lo stage of a k-block");
                 mbar_wait(empty_bar(it % T2_LO_STAGES), ((uint32_t)(it / T2_LO_STAGES) & 1u) ^ 1u);
                 // plain shared-memory pointers: the compiler batches the eight loads of a tile ahead of the math and the stores
-                const uint4* __restrict__ src = reinterpret_cast<const uint4*>(smem_raw + (hi_tiles(it) - smem_u32(smem_raw))) + ct;
+                uint4* __restrict__ src = reinterpret_cast<uint4*>(smem_raw + (hi_tiles(it) - smem_u32(smem_raw))) + ct;
                 uint4* __restrict__ dst = reinterpret_cast<uint4*>(smem_raw + (lo_tiles(it) - smem_u32(smem_raw))) + ct;
                 constexpr int QUADS = TC_TILE_BYTES / (16 * 32 * T2_CONV_WARPS);      // 8 float4 per thread and tile
 #pragma unroll 1
@@ -595,14 +595,18 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                     for (int j = 0; j < QUADS; ++j) x[j] = src[(tile * QUADS + j) * (32 * T2_CONV_WARPS)];
 #pragma unroll
                     for (int j = 0; j < QUADS; ++j) {
-                        // lo = x - trunc_tf32(x), exact in fp32 (13 significant bits); the tensor core truncates it to tf32 itself.
-                        // (Rounding it here - cvt.rna.tf32 is emulated with 3 instructions on sm_100a - made the converter the
-                        // bottleneck: 1370 of the 2110 cycles per k-block; the truncation adds < 2^-20 |a||b| to the Gram error.)
-                        uint4 l;
-                        l.x = __float_as_uint(__uint_as_float(x[j].x) - __uint_as_float(x[j].x & 0xFFFFE000u));
-                        l.y = __float_as_uint(__uint_as_float(x[j].y) - __uint_as_float(x[j].y & 0xFFFFE000u));
-                        l.z = __float_as_uint(__uint_as_float(x[j].z) - __uint_as_float(x[j].z & 0xFFFFE000u));
-                        l.w = __float_as_uint(__uint_as_float(x[j].w) - __uint_as_float(x[j].w & 0xFFFFE000u));
+                        // hi = tf32(x), rounded to nearest, replaces the raw word in place; lo = x - hi, exact and SIGNED.
+                        // Feeding the raw word (the tensor core truncates it) with lo = x - trunc(x) saves this store and was
+                        // the first version, but then hi.hi, hi.lo and lo.hi are all biased the same way, and the tensor core's
+                        // accumulator, which truncates every product to its own ulp, drifts three times as far on same-sign
+                        // sums: 1.8e-5 |k|^2 on the diagonal at d = 768 against 6e-6 with a rounded hi (bar: 1e-5).
+                        // (hi by integer round-half-up on the 13 dropped bits, lo = x - hi exact and signed: 3 ALU instructions per key)
+                        uint4 h, l;
+                        h.x = (x[j].x + 0x1000u) & 0xFFFFE000u; h.y = (x[j].y + 0x1000u) & 0xFFFFE000u;
+                        h.z = (x[j].z + 0x1000u) & 0xFFFFE000u; h.w = (x[j].w + 0x1000u) & 0xFFFFE000u;
+                        l.x = __float_as_uint(__uint_as_float(x[j].x) - __uint_as_float(h.x)); l.y = __float_as_uint(__uint_as_float(x[j].y) - __uint_as_float(h.y));
+                        l.z = __float_as_uint(__uint_as_float(x[j].z) - __uint_as_float(h.z)); l.w = __float_as_uint(__uint_as_float(x[j].w) - __uint_as_float(h.w));
+                        src[(tile * QUADS + j) * (32 * T2_CONV_WARPS)] = h;
                         dst[(tile * QUADS + j) * (32 * T2_CONV_WARPS)] = l;
                     }
                 }

@@ -102,6 +102,23 @@ def test_config2_resnet50_snip_8_batches_full_size():
     assert int((s_fused < thr).sum()) < k <= int((s_fused <= thr).sum())
     kept = unpack_bits(plan, mask, numels)
     assert torch.equal(kept, s_fused > thr) and res["n_kept"] == int(kept.sum())
+    # the default sequence of bench.py: score pass fused with the select's sweep, emit by patching
+    s_sweep = torch.full((n,), -1.0, device=DEV)
+    plan.bind(L.SLOT_SCORE, views(s_sweep, numels))
+    mask2 = plan.new_mask()
+    plan.snip_mask_build([plan.pointer_table(L.SLOT_G, views(g, numels)) for g in grads], k, mask2)
+    res2 = plan.result()
+    assert torch.equal(s_sweep, s_fused) and torch.equal(mask2, mask)
+    assert {key: res2[key] for key in ("k", "n_less", "n_equal", "n_kept", "threshold")} == {key: res[key] for key in ("k", "n_less", "n_equal", "n_kept", "threshold")}
+    assert res2["passes_full"] == 1, "the sampled bracket should hold on this distribution"
+    # every sparsity of config 5's sweep through the same sequence
+    for s in (0.5, 0.8, 0.95, 0.99):
+        ks = int(n * s)
+        m = plan.new_mask(); plan.snip_mask_build([plan.pointer_table(L.SLOT_G, views(g, numels)) for g in grads], ks, m)
+        r = plan.result()
+        t = torch.tensor(r["threshold"], device=DEV)
+        assert int((s_fused < t).sum()) < ks <= int((s_fused <= t).sum()), s
+        assert torch.equal(unpack_bits(plan, m, numels), s_fused > t), s
 
 
 def test_config4_vit_b16_iterative_pruning_with_masked_steps():

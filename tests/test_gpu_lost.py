@@ -152,6 +152,28 @@ def test_lost_batched_varlen_matches_oracle():
             assert box[i].tolist() == [float(v) for v in epred], i
 
 
+@pytest.mark.parametrize("d", [33, 100, 384 + 4, 768])
+def test_lost_feature_widths_and_layouts(d):
+    """Key widths that are not a multiple of the 32-wide k-block (TMA zero fill past d), a ResNet-like width, and the
+    layouts that decide whether the keys can be read in place: contiguous [B, N, d], a column slice of a wider buffer
+    (row stride > d), and a view whose base is 4 bytes off (no TMA: the pre-split path must take over)."""
+    g = torch.Generator(device="cpu").manual_seed(d)
+    n_side = (12, 19)
+    n = n_side[0] * n_side[1]
+    wide = torch.randn(3, n, d + 8, generator=g)
+    layouts = {"contiguous": wide[:, :, :d].contiguous().to(DEV),
+               "column slice": wide.to(DEV)[:, :, 4:4 + d],                     # row stride d + 8, base 16 bytes in
+               "4 bytes off": wide.to(DEV)[:, :, 1:1 + d]}
+    for name, feats in layouts.items():
+        out = OD.lost_batched(feats, list(n_side), [16, 16], (3, n_side[0] * 16, n_side[1] * 16), k_patches=100, return_A=True)
+        for i in range(3):
+            f = feats[i].cpu().numpy()
+            epred, eA, escores, eseed = LO.lost(np.ascontiguousarray(f), list(n_side), [16, 16], (3, n_side[0] * 16, n_side[1] * 16), 100)
+            ndiff = _check_gram_and_degree(np.ascontiguousarray(f), out["A"][i], out["degree"][i].cpu().numpy(), (-escores).astype(np.int32))
+            if ndiff == 0 and int(out["status"][i]) == 0:
+                assert int(out["seed"][i]) == eseed and out["box"][i].tolist() == [float(v) for v in epred], (name, i)
+
+
 def test_lost_batched_uniform_tensor_and_random_features():
     g = torch.Generator(device="cpu").manual_seed(0)
     feats = torch.randn(6, 900, 384, generator=g)
@@ -187,8 +209,9 @@ def test_lost_batched_repeatable_and_impls_agree(gram_impl):
         Ar = torch.cat([a.reshape(-1) for a in ref["A"]])
         scale = feats.norm(dim=2).max() ** 2
         assert float((A0 - Ar).abs().max() / scale) < 1e-5
-        # not the same bits: tc2d truncates to tf32 where the split kernel rounds, and a mirrored entry accumulates
-        # hi.lo and lo.hi in the other order than a directly computed one (128- vs 256-wide diagonal tiles)
+        # not the same bits: tc2d leaves lo = x - hi unrounded (the tensor core truncates it), and in tc a mirrored entry
+        # accumulates hi.lo and lo.hi in the other order than a directly computed one (128- vs 256-wide diagonal tiles);
+        # the accuracy class and (almost all of) the degrees agree
         same = torch.cat(ref["degree"]) == d0
         assert float(same.float().mean()) > 0.95
 
