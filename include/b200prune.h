@@ -246,8 +246,9 @@ typedef struct b200p_lost_image_t {
 #define B200P_LOST_GRAM_FFMA   0   /* fp32 CUDA-core Gram                                   */
 #define B200P_LOST_GRAM_TC     1   /* TMA + tcgen05 3xTF32 error-compensated Gram, one CTA per 128x128 tile */
 #define B200P_LOST_GRAM_TC2    2   /* the same on CTA pairs: tcgen05.mma.cta_group::2, 256x256 tiles, features pre-split into hi/lo arrays */
-#define B200P_LOST_GRAM_TC2D   3   /* CTA pairs reading the caller's features in place (TMA on d_feats, lo tiles derived in shared memory);
-                                      falls back to TC2 when the layout is not TMA-addressable (default) */
+#define B200P_LOST_GRAM_TC2D   3   /* default: CTA pairs reading the caller's features in place (TMA on d_feats, hi/lo tiles derived in
+                                      shared memory); falls back to TC2 when the layout is not TMA-addressable and to FFMA for keys wider
+                                      than 768 (the tensor cores' truncating accumulator drifts ~1.2e-8 d |k|^2: past the 1e-5 bar there) */
 int  b200p_lost_workspace_bytes(int n_images, int64_t total_patches, int64_t total_a, int d, int gram_impl, int64_t* out);
 int  b200p_lost_batched(int device, const float* d_feats, int64_t row_stride, int d,
                         const b200p_lost_image_t* h_meta, int n_images, int k_patches,

@@ -20,6 +20,7 @@ namespace b200p {
 
 constexpr int kLostMaxPatches = 4096;     // per image (ViT-S/8 at 480x480 = 3600)
 constexpr int kFinThreads = 512;
+constexpr int kLostMaxTensorCoreWidth = 768;   // widest key the default (TC2D) Gram keeps on the tensor cores, see b200p_lost_batched
 
 // image records travel as kernel arguments (no pageable-memcpy stream sync, no staging buffer)
 constexpr int kMetaPerLaunch = 256;
@@ -436,6 +437,11 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     int n_max = 0;
     B200P_REQUIRE(k_patches <= 1024, B200P_EINVAL, "lost_batched: k_patches must be <= 1024");
     bool vec = (((uintptr_t)d_feats) & 15u) == 0 && (row_stride & 3) == 0;
+    // The tensor cores truncate every product to the accumulator's ulp, so a same-sign sum (the squared norms on the
+    // diagonal) drifts by ~1.2e-8 d |k|^2: 4.9e-6 at d = 384, 9.3e-6 at 768, 2.2e-5 at 2048 (tools/gram_error_probe.py),
+    // whatever the operand split.  The default keeps the 1e-5 parity bar by computing wide keys (ResNet-50 features,
+    // main_lost_original.py:277-280) on the fp32 FMA path (1.6e-6); an explicit TC / TC2 request is honoured as is.
+    if (gram_impl == B200P_LOST_GRAM_TC2D && d > kLostMaxTensorCoreWidth) gram_impl = B200P_LOST_GRAM_FFMA;
     int tc_mode = gram_impl == B200P_LOST_GRAM_TC ? LOST_TC_SINGLE : LOST_TC_PAIR;
     if (gram_impl == B200P_LOST_GRAM_TC2D && lost_tc_direct_ok(d_feats, (long long)row_stride, d, h_meta, n_images)) tc_mode = LOST_TC_PAIR_DIRECT;
     for (int b = 0; b < n_images; ++b) {
