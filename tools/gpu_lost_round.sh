@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-python __graft_entry__.py --smoke 2>&1 | tail -3
-timeout 600 python -m pytest tests/test_gpu_lost.py tests/test_gpu_fullsize.py -m gpu -q -x --timeout 120 -k "widths or config2 or tc2d" > gpurun_out/pytest_lost.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_lost.log
+timeout 300 python -m pytest tests/test_gpu_lost.py -m gpu -q -x --timeout 60 -k "tc2d" 2>&1 | tail -2
+timeout 60 python tools/lost_probe.py 256 20 3; timeout 60 python tools/lost_probe.py 256 20 3; timeout 60 python tools/lost_probe.py 1024 5 3
