@@ -355,12 +355,9 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {       // arrives
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  :: "r"(bar), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {   // bar: shared::cluster address (possibly the peer's)
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
-}
 // Arrival with the default semantics (release at CTA scope), the form CUTLASS's ClusterBarrier::arrive(cta_id) uses to
 // hand smem written by transform warps (after fence.proxy.async) to a UMMA issued by the pair's leader.  The
-// release.cluster form above costs a MEMBAR.ALL.GPU per arrival.
+// mbarrier.arrive.release.cluster form costs a MEMBAR.ALL.GPU per arrival.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar) : "memory");
 }
