@@ -632,7 +632,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             float* __restrict__ A = A_base + im.a_off;
             int* __restrict__ deg = degree_base + im.out_off;
             const bool vec_store = (im.n & 3) == 0 && (((uintptr_t)A) & 15u) == 0;
-            const bool interior = mirror && row0 + T2_BM <= im.n && col0 + T2_BN <= im.n && vec_store;   // no bounds, no diagonal
+            const float thr0 = fmaxf(threshold, 0.f);                  // (i != j ? max(A_ij, 0) : 0) > threshold  <=>  A_ij > thr0 off the diagonal
             int cnt = 0;
 #pragma unroll 1
             for (int ch = 4 * hsel; ch < 4 * hsel + 4; ++ch) {
@@ -664,19 +664,39 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                     }
                     __syncwarp();                                    // the buffer is rewritten by the next chunk
                 }
-                if (interior) {
-                    int colcnt = 0;
+                // Fast paths, decided per 32x32 chunk: every element inside the image and none on the diagonal (a diagonal tile
+                // holds the diagonal only in its chunks with gi0 == gj0).  The epilogue is bound by dependent ALU latency with two
+                // warps per scheduler (clock64: 3100 cycles for a diagonal-tile chunk on the general path, without a single store),
+                // so only the ragged last chunks and the 32 diagonal chunks of an image pay for the per-element tests.
+                const bool full = vec_store && gi0 + 32 <= im.n && gj0 + 32 <= im.n && (mirror || gj0 != gi0);
+                if (full && mirror) {
+                    int colcnt = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
                     float* __restrict__ col = A + (long long)gj0 * im.n + gi;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float v = __uint_as_float(r[c]);
-                        const bool pos = v > threshold && v > 0.f;
-                        cnt += pos ? 1 : 0;
-                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, pos);
-                        if (lane == c) colcnt = __popc(bal);
-                        col[(long long)c * im.n] = v;            // transposed: lanes = consecutive addresses
+                    for (int c = 0; c < 32; c += 4) {
+                        const bool p0 = __uint_as_float(r[c]) > thr0, p1 = __uint_as_float(r[c + 1]) > thr0;
+                        const bool p2 = __uint_as_float(r[c + 2]) > thr0, p3 = __uint_as_float(r[c + 3]) > thr0;
+                        c0 += p0; c1 += p1; c2 += p2; c3 += p3;
+                        const unsigned b0 = __ballot_sync(0xFFFFFFFFu, p0), b1 = __ballot_sync(0xFFFFFFFFu, p1);
+                        const unsigned b2 = __ballot_sync(0xFFFFFFFFu, p2), b3 = __ballot_sync(0xFFFFFFFFu, p3);
+                        if ((lane >> 2) == (c >> 2)) colcnt = __popc((lane & 3) == 0 ? b0 : (lane & 3) == 1 ? b1 : (lane & 3) == 2 ? b2 : b3);
+                        col[(long long)(c + 0) * im.n] = __uint_as_float(r[c]);          // transposed: lanes = consecutive addresses
+                        col[(long long)(c + 1) * im.n] = __uint_as_float(r[c + 1]);
+                        col[(long long)(c + 2) * im.n] = __uint_as_float(r[c + 2]);
+                        col[(long long)(c + 3) * im.n] = __uint_as_float(r[c + 3]);
                     }
+                    cnt += (c0 + c1) + (c2 + c3);
                     if (colcnt) atomicAdd(deg + gj0 + lane, colcnt);
+                    continue;
+                }
+                if (full) {                                       // diagonal tile, chunk off the diagonal: both triangles are computed, count only
+                    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        c0 += __uint_as_float(r[c]) > thr0; c1 += __uint_as_float(r[c + 1]) > thr0;
+                        c2 += __uint_as_float(r[c + 2]) > thr0; c3 += __uint_as_float(r[c + 3]) > thr0;
+                    }
+                    cnt += (c0 + c1) + (c2 + c3);
                     continue;
                 }
                 int colcnt = 0;
