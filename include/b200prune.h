@@ -111,6 +111,10 @@ typedef struct b200p_ptrtable b200p_ptrtable;
 int  b200p_ptrtable_create(b200p_plan* plan, int slot, const void* const* h_ptrs, void* stream,
                            b200p_ptrtable** out);
 int  b200p_ptrtable_destroy(b200p_ptrtable* table);
+/* Re-point n existing tables (of one plan, same slot) at new per-segment pointers — the fresh gradient tensors autograd
+ * hands over for the next mask build (train.py:258-269) — in ONE small launch: the pointers travel as kernel arguments
+ * (up to 1024 per launch), nothing is allocated, nothing synchronises.  h_ptrs[i] is the pointer list of tables[i]. */
+int  b200p_ptrtables_update(b200p_ptrtable* const* tables, const void* const* const* h_ptrs, int n_tables, int slot, void* stream);
 int  b200p_plan_bind_table(b200p_plan* plan, int slot, const b200p_ptrtable* table);
 /* options */
 #define B200P_OPT_SELECT_IMPL   1
@@ -230,8 +234,12 @@ int  b200p_masked_sgd_step(b200p_plan* plan, const uint32_t* d_mask, float lr, f
  * Outputs (device): degree int32 [sum n_b] (the call zeroes d_degree[min out_offset, max out_offset
  * + n_b) first), seed int32 [B], box float [B,4] (xmin,ymin,xmax,ymax in pixels, exact integers when
  * the scales are integers, object_discovery.py:120-128), status int32 [B]
- * (0 ok, 1 = "The seed is in the background component", object_discovery.py:110-111).
- * d_A (nullable): fp32 Gram matrices, image b at d_A + a_offset[b], n_b x n_b row-major.
+ * (0 ok, 1 = "The seed is in the background component", object_discovery.py:110-111; 2 = internal: the finish
+ * kernel gave up waiting for the Gram kernel, never expected).
+ * d_A (nullable): fp32 Gram matrices, image b at d_A + a_offset[b], n_b x n_b row-major.  With d_A == NULL and a pair
+ * Gram (TC2 / TC2D, keys up to 768 wide) NO Gram matrix is materialised anywhere: the Gram epilogue only counts, and
+ * A[seed, potentials] and M = K (sum of the similar keys) come from the keys (object_discovery.py:61-62 as two skinny
+ * mat-vecs; same signs wherever an entry is decidable in fp32).
  * h_meta is a host array of B records; it is consumed before the call returns.  At most 4096
  * patches per image and k_patches <= 1024.  Workspace: b200p_lost_workspace_bytes(). */
 typedef struct b200p_lost_image_t {
@@ -255,6 +263,10 @@ int  b200p_lost_batched(int device, const float* d_feats, int64_t row_stride, in
                         float* d_A, int32_t* d_degree, int32_t* d_seed, float* d_box,
                         int32_t* d_status, void* d_workspace, int64_t workspace_bytes,
                         int gram_impl, void* stream);
+
+/* Measurement aid: globaltimer (ns) trace of the last count-only b200p_lost_batched call: [Gram first CTA start, Gram last
+ * CTA end, first finish CTA past its wait, last finish CTA end].  Synchronises the device. */
+int  b200p_lost_last_trace(uint64_t* h_out4);
 
 /* patch_scoring(M, threshold) of object_discovery.py:72-90 on a given n x n matrix (row stride lda):
  * d_degree[i] = #{j : (i != j ? max(A_ij, 0) : 0) > threshold}; d_sel = patches by ascending degree,

@@ -99,3 +99,33 @@ def planted_object_feats(rng, grid=(30, 30), d=384, rows=(8, 18), cols=(10, 22),
     feats = base + noise * rng.standard_normal((h * w, d)).astype(F32)
     feats = feats - feats.mean(axis=0, keepdims=True)
     return feats.astype(F32)
+
+
+def lost_from_degrees(feats, degree, dims, scales, init_image_size, k_patches=100, ulps=64.0):
+    """Checker for implementations whose Gram entries differ from the reference's in rounding only.
+
+    Takes the DEGREES the implementation produced (they may differ from the reference's where a Gram entry is within
+    rounding of zero; the caller checks that separately against the fp64 Gram) and replays the rest of
+    object_discovery.py:57-67 in float64: seed = stable argmin, potentials, similars (A[seed, p] > 0), M = sum of the
+    similar rows, flood fill, box.  Returns (seed, pred or None when the seed is background, decidable): `decidable` is
+    False when some A[seed, p] or some M_j lies within `ulps` fp32 ulps of zero relative to its natural scale
+    (|k_seed||k_p|, resp. |k_j| sqrt(sum_s |k_s|^2): the rounding of a length-d fp32 dot product / of the reference's own
+    fp32 row sum), i.e. when fp32 implementations may legitimately disagree on the sign.  seed is always binding."""
+    eps = float(np.finfo(F32).eps)
+    f = np.asarray(feats, np.float64)
+    A = f @ f.T
+    norms = np.sqrt(np.maximum(np.diag(A), 0.0))
+    sel = np.argsort(np.asarray(degree, np.int64), kind="stable")
+    seed = int(sel[0])
+    pot = sel[:k_patches]
+    a = A[seed, pot]
+    decidable = bool(np.all(np.abs(a) > ulps * eps * norms[seed] * norms[pot]))
+    sim = pot[a > 0.0]
+    M = A[sim, :].sum(axis=0)
+    tol = ulps * eps * norms * np.sqrt(np.sum(norms[sim] ** 2))
+    decidable = decidable and bool(np.all(np.abs(M) > tol))
+    try:
+        pred, _ = detect_box(M, seed, dims, scales=scales, initial_im_size=init_image_size[1:])
+    except ValueError:
+        pred = None
+    return seed, pred, decidable

@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200p_plan_bind": (_I, [_P, _I, ctypes.POINTER(_P), _P]),
     "b200p_ptrtable_create": (_I, [_P, _I, ctypes.POINTER(_P), _P, ctypes.POINTER(_P)]),
     "b200p_ptrtable_destroy": (_I, [_P]),
+    "b200p_ptrtables_update": (_I, [ctypes.POINTER(_P), ctypes.POINTER(_P), _I, _I, _P]),
     "b200p_plan_bind_table": (_I, [_P, _I, _P]),
     "b200p_plan_set_option": (_I, [_P, _I, _I64]),
     "b200p_plan_kernel_time_ms": (_I, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),
@@ -99,6 +100,7 @@ SIGNATURES = {
     "b200p_lost_workspace_bytes": (_I, [_I, _I64, _I64, _I, _I, ctypes.POINTER(_I64)]),
     "b200p_lost_batched": (_I, [_I, _P, _I64, _I, ctypes.POINTER(LostImage), _I, _I, _P, _P, _P, _P, _P,
                                 _P, _I64, _I, _P]),
+    "b200p_lost_last_trace": (_I, [ctypes.POINTER(_U64)]),
     "b200p_lost_patch_scoring": (_I, [_I, _P, _I, _I64, _F, _P, _P, _P]),
     "b200p_lost_detect_box": (_I, [_I, _P, _I, _I, _I, _F, _F, _I, _I, _P, _P, _P, _P]),
     "b200p_snip_mask_build_host": (_I, [_P, _P, ctypes.POINTER(_P), _I, _U64, _P, ctypes.POINTER(SelectResult)]),

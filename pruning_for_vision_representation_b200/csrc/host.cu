@@ -71,8 +71,7 @@ extern "C" int b200p_snip_mask_build_host(b200p_plan* p, const float* h_w, const
         rc = b200p_select_begin(p, 0, B200P_MODE_SNIP_STRICT, 0, comp); if (rc) return rc;
         rc = b200p_emit_masks(p, B200P_KEY_SCORE, B200P_MODE_SNIP_STRICT, 3, -1.0f, nullptr, p->arena_mask, 0, 0, -1, comp);
     } else {
-        rc = b200p_select_kth(p, B200P_KEY_SCORE, nullptr, k, B200P_MODE_SNIP_STRICT, comp); if (rc) return rc;
-        rc = b200p_emit_masks(p, B200P_KEY_SCORE, B200P_MODE_SNIP_STRICT, 0, 0.f, nullptr, p->arena_mask, 0, 0, -1, comp);
+        rc = b200p_mask_build(p, B200P_KEY_SCORE, nullptr, k, B200P_MODE_SNIP_STRICT, p->arena_mask, comp);      // sweep + patching emit
     }
     if (rc) return rc;
     B200P_CUDA(cudaMemcpyAsync(h_mask_out, p->arena_mask, mbytes, cudaMemcpyDeviceToHost, comp));
@@ -100,8 +99,7 @@ extern "C" int b200p_magnitude_mask_build_host(b200p_plan* p, const float* h_w, 
         rc = b200p_select_begin(p, 0, B200P_MODE_EXACT_K, 0, comp); if (rc) return rc;
         rc = b200p_emit_masks(p, B200P_KEY_ABS_W, B200P_MODE_EXACT_K, 1, 0.f, old_mask, p->arena_mask, 0, 0, -1, comp);
     } else {
-        rc = b200p_select_kth(p, B200P_KEY_ABS_W, old_mask, k, B200P_MODE_EXACT_K, comp); if (rc) return rc;
-        rc = b200p_emit_masks(p, B200P_KEY_ABS_W, B200P_MODE_EXACT_K, 0, 0.f, old_mask, p->arena_mask, 0, 0, -1, comp);
+        rc = b200p_mask_build(p, B200P_KEY_ABS_W, old_mask, k, B200P_MODE_EXACT_K, p->arena_mask, comp);
     }
     if (rc) return rc;
     B200P_CUDA(cudaMemcpyAsync(h_mask_out, p->arena_mask, mbytes, cudaMemcpyDeviceToHost, comp));

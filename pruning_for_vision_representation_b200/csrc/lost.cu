@@ -15,6 +15,7 @@
 #include "lost_common.cuh"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace b200p {
 
@@ -239,12 +240,41 @@ __device__ __forceinline__ void write_box(float* out, const int (&b)[4], float s
 }
 
 // ---- K7: seed, seed expansion, box --------------------------------------------------------------
+// dot product of two key rows by one warp: lane l takes float4 l, l + 32, ... (scalar elements when the layout is not
+// 16-byte granular), then a butterfly sum: the same order on every run.
+__device__ __forceinline__ float warp_dot(const float* __restrict__ a, const float* __restrict__ b, int d, bool vec) {
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    if (vec) {
+        const int d4 = d >> 2;
+        for (int c = lane; c < d4; c += 32) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(a) + c), y = *(reinterpret_cast<const float4*>(b) + c);
+            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+        }
+        for (int c = 4 * d4 + lane; c < d; c += 32) acc = fmaf(__ldg(a + c), b[c], acc);
+    } else {
+        for (int c = lane; c < d; c += 32) acc = fmaf(__ldg(a + c), b[c], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    return acc;
+}
+
+// FROM_KEYS = false: A was materialised (the caller asked for it): similars and M are read from it, rows added in the
+//                    reference's order (object_discovery.py:61-62).
+// FROM_KEYS = true:  count-only Gram, no A anywhere.  A[seed, p] = k_seed . k_p for the <= k_patches potentials and
+//                    M = K (sum of the similar keys) — two skinny mat-vecs over the image's keys instead of 2 n^2
+//                    floats written and 100 rows read back.  Same signs as the reference wherever an entry is decidable
+//                    in fp32 (|M_j| above the rounding of a length-d dot product); M itself is not bit-identical.
+template <bool FROM_KEYS>
 __global__ void __launch_bounds__(kFinThreads)
 k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A_base, const int* __restrict__ degree_base,
               int k_patches, int n_max, int* __restrict__ seed_out, float* __restrict__ box_out, int* __restrict__ status_out,
-              float* __restrict__ M_out) {
+              float* __restrict__ M_out, const float* __restrict__ feats, long long row_stride, int d, int vec_ok,
+              const unsigned int* __restrict__ done) {
     // dynamic shared memory, sized for the largest image of the batch (n_max):
     //   int deg[n_max] | int hist[n_max+1 (+pad)] | int list[1024] | int sorted[1024] | u8 flag[n_max] | u8 comp[n_max]
+    //   | FROM_KEYS: float vsum[d_pad4] | float kseed[d_pad4] | u8 simflag[1024]
     extern __shared__ __align__(16) unsigned char s_dyn[];
     int* s_deg = reinterpret_cast<int*>(s_dyn);
     int* s_hist = s_deg + n_max;
@@ -252,15 +282,45 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
     int* s_sorted = s_list + 1024;
     unsigned char* s_flag = reinterpret_cast<unsigned char*>(s_sorted + 1024);   // foreground of M
     unsigned char* s_comp = s_flag + n_max;
+    const int d_pad4 = (d + 3) & ~3;
+    float* s_vsum = reinterpret_cast<float*>(s_comp + n_max);                     // n_max is a multiple of 16
+    float* s_kseed = s_vsum + d_pad4;
+    unsigned char* s_simflag = reinterpret_cast<unsigned char*>(s_kseed + d_pad4);
     __shared__ int s_warp[33];
     __shared__ unsigned long long s_best;
     __shared__ int s_red[4];
     __shared__ int s_cut[3];
 
-    const LostImageDev im = meta[blockIdx.x];
+    const int img = (int)blockIdx.x;
+    const LostImageDev im = meta[img];
     const int n = im.n, tid = threadIdx.x, nt = blockDim.x;
-    const float* __restrict__ A = A_base + im.a_off;
+    if (FROM_KEYS && done) {
+        // launched as a programmatic dependent of the count-only Gram kernel: wait until every epilogue warp of every tile
+        // of this image has released its degree contributions (16 warps per 256x256 tile)
+        if (tid == 0) {
+            const unsigned t2 = (unsigned)(n + 255) / 256u, expected = 16u * (t2 * (t2 + 1u) / 2u);
+            unsigned seen = 0;
+            // bounded (~2 s): a protocol error must surface as status 2, never as a hung GPU
+            for (unsigned spin = 0; spin < (1u << 23); ++spin) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + img) : "memory");
+                if (seen >= expected) break;
+                __nanosleep(256);
+            }
+            s_red[0] = seen >= expected ? 1 : 0;
+        }
+        if (tid == 0) atomicMin(const_cast<unsigned long long*>(reinterpret_cast<const unsigned long long*>(done)) - 2, lost_globaltimer());
+        __syncthreads();
+        const bool ready = s_red[0] != 0;
+        __syncthreads();
+        if (!ready) {
+            if (tid == 0) { seed_out[img] = -1; status_out[img] = 2; float* o = box_out + 4 * (long long)img; o[0] = o[1] = o[2] = o[3] = 0.f; }
+            return;
+        }
+    }
+    const float* __restrict__ A = FROM_KEYS ? nullptr : A_base + im.a_off;
+    const float* __restrict__ F = FROM_KEYS ? feats + im.feat_off : nullptr;
     const int* __restrict__ deg = degree_base + im.out_off;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
 
     // degrees, seed = lowest degree, lowest index among equals (stable argsort, object_discovery.py:57,88)
     if (tid == 0) s_best = ~0ull;
@@ -268,7 +328,7 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
     __syncthreads();
     unsigned long long best = ~0ull;
     for (int j = tid; j < n; j += nt) {
-        const int dg = deg[j];
+        const int dg = __ldcg(deg + j);                     // L2: the counts may have been produced by a kernel still in flight
         s_deg[j] = dg;
         const unsigned long long key = ((unsigned long long)(unsigned)dg << 32) | (unsigned)j;
         best = key < best ? key : best;
@@ -279,6 +339,7 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
     if ((tid & 31) == 0) atomicMin(&s_best, best);
     __syncthreads();
     const int seed = (int)(s_best & 0xFFFFFFFFu);
+    if (FROM_KEYS) for (int c = tid; c < d; c += nt) s_kseed[c] = F[(long long)seed * row_stride + c];
 
     // cut-off degree D: the k lowest-degree patches are those with degree < D plus the first
     // `quota` (by index) of degree == D
@@ -300,8 +361,41 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
     }
     __syncthreads();
     const int D = s_cut[0], quota = s_cut[1];
-    // membership + similars (A[seed, p] > 0 on the unmodified A, object_discovery.py:61)
-    {
+    if (FROM_KEYS) {
+        // potentials in index order -> s_sorted (scratch), then one warp per potential: A[seed, p] = k_seed . k_p
+        int carry = 0, n_pot = 0;
+        for (int base = 0; base < n; base += nt) {
+            const int j = base + tid;
+            const int is_eq = (j < n && s_deg[j] == D) ? 1 : 0;
+            int total;
+            const int eq_rank = block_excl_scan(is_eq, s_warp, &total) + carry;
+            carry += total;
+            const int member = (j < n && (s_deg[j] < D || (is_eq && eq_rank < quota))) ? 1 : 0;
+            int tot2;
+            const int pos = block_excl_scan(member, s_warp, &tot2) + n_pot;
+            if (member && pos < 1024) s_sorted[pos] = j;
+            n_pot += tot2;
+            __syncthreads();
+        }
+        n_pot = min(n_pot, 1024);
+        for (int i = warp; i < n_pot; i += nwarps) {
+            const float a = warp_dot(F + (long long)s_sorted[i] * row_stride, s_kseed, d, vec_ok != 0);
+            if (lane == 0) s_simflag[i] = a > 0.0f ? 1 : 0;              // object_discovery.py:61 on the unmodified A
+        }
+        __syncthreads();
+        int n_sim = 0;
+        for (int base = 0; base < n_pot; base += nt) {
+            const int i = base + tid;
+            const int sim = (i < n_pot && s_simflag[i]) ? 1 : 0;
+            int tot2;
+            const int pos = block_excl_scan(sim, s_warp, &tot2) + n_sim;
+            if (sim) s_list[pos] = s_sorted[i];
+            n_sim += tot2;
+            __syncthreads();
+        }
+        if (tid == 0) s_cut[2] = n_sim;
+    } else {
+        // membership + similars (A[seed, p] > 0 on the unmodified A, object_discovery.py:61)
         int carry = 0, n_sim = 0;
         for (int base = 0; base < n; base += nt) {
             const int j = base + tid;
@@ -335,30 +429,86 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
         s_sorted[rank] = p;
     }
     __syncthreads();
-    // M = sum over similars of A[s, :], rows added in that order (object_discovery.py:62)
-    for (int j = tid; j < n; j += nt) {
-        float m = 0.f;
-        int r = 0;
-        for (; r + 8 <= n_sim; r += 8) {                       // 8 independent loads in flight, then the ordered adds
-            float v[8];
+    if (FROM_KEYS) {
+        // v = sum of the similar keys, added in that order; then M_j = k_j . v, one warp per row, four rows in flight
+        for (int c = tid; c < d_pad4; c += nt) {
+            float v = 0.f;
+            if (c < d) {
+                int r = 0;
+                for (; r + 8 <= n_sim; r += 8) {
+                    float x[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldg(A + (long long)s_sorted[r + u] * n + j);
+                    for (int u = 0; u < 8; ++u) x[u] = __ldg(F + (long long)s_sorted[r + u] * row_stride + c);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) m = __fadd_rn(m, v[u]);
+                    for (int u = 0; u < 8; ++u) v = __fadd_rn(v, x[u]);
+                }
+                for (; r < n_sim; ++r) v = __fadd_rn(v, __ldg(F + (long long)s_sorted[r] * row_stride + c));
+            }
+            s_vsum[c] = v;
         }
-        for (; r < n_sim; ++r) m = __fadd_rn(m, __ldg(A + (long long)s_sorted[r] * n + j));
-        s_flag[j] = m > 0.0f ? 1 : 0;
-        if (M_out) M_out[im.out_off + j] = m;
+        __syncthreads();
+        if (vec_ok && (d & 3) == 0) {
+            const int d4 = d >> 2;
+            const float4* __restrict__ v4 = reinterpret_cast<const float4*>(s_vsum);
+            for (int j0 = 4 * warp; j0 < n; j0 += 4 * nwarps) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const float4* rowp[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rowp[u] = reinterpret_cast<const float4*>(F + (long long)min(j0 + u, n - 1) * row_stride);
+                for (int c = lane; c < d4; c += 32) {
+                    float4 x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) x[u] = __ldg(rowp[u] + c);
+                    const float4 y = v4[c];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        acc[u] = fmaf(x[u].x, y.x, acc[u]); acc[u] = fmaf(x[u].y, y.y, acc[u]);
+                        acc[u] = fmaf(x[u].z, y.z, acc[u]); acc[u] = fmaf(x[u].w, y.w, acc[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xFFFFFFFFu, acc[u], o);
+                    if (lane == 0 && j0 + u < n) {
+                        s_flag[j0 + u] = acc[u] > 0.0f ? 1 : 0;
+                        if (M_out) M_out[im.out_off + j0 + u] = acc[u];
+                    }
+                }
+            }
+        } else {
+            for (int j = warp; j < n; j += nwarps) {
+                const float m = warp_dot(F + (long long)j * row_stride, s_vsum, d, false);
+                if (lane == 0) { s_flag[j] = m > 0.0f ? 1 : 0; if (M_out) M_out[im.out_off + j] = m; }
+            }
+        }
+    } else {
+        // M = sum over similars of A[s, :], rows added in that order (object_discovery.py:62)
+        for (int j = tid; j < n; j += nt) {
+            float m = 0.f;
+            int r = 0;
+            for (; r + 8 <= n_sim; r += 8) {                       // 8 independent loads in flight, then the ordered adds
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(A + (long long)s_sorted[r + u] * n + j);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) m = __fadd_rn(m, v[u]);
+            }
+            for (; r < n_sim; ++r) m = __fadd_rn(m, __ldg(A + (long long)s_sorted[r] * n + j));
+            s_flag[j] = m > 0.0f ? 1 : 0;
+            if (M_out) M_out[im.out_off + j] = m;
+        }
     }
     __syncthreads();
     int box[4];
     const bool ok = component_box(s_flag, s_comp, n, im.dim0, im.dim1, seed, s_red, box);
     if (tid == 0) {
-        seed_out[blockIdx.x] = seed;
-        status_out[blockIdx.x] = ok ? 0 : 1;
-        float* o = box_out + 4 * (long long)blockIdx.x;
+        seed_out[img] = seed;
+        status_out[img] = ok ? 0 : 1;
+        float* o = box_out + 4 * (long long)img;
         if (ok) write_box(o, box, im.s0, im.s1, im.img_h, im.img_w);
         else { o[0] = o[1] = o[2] = o[3] = 0.f; }
+        if (FROM_KEYS && done) atomicMax(const_cast<unsigned long long*>(reinterpret_cast<const unsigned long long*>(done)) - 1, lost_globaltimer());
     }
 }
 
@@ -414,8 +564,25 @@ using namespace b200p;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// The pair kernels (TC2 / TC2D on keys the tensor cores take) run count-only when the caller does not ask for A:
+// no Gram matrix is materialised anywhere, the finish kernel works from the keys.
+static bool lost_count_only(int gram_impl, int d) {
+    return gram_impl == B200P_LOST_GRAM_TC2 || (gram_impl == B200P_LOST_GRAM_TC2D && d <= kLostMaxTensorCoreWidth);
+}
+
+static const unsigned int* g_last_done = nullptr;
+// measurement aid: globaltimer (ns) trace of the last count-only call on this thread's device: Gram first CTA start, Gram
+// last CTA end, first finish CTA past its wait, last finish CTA end.  Synchronises the device.
+extern "C" int b200p_lost_last_trace(uint64_t* h_out4) {
+    B200P_REQUIRE(h_out4 != nullptr && g_last_done != nullptr, B200P_ESTATE, "lost_last_trace: no count-only call yet");
+    B200P_CUDA(cudaDeviceSynchronize());
+    B200P_CUDA(cudaMemcpy(h_out4, reinterpret_cast<const unsigned long long*>(g_last_done) - 4, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return B200P_OK;
+}
+
 extern "C" int b200p_lost_workspace_bytes(int n_images, int64_t total_patches, int64_t total_a, int d, int gram_impl, int64_t* out) {
     B200P_REQUIRE(out != nullptr && n_images >= 0 && total_patches >= 0 && total_a >= 0 && d >= 1, B200P_EINVAL, "lost_workspace_bytes: bad argument");
+    if (lost_count_only(gram_impl, d)) total_a = 0;
     size_t bytes = align_up((size_t)n_images * sizeof(LostImageDev), 256) + align_up((size_t)total_a * sizeof(float), 256) + 256;
     if (gram_impl != B200P_LOST_GRAM_FFMA) bytes += align_up(lost_tc_workspace_bytes(n_images, total_patches, d), 256);
     *out = (int64_t)bytes;
@@ -437,6 +604,7 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     int n_max = 0;
     B200P_REQUIRE(k_patches <= 1024, B200P_EINVAL, "lost_batched: k_patches must be <= 1024");
     bool vec = (((uintptr_t)d_feats) & 15u) == 0 && (row_stride & 3) == 0;
+    const bool count_only = d_A == nullptr && lost_count_only(gram_impl, d);
     // The tensor cores truncate every product to the accumulator's ulp, so a same-sign sum (the squared norms on the
     // diagonal) drifts by ~1.2e-8 d |k|^2: 4.9e-6 at d = 384, 9.3e-6 at 768, 2.2e-5 at 2048 (tools/gram_error_probe.py),
     // whatever the operand split.  The default keeps the 1e-5 parity bar by computing wide keys (ResNet-50 features,
@@ -470,12 +638,12 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     }
     B200P_REQUIRE(tile_base < (1ll << 31), B200P_EINVAL, "lost_batched: too many tiles in one call");
     const size_t meta_bytes = align_up((size_t)n_images * sizeof(LostImageDev), 256);
-    const size_t a_bytes = d_A ? 0 : align_up((size_t)total_a * sizeof(float), 256);
+    const size_t a_bytes = (d_A || count_only) ? 0 : align_up((size_t)total_a * sizeof(float), 256);
     const size_t tc_bytes = gram_impl != B200P_LOST_GRAM_FFMA ? align_up(lost_tc_workspace_bytes(n_images, total_patches, d), 256) : 0;
     const size_t need = meta_bytes + a_bytes + tc_bytes;
     B200P_REQUIRE((size_t)workspace_bytes >= need, B200P_EINVAL, "lost_batched: workspace too small (see b200p_lost_workspace_bytes)");
     LostImageDev* d_meta = (LostImageDev*)d_workspace;
-    float* A_base = d_A ? d_A : (float*)((char*)d_workspace + meta_bytes);
+    float* A_base = d_A ? d_A : count_only ? nullptr : (float*)((char*)d_workspace + meta_bytes);
     LostImageDev step;
     if (lost_meta_uniform(meta, step)) {
         k_lost_gen_meta<<<(n_images + 255) / 256, 256, 0, st>>>(d_meta, meta[0], step, n_images);
@@ -490,25 +658,57 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     }
     // the call owns d_degree[min out_offset, max out_offset + n): cleared in one go
     B200P_CUDA(cudaMemsetAsync(d_degree + deg_lo, 0, (size_t)(deg_hi - deg_lo) * sizeof(int32_t), st));
-    if (gram_impl != B200P_LOST_GRAM_FFMA) {
-        void* tc_ws = (char*)d_workspace + meta_bytes + a_bytes;
-        int rc = lost_gram_tc(d_feats, (long long)row_stride, d, d_meta, meta, total_patches, n_max, A_base, d_degree, tc_ws, tc_bytes,
-                              vec ? 1 : 0, st, tc_mode);
-        if (rc) return rc;
-    } else {
+    n_max = (n_max + 15) & ~15;
+    size_t fin_smem = (size_t)n_max * 4 + (size_t)((n_max + 1 + 3) & ~3) * 4 + 2 * 1024 * 4 + 2 * (size_t)n_max;
+    if (count_only) fin_smem += 2 * (size_t)((d + 3) & ~3) * 4 + 1024;
+    B200P_REQUIRE(fin_smem <= 96 * 1024, B200P_EINVAL, "lost_batched: keys too wide for the finish kernel's shared memory");
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_finish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_finish<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    if (gram_impl == B200P_LOST_GRAM_FFMA) {
         k_lost_gram_ffma<<<(int)tile_base, GT, 0, st>>>(d_feats, (long long)row_stride, d, d_meta, n_images, A_base, d_degree,
                                                        0.0f, vec ? 1 : 0);
         B200P_LAUNCH_CHECK("k_lost_gram_ffma");
     }
-    n_max = (n_max + 15) & ~15;
-    const size_t fin_smem = (size_t)n_max * 4 + (size_t)((n_max + 1 + 3) & ~3) * 4 + 2 * 1024 * 4 + 2 * (size_t)n_max;
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200P_CUDA(cudaFuncSetAttribute(k_lost_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
+    LostGramPlan gp;
+    if (gram_impl != B200P_LOST_GRAM_FFMA) {
+        void* tc_ws = (char*)d_workspace + meta_bytes + a_bytes;
+        int rc = lost_gram_prepare(&gp, d_feats, (long long)row_stride, d, d_meta, meta, total_patches, n_max, tc_ws, tc_bytes,
+                                   vec ? 1 : 0, st, tc_mode, count_only);
+        if (rc) return rc;
     }
-    k_lost_finish<<<n_images, kFinThreads, fin_smem, st>>>(d_meta, A_base, d_degree, k_patches, n_max, d_seed, d_box, d_status, nullptr);
-    B200P_LAUNCH_CHECK("k_lost_finish");
+    if (!count_only) {
+        if (gram_impl != B200P_LOST_GRAM_FFMA) { int rc = lost_gram_run(gp, 0, gp.n_tiles2, A_base, d_degree, st); if (rc) return rc; }
+        k_lost_finish<false><<<n_images, kFinThreads, fin_smem, st>>>(d_meta, A_base, d_degree, k_patches, n_max, d_seed, d_box, d_status, nullptr,
+                                                                      d_feats, (long long)row_stride, d, vec ? 1 : 0, nullptr);
+        B200P_LAUNCH_CHECK("k_lost_finish");
+        return B200P_OK;
+    }
+    // Count-only: the finish kernel is launched as a programmatic dependent of the Gram kernel (which triggers right at
+    // its start, i.e. once all of its persistent CTAs are resident): finish CTAs slip onto the SMs beside the Gram CTAs
+    // (384 threads, ~22 KB of shared memory next to 193 KB) and CTA b waits on image b's completion counter, which the Gram
+    // epilogue releases per tile.  The finish of an image runs while its keys are still in L2 and under the Gram of the
+    // following images; only the last images' finish is exposed.  The Gram kernel never waits on the finish kernel, so
+    // the pair cannot deadlock; without room on the SMs the finish CTAs simply start when Gram CTAs retire.
+    int rc = lost_gram_run(gp, 0, gp.n_tiles2, nullptr, d_degree, st); if (rc) return rc;
+    const bool beside = fin_smem <= 30 * 1024;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_images); cfg.blockDim = dim3(beside ? 256 : kFinThreads); cfg.dynamicSmemBytes = fin_smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    static const int fin_env = [] { const char* e = getenv("B200P_LOST_FINISH"); return e ? atoi(e) : 1; }();      // experiments: 0 skip, 2 no PDL
+    if (fin_env == 0) return B200P_OK;
+    if (fin_env == 2) { cfg.numAttrs = 0; cfg.blockDim = dim3(kFinThreads); }
+    g_last_done = gp.d_done;
+    B200P_CUDA(cudaLaunchKernelEx(&cfg, k_lost_finish<true>, (const LostImageDev*)d_meta, (const float*)nullptr, (const int*)d_degree, k_patches, n_max,
+                                  d_seed, d_box, d_status, (float*)nullptr, d_feats, (long long)row_stride, d, vec ? 1 : 0,
+                                  (const unsigned int*)gp.d_done));
     return B200P_OK;
 }
 

@@ -18,6 +18,10 @@ struct LostImageDev {
     int pad_;
 };
 
+__device__ __forceinline__ unsigned long long lost_globaltimer() {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+
 __device__ __forceinline__ int find_image(const LostImageDev* __restrict__ meta, int n_images, int cta) {
     int lo = 0, hi = n_images - 1;
     while (lo < hi) {
@@ -31,8 +35,16 @@ __device__ __forceinline__ int find_image(const LostImageDev* __restrict__ meta,
 enum { LOST_TC_SINGLE = 0, LOST_TC_PAIR = 1, LOST_TC_PAIR_DIRECT = 2 };
 size_t lost_tc_workspace_bytes(int n_images, long long total_patches, int d);
 bool lost_tc_direct_ok(const float* d_feats, long long row_stride, int d, const b200p_lost_image_t* h_meta, int n_images);
-int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
-                 const std::vector<LostImageDev>& meta, long long total_patches, int n_max, float* A_base,
-                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st, int mode);
+struct Tile2;
+struct LostGramPlan {
+    alignas(64) unsigned char tm_hi[128], tm_lo[128];     // CUtensorMap storage (cuda.h stays out of this header)
+    const Tile2* tab; const LostImageDev* d_meta;
+    unsigned int* d_done;                                  // count-only: per-image completion counters (epilogue warps x tiles)
+    int n_tiles2, n_tiles1, n_images, mode, d_pad, sms;
+};
+int lost_gram_prepare(LostGramPlan* gp, const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
+                      const std::vector<LostImageDev>& meta, long long total_patches, int n_max, void* ws, size_t ws_bytes,
+                      int vec_ok, cudaStream_t st, int mode, bool count_only);
+int lost_gram_run(const LostGramPlan& gp, int t_begin, int t_end, float* A_base, int* d_degree, cudaStream_t st);
 
 }  // namespace b200p

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "lost_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace b200p {
 
@@ -330,8 +331,9 @@ k_lost_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 constexpr int T2_BM = 128, T2_BN = 256, T2_TILE = 256;           // rows per CTA, columns per tile, tile edge
 constexpr int T2_ACC = 2, T2_TMEM_COLS = T2_ACC * T2_BN;         // 512 columns: all of TMEM
 constexpr int T2_THREADS = 320;                                  // TMA warp, MMA warp, 8 epilogue warps
-constexpr int T2_CONV_WARPS = 4;                                 // direct mode: + 4 warps deriving the lo tiles in shared memory
-constexpr int T2_THREADS_DIRECT = T2_THREADS + 32 * T2_CONV_WARPS;
+// direct mode: + converter warps deriving the lo tiles in shared memory: 4 next to the storing epilogue (168 registers per
+// thread), 8 in count-only mode (79 registers): two per scheduler halve the time from "raw tile landed" to "lo tile ready"
+__host__ __device__ constexpr int t2_threads(bool direct, int conv_warps) { return T2_THREADS + (direct ? 32 * conv_warps : 0); }
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;                      // clears the CTA-rank bit of a shared::cluster address (rank 0 of the pair)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -407,8 +409,13 @@ struct __align__(16) Tile2 {
 constexpr int kT2Share = 1 << 9, kT2Diag = 1 << 10;
 
 __global__ void __launch_bounds__(128)
-k_lost_tile_table(const LostImageDev* __restrict__ meta, int n_images, int n_tiles, Tile2* __restrict__ tab) {
+k_lost_tile_table(const LostImageDev* __restrict__ meta, int n_images, int n_tiles, Tile2* __restrict__ tab, unsigned int* __restrict__ done) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (done && t < n_images) done[t] = 0u;          // count-only: per-image completion counters, see k_lost_finish
+    if (done && t == 0) {                            // globaltimer trace in front of the counters: Gram start / end, finish start / end
+        unsigned long long* tr = reinterpret_cast<unsigned long long*>(done) - 4;
+        tr[0] = ~0ull; tr[1] = 0ull; tr[2] = ~0ull; tr[3] = 0ull;
+    }
     if (t >= n_tiles) return;
     const TileCoord tc = decode_tile2(meta, n_images, t);
     const LostImageDev im = meta[tc.img];
@@ -418,7 +425,7 @@ k_lost_tile_table(const LostImageDev* __restrict__ meta, int n_images, int n_til
     e.b_row0 = im.row_base + tc.tj * T2_TILE;
     const bool diag = tc.ti == tc.tj;
     e.info = ncols | (diag && ncols == T2_BN ? kT2Share : 0) | (diag ? kT2Diag : 0) | (tc.ti << 12) | (tc.tj << 16);
-    e.n = im.n; e.a_off = im.a_off; e.out_off = im.out_off;
+    e.n = im.n; e.a_off = done ? (long long)tc.img : im.a_off; e.out_off = im.out_off;      // count-only: no A, the slot carries the image index
     tab[t] = e;
 }
 __device__ __forceinline__ Tile2 load_tile2(const Tile2* __restrict__ tab, int t, int n_tiles) {
@@ -444,22 +451,31 @@ __device__ __forceinline__ Tile2 load_tile2(const Tile2* __restrict__ tab, int t
 //               (the conversion of k-blocks i+1, i+2 overlaps the MMAs of i; 4 + 2 stages measure the same)
 //   epilogue:   8 warps x 32 x 32 floats, 16-B XOR swizzle: the row-major copy of A is transposed through
 //               shared memory so that one store instruction writes four full 128-B lines           32 KB
-constexpr int T2_RAW_STAGES = 3, T2_LO_STAGES = 3;
-constexpr int T2_RING_BYTES = TC_STAGES * TC_STAGE_BYTES;        // == (T2_RAW_STAGES + T2_LO_STAGES) * 2 tiles
-constexpr int T2_STAGING_BYTES = 8 * 32 * 32 * 4;
+//   count-only (WRITE_A = false): the caller did not ask for A (b200p_lost_batched with d_A == NULL).  Nothing is stored:
+//               the epilogue only counts positive entries per row and column, the finish kernel gets A[seed, :] and
+//               M from the keys (two skinny mat-vecs).  No staging buffer: 193 KB, which leaves room on the SM for a
+//               CTA of the finish kernel of the previous sub-batch (b200p_lost_batched overlaps the two).
+constexpr int T2_LO_STAGES = 3;
+constexpr int T2_RING_BYTES = TC_STAGES * TC_STAGE_BYTES;        // == (3 raw + 3 lo) * 2 tiles
+constexpr int T2_STAGING_BYTES = 8 * 32 * 32 * 4;               // == one raw stage (2 tiles)
 constexpr size_t T2_SMEM_BYTES = (size_t)T2_RING_BYTES + T2_STAGING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-static_assert(T2_RING_BYTES == (T2_RAW_STAGES + T2_LO_STAGES) * 2 * TC_TILE_BYTES, "ring layouts must have the same size");
+static_assert(T2_RING_BYTES == (3 + T2_LO_STAGES) * 2 * TC_TILE_BYTES, "ring layouts must have the same size");
+constexpr size_t T2_SMEM_COUNT_BYTES = (size_t)T2_RING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 static_assert(T2_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-template <bool DIRECT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DIRECT ? T2_THREADS_DIRECT : T2_THREADS, 1)
+template <bool DIRECT, bool WRITE_A, int T2_CONV_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2_threads(DIRECT, T2_CONV_WARPS), 1)
 k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                 const Tile2* __restrict__ tab, int n_tiles, float* __restrict__ A_base,
-                int* __restrict__ degree_base, float threshold, int d_pad) {
+                int* __restrict__ degree_base, float threshold, int d_pad, unsigned int* __restrict__ done) {
     extern __shared__ uint8_t smem_raw[];
+    // a dependent kernel (the count-only finish) may be scheduled beside this grid as soon as all of its CTAs are running
+    if (!WRITE_A) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!WRITE_A && done && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(done) - 4, lost_globaltimer());
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t staging_base = smem_base + T2_RING_BYTES;
-    const uint32_t bar_base = staging_base + T2_STAGING_BYTES;
+    const uint32_t bar_base = staging_base + (WRITE_A ? T2_STAGING_BYTES : 0);      // count-only: no staging buffer (T2_SMEM_COUNT_BYTES)
+    constexpr int T2_RAW_STAGES = 3;
     constexpr int NFULL = DIRECT ? T2_RAW_STAGES : TC_STAGES;     // stages the TMA fills
     auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // [4]
     auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };                // [4]
@@ -469,9 +485,12 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     const uint32_t tmem_slot = bar_base + 8u * 20;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     // operand tile addresses of k-block `it`
-    auto hi_tiles = [&](int it) { return DIRECT ? smem_base + (uint32_t)(it % T2_RAW_STAGES) * (2 * TC_TILE_BYTES)
-                                                : smem_base + (uint32_t)(it % TC_STAGES) * TC_STAGE_BYTES; };
-    auto lo_tiles = [&](int it) { return DIRECT ? smem_base + (uint32_t)(T2_RAW_STAGES * 2 + (it % T2_LO_STAGES) * 2) * TC_TILE_BYTES
+    auto hi_tiles = [&](int it) {
+        if (!DIRECT) return smem_base + (uint32_t)(it % TC_STAGES) * TC_STAGE_BYTES;
+        const int s = it % T2_RAW_STAGES;
+        return s < 3 ? smem_base + (uint32_t)s * (2 * TC_TILE_BYTES) : staging_base;
+    };
+    auto lo_tiles = [&](int it) { return DIRECT ? smem_base + (uint32_t)(3 * 2 + (it % T2_LO_STAGES) * 2) * TC_TILE_BYTES
                                                 : smem_base + (uint32_t)(it % TC_STAGES) * TC_STAGE_BYTES + 2 * TC_TILE_BYTES; };
     // each pair of tiles is [A | B]
 
@@ -577,10 +596,12 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             nxt = load_tile2(tab, t + n_clusters, n_tiles);
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 mbar_wait(full_bar(it % T2_RAW_STAGES), (uint32_t)(it / T2_RAW_STAGES) & 1u);          // this CTA's raw tiles have landed
-                // the MMAs three k-blocks back are done with the lo stage: the rings have the same length, so the raw stage's
-                // empty barrier says so too (a second tcgen05.commit per k-block for a separate barrier costs ~0.1 ms per call)
-                static_assert(T2_RAW_STAGES == T2_LO_STAGES, "one empty barrier serves the raw and the lo stage of a k-block");
-                mbar_wait(empty_bar(it % T2_LO_STAGES), ((uint32_t)(it / T2_LO_STAGES) & 1u) ^ 1u);
+                // the lo stage is free once the MMAs of k-block it - 3 are done: the commit that freed THAT k-block's raw
+                // stage says so (a second tcgen05.commit per k-block for a separate barrier costs ~0.1 ms per call)
+                if (it >= T2_LO_STAGES) {
+                    const int j = it - T2_LO_STAGES;
+                    mbar_wait(empty_bar(j % T2_RAW_STAGES), (uint32_t)(j / T2_RAW_STAGES) & 1u);
+                }
                 // plain shared-memory pointers: the compiler batches the eight loads of a tile ahead of the math and the stores
                 uint4* __restrict__ src = reinterpret_cast<uint4*>(smem_raw + (hi_tiles(it) - smem_u32(smem_raw))) + ct;
                 uint4* __restrict__ dst = reinterpret_cast<uint4*>(smem_raw + (lo_tiles(it) - smem_u32(smem_raw))) + ct;
@@ -629,9 +650,9 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             const int row0 = (im.info >> 12 & 15) * T2_TILE + (int)rank * T2_BM, col0 = (im.info >> 16 & 15) * T2_TILE;
             const bool mirror = (im.info & kT2Diag) == 0;       // a diagonal 256-tile holds both triangles already
             const int gi0 = row0 + q * 32, gi = gi0 + lane;
-            float* __restrict__ A = A_base + im.a_off;
+            float* __restrict__ A = WRITE_A ? A_base + im.a_off : nullptr;
             int* __restrict__ deg = degree_base + im.out_off;
-            const bool vec_store = (im.n & 3) == 0 && (((uintptr_t)A) & 15u) == 0;
+            const bool vec_store = !WRITE_A || ((im.n & 3) == 0 && (((uintptr_t)A) & 15u) == 0);      // count-only: the fast paths store nothing
             const float thr0 = fmaxf(threshold, 0.f);                  // (i != j ? max(A_ij, 0) : 0) > threshold  <=>  A_ij > thr0 off the diagonal
             int cnt = 0;
 #pragma unroll 1
@@ -641,7 +662,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_BN + ch * 32), r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (vec_store) {
+                if (WRITE_A && vec_store) {
                     // row-major copy through shared memory: lane i parks its row (8 float4, 16-B groups XOR-swizzled by
                     // i & 7: conflict-free both ways), then lane l picks up columns 4 (l & 7) .. +3 of rows 4 p + (l >> 3)
                     // and one store instruction covers four complete 128-B lines of A
@@ -671,7 +692,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                 const bool full = vec_store && gi0 + 32 <= im.n && gj0 + 32 <= im.n && (mirror || gj0 != gi0);
                 if (full && mirror) {
                     int colcnt = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-                    float* __restrict__ col = A + (long long)gj0 * im.n + gi;
+                    float* __restrict__ col = WRITE_A ? A + (long long)gj0 * im.n + gi : nullptr;
 #pragma unroll
                     for (int c = 0; c < 32; c += 4) {
                         const bool p0 = __uint_as_float(r[c]) > thr0, p1 = __uint_as_float(r[c + 1]) > thr0;
@@ -680,10 +701,12 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                         const unsigned b0 = __ballot_sync(0xFFFFFFFFu, p0), b1 = __ballot_sync(0xFFFFFFFFu, p1);
                         const unsigned b2 = __ballot_sync(0xFFFFFFFFu, p2), b3 = __ballot_sync(0xFFFFFFFFu, p3);
                         if ((lane >> 2) == (c >> 2)) colcnt = __popc((lane & 3) == 0 ? b0 : (lane & 3) == 1 ? b1 : (lane & 3) == 2 ? b2 : b3);
-                        col[(long long)(c + 0) * im.n] = __uint_as_float(r[c]);          // transposed: lanes = consecutive addresses
-                        col[(long long)(c + 1) * im.n] = __uint_as_float(r[c + 1]);
-                        col[(long long)(c + 2) * im.n] = __uint_as_float(r[c + 2]);
-                        col[(long long)(c + 3) * im.n] = __uint_as_float(r[c + 3]);
+                        if (WRITE_A) {
+                            col[(long long)(c + 0) * im.n] = __uint_as_float(r[c]);          // transposed: lanes = consecutive addresses
+                            col[(long long)(c + 1) * im.n] = __uint_as_float(r[c + 1]);
+                            col[(long long)(c + 2) * im.n] = __uint_as_float(r[c + 2]);
+                            col[(long long)(c + 3) * im.n] = __uint_as_float(r[c + 3]);
+                        }
                     }
                     cnt += (c0 + c1) + (c2 + c3);
                     if (colcnt) atomicAdd(deg + gj0 + lane, colcnt);
@@ -710,11 +733,11 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                     if (mirror) {
                         const unsigned bal = __ballot_sync(0xFFFFFFFFu, pos);
                         if (lane == c) colcnt = __popc(bal);
-                        if (in) A[(long long)gj * im.n + gi] = v;
+                        if (WRITE_A && in) A[(long long)gj * im.n + gi] = v;
                     }
                 }
                 if (mirror && colcnt && gj0 + lane < im.n) atomicAdd(deg + gj0 + lane, colcnt);
-                if (!vec_store && gi < im.n) {          // unaligned A: scalar row stores
+                if (WRITE_A && !vec_store && gi < im.n) {          // unaligned A: scalar row stores
                     float* dst = A + (long long)gi * im.n + gj0;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) if (gj0 + c < im.n) dst[c] = __uint_as_float(r[c]);
@@ -723,10 +746,16 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             if (gi < im.n && cnt) atomicAdd(deg + gi, cnt);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive_cluster_relaxed(tmem_empty_bar(acc) & kPeerMask);  // 2 x 256 arrivals on the leader's barrier
+            if (!WRITE_A && done) {
+                // this warp's degree contributions of the tile are out: release them to the finish kernel (one count per warp)
+                __syncwarp();
+                if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(done + im.a_off) : "memory");
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                                          // both CTAs are done with TMEM and with each other's barriers
+    if (!WRITE_A && done && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(done) - 3, lost_globaltimer());
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)T2_TMEM_COLS) : "memory");
     }
@@ -765,7 +794,7 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, int col
 // upper bound of the 256x256 tile records of a batch: an image of n <= 4096 patches has T = ceil(n / 256) <= 16
 // tile rows and T (T + 1) / 2 <= 8.5 T tiles
 static size_t tile_table_bytes(int n_images, long long total_patches) {
-    return ((size_t)(9 * (total_patches / T2_TILE + n_images)) + 16) * sizeof(Tile2);
+    return ((size_t)(9 * (total_patches / T2_TILE + n_images)) + 16) * sizeof(Tile2) + 32 + (size_t)n_images * sizeof(unsigned int);
 }
 
 size_t lost_tc_workspace_bytes(int n_images, long long total_patches, int d) {
@@ -784,25 +813,33 @@ bool lost_tc_direct_ok(const float* d_feats, long long row_stride, int d, const 
     return true;
 }
 
-int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
-                 const std::vector<LostImageDev>& meta, long long total_patches, int n_max, float* A_base,
-                 int* d_degree, void* ws, size_t ws_bytes, int vec_ok, cudaStream_t st, int mode) {
+// Set-up of one b200p_lost_batched call: tile table, tensor maps (and the hi/lo split for the pre-split modes).
+int lost_gram_prepare(LostGramPlan* gp, const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
+                      const std::vector<LostImageDev>& meta, long long total_patches, int n_max, void* ws, size_t ws_bytes,
+                      int vec_ok, cudaStream_t st, int mode, bool count_only) {
+    static_assert(sizeof(CUtensorMap) == sizeof(gp->tm_hi), "tensor map storage");
     const int n_images = (int)meta.size();
     const int d_pad = (d + TC_BK - 1) / TC_BK * TC_BK;
     const LostImageDev& last = meta.back();
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    alignas(64) CUtensorMap tm_hi, tm_lo;
+    gp->mode = mode; gp->d_pad = d_pad; gp->sms = sms; gp->d_meta = d_meta; gp->n_images = n_images;
+    CUtensorMap* tm_hi = reinterpret_cast<CUtensorMap*>(gp->tm_hi);
+    CUtensorMap* tm_lo = reinterpret_cast<CUtensorMap*>(gp->tm_lo);
     const int T2 = (last.n + T2_TILE - 1) / T2_TILE;
-    const int n_tiles2 = last.pair2_base + T2 * (T2 + 1) / 2;
-    const int grid2 = 2 * (n_tiles2 < sms / 2 ? n_tiles2 : sms / 2);       // one cluster (CTA pair) per two SMs
+    gp->n_tiles2 = last.pair2_base + T2 * (T2 + 1) / 2;
+    gp->n_tiles1 = last.pair_base + last.tiles * (last.tiles + 1) / 2;
     // workspace: [tile table | hi | lo]
     const size_t tab_bytes = (tile_table_bytes(n_images, total_patches) + 255) / 256 * 256;
     Tile2* tab = (Tile2*)(((uintptr_t)ws + 15) & ~(uintptr_t)15);
+    gp->tab = tab;
+    gp->d_done = nullptr;
     if (mode != LOST_TC_SINGLE) {
-        if (ws_bytes < tab_bytes || (size_t)n_tiles2 * sizeof(Tile2) + 16 > tab_bytes) { set_error("lost_batched: tensor-core workspace too small"); return B200P_EINVAL; }
-        k_lost_tile_table<<<(n_tiles2 + 127) / 128, 128, 0, st>>>(d_meta, n_images, n_tiles2, tab);
+        if (ws_bytes < tab_bytes || (size_t)gp->n_tiles2 * sizeof(Tile2) + 16 + 32 + (size_t)n_images * 4 > tab_bytes) { set_error("lost_batched: tensor-core workspace too small"); return B200P_EINVAL; }
+        if (count_only) gp->d_done = reinterpret_cast<unsigned int*>(tab + gp->n_tiles2) + 8;   // behind the tile records: 4 x u64 trace, counters
+        const int work = gp->n_tiles2 > n_images ? gp->n_tiles2 : n_images;
+        k_lost_tile_table<<<(work + 127) / 128, 128, 0, st>>>(d_meta, n_images, gp->n_tiles2, tab, gp->d_done);
         B200P_LAUNCH_CHECK("k_lost_tile_table");
     }
     ws = (char*)ws + tab_bytes; ws_bytes -= ws_bytes < tab_bytes ? ws_bytes : tab_bytes;
@@ -810,14 +847,8 @@ int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostIm
         // meta[].row_base holds each image's first row in the caller's array (set by the caller of this function)
         long long rows = 0;
         for (const LostImageDev& m : meta) if ((long long)m.row_base + m.n > rows) rows = (long long)m.row_base + m.n;
-        int rc = make_map(&tm_hi, d_feats, rows, d, row_stride); if (rc) return rc;
-        static bool attr3_set = false;
-        if (!attr3_set) {
-            B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
-            attr3_set = true;
-        }
-        k_lost_gram_tc2<true><<<grid2, T2_THREADS_DIRECT, T2_SMEM_BYTES, st>>>(tm_hi, tm_hi, tab, n_tiles2, A_base, d_degree, 0.0f, d_pad);
-        B200P_LAUNCH_CHECK("k_lost_gram_tc2<direct>");
+        int rc = make_map(tm_hi, d_feats, rows, d, row_stride); if (rc) return rc;
+        *tm_lo = *tm_hi;
         return B200P_OK;
     }
     const size_t arr = ((size_t)total_patches * d_pad * sizeof(float) + 1023) / 1024 * 1024;
@@ -831,27 +862,48 @@ int lost_gram_tc(const float* d_feats, long long row_stride, int d, const LostIm
     dim3 sgrid((unsigned)((quads + 255) / 256), (unsigned)n_images);
     k_lost_split_tf32<<<sgrid, 256, 0, st>>>(d_feats, row_stride, d, d_pad, d_meta, hi, lo, vec_ok);
     B200P_LAUNCH_CHECK("k_lost_split_tf32");
-    int rc = make_map(&tm_hi, hi, total_patches, d_pad, d_pad); if (rc) return rc;
-    rc = make_map(&tm_lo, lo, total_patches, d_pad, d_pad); if (rc) return rc;
-    if (mode == LOST_TC_PAIR) {
-        static bool attr2_set = false;
-        if (!attr2_set) {
-            B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
-            attr2_set = true;
-        }
-        k_lost_gram_tc2<false><<<grid2, T2_THREADS, T2_SMEM_BYTES, st>>>(tm_hi, tm_lo, tab, n_tiles2, A_base, d_degree, 0.0f, d_pad);
-        B200P_LAUNCH_CHECK("k_lost_gram_tc2");
-        return B200P_OK;
-    }
+    int rc = make_map(tm_hi, hi, total_patches, d_pad, d_pad); if (rc) return rc;
+    return make_map(tm_lo, lo, total_patches, d_pad, d_pad);
+}
+
+// Gram + degrees of the 256x256 tiles [t_begin, t_end) of the table (pair modes; images own consecutive tiles, so a
+// range of images is a range of tiles).  A_base == nullptr: count-only.  The single-CTA cross-check kernel always runs
+// the whole batch.
+int lost_gram_run(const LostGramPlan& gp, int t_begin, int t_end, float* A_base, int* d_degree, cudaStream_t st) {
+    const CUtensorMap& tm_hi = *reinterpret_cast<const CUtensorMap*>(gp.tm_hi);
+    const CUtensorMap& tm_lo = *reinterpret_cast<const CUtensorMap*>(gp.tm_lo);
     static bool attr_set = false;
     if (!attr_set) {
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_COUNT_BYTES));
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_COUNT_BYTES));
         B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        // count-only kernels: ask for the full 228 KB shared-memory carve-out (their own 194 KB would select the 196 KB
+        // configuration), so that a CTA of the finish kernel finds room on the same SM
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<true, false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<false, false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
-    const int n_tiles = last.pair_base + last.tiles * (last.tiles + 1) / 2;
-    const int grid = n_tiles < sms ? n_tiles : sms;                  // persistent: one CTA per SM
-    k_lost_gram_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_hi, tm_lo, d_meta, n_images, n_tiles, A_base, d_degree, 0.0f, d_pad);
-    B200P_LAUNCH_CHECK("k_lost_gram_tc");
+    if (gp.mode == LOST_TC_SINGLE) {
+        const int grid = gp.n_tiles1 < gp.sms ? gp.n_tiles1 : gp.sms;      // persistent: one CTA per SM
+        k_lost_gram_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_hi, tm_lo, gp.d_meta, gp.n_images, gp.n_tiles1, A_base, d_degree, 0.0f, gp.d_pad);
+        B200P_LAUNCH_CHECK("k_lost_gram_tc");
+        return B200P_OK;
+    }
+    const int nt = t_end - t_begin;
+    if (nt <= 0) return B200P_OK;
+    const int grid2 = 2 * (nt < gp.sms / 2 ? nt : gp.sms / 2);             // one cluster (CTA pair) per two SMs
+    const Tile2* tab = gp.tab + t_begin;
+    if (gp.mode == LOST_TC_PAIR_DIRECT) {
+        if (A_base) k_lost_gram_tc2<true, true, 4><<<grid2, t2_threads(true, 4), T2_SMEM_BYTES, st>>>(tm_hi, tm_hi, tab, nt, A_base, d_degree, 0.0f, gp.d_pad, nullptr);
+        else        k_lost_gram_tc2<true, false, 4><<<grid2, t2_threads(true, 4), T2_SMEM_COUNT_BYTES, st>>>(tm_hi, tm_hi, tab, nt, nullptr, d_degree, 0.0f, gp.d_pad, gp.d_done);
+        B200P_LAUNCH_CHECK("k_lost_gram_tc2<direct>");
+    } else {
+        if (A_base) k_lost_gram_tc2<false, true, 4><<<grid2, T2_THREADS, T2_SMEM_BYTES, st>>>(tm_hi, tm_lo, tab, nt, A_base, d_degree, 0.0f, gp.d_pad, nullptr);
+        else        k_lost_gram_tc2<false, false, 4><<<grid2, T2_THREADS, T2_SMEM_COUNT_BYTES, st>>>(tm_hi, tm_lo, tab, nt, nullptr, d_degree, 0.0f, gp.d_pad, gp.d_done);
+        B200P_LAUNCH_CHECK("k_lost_gram_tc2");
+    }
     return B200P_OK;
 }
 

@@ -249,6 +249,61 @@ extern "C" int b200p_ptrtable_create(b200p_plan* p, int slot, const void* const*
     return B200P_OK;
 }
 
+namespace b200p {
+// several tables in one launch: up to 1024 segment pointers travel as kernel arguments
+constexpr int kMultiPtrs = 1024, kMultiTabs = 16;
+struct PtrPackBig { void* p[kMultiPtrs]; };
+struct TabPack { void** tab[kMultiTabs]; };
+__global__ void k_fill_chunk_ptrs_multi(TabPack tabs, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_elem0,
+                                        PtrPackBig pack, int n_seg, int n_tabs, int elem_size, int64_t n_chunks) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chunks * n_tabs) return;
+    const int t = (int)(i / n_chunks);
+    const int64_t c = i - (int64_t)t * n_chunks;
+    tabs.tab[t][c] = (char*)pack.p[t * n_seg + chunk_seg[c]] + chunk_elem0[c] * elem_size;
+}
+}  // namespace b200p
+
+extern "C" int b200p_ptrtables_update(b200p_ptrtable* const* tables, const void* const* const* h_ptrs, int n_tables, int slot, void* stream) {
+    B200P_REQUIRE(tables != nullptr && h_ptrs != nullptr && n_tables >= 1, B200P_EINVAL, "ptrtables_update: bad argument");
+    B200P_REQUIRE(slot >= 0 && slot < B200P_NUM_SLOTS, B200P_EINVAL, "ptrtables_update: bad slot");
+    b200p_plan* p = tables[0] ? tables[0]->plan : nullptr;
+    B200P_REQUIRE(p != nullptr, B200P_EINVAL, "ptrtables_update: null table");
+    for (int i = 0; i < n_tables; ++i)
+        B200P_REQUIRE(tables[i] != nullptr && tables[i]->plan == p && h_ptrs[i] != nullptr, B200P_EINVAL, "ptrtables_update: tables must belong to one plan");
+    B200P_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int elem = slot_elem_size(slot);
+    if (p->n_seg > kMultiPtrs) {                       // more segments than one launch carries: table by table
+        for (int i = 0; i < n_tables; ++i) { int rc = fill_table(p, tables[i]->d_tab, h_ptrs[i], elem, st, &tables[i]->vec_ok); if (rc) return rc; }
+        return B200P_OK;
+    }
+    const int per = kMultiPtrs / p->n_seg < kMultiTabs ? kMultiPtrs / p->n_seg : kMultiTabs;
+    for (int i0 = 0; i0 < n_tables; i0 += per) {
+        const int nt = n_tables - i0 < per ? n_tables - i0 : per;
+        PtrPackBig pack; TabPack tabs;
+        for (int i = 0; i < nt; ++i) {
+            bool vec = true;
+            tabs.tab[i] = tables[i0 + i]->d_tab;
+            for (int t = 0; t < p->n_seg; ++t) {
+                const void* q = h_ptrs[i0 + i][t];
+                B200P_REQUIRE(q != nullptr, B200P_EINVAL, "ptrtables_update: null segment pointer");
+                pack.p[i * p->n_seg + t] = const_cast<void*>(q);
+                if ((uintptr_t)q & 15u) vec = false;
+            }
+            tables[i0 + i]->vec_ok = vec;
+        }
+        const int64_t work = p->n_chunks * nt;
+        k_fill_chunk_ptrs_multi<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(tabs, p->d_chunk_seg, p->d_chunk_elem0, pack, p->n_seg, nt, elem, p->n_chunks);
+        B200P_LAUNCH_CHECK("k_fill_chunk_ptrs_multi");
+    }
+    // a table currently bound to a slot keeps its binding; refresh the slot's vector flag
+    for (int i = 0; i < n_tables; ++i)
+        for (int sl = 0; sl < B200P_NUM_SLOTS; ++sl)
+            if (p->d_tab[sl] == tables[i]->d_tab) p->vec_ok[sl] = tables[i]->vec_ok;
+    return B200P_OK;
+}
+
 extern "C" int b200p_ptrtable_destroy(b200p_ptrtable* t) {
     if (!t) return B200P_OK;
     if (t->plan) {

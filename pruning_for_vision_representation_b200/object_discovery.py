@@ -38,17 +38,67 @@ def _box_to_pred(box, scales):
     return [int(round(v)) for v in box] if ints else [float(v) for v in box]
 
 
+_META_DTYPE = np.dtype([("feat_offset", "<i8"), ("a_offset", "<i8"), ("out_offset", "<i8"), ("dim0", "<i4"), ("dim1", "<i4"),
+                        ("img_h", "<i4"), ("img_w", "<i4"), ("scale0", "<f4"), ("scale1", "<f4")])
+assert _META_DTYPE.itemsize == ctypes.sizeof(LostImage)
+
+
+def _meta_records(feat_offs, dims, scales, sizes):
+    """b200p_lost_image_t records of a batch as one numpy structured array (no per-image Python objects): `dims` and
+    `sizes` are one pair / triple for the whole batch or one per image."""
+    B = len(feat_offs)
+    rec = np.zeros(B, _META_DTYPE)
+    dims = np.asarray(dims, np.int64).reshape(-1, 2)
+    rec["dim0"], rec["dim1"] = dims[:, 0], dims[:, 1]
+    ns = (rec["dim0"].astype(np.int64) * rec["dim1"]) + np.zeros(B, np.int64)
+    rec["feat_offset"] = feat_offs
+    rec["out_offset"][1:] = np.cumsum(ns)[:-1]
+    rec["a_offset"][1:] = np.cumsum(ns * ns)[:-1]
+    if sizes is not None:
+        sz = np.asarray(sizes, np.int64)
+        sz = sz.reshape(-1, sz.shape[-1])
+        rec["img_h"], rec["img_w"] = sz[:, -2], sz[:, -1]
+    rec["scale0"], rec["scale1"] = float(scales[0]), float(scales[1])
+    return rec, ns
+
+
+class _Split:
+    """List-like view of a flat tensor cut into per-image pieces; the pieces are only made when asked for (a batch of
+    256 images would otherwise pay for 256 tensor views per call)."""
+
+    def __init__(self, flat, sizes, shapes=None):
+        self.flat, self.sizes, self.shapes = flat, sizes, shapes
+        self.starts = np.concatenate(([0], np.cumsum(sizes)))
+
+    def __len__(self):
+        return len(self.sizes)
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += len(self.sizes)
+        t = self.flat[int(self.starts[i]):int(self.starts[i + 1])]
+        return t.view(*self.shapes[i]) if self.shapes is not None else t
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self.sizes)))
+
+
 class _Batch:
     """Device buffers of one b200p_lost_batched call."""
 
-    def __init__(self, feats, row_stride, d, metas, dev, want_A, k_patches, gram_impl):
+    def __init__(self, feats, row_stride, d, metas, dev, want_A, k_patches, gram_impl, ns=None):
         lib = L.require_cuda()
         if gram_impl is None:
             gram_impl = DEFAULT_GRAM_IMPL
         n_images = len(metas)
-        arr = (LostImage * n_images)(*metas)
-        ns = [m.dim0 * m.dim1 for m in metas]
-        total_p, total_a = sum(ns), sum(n * n for n in ns)
+        if isinstance(metas, np.ndarray):
+            arr = ctypes.cast(metas.ctypes.data, ctypes.POINTER(LostImage))
+            self._metas = metas
+            total_p, total_a = int(ns.sum()), int((ns * ns).sum())
+        else:
+            arr = (LostImage * n_images)(*metas)
+            ns = np.array([m.dim0 * m.dim1 for m in metas], np.int64)
+            total_p, total_a = int(ns.sum()), int((ns * ns).sum())
         ws_bytes = ctypes.c_int64()
         check(lib.b200p_lost_workspace_bytes(n_images, total_p, 0 if want_A else total_a, int(d), gram_impl, ctypes.byref(ws_bytes)),
               "lost_workspace_bytes")
@@ -120,9 +170,9 @@ def lost_batched(feats, dims, scales, init_image_sizes, k_patches=100, return_A=
             feats = feats.contiguous()
         B, n, d = feats.shape
         base, row_stride = feats, feats.stride(1)
-        feat_offs = [i * feats.stride(0) for i in range(B)]
-        dims_l = [dims] * B
-        sizes_l = init_image_sizes if isinstance(init_image_sizes, list) else [init_image_sizes] * B
+        feat_offs = np.arange(B, dtype=np.int64) * feats.stride(0)
+        dims_l = dims
+        sizes_l = init_image_sizes
     else:
         feats = list(feats)
         for f in feats:
@@ -135,16 +185,11 @@ def lost_batched(feats, dims, scales, init_image_sizes, k_patches=100, return_A=
             feat_offs.append(o * d); o += f.shape[0]
         B = len(feats)
         dims_l, sizes_l = list(dims), list(init_image_sizes)
-    metas, a_off, out_off = [], 0, 0
-    for i in range(B):
-        n_i = int(dims_l[i][0]) * int(dims_l[i][1])
-        metas.append(_meta(feat_offs[i], a_off, out_off, dims_l[i], scales, sizes_l[i]))
-        a_off += n_i * n_i
-        out_off += n_i
-    b = _Batch(base, row_stride, d, metas, base.device, return_A, k_patches, gram_impl)
-    out = {"box": b.box, "seed": b.seed, "status": b.status, "degree": list(torch.split(b.degree, b.ns)), "_keepalive": b}
+    metas, ns = _meta_records(feat_offs, dims_l, scales, sizes_l)
+    b = _Batch(base, row_stride, d, metas, base.device, return_A, k_patches, gram_impl, ns)
+    out = {"box": b.box, "seed": b.seed, "status": b.status, "degree": _Split(b.degree, ns), "_keepalive": b}
     if return_A:
-        out["A"] = [a.view(n_i, n_i) for a, n_i in zip(torch.split(b.A, [n_i * n_i for n_i in b.ns]), b.ns)]
+        out["A"] = _Split(b.A, ns * ns, [(int(n_i), int(n_i)) for n_i in ns])
     return out
 
 

@@ -95,6 +95,23 @@ class ParamPlan:
         tensors, ptrs = self._validate(slot, tensors)
         return PtrTable(self, slot, ptrs, tensors)
 
+    def update_tables(self, tables, tensor_lists):
+        """Re-point existing pointer tables at new tensor sets (the next build's gradients) in one launch."""
+        tables = list(tables)
+        slot = tables[0].slot
+        arrs = []
+        for tab, tensors in zip(tables, tensor_lists):
+            if tab.plan is not self or tab.slot != slot:
+                raise B200PruneError("update_tables: tables must belong to this plan and one slot")
+            tensors, ptrs = self._validate(slot, tensors)
+            tab.tensors = tensors
+            arrs.append(ptrs)
+        tab_arr = (ctypes.c_void_p * len(tables))(*[t.handle for t in tables])
+        ptr_arr = (ctypes.c_void_p * len(tables))(*[ctypes.cast(a, ctypes.c_void_p) for a in arrs])
+        check(self.lib.b200p_ptrtables_update(tab_arr, ptr_arr, len(tables), slot, _stream_ptr(self.device)), "ptrtables_update")
+        self._update_keepalive = arrs
+        return self
+
     def bind_table(self, table):
         if table.plan is not self:
             raise B200PruneError("bind_table: table belongs to another plan")

@@ -172,7 +172,7 @@ def test_config3_lost_batch_256_deterministic_and_sane():
     assert (box[:, 0] < box[:, 2]).all() and (box[:, 1] < box[:, 3]).all() and box.min() >= 0 and box.max() <= 480
     sx, sy = (seed % 30) * 16, (seed // 30) * 16            # the seed patch lies inside its box
     assert ((box[:, 0] <= sx) & (sx < box[:, 2]) & (box[:, 1] <= sy) & (sy < box[:, 3])).all()
-    deg = torch.stack(a["degree"])
+    deg = torch.stack(list(a["degree"]))
     A0 = feats[0] @ feats[0].T
     ref_deg = ((A0 > 0).sum(dim=1) - 1).to(torch.int32)     # minus the diagonal
     assert int((deg[0] != ref_deg).sum()) <= 2              # sign of near-zero entries may differ between summation orders

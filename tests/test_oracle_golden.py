@@ -116,6 +116,18 @@ def test_lost_matches_reference(golden_dir):
         np.testing.assert_allclose(A[:4, :6], z[f"{name}_A_probe"], rtol=1e-5, atol=1e-4)
 
 
+def test_lost_replay_from_degrees_matches_reference(golden_dir):
+    """The fp64 replay the GPU tests use as their checker reproduces the reference's seed and box from the reference's
+    own degrees, and calls every golden decidable."""
+    z = _load(golden_dir, "lost_cases.npz")
+    meta = json.load(open(os.path.join(golden_dir, "lost_cases.json")))
+    for name, m in meta.items():
+        seed, pred, decidable = LO.lost_from_degrees(z[f"{name}_feats"], z[f"{name}_degree"], m["dims"], m["scales"],
+                                                     tuple(m["init_image_size"]), m["k_patches"])
+        assert seed == m["seed"] and [int(v) for v in pred] == m["pred"], name
+        assert decidable or name.startswith("random"), name
+
+
 def test_lost_background_seed_raises():
     M = -np.ones(12, np.float32)
     with pytest.raises(ValueError, match="background"):
