@@ -79,6 +79,10 @@ typedef struct b200p_select_result_t {
     uint32_t thr_key;    /* its 31-bit integer key                                           */
     uint32_t passes_full;/* how many full-data passes the select needed (2 or 3)             */
     uint32_t collected;  /* candidates gathered in pass 2 (0 if histogram mode)              */
+    uint32_t miss;       /* sampled select only: 1 = the bracket missed rank k.  One GPU: the exact */
+                         /* select ran inside the same launch, the result is valid.  Sharded        */
+                         /* (b200p_sharded_mask_build): the result is NOT valid, rerun staged.       */
+    uint32_t reserved_;
 } b200p_select_result_t;
 
 const char* b200p_last_error(void);
@@ -205,6 +209,51 @@ int  b200p_snip_mask_build(b200p_plan* plan, const b200p_ptrtable* const* g_tabl
  * d_prov_target: nullable, where the provisional mask of the sweep goes (the d_new_mask of a following plain emit). */
 int  b200p_snip_score_select(b200p_plan* plan, const b200p_ptrtable* const* g_tables, int n_sets, uint64_t k,
                              uint32_t* d_prov_target, void* stream);
+
+/* ---- parameter-sharded mask build over peer memory (no reference counterpart: under DDP the reference's
+ * ranks prune independently and end up with different masks, train.py:604-607, 622-628) ------------------------------
+ * One process per GPU.  Every rank creates a comm of the same geometry; the peer-visible WINDOW (flags, histogram /
+ * gather slots, the full packed mask, a score area of `score_cap` floats per source rank) is exchanged as a CUDA IPC
+ * handle (64 bytes, e.g. through torch.distributed.all_gather) or, for plans that live on one device, as plain
+ * pointers.  The kernels then talk through the windows directly: the last CTA of the select's sample and sweep kernels
+ * all-reduces its histogram by pushing it into every peer's window, the finish kernel all-gathers 4 KB, the emit's
+ * result is pushed as packed words — no NCCL call, no host round trip inside a build.  At most 8 ranks (one node). */
+typedef struct b200p_comm b200p_comm;
+int  b200p_comm_create(int device, int rank, int world, int64_t mask_words, int64_t score_cap, b200p_comm** out);
+int  b200p_comm_destroy(b200p_comm* comm);
+int64_t b200p_comm_window_bytes(const b200p_comm* comm);
+void* b200p_comm_window(const b200p_comm* comm);                 /* device address of the own window            */
+void* b200p_comm_mask_ptr(const b200p_comm* comm);               /* the full packed mask inside the own window  */
+void* b200p_comm_score_ptr(const b200p_comm* comm);              /* score area: world parts of score_cap floats */
+int64_t b200p_comm_score_cap(const b200p_comm* comm);
+int  b200p_comm_ipc_handle(b200p_comm* comm, void* h_out64);     /* cudaIpcMemHandle_t of the own window         */
+int  b200p_comm_connect_ipc(b200p_comm* comm, const void* h_handles /* world x 64 bytes, rank order */);
+int  b200p_comm_connect_local(b200p_comm* comm, void* const* h_peer_windows /* world device pointers */);
+/* 0 = fine, ch + 1 = a wait on channel ch ran out (a peer never arrived; bounded spin, ~2 s).  Synchronises. */
+int  b200p_comm_error(b200p_comm* comm, void* stream);
+int  b200p_comm_barrier(b200p_comm* comm, void* stream);
+/* Every rank pushes the mask words of its chunk range (already in its window) into every peer's window; when the kernel
+ * ends on a rank, all slices have arrived there: b200p_comm_mask_ptr() holds the full mask. */
+int  b200p_comm_mask_allgather(b200p_comm* comm, b200p_plan* plan, int64_t chunk_begin, int64_t chunk_end, void* stream);
+/* SCORE-slot pointer table whose entries point into the OWNING ranks' score areas (h_bounds: world + 1 chunk bounds):
+ * with it bound, b200p_score_accumulate(_multi) writes each chunk's partial scores straight into the owner's window —
+ * the local score pass and the score exchange are one kernel.  Follow with b200p_comm_barrier and b200p_sum_parts
+ * (parts added in rank = mini-batch order). */
+int  b200p_comm_score_push_table(b200p_comm* comm, b200p_plan* plan, const int64_t* h_bounds, void* stream, b200p_ptrtable** out);
+/* k-th smallest over ALL ranks' chunk ranges + packed mask of the whole set in every window: sample -> sweep of the own
+ * range -> exact key -> ties -> emit -> mask all-gather, see csrc/select.cu.  Same results as b200p_mask_build on one GPU
+ * (bit-identical masks, threshold, tie policy).  Check b200p_select_result().miss before using the mask. */
+/* `stages`: 0 = the whole sequence; a bit set runs single stages (in this order), which is what lets several ranks that
+ * live in ONE process be interleaved stage by stage on their own streams (tests with virtual ranks). */
+#define B200P_SHARD_SAMPLE  1
+#define B200P_SHARD_SWEEP   2
+#define B200P_SHARD_FINISH  4
+#define B200P_SHARD_TIES    8
+#define B200P_SHARD_EMIT   16
+#define B200P_SHARD_PUSH   32
+#define B200P_SHARD_ALL    63
+int  b200p_sharded_mask_build(b200p_plan* plan, b200p_comm* comm, int key_source, const uint32_t* d_old_mask, uint64_t k, int mode,
+                              int64_t chunk_begin, int64_t chunk_end, int stages, void* stream);
 
 /* ---- K5: sparsity (train.py:347-369) ------------------------------------------------ */
 /* d_out[0] = # elements with (mask bit == 0 or W == 0)  (d_mask nullable -> counts W == 0),

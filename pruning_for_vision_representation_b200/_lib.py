@@ -21,6 +21,7 @@ EMIT_MASKF, EMIT_WEFF = 1, 2
 SGD_NESTEROV, SGD_FIRST_STEP, SGD_EMIT_WEFF, SGD_EMIT_WEFF16 = 1, 2, 4, 8
 LOST_GRAM_FFMA, LOST_GRAM_TC, LOST_GRAM_TC2, LOST_GRAM_TC2D = 0, 1, 2, 3
 OPT_SELECT_IMPL, OPT_TIME_SWEEP = 1, 2
+SHARD_SAMPLE, SHARD_SWEEP, SHARD_FINISH, SHARD_TIES, SHARD_EMIT, SHARD_PUSH, SHARD_ALL = 1, 2, 4, 8, 16, 32, 63
 SELECT_SAMPLED, SELECT_EXACT = 0, 1
 
 
@@ -34,6 +35,7 @@ class SelectResult(ctypes.Structure):
         ("n_equal", ctypes.c_uint64), ("quota", ctypes.c_uint64), ("n_kept", ctypes.c_uint64),
         ("threshold", ctypes.c_float), ("thr_key", ctypes.c_uint32),
         ("passes_full", ctypes.c_uint32), ("collected", ctypes.c_uint32),
+        ("miss", ctypes.c_uint32), ("reserved_", ctypes.c_uint32),
     ]
 
     def as_dict(self):
@@ -103,11 +105,27 @@ SIGNATURES = {
     "b200p_lost_last_trace": (_I, [ctypes.POINTER(_U64)]),
     "b200p_lost_patch_scoring": (_I, [_I, _P, _I, _I64, _F, _P, _P, _P]),
     "b200p_lost_detect_box": (_I, [_I, _P, _I, _I, _I, _F, _F, _I, _I, _P, _P, _P, _P]),
+    "b200p_comm_create": (_I, [_I, _I, _I, _I64, _I64, ctypes.POINTER(_P)]),
+    "b200p_comm_destroy": (_I, [_P]),
+    "b200p_comm_window_bytes": (_I64, [_P]),
+    "b200p_comm_window": (_P, [_P]),
+    "b200p_comm_mask_ptr": (_P, [_P]),
+    "b200p_comm_score_ptr": (_P, [_P]),
+    "b200p_comm_score_cap": (_I64, [_P]),
+    "b200p_comm_ipc_handle": (_I, [_P, _P]),
+    "b200p_comm_connect_ipc": (_I, [_P, _P]),
+    "b200p_comm_connect_local": (_I, [_P, ctypes.POINTER(_P)]),
+    "b200p_comm_error": (_I, [_P, _P]),
+    "b200p_comm_barrier": (_I, [_P, _P]),
+    "b200p_comm_mask_allgather": (_I, [_P, _P, _I64, _I64, _P]),
+    "b200p_comm_score_push_table": (_I, [_P, _P, ctypes.POINTER(_I64), _P, ctypes.POINTER(_P)]),
+    "b200p_sharded_mask_build": (_I, [_P, _P, _I, _P, _U64, _I, _I64, _I64, _I, _P]),
     "b200p_snip_mask_build_host": (_I, [_P, _P, ctypes.POINTER(_P), _I, _U64, _P, ctypes.POINTER(SelectResult)]),
     "b200p_magnitude_mask_build_host": (_I, [_P, _P, _P, _U64, _P, ctypes.POINTER(SelectResult)]),
 }
 
 _lib = None
+ABI_VERSION = 200            # must equal b200p_version() of the loaded library (struct layouts / signatures above)
 
 
 def load(build_if_missing=True):
@@ -115,15 +133,21 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
     if not os.path.exists(LIB_PATH):
         if not build_if_missing:
             raise B200PruneError(f"{LIB_PATH} is missing; run `python -m pruning_for_vision_representation_b200.build`")
-        from . import build as _build
         _build.build()
+    # a library older than the binding is caught by the ABI version below (no mtime games: file times do not survive the
+    # trip to the GPU box, and several ranks must never rebuild the same file at once)
     try:
         lib = ctypes.CDLL(LIB_PATH)
     except OSError as e:  # e.g. libcudart not found
         raise B200PruneError(f"cannot load {LIB_PATH}: {e}") from e
+    lib.b200p_version.restype = ctypes.c_int
+    if lib.b200p_version() != ABI_VERSION:
+        raise B200PruneError(f"{LIB_PATH} has ABI version {lib.b200p_version()}, this binding needs {ABI_VERSION}: rebuild it "
+                             "(`python -m pruning_for_vision_representation_b200.build --force`)")
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200prune.so")
-SOURCES = ["plan.cu", "score.cu", "select.cu", "emit.cu", "sgd.cu", "lost.cu", "lost_tc.cu", "host.cu"]
+SOURCES = ["plan.cu", "score.cu", "select.cu", "emit.cu", "sgd.cu", "lost.cu", "lost_tc.cu", "host.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",
@@ -22,6 +22,13 @@ def _nvcc():
         if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
             return cand
     return "nvcc"
+
+
+def can_build():
+    """nvcc reachable (the GPU box has the same image; a box without the toolkit loads the shipped library as is)."""
+    import shutil
+    n = _nvcc()
+    return os.path.exists(n) if os.path.isabs(n) else shutil.which(n) is not None
 
 
 def needs_build():

@@ -1,0 +1,144 @@
+// comm.cuh — peer-memory window of one rank and the in-kernel collectives built on it.
+//
+// the sharded mask build needs three tiny exchanges (sample histogram, bracket histogram + below-count,
+// window histogram) and one bulk one (packed mask words; partial SNIP scores).  Over NVLink 5 / NVSwitch every GPU can
+// store into every peer's memory, so none of them is an NCCL call here: each rank exposes one WINDOW (cudaMalloc'd,
+// opened by the peers through CUDA IPC, or plain pointers when the "ranks" are plans on one device), and the kernel that
+// produces the data pushes it straight into the peers' windows and raises a flag there.  The last CTA of the select's
+// sample / sweep kernels does the all-reduce itself, between its own histogram flush and its own scan: no launch, no
+// host round trip, no separate reduction kernel.
+//
+// Protocol (every rank runs the same sequence of operations, SPMD):
+//   * an operation on channel ch carries a sequence number seq = 1, 2, 3, ... (host-side counter per channel, passed as
+//     a kernel argument); payload slots are double-buffered by seq & 1;
+//   * writer r: stores its payload into slot [seq & 1][r] of EVERY rank's window (its own included), then
+//     __threadfence_system(), then st.release.sys of seq into flag[ch][r] of every window;
+//   * reader: spins (bounded) on ld.acquire.sys of its OWN window's flag[ch][p] >= seq for all p, then reads the slots.
+//   A rank can be at most one operation ahead of the slowest one on a channel (it needs everybody's seq before it can
+//   finish seq), so slot seq & 1 is never overwritten while somebody still reads seq - 2's data... which every rank
+//   finished before it wrote seq - 1.
+//   * a spin that runs out (~2 s) sets CommDev::err_flag and returns false: a broken peer shows up as an error code,
+//     never as a hung GPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200p {
+
+constexpr int kCommMaxWorld = 8;
+// channels
+enum { CH_HIST = 0, CH_GATHER = 1, CH_MASK = 2, CH_BARRIER = 3, CH_COUNT = 4 };
+constexpr int kCommHistBins = 4096, kCommHistExtra = 8;            // u32 bins + u64 extras per rank slot
+constexpr int kCommGatherWords = 1024 + 8;                         // u32 window histogram + scalars per rank slot
+
+// byte offsets inside a window (identical on every rank)
+struct CommLayout {
+    long long flags;        // u32 [CH_COUNT][kCommMaxWorld]
+    long long err;          // u32 error flag (own window only)
+    long long hist_bins;    // u32 [2][world][kCommHistBins]
+    long long hist_extra;   // u64 [2][world][kCommHistExtra]
+    long long gather;       // u32 [2][world][kCommGatherWords]
+    long long mask;         // u32 [mask_words]: the full packed mask, every rank's slice pushed in by its owner
+    long long score;        // f32 [world][score_cap]: partial SNIP scores of THIS rank's slice, one part per source rank
+    long long total;
+};
+
+struct CommDev {
+    char* win[kCommMaxWorld];      // mapped base of every rank's window (win[rank] is the own one)
+    CommLayout lay;
+    long long score_cap;           // elements per part of the score area
+    int rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t* comm_flag(const CommDev& c, int dst_rank, int ch, int src_rank) {
+    return reinterpret_cast<uint32_t*>(c.win[dst_rank] + c.lay.flags) + ch * kCommMaxWorld + src_rank;
+}
+
+// Called by ALL threads of one CTA after they have stored their part of the payload into the peers' windows:
+// publishes seq to every rank, then waits for every rank's seq.  Returns false on a time-out (err flag set).
+__device__ __forceinline__ bool comm_signal_and_wait(const CommDev& c, int ch, uint32_t seq) {
+    __shared__ int s_comm_ok;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_comm_ok = 1;
+    __syncthreads();
+    if ((int)threadIdx.x < c.world) {
+        st_release_sys_u32(comm_flag(c, threadIdx.x, ch, c.rank), seq);
+        const uint32_t* f = comm_flag(c, c.rank, ch, threadIdx.x);
+        bool ok = false;
+        for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+            // sequence numbers only grow; compare as a signed distance so that a wrap is harmless
+            if ((int32_t)(ld_acquire_sys_u32(f) - seq) >= 0) { ok = true; break; }
+            if (spin > 64) __nanosleep(128);
+        }
+        if (!ok) { s_comm_ok = 0; *reinterpret_cast<volatile uint32_t*>(c.win[c.rank] + c.lay.err) = 1u + (uint32_t)ch; }
+    }
+    __syncthreads();
+    return s_comm_ok != 0;
+}
+
+// All-reduce (sum) of a 4096-bin u64 histogram + 8 u64 extras that lives in this rank's global memory, by ONE CTA of
+// kThreads threads (the last CTA of the kernel that produced it).  Per-rank counts fit 32 bits (< 2^32 keys per rank).
+// On return `hist` holds the sums on every rank (bit-identical: integer adds).
+__device__ __forceinline__ bool comm_allreduce_hist(const CommDev& c, uint32_t seq, unsigned long long* __restrict__ hist) {
+    const int tid = threadIdx.x, nt = blockDim.x, slot = seq & 1u;
+    // pack own bins to u32 once, then push to every window
+    for (int b4 = tid; b4 < kCommHistBins / 4; b4 += nt) {
+        uint4 v;
+        v.x = (uint32_t)((volatile unsigned long long*)hist)[4 * b4 + 0]; v.y = (uint32_t)((volatile unsigned long long*)hist)[4 * b4 + 1];
+        v.z = (uint32_t)((volatile unsigned long long*)hist)[4 * b4 + 2]; v.w = (uint32_t)((volatile unsigned long long*)hist)[4 * b4 + 3];
+        for (int p = 0; p < c.world; ++p) {
+            uint4* dst = reinterpret_cast<uint4*>(c.win[p] + c.lay.hist_bins) + ((size_t)(slot * c.world + c.rank) * (kCommHistBins / 4) + b4);
+            *dst = v;
+        }
+    }
+    if (tid < kCommHistExtra) {
+        const unsigned long long e = ((volatile unsigned long long*)hist)[kCommHistBins + tid];
+        for (int p = 0; p < c.world; ++p)
+            reinterpret_cast<unsigned long long*>(c.win[p] + c.lay.hist_extra)[(size_t)(slot * c.world + c.rank) * kCommHistExtra + tid] = e;
+    }
+    if (!comm_signal_and_wait(c, CH_HIST, seq)) return false;
+    const uint32_t* bins = reinterpret_cast<const uint32_t*>(c.win[c.rank] + c.lay.hist_bins) + (size_t)slot * c.world * kCommHistBins;
+    for (int b = tid; b < kCommHistBins; b += nt) {
+        unsigned long long s = 0;
+        for (int r = 0; r < c.world; ++r) s += __ldcg(bins + (size_t)r * kCommHistBins + b);
+        hist[b] = s;
+    }
+    if (tid < kCommHistExtra) {
+        const unsigned long long* ex = reinterpret_cast<const unsigned long long*>(c.win[c.rank] + c.lay.hist_extra) + (size_t)slot * c.world * kCommHistExtra;
+        unsigned long long s = 0;
+        for (int r = 0; r < c.world; ++r) s += __ldcg(ex + (size_t)r * kCommHistExtra + tid);
+        hist[kCommHistBins + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    return true;
+}
+
+}  // namespace b200p
+
+// host object
+struct b200p_comm {
+    int device = 0, rank = 0, world = 1;
+    char* window = nullptr;                 // own window (cudaMalloc)
+    b200p::CommLayout lay{};
+    long long mask_words = 0, score_cap = 0;
+    char* peers[b200p::kCommMaxWorld] = {nullptr};
+    bool opened_ipc[b200p::kCommMaxWorld] = {false};
+    bool connected = false;
+    uint32_t seq[b200p::CH_COUNT] = {0, 0, 0, 0};      // last sequence number used per channel
+    b200p::CommDev dev() const {
+        b200p::CommDev d;
+        for (int i = 0; i < b200p::kCommMaxWorld; ++i) d.win[i] = peers[i];
+        d.lay = lay; d.score_cap = score_cap; d.rank = rank; d.world = world;
+        return d;
+    }
+};

@@ -159,6 +159,8 @@ struct b200p_plan {
     // emit-by-patch: valid for the emit that directly follows b200p_select_kth with the same arguments
     uint32_t* prov_target = nullptr;        // where the sweep writes the provisional mask (nullptr: d_prov)
     bool prov_armed = false; int prov_key_source = -1; int prov_mode = -1; const uint32_t* prov_old_mask = nullptr;
+    int64_t prov_c0 = 0, prov_c1 = 0;       // chunk range the sweep covered (the whole set on one GPU, the rank's slice when sharded)
+    unsigned long long* d_rank_ties = nullptr;   // [8] sharded select: every rank's count of the threshold key (k_sharded_finish)
     // lazily created arena for the host-buffer entry points
     float* arena_w = nullptr; float* arena_g[2] = {nullptr, nullptr}; float* arena_score = nullptr;
     uint32_t* arena_mask = nullptr; uint32_t* arena_old_mask = nullptr;
@@ -193,6 +195,8 @@ void set_error(const std::string& msg);
 int  plan_time_mark(b200p_plan* p, int which, cudaStream_t st);
 int  cuda_fail(cudaError_t e, const char* what);
 }  // namespace b200p
+struct b200p_comm;
+extern "C" int b200p_comm_mask_allgather(b200p_comm* c, b200p_plan* p, int64_t chunk_begin, int64_t chunk_end, void* stream);
 
 #define B200P_CUDA(call)                                                        \
     do { cudaError_t e__ = (call);                                              \

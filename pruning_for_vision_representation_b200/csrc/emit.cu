@@ -371,7 +371,7 @@ extern "C" int b200p_emit_masks(b200p_plan* p, int key_source, int mode, int for
     // parameter set and without fused fp32 outputs.  Whether the provisional mask is valid is only known on the
     // device (the select may have fallen back to histogram mode), so the full pass is still launched and exits at
     // once when the patch has done the job.
-    const bool patch = p->prov_armed && force == 0 && outputs == 0 && chunk_begin == 0 && chunk_end == p->n_chunks &&
+    const bool patch = p->prov_armed && force == 0 && outputs == 0 && chunk_begin == p->prov_c0 && chunk_end == p->prov_c1 &&
                        p->prov_key_source == key_source && p->prov_mode == mode && p->prov_old_mask == d_old_mask;
     uint32_t* prov = p->prov_target ? p->prov_target : p->d_prov;
     p->prov_armed = false; p->prov_target = nullptr;
@@ -393,7 +393,8 @@ extern "C" int b200p_emit_masks(b200p_plan* p, int key_source, int mode, int for
     k_emit_masks<<<p->grid_for(chunk_end - chunk_begin, 4), kThreads, 0, st>>>(a, chunk_begin, chunk_end);
     B200P_LAUNCH_CHECK("k_emit_masks");
     if (patch && prov != d_new_mask)
-        B200P_CUDA(cudaMemcpyAsync(d_new_mask, prov, (size_t)p->n_chunks * kWordsPerChunk * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        B200P_CUDA(cudaMemcpyAsync(d_new_mask + chunk_begin * kWordsPerChunk, prov + chunk_begin * kWordsPerChunk,
+                                   (size_t)(chunk_end - chunk_begin) * kWordsPerChunk * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     return B200P_OK;
 }
 

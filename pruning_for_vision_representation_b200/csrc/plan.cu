@@ -15,7 +15,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 using namespace b200p;
 
 extern "C" const char* b200p_last_error(void) { return g_last_error.c_str(); }
-extern "C" int b200p_version(void) { return 100; }
+extern "C" int b200p_version(void) { return 200; }
 extern "C" int b200p_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -86,6 +86,8 @@ extern "C" int b200p_plan_create(int device, int n_segments, const int64_t* h_nu
     TRY(cudaMalloc(&p->d_cand_pos, cand_capacity * sizeof(uint32_t)));
     TRY(cudaMalloc(&p->d_chunk_ties, chunks * sizeof(uint32_t)));
     TRY(cudaMalloc(&p->d_prov, chunks * kWordsPerChunk * sizeof(uint32_t)));
+    TRY(cudaMalloc(&p->d_rank_ties, 8 * sizeof(unsigned long long)));
+    TRY(cudaMemset(p->d_rank_ties, 0, 8 * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_hist, 0, (kHistBins + kHistExtra) * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_state, 0, sizeof(SelState)));
     TRY(cudaMemset(p->d_chunk_ties, 0, chunks * sizeof(uint32_t)));
@@ -101,7 +103,7 @@ extern "C" int b200p_plan_destroy(b200p_plan* p) {
     cudaFree(p->d_chunk_seg); cudaFree(p->d_chunk_n); cudaFree(p->d_chunk_elem0);
     for (int s = 0; s < B200P_NUM_SLOTS; ++s) cudaFree(p->d_tab_own[s]);
     cudaFree(p->d_hist); cudaFree(p->d_state); cudaFree(p->d_cand_key); cudaFree(p->d_cand_pos);
-    cudaFree(p->d_chunk_ties); cudaFree(p->d_prov);
+    cudaFree(p->d_chunk_ties); cudaFree(p->d_prov); cudaFree(p->d_rank_ties);
     for (int i = 0; i < 2; ++i) if (p->arena_gtab[i]) { b200p_ptrtable_destroy(p->arena_gtab[i]); p->arena_gtab[i] = nullptr; }
     cudaFree(p->arena_w); cudaFree(p->arena_g[0]); cudaFree(p->arena_g[1]); cudaFree(p->arena_score);
     cudaFree(p->arena_mask); cudaFree(p->arena_old_mask);

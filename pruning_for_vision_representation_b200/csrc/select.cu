@@ -18,6 +18,7 @@
 // separately) exist so that a parameter-sharded multi-GPU select can all-reduce the
 // histogram between them.
 #include "common.cuh"
+#include "comm.cuh"
 #include <cooperative_groups.h>
 
 namespace b200p {
@@ -205,6 +206,7 @@ struct PassArgs {
     int fuse_init;
     unsigned long long k;
     uint32_t mode, allow_collect;
+    uint32_t comm_seq;       // != 0: sharded select, the last CTA of the bracket sweep all-reduces {fine histogram, below}
 };
 
 // ---- slim sweep used by exact pass 1 and by the bracket pass of the sampled select ------------
@@ -630,11 +632,13 @@ struct SampleArgs {
     unsigned long long* hist;
     SelState* st;
     unsigned int* ticket;
-    int64_t n_chunks;
+    int64_t n_chunks;        // chunks sampled: [c_begin, c_begin + n_chunks)
+    int64_t c_begin;         // first chunk of this rank's range (0 on one GPU)
     int vec_ok;
     unsigned long long k, n_total;
     uint32_t mode;
     uint32_t sigmas;         // bracket half-width in standard deviations of the sample rank (8; 12 for clustered granules)
+    uint32_t comm_seq;       // != 0: parameter-sharded select, the last CTA all-reduces the histogram over the ranks first
 };
 
 // exclusive prefix of this thread's 16 bins over the CTA (kScanThreads threads) and the grand total
@@ -718,7 +722,7 @@ __device__ __forceinline__ void sample_tail(const SampleArgs& a, unsigned long l
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_select_sample(SampleArgs a) {
+k_select_sample(SampleArgs a, CommDev comm) {
     __shared__ uint32_t s_hist[kHistBins];
     __shared__ unsigned long long s_warp[9];
     __shared__ unsigned long long s_alive;
@@ -730,7 +734,8 @@ k_select_sample(SampleArgs a) {
     if (a.old_mask) {
         unsigned long long cnt = 0;
         const int64_t words = a.n_chunks * kWordsPerChunk;
-        for (int64_t w = gtid; w < words; w += nthreads) cnt += __popc(__ldg(a.old_mask + w));
+        const uint32_t* __restrict__ mw = a.old_mask + a.c_begin * kWordsPerChunk;
+        for (int64_t w = gtid; w < words; w += nthreads) cnt += __popc(__ldg(mw + w));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
         if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_alive, cnt);
@@ -745,7 +750,7 @@ k_select_sample(SampleArgs a) {
         for (int u = 0; u < 4; ++u) {
             const int64_t sl = s0 + u * nthreads;
             on[u] = sl < slots;
-            cc[u] = on[u] ? (sl >> 4) : 0;
+            cc[u] = a.c_begin + (on[u] ? (sl >> 4) : 0);
             const int i = (int)(sl & 15);
             e0[u] = 256 * i + 4 * (int)((cc[u] + 5 * i) & 63);
             n[u] = __ldg(a.chunk_n + cc[u]);
@@ -783,7 +788,12 @@ k_select_sample(SampleArgs a) {
     }
     if (threadIdx.x == 0 && s_alive) atomicAdd(a.hist + kHistBins + 0, s_alive);
     if (!last_cta_arrives(a.ticket)) return;
+    // parameter-sharded select: sum the sample histograms (and alive counts) of all ranks right here, then every rank
+    // derives the same bracket
+    bool comm_ok = true;
+    if (a.comm_seq) comm_ok = comm_allreduce_hist(comm, a.comm_seq, a.hist);
     sample_tail(a, s_warp, s_bkt);
+    if (!comm_ok && threadIdx.x == 0) { a.st->sample_ok = 0u; a.st->miss = 1u; }
 }
 
 // last CTA of a bracket sweep: verify that rank k is inside the bracket, narrow to a 1024-key window
@@ -826,7 +836,7 @@ __device__ __forceinline__ void bracket_tail(const PassArgs& a, uint32_t base, u
 // alive bitmap once per thread, and leaves everything that concerns the ~1 % matching keys (fine
 // histogram, staging, position) to a divergent slow path that extracts the key by index.
 __global__ void __launch_bounds__(kThreads, 4)
-k_select_bracket(PassArgs a) {
+k_select_bracket(PassArgs a, CommDev comm) {
     __shared__ uint32_t s_hist[kHistBins];
     __shared__ unsigned long long s_warp[9];
     __shared__ unsigned long long s_below;
@@ -848,7 +858,93 @@ k_select_bracket(PassArgs a) {
     }
     if (threadIdx.x == 0 && s_below) atomicAdd(a.hist + kHistBins + 1, s_below);
     if (!last_cta_arrives(a.ticket)) return;
+    bool comm_ok = true;
+    if (a.comm_seq) comm_ok = comm_allreduce_hist(comm, a.comm_seq, a.hist);
     bracket_tail(a, base, s_warp);
+    if (!comm_ok && threadIdx.x == 0) { st->miss = 1u; st->collect = 0u; st->prov_ok = 0u; }
+}
+
+// ---- B (sharded): exact key from the window histograms of all ranks -----------------------------------------------
+// Each rank histograms the candidates it collected (its chunk range only) over the 1024-key window the bracket tail
+// chose; the last CTA all-GATHERS the 1024 counts of every rank (4 KB per rank), sums them, finds the key of rank k and,
+// because it holds every rank's count of that key, also knows how many tied keys live in lower-ranked slices: the tie
+// bookkeeping of SURVEY 8e needs no collective of its own.
+__global__ void __launch_bounds__(kThreads)
+k_sharded_finish(PassArgs a, CommDev comm, uint32_t seq, unsigned long long* __restrict__ rank_ties) {
+    __shared__ uint32_t s_hist[kWindow];
+    __shared__ unsigned long long s_warp[9];
+    __shared__ int s_bin;
+    SelState* __restrict__ st = a.st;
+    if (st->miss) return;                            // same on every rank: the builder reruns the exact staged select
+    for (int b = threadIdx.x; b < kWindow; b += kThreads) s_hist[b] = 0;
+    __syncthreads();
+    const uint32_t n = st->cand_count, win_lo = st->win_lo;
+    const uint32_t stride = gridDim.x * kThreads;
+    for (uint32_t i0 = blockIdx.x * kThreads + threadIdx.x; i0 < n; i0 += 8 * stride) {
+        uint32_t kk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) kk[u] = i0 + u * stride < n ? __ldg(a.cand_key + i0 + u * stride) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t d = kk[u] - win_lo;
+            if (i0 + u * stride < n && d < (uint32_t)kWindow) atomicAdd(&s_hist[d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kWindow; b += kThreads) {
+        const uint32_t v = s_hist[b];
+        if (v) atomicAdd(a.hist + b, (unsigned long long)v);
+    }
+    if (!last_cta_arrives(a.ticket)) return;
+    const int tid = threadIdx.x, slot = seq & 1u;
+    // push the own 1024 counts (4 per thread) into every window, wait for everybody's
+    {
+        uint4 v;
+        v.x = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 0]; v.y = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 1];
+        v.z = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 2]; v.w = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 3];
+        for (int p = 0; p < comm.world; ++p)
+            reinterpret_cast<uint4*>(comm.win[p] + comm.lay.gather)[(size_t)(slot * comm.world + comm.rank) * (kCommGatherWords / 4) + tid] = v;
+    }
+    const bool comm_ok = comm_signal_and_wait(comm, CH_GATHER, seq);
+    const uint32_t* __restrict__ g = reinterpret_cast<const uint32_t*>(comm.win[comm.rank] + comm.lay.gather) + (size_t)slot * comm.world * kCommGatherWords;
+    unsigned long long local[kBinsPerThread];
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) {
+        const int b = tid * kBinsPerThread + i;
+        unsigned long long sum = 0;
+        if (b < kWindow) for (int r = 0; r < comm.world; ++r) sum += __ldcg(g + (size_t)r * kCommGatherWords + b);
+        local[i] = sum;
+    }
+    unsigned long long total;
+    unsigned long long running = block_prefix16(local, s_warp, total);
+    const unsigned long long k = st->k;
+    if (tid == 0) s_bin = -1;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) {
+        const unsigned long long v = local[i];
+        if (v != 0 && running < k && k <= running + v) {
+            const int b = tid * kBinsPerThread + i;
+            const uint32_t key = win_lo + (uint32_t)b;
+            st->n_less += running;
+            st->k = k - running;
+            st->prefix = key; st->thr_key = key; st->threshold = key_to_float(key);
+            st->n_equal = v; st->quota = k - running;
+            st->need_ties = (st->mode == B200P_MODE_EXACT_K && (k - running) < v) ? 1u : 0u;
+            st->tie_chunk = -1; st->tie_resid = 0; st->tie_seen = 0;
+            s_bin = b;
+        }
+        running += v;
+    }
+    __syncthreads();
+    if (s_bin < 0 || !comm_ok) {                     // cannot happen after a verified bracket; treated like a miss
+        if (tid == 0) { st->miss = 1u; st->collect = 0u; st->prov_ok = 0u; }
+    } else if (tid < kCommMaxWorld) {
+        rank_ties[tid] = tid < comm.world ? (unsigned long long)__ldcg(g + (size_t)tid * kCommGatherWords + s_bin) : 0ull;
+    }
+    __syncthreads();
+    if (tid == 0) *a.ticket = 0u;
+    clear_hist(a.hist);
 }
 
 // =============================================================================================
@@ -1303,6 +1399,7 @@ static void fill_pass_args(b200p_plan* p, PassArgs& a, int key_source, const uin
     a.cand_key = p->d_cand_key; a.cand_pos = p->d_cand_pos; a.ticket = ticket_ptr(p); a.cand_capacity = p->cand_capacity;
     a.c_begin = c0; a.c_end = c1; a.vec_ok = p->vec_ok[slot] ? 1 : 0; a.fuse_scan = fuse_scan;
     a.fuse_init = fuse_init; a.k = k; a.mode = (uint32_t)mode; a.allow_collect = allow_collect ? 1u : 0u;
+    a.comm_seq = 0u;
 }
 
 static int select_kth_exact(b200p_plan* p, int key_source, const uint32_t* d_old_mask, uint64_t k, int mode, cudaStream_t st) {
@@ -1328,15 +1425,15 @@ static int select_kth_sampled(b200p_plan* p, int key_source, const uint32_t* d_o
     // S: 1/16 sample
     SampleArgs sa;
     sa.chunk_n = p->d_chunk_n; sa.key_tab = p->tab(slot); sa.old_mask = d_old_mask; sa.hist = p->d_hist; sa.st = p->d_state;
-    sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.vec_ok = p->vec_ok[slot] ? 1 : 0;
+    sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.c_begin = 0; sa.comm_seq = 0u; sa.vec_ok = p->vec_ok[slot] ? 1 : 0;
     sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)mode; sa.sigmas = 8u;
     const int64_t sblocks = (p->n_chunks * kSampleSlotsPerChunk + 4 * kThreads - 1) / (4 * kThreads);
-    k_select_sample<<<p->grid_for(sblocks, 1), kThreads, 0, st>>>(sa);
+    k_select_sample<<<p->grid_for(sblocks, 1), kThreads, 0, st>>>(sa, CommDev());
     B200P_LAUNCH_CHECK("k_select_sample");
     // A: bracket sweep
     PassArgs a;
     fill_pass_args(p, a, key_source, d_old_mask, 0, p->n_chunks, 1, 0, k, mode, 1, true);
-    k_select_bracket<<<p->grid_for((p->n_chunks + 1) / 2, 4), kThreads, 0, st>>>(a);
+    k_select_bracket<<<p->grid_for((p->n_chunks + 1) / 2, 4), kThreads, 0, st>>>(a, CommDev());
     B200P_LAUNCH_CHECK("k_select_bracket");
     // B: finish (cooperative: grid-wide barriers between its phases)
     int64_t work = p->n_chunks;
@@ -1360,8 +1457,77 @@ extern "C" int b200p_select_kth(b200p_plan* p, int key_source, const uint32_t* d
     B200P_CUDA(cudaSetDevice(p->device));
     // the emit that follows with the same arguments can patch the provisional mask instead of re-reading the keys
     p->prov_armed = true; p->prov_key_source = key_source; p->prov_mode = mode; p->prov_old_mask = d_old_mask;
+    p->prov_c0 = 0; p->prov_c1 = p->n_chunks;
     if (p->select_impl == B200P_SELECT_EXACT) return select_kth_exact(p, key_source, d_old_mask, k, mode, (cudaStream_t)stream);
     return select_kth_sampled(p, key_source, d_old_mask, k, mode, (cudaStream_t)stream);
+}
+
+// ---- parameter-sharded select + emit + mask all-gather over peer memory ----------------------------------
+// Rank r owns chunks [c0, c1).  Sequence (all on `stream`, no host round trip, no NCCL):
+//   S  k_select_sample   over the own range; last CTA: all-reduce of the sample histogram + alive count -> bracket
+//   A  k_select_bracket  ONE sweep of the own range; provisional mask words go straight into the window's mask area;
+//                        last CTA: all-reduce of {fine histogram, below} -> verified bracket, 1024-key window
+//   B  k_sharded_finish  window histogram of the own candidates; last CTA: all-gather -> exact key, tie bookkeeping
+//   T  k_tie_count / k_tie_scan (EXACT_K): which of the own tied keys are pruned (ties in lower ranks come first)
+//   E  k_emit_masks      patches the own candidates' bits
+//   P  k_mask_push       own words -> every window; the kernel ends when every rank's words have arrived here
+// A bracket miss (never observed on real weight sets; constant tensors do it) leaves SelState::miss = 1 on every rank:
+// the host side checks it where it reads the result anyway and reruns the staged exact select.
+extern "C" int b200p_sharded_mask_build(b200p_plan* p, b200p_comm* c, int key_source, const uint32_t* d_old_mask, uint64_t k, int mode,
+                                        int64_t chunk_begin, int64_t chunk_end, int stages, void* stream) {
+    B200P_REQUIRE(p != nullptr && c != nullptr && c->connected, B200P_ESTATE, "sharded_mask_build: null argument / comm not connected");
+    int rc = check_key_source(p, key_source, "sharded_mask_build"); if (rc) return rc;
+    B200P_REQUIRE(k >= 1 && k <= (uint64_t)p->total, B200P_EINVAL, "sharded_mask_build: k must be in [1, N]");
+    B200P_REQUIRE(mode == B200P_MODE_SNIP_STRICT || mode == B200P_MODE_EXACT_K, B200P_EINVAL, "sharded_mask_build: bad mode");
+    B200P_REQUIRE(chunk_begin >= 0 && chunk_begin <= chunk_end && chunk_end <= p->n_chunks, B200P_EINVAL, "sharded_mask_build: bad chunk range");
+    B200P_REQUIRE(c->mask_words == p->n_chunks * kWordsPerChunk, B200P_EINVAL, "sharded_mask_build: the window's mask area does not match the plan");
+    B200P_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int slot = key_slot(key_source);
+    const int64_t nc = chunk_end - chunk_begin;
+    uint32_t* d_mask = reinterpret_cast<uint32_t*>(c->window + c->lay.mask);
+    const CommDev cd = c->dev();
+    if (stages == 0) stages = B200P_SHARD_ALL;
+    // S
+    if (stages & B200P_SHARD_SAMPLE) {
+    SampleArgs sa;
+    sa.chunk_n = p->d_chunk_n; sa.key_tab = p->tab(slot); sa.old_mask = d_old_mask; sa.hist = p->d_hist; sa.st = p->d_state;
+    sa.ticket = ticket_ptr(p); sa.n_chunks = nc; sa.c_begin = chunk_begin; sa.vec_ok = p->vec_ok[slot] ? 1 : 0;
+    sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)mode; sa.sigmas = 8u;
+    sa.comm_seq = ++c->seq[CH_HIST];
+    const int64_t sblocks = (nc * kSampleSlotsPerChunk + 4 * kThreads - 1) / (4 * kThreads);
+    k_select_sample<<<p->grid_for(sblocks, 1), kThreads, 0, st>>>(sa, cd);
+    B200P_LAUNCH_CHECK("k_select_sample");
+    }
+    // A
+    p->prov_target = d_mask;
+    p->prov_armed = true; p->prov_key_source = key_source; p->prov_mode = mode; p->prov_old_mask = d_old_mask;
+    p->prov_c0 = chunk_begin; p->prov_c1 = chunk_end;
+    PassArgs a;
+    fill_pass_args(p, a, key_source, d_old_mask, chunk_begin, chunk_end, 1, 0, k, mode, 1, true);
+    if (stages & B200P_SHARD_SWEEP) {
+        a.comm_seq = ++c->seq[CH_HIST];
+        k_select_bracket<<<p->grid_for(nc > 1 ? (nc + 1) / 2 : 1, 4), kThreads, 0, st>>>(a, cd);
+        B200P_LAUNCH_CHECK("k_select_bracket");
+    }
+    // B
+    if (stages & B200P_SHARD_FINISH) {
+        const int64_t cblocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
+        k_sharded_finish<<<p->grid_for(cblocks, 1), kThreads, 0, st>>>(a, cd, ++c->seq[CH_GATHER], p->d_rank_ties);
+        B200P_LAUNCH_CHECK("k_sharded_finish");
+    }
+    // T
+    if ((stages & B200P_SHARD_TIES) && mode == B200P_MODE_EXACT_K) {
+        rc = launch_tie_count(p, key_source, d_old_mask, chunk_begin, chunk_end, st); if (rc) return rc;
+        k_tie_scan<<<1, 1024, 0, st>>>(p->d_state, p->d_chunk_ties, chunk_begin, chunk_end, 0ull, p->d_rank_ties, c->rank);
+        B200P_LAUNCH_CHECK("k_tie_scan");
+    }
+    // E, P
+    if (stages & B200P_SHARD_EMIT) {
+        rc = b200p_emit_masks(p, key_source, mode, 0, 0.f, d_old_mask, d_mask, 0, chunk_begin, chunk_end, stream); if (rc) return rc;
+    }
+    if (stages & B200P_SHARD_PUSH) return b200p_comm_mask_allgather(c, p, chunk_begin, chunk_end, stream);
+    return B200P_OK;
 }
 
 // ---- fused SNIP mask build ------------------------------------------------------------------------
@@ -1424,10 +1590,11 @@ extern "C" int b200p_snip_score_select(b200p_plan* p, const b200p_ptrtable* cons
     // an emit that follows with the same arguments patches the provisional mask the sweep writes (into d_prov_target if given)
     p->prov_target = d_prov_target;
     p->prov_armed = true; p->prov_key_source = B200P_KEY_SCORE; p->prov_mode = B200P_MODE_SNIP_STRICT; p->prov_old_mask = nullptr;
+    p->prov_c0 = 0; p->prov_c1 = p->n_chunks;
     // S': sample
     SampleArgs sa;
     sa.chunk_n = p->d_chunk_n; sa.key_tab = p->tab(B200P_SLOT_SCORE); sa.old_mask = nullptr; sa.hist = p->d_hist; sa.st = p->d_state;
-    sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.vec_ok = vec ? 1 : 0;
+    sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.c_begin = 0; sa.comm_seq = 0u; sa.vec_ok = vec ? 1 : 0;
     sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)B200P_MODE_SNIP_STRICT; sa.sigmas = 12u;
     const int64_t sblocks = (p->n_chunks * kSnipGranulesPerChunk + kThreads - 1) / kThreads;      // one granule per thread
     if (acc) launch_snip_sample<true>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE));
@@ -1470,5 +1637,6 @@ extern "C" int b200p_select_result(b200p_plan* p, b200p_select_result_t* h_out, 
     h_out->k = s.k_request; h_out->n_valid = s.n_valid; h_out->n_less = s.n_less; h_out->n_equal = s.n_equal;
     h_out->quota = s.quota; h_out->n_kept = s.n_kept; h_out->threshold = s.threshold; h_out->thr_key = s.thr_key;
     h_out->passes_full = s.passes_full ? s.passes_full : (s.collect ? 2u : 3u); h_out->collected = s.collect ? s.cand_count : 0u;
+    h_out->miss = s.miss; h_out->reserved_ = 0u;
     return B200P_OK;
 }

@@ -21,10 +21,13 @@ finishes with the same mask by construction.
 host logic is exercised on CPU with a numpy stand-in for the kernels and the gloo backend
 (tests/test_distributed_cpu.py).
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
 from . import _lib as L
+from ._lib import B200PruneError, check
 
 
 def chunk_partition(n_chunks, world):
@@ -177,3 +180,172 @@ class ShardedMaskBuilder:
         t = torch.tensor([t0.elapsed_time(t1) / steps], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return float(t.item())
+
+
+# =============================================================================================
+# Peer-memory path: the same build with NO NCCL call inside it (csrc/comm.cuh, csrc/comm.cu, csrc/select.cu)
+# =============================================================================================
+class PeerComm:
+    """One rank's window into the peers' memory (b200p_comm).  The kernels of the sharded build push their histograms,
+    mask words and partial scores straight into the peers' windows over NVLink; torch.distributed is only used ONCE, to
+    hand the 64-byte CUDA IPC handles around."""
+
+    def __init__(self, plan, rank, world, score_cap=0):
+        self.lib = L.require_cuda()
+        self.plan, self.rank, self.world = plan, int(rank), int(world)
+        handle = ctypes.c_void_p()
+        check(self.lib.b200p_comm_create(plan.index, self.rank, self.world, plan.mask_words, int(score_cap), ctypes.byref(handle)),
+              "comm_create")
+        self.handle = handle
+        self.score_cap = int(self.lib.b200p_comm_score_cap(handle))
+
+    @classmethod
+    def from_process_group(cls, plan, group=None, score_cap=0):
+        """One comm per rank of `group` (one process per GPU, one node), windows opened through CUDA IPC."""
+        group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        comm = cls(plan, rank, world, score_cap)
+        if world > 1:
+            buf = ctypes.create_string_buffer(64)
+            check(comm.lib.b200p_comm_ipc_handle(comm.handle, buf), "comm_ipc_handle")
+            mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(plan.device)
+            allh = torch.empty(world * 64, dtype=torch.uint8, device=plan.device)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            raw = bytes(allh.cpu().numpy().tobytes())
+            check(comm.lib.b200p_comm_connect_ipc(comm.handle, raw), "comm_connect_ipc")
+            dist.barrier(group=group)           # every rank has mapped every window before the first kernel touches one
+        return comm
+
+    @staticmethod
+    def connect_local(comms):
+        """Comms of plans that live in ONE process (virtual ranks on one device, tests): plain pointers, no IPC."""
+        wins = [int(c.lib.b200p_comm_window(c.handle)) for c in comms]
+        arr = (ctypes.c_void_p * len(wins))(*wins)
+        for c in comms:
+            check(c.lib.b200p_comm_connect_local(c.handle, arr), "comm_connect_local")
+
+    def mask_tensor(self):
+        """int32 view [mask_words] of the full packed mask inside the own window (valid after a build's all-gather)."""
+        return self.plan.device_view(self.lib.b200p_comm_mask_ptr(self.handle), self.plan.mask_words, torch.int32, self)
+
+    def score_area(self):
+        return self.plan.device_view(self.lib.b200p_comm_score_ptr(self.handle), self.world * self.score_cap, torch.float32, self)
+
+    def barrier(self):
+        check(self.lib.b200p_comm_barrier(self.handle, _stream(self.plan)), "comm_barrier")
+
+    def error(self):
+        return int(self.lib.b200p_comm_error(self.handle, _stream(self.plan)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.b200p_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _stream(plan):
+    return ctypes.c_void_p(torch.cuda.current_stream(plan.device).cuda_stream)
+
+
+class PeerShardedBuilder:
+    """Parameter-sharded mask build over peer memory.  Rank r owns the contiguous chunk range bounds[r]:bounds[r+1];
+    every rank ends with the full packed mask in `self.mask` (a view of its window), bit-identical to the single-GPU
+    build.  Per build: sample -> sweep of the own slice -> exact key -> ties -> patch emit -> mask push, with the three
+    small exchanges done by the last CTA of the kernel that produced the data (no launch, no NCCL, no host sync).
+
+    SNIP: `snip_build` first folds this rank's gradient sets into partial scores that the score kernel writes straight
+    into the OWNER's window (score pass + all-to-all in one kernel), then the owner adds the parts in rank order."""
+
+    def __init__(self, plan, comm, fallback=None):
+        from .plan import PtrTable
+        self.plan, self.comm, self.fallback = plan, comm, fallback
+        self.world, self.rank = comm.world, comm.rank
+        self.bounds = chunk_partition(plan.n_chunks, self.world)
+        self.c0, self.c1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self.flat_bounds = [plan.chunk_flat_start(c) for c in self.bounds]
+        self.f0, self.f1 = self.flat_bounds[self.rank], self.flat_bounds[self.rank + 1]
+        self.mask = comm.mask_tensor()
+        self._push_table = None
+        self._PtrTable = PtrTable
+        self._last = None
+
+    # ---- magnitude (replicated weights: nothing but histograms, 4 KB of counts and mask words crosses the ranks) -------
+    def magnitude_build(self, k, old_mask=None):
+        p = self.plan
+        if k == 0:                                              # prune.py:533: mask unchanged
+            p.select_begin(0, L.MODE_EXACT_K)
+            p.emit_masks(L.KEY_ABS_W, L.MODE_EXACT_K, self.mask, old_mask, force=1, chunk_begin=self.c0, chunk_end=self.c1)
+            self._allgather()
+            self._last = None
+            return 2
+        self._build(L.KEY_ABS_W, old_mask, k, L.MODE_EXACT_K)
+        return 7
+
+    # ---- SNIP ----------------------------------------------------------------------------------------------------------
+    def snip_build(self, g_tables, k, score_flat, local_score_table):
+        """g_tables: this rank's gradient sets (PtrTables, mini-batch order); score_flat: [N] fp32 whose slice [f0:f1)
+        receives the summed scores; local_score_table: PtrTable of the SCORE slot over score_flat."""
+        p, c = self.plan, self.comm
+        if c.score_cap < max(b - a for a, b in zip(self.flat_bounds[:-1], self.flat_bounds[1:])):
+            raise B200PruneError("snip_build: the comm was created without a score area (score_cap)")
+        if self._push_table is None:
+            arr = (ctypes.c_int64 * (self.world + 1))(*self.bounds)
+            h = ctypes.c_void_p()
+            check(p.lib.b200p_comm_score_push_table(c.handle, p.handle, arr, _stream(p), ctypes.byref(h)), "comm_score_push_table")
+            self._push_table = self._PtrTable(p, L.SLOT_SCORE, None, [], handle=h)
+        p.bind_table(self._push_table)
+        # every rank starts with the chunks of its right-hand neighbour, so that at any moment the G ranks store into G
+        # different windows (an all-to-all, not G incasts)
+        rot = self.bounds[(self.rank + 1) % self.world]
+        p.score_accumulate_multi(g_tables, accumulate=False, chunk_begin=rot, chunk_end=p.n_chunks)
+        if rot > 0:
+            p.score_accumulate_multi(g_tables, accumulate=False, chunk_begin=0, chunk_end=rot)
+        c.barrier()                                             # every rank's parts have landed in every window
+        n_own = self.f1 - self.f0
+        p.sum_parts(score_flat[self.f0:self.f1], c.score_area(), self.world, c.score_cap, n_own)
+        p.bind_table(local_score_table)
+        n = p.total
+        if k >= n or k <= 0:                                    # train.py:300-303
+            p.select_begin(0, L.MODE_SNIP_STRICT)
+            p.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, self.mask, None, force=3,
+                         forced_threshold=float("inf") if k >= n else -1.0, chunk_begin=self.c0, chunk_end=self.c1)
+            self._allgather()
+            self._last = None
+            return 6
+        self._build(L.KEY_SCORE, None, k, L.MODE_SNIP_STRICT)
+        return 10
+
+    def _allgather(self):
+        check(self.plan.lib.b200p_comm_mask_allgather(self.comm.handle, self.plan.handle, self.c0, self.c1, _stream(self.plan)),
+              "comm_mask_allgather")
+
+    def _build(self, key_source, old_mask, k, mode, stages=0):
+        p = self.plan
+        check(p.lib.b200p_sharded_mask_build(p.handle, self.comm.handle, key_source,
+                                             ctypes.c_void_p(old_mask.data_ptr()) if old_mask is not None else None,
+                                             int(k), mode, self.c0, self.c1, int(stages), _stream(p)), "sharded_mask_build")
+        self._last = (key_source, old_mask, int(k), mode)
+
+    def check(self):
+        """Result block of the last build (synchronises, like the reference's `.item()` for its threshold print).  Raises
+        if a peer never arrived; reruns the staged exact select (NCCL histogram all-reduces) if the bracket missed."""
+        err = self.comm.error()
+        if err:
+            raise B200PruneError(f"sharded build: wait on channel {err - 1} timed out (a peer rank never arrived)")
+        res = self.plan.result()
+        if res["miss"] and self._last is not None:
+            if self.fallback is None:
+                raise B200PruneError("sharded build: the sampled bracket missed and no staged fallback builder was given")
+            key_source, old_mask, k, mode = self._last
+            self.fallback.select(key_source, k, mode, old_mask)
+            self.fallback.emit(key_source, mode, self.mask, old_mask)
+            res = self.plan.result()
+        strict = self._last is not None and self._last[3] == L.MODE_SNIP_STRICT
+        res["n_kept"] = res["n_valid"] - res["n_less"] - (res["n_equal"] if strict else res["quota"])
+        return res

@@ -267,6 +267,10 @@ class ParamPlan:
                                              _stream_ptr(self.device)), "masked_sgd_step")
 
     # ---- workspace views (for collectives between select stages) -----------------------
+    def device_view(self, ptr, count, dtype, owner=None):
+        """torch view of `count` elements of device memory owned by the library (plan workspace, comm window)."""
+        return _device_view(ptr, count, dtype, self.device, owner if owner is not None else self)
+
     def hist_tensor(self):
         """int64 view [4096] of the plan's global histogram (device memory owned by the plan)."""
         return _device_view(self.lib.b200p_plan_hist_ptr(self.handle), 4096, torch.int64, self.device, self)
@@ -295,11 +299,12 @@ class ParamPlan:
 class PtrTable:
     """Handle on a b200p_ptrtable (per-chunk device pointer table of one tensor set)."""
 
-    def __init__(self, plan, slot, ptrs, tensors):
+    def __init__(self, plan, slot, ptrs, tensors, handle=None):
         self.plan, self.slot, self.tensors = plan, slot, tensors
-        handle = ctypes.c_void_p()
-        check(plan.lib.b200p_ptrtable_create(plan.handle, slot, ptrs, _stream_ptr(plan.device), ctypes.byref(handle)),
-              "ptrtable_create")
+        if handle is None:
+            handle = ctypes.c_void_p()
+            check(plan.lib.b200p_ptrtable_create(plan.handle, slot, ptrs, _stream_ptr(plan.device), ctypes.byref(handle)),
+                  "ptrtable_create")
         self.handle = handle
 
     def close(self):

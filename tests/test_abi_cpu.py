@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in include/b200prune.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert lib.b200p_version() >= 100
+    assert lib.b200p_version() == _lib.ABI_VERSION
 
 
 def test_constants_match_header():
@@ -40,7 +40,10 @@ def test_constants_match_header():
     assert (defs["B200P_MODE_SNIP_STRICT"], defs["B200P_MODE_EXACT_K"]) == (_lib.MODE_SNIP_STRICT, _lib.MODE_EXACT_K)
     assert (defs["B200P_SGD_NESTEROV"], defs["B200P_SGD_FIRST_STEP"], defs["B200P_SGD_EMIT_WEFF"], defs["B200P_SGD_EMIT_WEFF16"]) == \
         (_lib.SGD_NESTEROV, _lib.SGD_FIRST_STEP, _lib.SGD_EMIT_WEFF, _lib.SGD_EMIT_WEFF16)
-    assert ctypes.sizeof(_lib.SelectResult) == 64 and ctypes.sizeof(_lib.LostImage) == 48
+    assert ctypes.sizeof(_lib.SelectResult) == 72 and ctypes.sizeof(_lib.LostImage) == 48
+    assert (defs["B200P_SHARD_SAMPLE"], defs["B200P_SHARD_SWEEP"], defs["B200P_SHARD_FINISH"], defs["B200P_SHARD_TIES"], defs["B200P_SHARD_EMIT"],
+            defs["B200P_SHARD_PUSH"], defs["B200P_SHARD_ALL"]) == (_lib.SHARD_SAMPLE, _lib.SHARD_SWEEP, _lib.SHARD_FINISH, _lib.SHARD_TIES,
+                                                                  _lib.SHARD_EMIT, _lib.SHARD_PUSH, _lib.SHARD_ALL)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="no-GPU behaviour")
@@ -69,4 +72,5 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
-                assert "oracle/" not in text or f.endswith(".py") is False or "test infrastructure" in text.lower() or True
+                # nor reaches it any other way: no path into oracle/ (or the staged reference) is ever built or executed
+                assert not re.search(r"""["'/]oracle["'/]|oracle\._ref|importlib\.import_module\(\s*["']oracle""", text), f
