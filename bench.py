@@ -1,31 +1,36 @@
 #!/usr/bin/env python
-"""bench.py — mask-build throughput of the B200 pruning hot path (BASELINE.json metric).
+"""bench.py — mask-build throughput of the B200 pruning hot path (BASELINE.json metric) and LOST images/s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-Workload (BASELINE.json configs[1]): ResNet-50 SNIP to 90 % sparsity, 8 synthetic mini-batches of
-gradients accumulated into the score, global k-th-smallest threshold, bit-packed mask emit.
-One "step" = one complete mask build (score accumulate x 8 -> radix select -> emit).
-`value` = prunable parameters masked per second (Gparams/s), inputs resident in HBM.
-`e2e`   = the same metric through the host-buffer C-ABI entry point
-          (b200p_snip_mask_build_host): weights and all gradient sets start in pinned HOST memory,
-          the packed mask and the result block come back to the host inside the timed region.
-`roofline` is for the dominant kernel of the step: k_score_multi (default --score-mode fused: all 8 resident
-          gradient sets folded in one pass, 4*(B+2) B/param) or k_score_accumulate (--score-mode streaming,
-          16 B/param/batch).
-`cpu_baseline` / `--impl reference`: the reference's own torch-CPU operator sequence
-          (oracle/torch_port.py) on the box's host cores.
+Workload (BASELINE.json configs[1]): ResNet-50 SNIP to 90 % sparsity, 8 synthetic mini-batches of gradients folded
+into the score, global k-th-smallest threshold, bit-packed mask.  One "step" = one complete mask build, INCLUDING
+the refresh of the 8 gradient pointer tables a real caller pays per build (fresh gradient tensors, one launch).
+Both arms use the same inputs: torchvision ResNet-50 init (seed 1) and g_b = 1e-3 * randn (CPU generator, seed
+300 + b), and each prints threshold, n_kept and the sha256 of the flat packed mask (`result`).
 
-N > 1 (launched under torchrun), default --dist-mode replicas: mask builds are independent units (one
-per model replica / sparsity level), so every rank builds the mask of its own replica from its own 8
-gradient sets with no data-path collective (weak scaling); value = N mask builds / max-over-ranks time.
---dist-mode sharded runs ONE mask build over the ranks (SURVEY §8e, strong scaling): local accumulate
--> NCCL all-to-all of score slices summed in rank order on the owner -> parameter-sharded select with
-a histogram all-reduce per radix pass -> every rank emits its slice of the packed mask -> all-reduce of
-the mask words.  For ResNet-50 that exchange (~100 MB per GPU) costs more than the whole single-GPU
-build (0.26 ms), see DESIGN.md §4.  Timing is the max over ranks of CUDA-event time.
+`value`      Gparams/s with the inputs resident in HBM (fused score + sweep).
+`roofline`   dominant kernel k_snip_score_sweep, timed by CUDA events on its own stream; `achieved` counts the fused
+             algorithmic figure 4*(B+2)+0.125 = 40.125 B/param; `contract` repeats the step in --score-mode streaming,
+             whose traffic is SURVEY §8(d)'s 16*B + 8.125 = 136.125 B/param, measured in the same run.
+`e2e`        the same build through b200p_snip_mask_build_host: weights and gradient sets in pinned HOST memory,
+             packed mask back on the host, median of >= 10 calls.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py) on the host
+             cores: multi-batch score accumulation in the reference's own operators (train.py:260,289; the reference has
+             no multi-batch mode), then train.snip_pruning itself on a 54-module stand-in whose weights are
+             the accumulated scores and whose loss is sum(w) (the hooks see g = 1, so its score is the accumulated
+             score bit for bit and its sort / threshold / custom_from_mask run on the real sizes).
+Extra legs in the same line: `with_fp32_masks` (the drop-in's fused fp32 weight_mask emit), `magnitude` (configs 1, 4, 5
+on one GPU), `lost` (config 3, uniform 900 x 384 and the VOC-shaped mix), and for N > 1 `sharded`: ONE ResNet-50 SNIP
+build over the N GPUs and the config-5 sweeps parameter-sharded, through the peer-memory path (no NCCL inside a build),
+each with a bit-identity flag against the single-GPU build of the same data.
+
+N > 1 (torchrun): `value` = N independent replicas' builds / max-over-ranks time (weak scaling, no data-path
+collective), the `sharded` leg is the strong-scaling path.  --dist-mode sharded makes the sharded SNIP build the
+headline value instead.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -41,9 +46,12 @@ if ROOT not in sys.path:
 MODEL = "resnet50"
 TARGET_SPARSITY = 0.9
 N_BATCHES = 8
-SCORE_BYTES_PER_PARAM = 16.0          # read w, g, acc; write acc
-SCORE_ASSIGN_BYTES_PER_PARAM = 12.0   # first batch: no acc read
-STEP_BYTES_PER_PARAM = 16.0 * N_BATCHES + 8.125
+CONTRACT_BYTES_PER_PARAM = 16.0 * N_BATCHES + 8.125
+FUSED_BYTES_PER_PARAM = 4.0 * (N_BATCHES + 2) + 0.125         # read w + B gradient sets, write score + mask
+MAGNITUDE_BYTES_PER_PARAM = 8.125
+SGD_BYTES_PER_PARAM = 22.125
+WORKLOAD = (f"{MODEL} SNIP mask build, target sparsity {TARGET_SPARSITY}, {N_BATCHES} mini-batches of synthetic gradients "
+            "(1e-3*randn, CPU generator seed 300+b) folded into the score, torchvision default init seed 1")
 
 
 def parse():
@@ -52,17 +60,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=11)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-lost", action="store_true", help="skip the LOST images/s leg")
+    ap.add_argument("--no-lost", action="store_true", help="skip the LOST legs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the magnitude / fp32-mask / contract / sharded legs")
     ap.add_argument("--dist-mode", default="replicas", choices=["replicas", "sharded"],
-                    help="N > 1: replicas = every rank builds the mask of its own model replica from its own 8 gradient "
-                         "sets (independent units, no collective, weak scaling); sharded = ONE mask build split over the "
-                         "ranks (batches shard the scores, parameters shard the select; NCCL exchange; strong scaling)")
-    ap.add_argument("--score-mode", default="sweep", choices=["sweep", "fused", "streaming"],
-                    help="fused: one pass over all resident gradient sets (4*(B+2) B/param); "
-                         "streaming: one accumulate launch per mini-batch (16 B/param/batch)")
+                    help="N > 1: what `value` is.  replicas = every rank builds the mask of its own replica (weak scaling, no "
+                         "collective); sharded = ONE build over the ranks through the peer-memory path (strong scaling)")
+    ap.add_argument("--score-mode", default="sweep", choices=["sweep", "fused", "streaming"])
     ap.add_argument("--no-clocks", action="store_true", help="skip the clock sampler and its keep-busy loops (ncu runs)")
     return ap.parse_args()
 
@@ -79,37 +85,37 @@ def peaks():
 
 
 # ---------------------------------------------------------------------------------------------
-# synthetic workload
-def model_numels():
-    from pruning_for_vision_representation_b200.shapes import prunable_numels
-    return prunable_numels(MODEL)
+# synthetic workload (identical in both arms: everything is generated on the CPU)
+_WEIGHT_CACHE = {}
 
 
-def make_weights_cpu(numels):
-    """ResNet-50 default init, torch.manual_seed(1); synthetic fan-in-scaled
-    normal weights of the same shapes if torchvision is unavailable."""
+def model_weights_cpu(name):
+    """flat fp32 weights of every Conv2d / Linear of torchvision `name`, default init, torch.manual_seed(1)."""
     import torch
+    if name in _WEIGHT_CACHE:
+        return _WEIGHT_CACHE[name]
+    from pruning_for_vision_representation_b200.shapes import prunable_numels
+    numels = prunable_numels(name)
     try:
         import torchvision
         torch.manual_seed(1)
-        m = torchvision.models.get_model(MODEL, weights=None, num_classes=1000)
-        ws = [mod.weight.detach().reshape(-1).clone() for mod in m.modules()
-              if isinstance(mod, (torch.nn.Conv2d, torch.nn.Linear))]
+        m = torchvision.models.get_model(name, weights=None, num_classes=1000)
+        ws = [mod.weight.detach().reshape(-1) for mod in m.modules() if isinstance(mod, (torch.nn.Conv2d, torch.nn.Linear))]
         assert [w.numel() for w in ws] == list(numels)
-        return torch.cat(ws), "torchvision resnet50 default init, seed 1"
+        out = (torch.cat(ws), numels, f"torchvision {name} default init, seed 1")
     except Exception as e:      # pragma: no cover
         g = torch.Generator().manual_seed(1)
-        return torch.randn(sum(numels), generator=g) * 0.02, f"0.02*randn (torchvision unavailable: {e})"
+        out = (torch.randn(sum(numels), generator=g) * 0.02, numels, f"0.02*randn (torchvision unavailable: {e})")
+    _WEIGHT_CACHE[name] = out
+    return out
 
 
-def make_grads(n_total, batch_ids, device):
-    """g_b = 1e-3 * randn, seed 300+b, generated on `device` (values differ between cpu and cuda
-    generators; each arm is self-consistent)."""
+def make_grads_cpu(n_total, batch_ids):
     import torch
     out = []
     for b in batch_ids:
-        g = torch.Generator(device=device).manual_seed(300 + b)
-        out.append(torch.randn(n_total, generator=g, device=device).mul_(1e-3))
+        g = torch.Generator().manual_seed(300 + b)
+        out.append(torch.randn(n_total, generator=g).mul_(1e-3))
     return out
 
 
@@ -119,6 +125,12 @@ def split_views(flat, numels):
         out.append(flat[off:off + n])
         off += n
     return out
+
+
+def flat_mask_sha256(bool_segments):
+    import numpy as np
+    bits = np.concatenate([np.asarray(b).reshape(-1).astype(bool) for b in bool_segments])
+    return hashlib.sha256(np.packbits(bits, bitorder="little").tobytes()).hexdigest()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -179,17 +191,67 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, numels, verbose=False):
-    """Times oracle/torch_port.snip_mask_build (the reference's torch-CPU operator sequence) on the
-    host cores.  Returns (Gparams/s, ms per step, sample description, cores)."""
+# the reference itself (oracle/_ref) on the host cores
+def load_reference():
+    """(train, object_discovery, kind): the staged unmodified reference, or (None, None, why) when oracle/_ref is absent."""
+    from oracle import make_ref
+    if not make_ref.available():
+        if os.path.isdir(make_ref.REF_SRC):
+            make_ref.make()
+        else:
+            return None, None, "oracle/_ref not staged (run python oracle/make_ref.py in the build container)"
+    t, od = make_ref.load()
+    return t, od, "reference"
+
+
+class _ScoreStub:
+    """Builds the 54-module stand-in that lets the UNMODIFIED train.snip_pruning run on pre-accumulated scores."""
+
+    @staticmethod
+    def make(score_views):
+        import torch
+        import torch.nn as nn
+
+        class Stub(nn.Module):
+            def __init__(self, views):
+                super().__init__()
+                self.mods = nn.ModuleList()
+                for v in views:
+                    lin = nn.Linear(1, 1, bias=False)          # isinstance(m, nn.Linear): train.py:263
+                    lin.weight = nn.Parameter(v)               # the accumulated score of this tensor, no copy
+                    self.mods.append(lin)
+
+            def forward(self, x):
+                tot = None
+                for m in self.mods:
+                    s = m.weight.sum()
+                    tot = s if tot is None else tot + s
+                return tot                                     # d/dw = 1 for every weight: the hooks see |g| = 1
+
+        return Stub(score_views)
+
+
+def reference_snip_build(ref_train, w_views, grads_views, sparsity):
+    """One mask build with the reference's code: returns (list of fp32 0/1 masks, accumulated flat score views)."""
     import torch
-    from oracle import torch_port as TP
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    acc = None
+    for grads in grads_views:                                  # multi-batch extension in the reference's own operators
+        part = [w.abs() * g.detach().clone().abs() for w, g in zip(w_views, grads)]      # train.py:260, 289
+        acc = part if acc is None else [a.add_(p) for a, p in zip(acc, part)]
+    model = _ScoreStub.make(acc)
+    x = torch.zeros(1)
+    ref_train.snip_pruning(model, [(x, x)], torch.device("cpu"), lambda out, tgt: out, sparsity)      # train.py:241-319, unmodified
+    masks = [m.weight_mask for m in model.mods]
+    return masks, acc
+
+
+def cpu_reference_run(steps, warmup, threads, verbose=False, budget_full_steps=24):
+    """Times the reference mask build on `threads` host threads.  Returns a dict (value in Gparams/s, ms, sample, result)."""
+    import torch
+    ref_train, _, kind = load_reference()
+    torch.set_num_threads(threads)
+    w_flat, numels, wsrc = model_weights_cpu(MODEL)
     n_total = sum(numels)
-    # bounded sample: the full parameter set costs ~5-8 s per mask build on a server CPU; when the
-    # requested step count would run past a few minutes, use a leading subset of the tensors.
-    budget_full_steps = 24
     frac = min(1.0, budget_full_steps / max(1, steps + warmup))
     use, acc = [], 0
     for n in numels:
@@ -197,42 +259,137 @@ def cpu_reference_run(steps, warmup, numels, verbose=False):
             break
         use.append(n); acc += n
     n_used = sum(use)
-    w_flat, wsrc = make_weights_cpu(numels)
     w = split_views(w_flat[:n_used], use)
-    grads = [split_views(g, use) for g in make_grads(n_used, range(N_BATCHES), "cpu")]
-    times = []
+    grads = [split_views(g[:n_used], use) for g in make_grads_cpu(n_total, range(N_BATCHES))]
+    if ref_train is None:
+        from oracle import torch_port as TP
+        kind = "port"
+    times, masks, scores = [], None, None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        masks, thr = TP.snip_mask_build(w, grads, TARGET_SPARSITY)
+        if ref_train is not None:
+            masks, scores = reference_snip_build(ref_train, w, grads, TARGET_SPARSITY)
+        else:
+            masks, _ = TP.snip_mask_build(w, grads, TARGET_SPARSITY)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
         if verbose:
-            print(f"[reference] step {i}: {dt:.3f} s thr={thr}", file=sys.stderr, flush=True)
+            print(f"[reference] step {i}: {dt:.3f} s", file=sys.stderr, flush=True)
     total = sum(times)
-    sample = (f"{len(use)}/{len(numels)} prunable tensors ({n_used} of {n_total} params), {N_BATCHES} batches, "
-              f"{steps} timed mask builds, torch {torch.__version__} CPU ops, {cores} threads; weights: {wsrc}")
-    return n_used * len(times) / total / 1e9, 1e3 * total / len(times), sample, cores
+    result = None
+    if n_used == n_total and masks is not None:
+        keep = [m.detach().numpy() != 0 for m in masks]
+        n_kept = int(sum(int(k.sum()) for k in keep))
+        thr = None
+        if scores is not None:
+            pruned_max = max(float(s.detach()[m == 0].max()) for s, m in zip(scores, masks) if bool((m == 0).any()))
+            thr = pruned_max                                   # strict compare: the threshold is the largest pruned score
+        result = {"threshold": thr, "n_kept": n_kept, "mask_sha256": flat_mask_sha256(keep)}
+    sample = (f"{len(use)}/{len(numels)} prunable tensors ({n_used} of {n_total} params), {N_BATCHES} batches, {len(times)} timed mask "
+              f"builds, torch {torch.__version__} CPU, {threads} threads; {'unmodified reference (oracle/_ref: train.snip_pruning on the accumulated scores)' if kind == 'reference' else 'oracle/torch_port (reference not staged)'}; weights: {wsrc}")
+    return {"value": n_used * len(times) / total / 1e9, "ms_per_step": 1e3 * total / len(times), "sample": sample, "cores": threads,
+            "kind": kind, "result": result}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    numels = model_numels()
-    val, ms, sample, cores = cpu_reference_run(args.steps, args.warmup, numels, verbose=True)
+    cores = os.cpu_count() or 1
+    r = cpu_reference_run(args.steps, args.warmup, cores, verbose=True)
+    one = cpu_reference_run(1, 0, 1, budget_full_steps=4) if args.steps + args.warmup <= 30 else None
     line = {
-        "impl": "reference", "metric": "mask-build Gparams/s (score+global top-k)", "value": val,
+        "impl": "reference", "metric": "mask-build Gparams/s (score+global top-k)", "value": r["value"],
         "unit": "Gparams/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{MODEL} SNIP {TARGET_SPARSITY} sparsity, {N_BATCHES} mini-batches of synthetic "
-                               "gradients, score accumulate + full sort threshold + mask (CPU, torch ops)"},
-        "cpu_baseline": {"value": val, "unit": "Gparams/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "Gparams/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": r["value"], "unit": "Gparams/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                         "one_thread": None if one is None else {"value": one["value"], "ms_per_step": one["ms_per_step"], "sample": one["sample"]}},
+        "e2e": {"value": r["value"], "unit": "Gparams/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "result": r["result"],
     }
     GUARD.emit(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def measure_tf32_peak(torch, dev, sustained_s=1.0):
+    """Dense TF32 matmul peak the way MEASURED_PEAKS.json measured bf16: torch.matmul 8192^3 (2 N^3 flop), allow_tf32."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev); b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(dev)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(sustained_s * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record(); torch.cuda.synchronize(dev)
+        flop = 2.0 * n ** 3
+        return {"burst_tflops": flop / (best * 1e-3) / 1e12, "sustained_tflops": flop * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": f"torch.matmul fp32 {n}^3 with allow_tf32, best of 10 (burst) / {reps} back to back (sustained), measured in this run"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def bind_to_gpu_numa(local):
+    """Pin this process to the CPUs of the GPU's NUMA node before pinned host buffers are allocated (first touch)."""
+    info = {"gpu_numa_node": None, "bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        info["gpu_numa_node"] = node
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = set()
+                for part in f.read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            allowed = os.sched_getaffinity(0) & cpus
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                info["bound"] = True
+                info["cpus"] = len(allowed)
+    except Exception as e:
+        info["note"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
+class L2Flush:
+    def __init__(self, torch, dev):
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def __call__(self):
+        self.buf.fill_(1)
+
+
+def timed_us(torch, fn, reps, flush=None):
+    """median microseconds of fn(), each call bracketed by CUDA events (L2 flushed before it when asked)."""
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    return statistics.median(ts)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -248,6 +405,7 @@ def run_b200(args):
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     L.require_cuda()
+    numa = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -255,42 +413,51 @@ def run_b200(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    numels = model_numels()
+    w_flat_cpu, numels, wsrc = model_weights_cpu(MODEL)
     n_total = sum(numels)
     k = int(n_total * TARGET_SPARSITY)                      # train.py:299
-    sharded = world > 1 and args.dist_mode == "sharded"
-    if sharded:
-        assert N_BATCHES % world == 0, "mini-batches must split evenly across ranks"
-        my_batches = list(range(rank * N_BATCHES // world, (rank + 1) * N_BATCHES // world))
-    else:
-        my_batches = [b + 1000 * rank for b in range(N_BATCHES)]     # every rank: its own full set of 8 gradient sets
-
-    w_flat_cpu, wsrc = make_weights_cpu(numels)
+    my_batches = [b + 1000 * rank for b in range(N_BATCHES)]          # rank 0 = the reference arm's data
     w_flat = w_flat_cpu.to(dev)
-    g_flat = make_grads(n_total, my_batches, dev)           # > L2: 8 x 102 MB streamed once per step
+    g_cpu = make_grads_cpu(n_total, my_batches)
+    g_flat = [g.to(dev) for g in g_cpu]                     # > L2: 8 x 102 MB streamed once per step
     s_flat = torch.empty(n_total, device=dev)
     plan = ParamPlan(numels, dev)
     plan.bind(L.SLOT_W, split_views(w_flat, numels)).bind(L.SLOT_SCORE, split_views(s_flat, numels))
-    g_tables = [plan.pointer_table(L.SLOT_G, split_views(g, numels)) for g in g_flat]
+    g_views = [split_views(g, numels) for g in g_flat]
+    g_tables = [plan.pointer_table(L.SLOT_G, v) for v in g_views]
     mask = plan.new_mask()
+    peak, peak_src = peaks()
+    flush = L2Flush(torch, dev)
 
-    if sharded:
-        from pruning_for_vision_representation_b200.distributed import ShardedMaskBuilder
-        builder = ShardedMaskBuilder(plan, dist.group.WORLD)
-
+    sharded_main = world > 1 and args.dist_mode == "sharded"
+    mode = args.score_mode
     launches = [0]
     score_events = []
-
-    sweep = args.score_mode == "sweep" and not sharded      # score pass + bracket sweep in one kernel (b200p_snip_mask_build)
-    fused = args.score_mode == "fused" or (args.score_mode == "sweep" and sharded)
-    if sweep:
+    if mode == "sweep":
         plan.time_sweep(True)
 
-    def step(record):
-        if sweep:
-            plan.snip_mask_build(g_tables, k, mask); launches[0] += 4      # sample, score+sweep, finish, emit
+    def refresh_tables():
+        # a caller gets fresh gradient tensors per build: all 8 tables re-pointed in one launch (pointers as kernel arguments)
+        plan.update_tables(g_tables, g_views); launches[0] += 1
+
+    # the Python-side validation of 8 x 54 tensors is host work a C++ caller does not have; precompute what it produces
+    import ctypes
+    refresh_tables()
+    tab_arr = (ctypes.c_void_p * len(g_tables))(*[t.handle for t in g_tables])
+    ptr_arrs = [(ctypes.c_void_p * len(numels))(*[v.data_ptr() for v in views]) for views in g_views]
+    ptr_arr = (ctypes.c_void_p * len(g_tables))(*[ctypes.cast(a, ctypes.c_void_p) for a in ptr_arrs])
+    stream_ptr = lambda: ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def refresh_tables_fast():
+        L.check(plan.lib.b200p_ptrtables_update(tab_arr, ptr_arr, len(g_tables), L.SLOT_G, stream_ptr()), "ptrtables_update")
+        launches[0] += 1
+
+    def step(record, smode=mode):
+        refresh_tables_fast()
+        if smode == "sweep":
+            plan.snip_mask_build(g_tables, k, mask); launches[0] += 4      # sample, score+sweep, finish, patching emit
             return
-        if fused:
+        if smode == "fused":
             if record:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -306,21 +473,16 @@ def run_b200(args):
                 plan.score_accumulate(i > 0); launches[0] += 1
                 if record:
                     e1.record(); score_events.append((i > 0, e0, e1))
-        if not sharded:
-            plan.mask_build(L.KEY_SCORE, k, L.MODE_SNIP_STRICT, mask); launches[0] += 4      # sample, sweep, finish, emit
-        else:
-            launches[0] += builder.snip_select_emit(s_flat, k, mask)
+        plan.mask_build(L.KEY_SCORE, k, L.MODE_SNIP_STRICT, mask); launches[0] += 4      # sample, sweep, finish, emit
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(max(3, args.warmup)):
         step(False)
     sync_all()
-    # clocks: sampled every 100 ms while the same step loop keeps the GPU busy before, during and
-    # after the (short) timed region, so every sample is taken under this load
     clocks = ClockSampler(local)
     if rank == 0 and not args.no_clocks:
         clocks.start()
@@ -343,7 +505,7 @@ def run_b200(args):
     keep_busy(0.5)
     launches[0] = 0
     sync_all()
-    if sweep:
+    if mode == "sweep":
         plan.kernel_time_ms()                 # discard the launches timed during warm-up
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -361,62 +523,101 @@ def run_b200(args):
         dist.all_reduce(tl)
         n_launches = int(tl.item())
     res = plan.result()
-    sweep_ms, sweep_n = plan.kernel_time_ms() if sweep else (0.0, 0)     # the launches of the timed region only
+    sweep_ms, sweep_n = plan.kernel_time_ms() if mode == "sweep" else (0.0, 0)
     keep_busy(0.4)
     clk = clocks.stop() if rank == 0 else None
+    result = {"threshold": res["threshold"], "n_less": res["n_less"], "n_equal": res["n_equal"], "n_kept": res["n_kept"],
+              "passes_full": res["passes_full"], "mask_sha256": flat_mask_sha256(plan.unpack_mask_host(mask))}
 
     acc_ms = [a.elapsed_time(b) for is_acc, a, b in score_events if is_acc]
     kernel_ms = sum(acc_ms) / max(1, len(acc_ms))
     n_timed = len(acc_ms)
-    if sweep:
+    if mode == "sweep":
         kernel_ms, n_timed = sweep_ms, sweep_n           # CUDA events recorded by the library around k_snip_score_sweep, same stream
-    peak, peak_src = peaks()
-    nb_local = len(my_batches)
-    # algorithmic bytes per launch of the dominant kernel: fused pass reads w and nb_local
-    # gradient sets and writes the score once; the streaming pass reads w, g, acc and writes acc
-    kernel_bytes = n_total * (4.0 * (nb_local + 2) + 0.125 if sweep else 4.0 * (nb_local + 2) if fused else SCORE_BYTES_PER_PARAM)
-    kernel_name = (f"k_snip_score_sweep<ACCUMULATE=0,B={nb_local}>" if sweep else
-                   f"k_score_multi<ACCUMULATE=0,B={nb_local}>" if fused else "k_score_accumulate<ACCUMULATE=1,VEC=1>")
-    # whole step: the fused score+sweep never re-reads the scores (no 4 B select read, no 4 B emit read)
-    step_bytes_per_param = (4.0 * (N_BATCHES + 2) + 0.125 if sweep else
-                            (4.0 * (N_BATCHES + 2) if fused else 16.0 * N_BATCHES) + 8.125)
-    achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9
+    kernel_bpp = FUSED_BYTES_PER_PARAM if mode == "sweep" else 4.0 * (N_BATCHES + 2) if mode == "fused" else 16.0
+    kernel_name = (f"k_snip_score_sweep<ACCUMULATE=0,B={N_BATCHES}>" if mode == "sweep" else
+                   f"k_score_multi<ACCUMULATE=0,B={N_BATCHES}>" if mode == "fused" else "k_score_accumulate<ACCUMULATE=1,VEC=1>")
+    step_bpp = (FUSED_BYTES_PER_PARAM if mode == "sweep" else (4.0 * (N_BATCHES + 2) if mode == "fused" else 16.0 * N_BATCHES) + 8.125)
+    achieved = n_total * kernel_bpp / (kernel_ms * 1e-3) / 1e9
     ms_per_step = elapsed_ms / args.steps
-    units = 1 if sharded else world                      # mask builds completed per step over all ranks
-    value = units * n_total / (ms_per_step * 1e-3) / 1e9
+    value = world * n_total / (ms_per_step * 1e-3) / 1e9
 
-    # ---- e2e: host buffers through the C-ABI (rank-local; N = 1 headline) -----------------------
+    # ---- the contract figure (16 B + 8.125 B/param) measured in the same run: streaming mode ------------------
+    contract = with_masks = None
+    if not args.no_extra and world == 1:
+        for _ in range(3):
+            step(False, "streaming")
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cs = max(5, min(20, args.steps))
+        c0.record()
+        for _ in range(cs):
+            step(False, "streaming")
+        c1.record(); torch.cuda.synchronize()
+        cms = c0.elapsed_time(c1) / cs
+        contract = {"bytes_per_param": CONTRACT_BYTES_PER_PARAM, "mode": "--score-mode streaming: one accumulate launch per mini-batch, then select + emit",
+                    "ms_per_step": cms, "value": n_total / (cms * 1e-3) / 1e9, "unit": "Gparams/s", "steps": cs,
+                    "step_GBps": n_total * CONTRACT_BYTES_PER_PARAM / (cms * 1e-3) / 1e9,
+                    "frac": n_total * CONTRACT_BYTES_PER_PARAM / (cms * 1e-3) / 1e9 / peak}
+        # drop-in variant: the fp32 weight_mask tensors of the checkpoint format come out of the emit as well (4 B/param more)
+        maskf = torch.empty(n_total, device=dev)
+        plan.bind(L.SLOT_MASKF, split_views(maskf, numels))
+        def with_f32():
+            refresh_tables_fast()
+            plan.snip_score_select(g_tables, k)
+            plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask, None, outputs=L.EMIT_MASKF)
+        for _ in range(3):
+            with_f32()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(cs):
+            with_f32()
+        c1.record(); torch.cuda.synchronize()
+        fms = c0.elapsed_time(c1) / cs
+        with_masks = {"what": "fused score + select, then the full emit with the fp32 weight_mask output (pruning.snip_pruning's sequence)",
+                      "ms_per_step": fms, "value": n_total / (fms * 1e-3) / 1e9, "unit": "Gparams/s", "steps": cs,
+                      "bytes_per_param": FUSED_BYTES_PER_PARAM + 8.0,
+                      "step_GBps": n_total * (FUSED_BYTES_PER_PARAM + 8.0) / (fms * 1e-3) / 1e9}
+        del maskf
+        step(False)                                      # leave `mask` = the default build's mask for the e2e comparison
+
+    # ---- e2e: host buffers through the C-ABI ------------------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        nb = len(my_batches)
         w_host = w_flat_cpu.pin_memory()
-        g_host = [g.cpu().pin_memory() for g in g_flat]
+        g_host = [g.pin_memory() for g in g_cpu]
         mask_host = torch.empty(plan.mask_words, dtype=torch.int32).pin_memory()
-        if not sharded:
-            for _ in range(1):
-                plan.snip_mask_build_host(w_host, g_host, k, mask_host)
-            sync_all()
+        plan.snip_mask_build_host(w_host, g_host, k, mask_host)
+        sync_all()
+        ts = []
+        for _ in range(max(10, args.e2e_steps)):
             tt = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                r2 = plan.snip_mask_build_host(w_host, g_host, k, mask_host)    # synchronises
-            e2e_s = (time.perf_counter() - tt) / args.e2e_steps
-            assert torch.equal(mask_host, mask.cpu()), "host-buffer path and resident path disagree"
-            if world > 1:
-                t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                e2e_s = float(t.item())
-            e2e = {"value": world * n_total / e2e_s / 1e9, "unit": "Gparams/s",
-                   "h2d_bytes_per_step": world * (1 + nb) * n_total * 4,
-                   "d2h_bytes_per_step": world * (plan.mask_words * 4 + 64),
-                   "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
-                   "api": "b200p_snip_mask_build_host (pinned host buffers in, packed mask out)"}
-        else:
-            e2e_ms = builder.e2e_host_steps(w_host, g_host, k, mask_host, args.e2e_steps)
-            e2e = {"value": n_total / (e2e_ms * 1e-3) / 1e9, "unit": "Gparams/s",
-                   "h2d_bytes_per_step": (1 + nb) * n_total * 4 * world,
-                   "d2h_bytes_per_step": (plan.mask_words * 4 + 64) * world,
-                   "ms_per_step": e2e_ms, "steps": args.e2e_steps,
-                   "api": "ShardedMaskBuilder.snip_mask_build_host (pinned host buffers in, packed mask out)"}
+            plan.snip_mask_build_host(w_host, g_host, k, mask_host)    # synchronises
+            ts.append(time.perf_counter() - tt)
+        e2e_s = statistics.median(ts)
+        assert torch.equal(mask_host, mask.cpu()), "host-buffer path and resident path disagree"
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": world * n_total / e2e_s / 1e9, "unit": "Gparams/s",
+               "h2d_bytes_per_step": world * (1 + N_BATCHES) * n_total * 4,
+               "d2h_bytes_per_step": world * (plan.mask_words * 4 + 72),
+               "ms_per_step": e2e_s * 1e3, "steps": len(ts), "statistic": "median", "ms_min": min(ts) * 1e3, "ms_max": max(ts) * 1e3,
+               "numa": numa, "api": "b200p_snip_mask_build_host (pinned host buffers in, packed mask out)"}
+        del w_host, g_host
+
+    magnitude = None
+    if not args.no_extra:
+        magnitude = magnitude_legs(torch, L, ParamPlan, dev, peak, flush)
+
+    sharded = None
+    if world > 1 and not args.no_extra:
+        sharded = sharded_legs(torch, dist, L, ParamPlan, dev, rank, world, peak, flush,
+                               dict(numels=numels, w_flat=w_flat, k=k, n_total=n_total), args)
+        if sharded_main and sharded.get("snip"):
+            value = sharded["snip"]["value"]; ms_per_step = sharded["snip"]["ms_per_step"]
 
     lost = None
     if not args.no_lost:
@@ -424,42 +625,44 @@ def run_b200(args):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, ms, sample, cores = cpu_reference_run(2, 1, numels)
-        cpu_base = {"value": v, "unit": "Gparams/s", "cores": cores, "kind": "port", "sample": sample,
-                    "ms_per_step": ms}
+        cores = os.cpu_count() or 1
+        r = cpu_reference_run(2, 1, cores)
+        one = cpu_reference_run(1, 0, 1, budget_full_steps=3)
+        cpu_base = {"value": r["value"], "unit": "Gparams/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                    "ms_per_step": r["ms_per_step"], "result": r["result"],
+                    "same_mask_as_gpu": (r["result"] or {}).get("mask_sha256") == result["mask_sha256"] if r["result"] else None,
+                    "one_thread": {"value": one["value"], "ms_per_step": one["ms_per_step"], "sample": one["sample"]}}
 
     if rank == 0:
         line = {
             "metric": "mask-build Gparams/s (score+global top-k)", "value": value, "unit": "Gparams/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if sharded_main else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{MODEL} SNIP mask build, target sparsity {TARGET_SPARSITY}, {N_BATCHES} mini-batches "
-                                   f"of synthetic gradients (1e-3*randn) accumulated, N={n_total} params in {len(numels)} tensors, "
-                                   f"k={k}", "weights": wsrc,
-                       "score_mode": ("sweep: one pass folds all resident gradient sets into the score (bit-identical to per-batch "
-                                      "accumulation) and classifies it against the sampled bracket; the scores are never read back"
-                                      if sweep else
-                                      "fused: all resident gradient sets folded in one pass, bit-identical to per-batch accumulation"
-                                      if fused else "streaming: one accumulate launch per mini-batch"),
-                       "l2": f"inputs larger than L2: {N_BATCHES // world} gradient sets x {n_total * 4 >> 20} MiB streamed per step",
+            "config": {"workload": WORKLOAD, "N": n_total, "tensors": len(numels), "k": k, "weights": wsrc,
+                       "score_mode": mode,
+                       "step": "refresh of the 8 gradient pointer tables (1 launch) + sample + fused score/sweep + finish + patching emit"
+                               if mode == "sweep" else mode,
+                       "l2": f"inputs larger than L2: {N_BATCHES} gradient sets x {n_total * 4 >> 20} MiB streamed per step",
                        "parallelism": ("1 GPU" if world == 1 else
-                                       f"batches split over {world} ranks, NCCL all-to-all score exchange + rank-order sum, "
-                                       "parameter-sharded radix select with histogram all-reduce (one mask build, strong scaling)" if sharded
-                                       else f"{world} independent mask builds, one model replica with its own 8 gradient sets per "
-                                            "rank, no data-path collective (weak scaling); --dist-mode sharded runs the NCCL path")},
-            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_snip_score_sweep" if sweep else "k_score_multi" if fused else "k_score_accumulate"),
+                                       f"ONE build over {world} ranks through the peer-memory path (strong scaling)" if sharded_main else
+                                       f"{world} independent mask builds, one model replica with its own 8 gradient sets per rank, no "
+                                       "data-path collective (weak scaling); the `sharded` leg is one build over all ranks")},
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": static_profile("k_snip_score_sweep_traffic_bytes") if mode == "sweep" else None,
+                         "traffic_source": "static: profiles/roofline_traffic.json (one ncu --set full capture, not measured in this run)",
                          "peak_source": peak_src, "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": kernel_bytes,
-                         "algorithmic_bytes_per_param": kernel_bytes / n_total,
+                         "algorithmic_bytes_per_param": kernel_bpp, "algorithmic_bytes_per_launch": n_total * kernel_bpp,
                          "launches_timed": n_timed,
-                         "step_algorithmic_bytes_per_param": step_bytes_per_param,
-                         "step_algorithmic_GBps": (n_total * step_bytes_per_param / (ms_per_step * 1e-3) / 1e9
-                                                   if world == 1 else None)},
-            "e2e": e2e, "cpu_baseline": cpu_base, "gpu_launches": n_launches, "clocks": clk, "lost": lost,
-            "result": {"threshold": res["threshold"], "n_less": res["n_less"], "n_equal": res["n_equal"],
-                       "n_kept": res["n_kept"], "passes_full": res["passes_full"]},
+                         "residency_bytes": N_BATCHES * n_total * 4,
+                         "residency_note": "the fused figure needs all B gradient sets resident (B x N x 4 bytes); `contract` is the per-batch streaming figure",
+                         "step_algorithmic_bytes_per_param": step_bpp,
+                         "step_GBps": n_total * step_bpp / (elapsed_ms / args.steps * 1e-3) / 1e9,
+                         "step_frac": n_total * step_bpp / (elapsed_ms / args.steps * 1e-3) / 1e9 / peak,
+                         "contract": contract},
+            "with_fp32_masks": with_masks,
+            "e2e": e2e, "cpu_baseline": cpu_base, "gpu_launches": n_launches, "clocks": clk,
+            "magnitude": magnitude, "sharded": sharded, "lost": lost, "result": result,
         }
         GUARD.emit(json.dumps(line))
     if world > 1:
@@ -467,14 +670,231 @@ def run_b200(args):
 
 
 # ---------------------------------------------------------------------------------------------
+def magnitude_legs(torch, L, ParamPlan, dev, peak, flush):
+    """BASELINE configs 1, 4, 5 on ONE GPU (device-resident weights, L2 flushed before every timed build):
+    select + ties + patching emit (b200p_mask_build), 8.125 algorithmic B/param."""
+    out = {"bytes_per_param": MAGNITUDE_BYTES_PER_PARAM, "l2": "256 MiB written between timed builds (L2 flush)", "legs": {}}
+
+    def leg(ms_us, n):
+        gb = n * MAGNITUDE_BYTES_PER_PARAM / (ms_us * 1e-6) / 1e9
+        return {"us": ms_us, "value": n / (ms_us * 1e-6) / 1e9, "unit": "Gparams/s", "GBps": gb, "frac": gb / peak}
+
+    # config 1: ResNet-18, 50 %, one shot
+    w, numels, src = model_weights_cpu("resnet18")
+    n = sum(numels)
+    wd = w.to(dev)
+    plan = ParamPlan(numels, dev)
+    plan.bind(L.SLOT_W, split_views(wd, numels))
+    m = plan.new_mask()
+    kk = round(0.5 * n)
+    plan.mask_build(L.KEY_ABS_W, kk, L.MODE_EXACT_K, m)
+    us = timed_us(torch, lambda: plan.mask_build(L.KEY_ABS_W, kk, L.MODE_EXACT_K, m), 9, flush)
+    r = plan.result()
+    d = leg(us, n); d.update(config="1: ResNet-18 global magnitude 50 %", N=n, k=kk, threshold=r["threshold"], n_equal=r["n_equal"],
+                             mask_sha256=flat_mask_sha256(plan.unpack_mask_host(m)), weights=src)
+    out["legs"]["resnet18_50"] = d
+    plan.close(); del wd
+
+    # config 4: ViT-B/16, 14 rounds of 20 % of the survivors, masked SGD steps in between
+    w, numels, src = model_weights_cpu("vit_b_16")
+    n = sum(numels)
+    wd = w.to(dev).clone()
+    plan = ParamPlan(numels, dev)
+    g = torch.randn(n, device=dev) * 1e-3
+    buf = torch.zeros(n, device=dev); weff16 = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    plan.bind(L.SLOT_W, split_views(wd, numels)).bind(L.SLOT_G, split_views(g, numels)).bind(L.SLOT_BUF, split_views(buf, numels))
+    plan.bind(L.SLOT_WEFF16, split_views(weff16, numels))
+    old, n_alive, rounds = None, n, []
+    import torch.nn.utils.prune as prune
+    for rnd in range(14):
+        kk = prune._compute_nparams_toprune(0.2, n_alive)
+        new = plan.new_mask()
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); plan.mask_build(L.KEY_ABS_W, kk, L.MODE_EXACT_K, new, old); b.record(); torch.cuda.synchronize()
+        rounds.append(a.elapsed_time(b) * 1e3)
+        old, n_alive = new, n_alive - kk
+        for s in range(2):                       # masked fine-tuning steps between rounds (fp32 update, bf16 weight for the forward)
+            plan.masked_sgd_step(old, 0.1, 0.9, 0.0, 1e-4, L.SGD_EMIT_WEFF16 | (L.SGD_FIRST_STEP if rnd == 0 and s == 0 else 0))
+    sgd_us = timed_us(torch, lambda: plan.masked_sgd_step(old, 0.1, 0.9, 0.0, 1e-4, L.SGD_EMIT_WEFF16), 7, flush)
+    d = leg(statistics.median(rounds), n)
+    d.update(config="4: ViT-B/16 iterative magnitude, 14 rounds of 20 % of the survivors (20 % -> 95.6 %), 2 masked SGD steps between rounds",
+             N=n, rounds_us=rounds, final_sparsity=100.0 * (n - n_alive) / n, weights=src,
+             masked_sgd={"us": sgd_us, "bytes_per_param": SGD_BYTES_PER_PARAM, "GBps": n * SGD_BYTES_PER_PARAM / (sgd_us * 1e-6) / 1e9,
+                         "frac": n * SGD_BYTES_PER_PARAM / (sgd_us * 1e-6) / 1e9 / peak})
+    out["legs"]["vit_b_16_iterative"] = d
+    plan.close(); del wd, g, buf, weff16
+
+    # config 5: threshold sweep over ResNet-152 and ViT-L/16
+    for name in ("resnet152", "vit_l_16"):
+        w, numels, src = model_weights_cpu(name)
+        n = sum(numels)
+        wd = w.to(dev)
+        plan = ParamPlan(numels, dev)
+        plan.bind(L.SLOT_W, split_views(wd, numels))
+        m = plan.new_mask()
+        levels = {}
+        for s in (0.5, 0.8, 0.9, 0.95, 0.99):
+            kk = round(s * n)
+            plan.mask_build(L.KEY_ABS_W, kk, L.MODE_EXACT_K, m)
+            us = timed_us(torch, lambda: plan.mask_build(L.KEY_ABS_W, kk, L.MODE_EXACT_K, m), 5, flush)
+            levels[str(s)] = leg(us, n)
+        d = leg(statistics.median([v["us"] for v in levels.values()]), n)
+        d.update(config=f"5: {name} one-shot magnitude at sparsity 0.5/0.8/0.9/0.95/0.99 (median over the levels)", N=n, levels=levels, weights=src)
+        out["legs"][f"{name}_sweep"] = d
+        plan.close(); del wd
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def sharded_legs(torch, dist, L, ParamPlan, dev, rank, world, peak, flush, rn50, args):
+    """ONE mask build over all ranks through the peer-memory path (csrc/comm.cuh): (i) ResNet-50 SNIP with the 8
+    mini-batches split over the ranks, (ii) BASELINE config 5: ResNet-152 / ViT-L/16 magnitude sweeps on replicated
+    weights, parameter-sharded.  Every result is compared bit for bit with the single-GPU build of the same data."""
+    from pruning_for_vision_representation_b200.distributed import PeerComm, PeerShardedBuilder
+    out = {"transport": "peer memory over NVLink (CUDA IPC windows): in-kernel histogram all-reduce / all-gather, mask-word push, "
+                        "fused score + scatter; no NCCL call inside a build", "world": world}
+
+    def all_max(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(flag):
+        t = torch.tensor([1 if flag else 0], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def timed_build(fn, reps):
+        ts = []
+        for _ in range(reps):
+            flush()
+            dist.barrier(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(all_max(a.elapsed_time(b) * 1e3))
+        return statistics.median(ts)
+
+    # ---- (i) ResNet-50 SNIP, one build over the ranks --------------------------------------------------------------------
+    numels, n, k = rn50["numels"], rn50["n_total"], rn50["k"]
+    if N_BATCHES % world == 0:
+        per = N_BATCHES // world
+        my = list(range(rank * per, (rank + 1) * per))
+        g_my = [g.to(dev) for g in make_grads_cpu(n, my)]
+        plan = ParamPlan(numels, dev)
+        plan.bind(L.SLOT_W, split_views(rn50["w_flat"], numels))
+        score = torch.zeros(n, device=dev)
+        local_tab = plan.pointer_table(L.SLOT_SCORE, split_views(score, numels))
+        gt = [plan.pointer_table(L.SLOT_G, split_views(g, numels)) for g in g_my]
+        comm = PeerComm.from_process_group(plan, score_cap=(plan.n_chunks + world - 1) // world * L.CHUNK)
+        b = PeerShardedBuilder(plan, comm)
+        b.snip_build(gt, k, score, local_tab)
+        res = b.check()
+        # reference on this GPU alone: per-rank partials, added in rank order, ordinary build
+        ref = ParamPlan(numels, dev)
+        ref.bind(L.SLOT_W, split_views(rn50["w_flat"], numels))
+        total = torch.empty(n, device=dev); part = torch.empty(n, device=dev)
+        for r in range(world):
+            gr = [g.to(dev) for g in make_grads_cpu(n, range(r * per, (r + 1) * per))]
+            ref.bind(L.SLOT_SCORE, split_views(part if r else total, numels))
+            ref.score_accumulate_multi([ref.pointer_table(L.SLOT_G, split_views(g, numels)) for g in gr])
+            if r:
+                total.add_(part)               # fp32 add in rank order, what k_sum_parts does
+            del gr
+        ref.bind(L.SLOT_SCORE, split_views(total, numels))
+        m_ref = ref.new_mask()
+        ref.mask_build(L.KEY_SCORE, k, L.MODE_SNIP_STRICT, m_ref)
+        r_ref = ref.result()
+        ident = torch.equal(b.mask, m_ref) and res["threshold"] == r_ref["threshold"] and res["miss"] == 0
+        ref.close(); del total, part
+        # stages (events between them, a few instrumented builds) and the back-to-back throughput
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        stage_ms = {"score_push": [], "exchange_sum": [], "select_emit_gather": []}
+        for _ in range(5):
+            dist.barrier(); torch.cuda.synchronize()
+            e = [ev() for _ in range(4)]
+            p = plan
+            p.bind_table(b._push_table)
+            e[0].record()
+            rot = b.bounds[(rank + 1) % world]
+            p.score_accumulate_multi(gt, accumulate=False, chunk_begin=rot, chunk_end=p.n_chunks)
+            if rot > 0:
+                p.score_accumulate_multi(gt, accumulate=False, chunk_begin=0, chunk_end=rot)
+            e[1].record()
+            comm.barrier()
+            p.sum_parts(score[b.f0:b.f1], comm.score_area(), world, comm.score_cap, b.f1 - b.f0)
+            p.bind_table(local_tab)
+            e[2].record()
+            b._build(L.KEY_SCORE, None, k, L.MODE_SNIP_STRICT)
+            e[3].record(); torch.cuda.synchronize()
+            for name, i in (("score_push", 0), ("exchange_sum", 1), ("select_emit_gather", 2)):
+                stage_ms[name].append(all_max(e[i].elapsed_time(e[i + 1])))
+        steps = max(10, min(50, args.steps))
+        dist.barrier(); torch.cuda.synchronize()
+        a0, a1 = ev(), ev()
+        a0.record()
+        for _ in range(steps):
+            b.snip_build(gt, k, score, local_tab)
+        a1.record(); torch.cuda.synchronize()
+        ms = all_max(a0.elapsed_time(a1) / steps)
+        res2 = b.check()
+        ident = ident and torch.equal(b.mask, m_ref) and res2["miss"] == 0
+        out["snip"] = {"what": f"ONE ResNet-50 SNIP mask build over {world} GPUs: {per} mini-batch(es) per rank, partial scores written into the "
+                               "owner's window by the score kernel, summed in rank order, parameter-sharded select, mask-word push",
+                       "value": n / (ms * 1e-3) / 1e9, "unit": "Gparams/s", "ms_per_step": ms, "steps": steps,
+                       "stage_ms": {k2: statistics.median(v) for k2, v in stage_ms.items()},
+                       "bit_identical_to_single_gpu": all_true(ident), "threshold": res2["threshold"], "n_kept": res2["n_kept"],
+                       "nvlink_bytes_per_rank": (world - 1) * (n // world) * 4,
+                       "bound_note": "the score exchange moves 4 B/param x (G-1)/G per rank over NVLink; one GPU streams 40 B/param from HBM at "
+                                     "~5.8 TB/s, so even a perfectly overlapped exchange cannot beat one GPU by more than ~1.8x on this workload"}
+        plan.close(); del g_my, score
+    # ---- (ii) config 5, parameter-sharded on replicated weights ------------------------------------------------------------
+    out["config5"] = {}
+    for name in ("resnet152", "vit_l_16"):
+        w, numels, src = model_weights_cpu(name)
+        n = sum(numels)
+        wd = w.to(dev)
+        plan = ParamPlan(numels, dev)
+        plan.bind(L.SLOT_W, split_views(wd, numels))
+        ref = ParamPlan(numels, dev)
+        ref.bind(L.SLOT_W, split_views(wd, numels))
+        comm = PeerComm.from_process_group(plan)
+        b = PeerShardedBuilder(plan, comm)
+        m_ref = ref.new_mask()
+        levels, ident_all = {}, True
+        for s in (0.5, 0.8, 0.9, 0.95, 0.99):
+            kk = round(s * n)
+            ref.mask_build(L.KEY_ABS_W, kk, L.MODE_EXACT_K, m_ref)
+            r_ref = ref.result()
+            b.magnitude_build(kk)
+            res = b.check()
+            ident = torch.equal(b.mask, m_ref) and res["threshold"] == r_ref["threshold"] and res["quota"] == r_ref["quota"] and res["miss"] == 0
+            ident_all = ident_all and ident
+            one_us = timed_us(torch, lambda: ref.mask_build(L.KEY_ABS_W, kk, L.MODE_EXACT_K, m_ref), 5, flush)
+            one_us = all_max(one_us)
+            sh_us = timed_build(lambda: b.magnitude_build(kk), 7)
+            levels[str(s)] = {"one_gpu_us": one_us, "sharded_us": sh_us, "speedup": one_us / sh_us,
+                              "value": n / (sh_us * 1e-6) / 1e9, "bit_identical": ident}
+        med = lambda key: statistics.median([v[key] for v in levels.values()])
+        out["config5"][name] = {"N": n, "levels": levels, "one_gpu_us": med("one_gpu_us"), "sharded_us": med("sharded_us"),
+                                "speedup": med("one_gpu_us") / med("sharded_us"), "value": n / (med("sharded_us") * 1e-6) / 1e9,
+                                "unit": "Gparams/s", "bit_identical_to_single_gpu": all_true(ident_all), "weights": src,
+                                "slice_bytes": n * 4 // world, "mask_bytes_pushed_per_rank": (world - 1) * (n // 8) // world}
+        plan.close(); ref.close(); del wd
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 LOST_N, LOST_D, LOST_DIMS, LOST_B = 900, 384, [30, 30], 256
 LOST_FLOP_PER_IMAGE = 2.0 * LOST_N * LOST_N * LOST_D          # SURVEY §8d: 622 080 000
+VOC_MIX = [([24, 32], (3, 375, 500)), ([35, 25], (3, 560, 400)), ([30, 30], (3, 480, 480)), ([32, 32], (3, 500, 500))]   # N = 768, 875, 900, 1024
 
 
 def lost_leg(args, dev, world, rank, dist):
-    """LOST ViT-S/16 images/s (BASELINE.json configs[2]): synthetic patch keys randn(B, 900, 384), seed 0
-    (+ rank), dims 30x30, scales 16, image 480x480, k_patches 100.  Images shard over ranks, no collective.
-    value = images/s with the keys resident in HBM; e2e = keys in pinned host memory -> boxes on the host."""
+    """LOST ViT-S/16 images/s (BASELINE.json configs[2]): synthetic patch keys randn(B, 900, 384), seed 0 (+ rank), dims
+    30x30, scales 16, image 480x480, k_patches 100; images shard over ranks, no collective.  value = images/s with the keys
+    resident in HBM; e2e = keys in pinned host memory -> boxes on the host.  `voc_mix`: the same through the varlen path
+    on a VOC-shaped mix of 768 / 875 / 900 / 1024 patches."""
     import numpy as np
     import torch
     from pruning_for_vision_representation_b200 import object_discovery as OD
@@ -488,7 +908,7 @@ def lost_leg(args, dev, world, rank, dist):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    steps = max(5, min(50, args.steps))
+    steps = max(10, min(50, args.steps))
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(steps):
@@ -496,6 +916,16 @@ def lost_leg(args, dev, world, rank, dist):
     t1.record()
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1) / steps
+    trace = None
+    try:
+        import ctypes
+        from pruning_for_vision_representation_b200 import _lib as L
+        tr = (ctypes.c_uint64 * 4)()
+        if L.load().b200p_lost_last_trace(tr) == 0:
+            trace = {"gram_kernel_us": (tr[1] - tr[0]) / 1e3, "first_finish_cta_ready_us": (tr[2] - tr[0]) / 1e3, "last_finish_cta_end_us": (tr[3] - tr[0]) / 1e3,
+                     "how": "globaltimer stamps written by the kernels of the last call (Gram first CTA start = 0)"}
+    except Exception:
+        pass
     # e2e: pinned host keys in, boxes / seeds / status back on the host
     box_h = torch.empty(LOST_B, 4).pin_memory(); seed_h = torch.empty(LOST_B, dtype=torch.int32).pin_memory()
     st_h = torch.empty(LOST_B, dtype=torch.int32).pin_memory()
@@ -505,20 +935,20 @@ def lost_leg(args, dev, world, rank, dist):
         box_h.copy_(o["box"], non_blocking=True); seed_h.copy_(o["seed"], non_blocking=True); st_h.copy_(o["status"], non_blocking=True)
         torch.cuda.synchronize()
     e2e_once()
-    tt = time.perf_counter()
-    for _ in range(3):
-        e2e_once()
-    e2e_ms = (time.perf_counter() - tt) / 3 * 1e3
+    ts = []
+    for _ in range(10):
+        tt = time.perf_counter(); e2e_once(); ts.append(time.perf_counter() - tt)
+    e2e_ms = statistics.median(ts) * 1e3
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(t[0]), float(t[1])
-    peak_tf32 = None
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak_tf32 = float(json.load(f)["bf16_tflops"]) / 2.0
-    except Exception:
-        peak_tf32 = 1590.0 / 2.0
+    tf32 = measure_tf32_peak(torch, dev) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([tf32["burst_tflops"], tf32["sustained_tflops"]] if rank == 0 else [0.0, 0.0], device=dev, dtype=torch.float64)
+        dist.broadcast(t, 0)
+        tf32 = tf32 or {"burst_tflops": float(t[0]), "sustained_tflops": float(t[1]), "how": "measured on rank 0"}
+    peak_tf32 = tf32["burst_tflops"]
     img_s = world * LOST_B / (ms * 1e-3)
     achieved = img_s / world * LOST_FLOP_PER_IMAGE / 1e12
     # flop the tensor cores execute per image: upper-triangular 256x256 tiles (256 rows each), the last column tile
@@ -527,57 +957,124 @@ def lost_leg(args, dev, world, rank, dist):
     last_cols = min(256, (LOST_N - (t2 - 1) * 256 + 15) // 16 * 16)
     exec_elems = sum(256 * (256 if tj < t2 - 1 else last_cols) for ti in range(t2) for tj in range(ti, t2))
     exec_flop = 3 * 2 * exec_elems * LOST_D
-    prof = {}
-    try:
-        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            prof = json.load(f)
-    except Exception:
-        pass
+    gram_us = trace["gram_kernel_us"] if trace else None
     leg = {"metric": "LOST ViT-S/16 images/sec", "value": img_s, "unit": "images/s", "ms_per_step": ms, "steps": steps,
            "config": {"workload": f"LOST on synthetic patch keys randn({LOST_B},{LOST_N},{LOST_D}) per GPU, dims 30x30, "
-                                  "k_patches 100, keys -> Gram -> degree -> seed -> expansion -> box; ViT forward excluded",
-                      "l2": f"{LOST_B} Gram matrices = {LOST_B * LOST_N * LOST_N * 4 >> 20} MiB written per step (> L2)"},
-           "roofline": {"bound": "tensor", "kernel": "k_lost_gram_tc2<direct> (TMA on the caller's keys + tcgen05.mma cta_group::2 kind::tf32, 3xTF32 with "
-                                                     "the lo tiles derived in shared memory, TMEM epilogue with fused degree)",
+                                  "k_patches 100, keys -> Gram -> degree -> seed -> expansion -> box; ViT forward excluded; no Gram matrix "
+                                  "is materialised (count-only epilogue, similars and M from the keys)",
+                      "l2": f"{LOST_B} x {LOST_N * LOST_D * 4 >> 10} KiB of keys = {LOST_B * LOST_N * LOST_D * 4 >> 20} MiB streamed per step (> L2)"},
+           "roofline": {"bound": "tensor", "kernel": "k_lost_gram_tc2<direct, count-only> (TMA on the caller's keys + tcgen05.mma cta_group::2 kind::tf32, 3xTF32 with "
+                                                     "the lo tiles derived in shared memory, TMEM epilogue counting the degrees)",
                         "achieved": achieved, "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32,
+                        "peak_sustained": tf32["sustained_tflops"], "peak_source": tf32["how"],
                         "executed_tflops": img_s / world * exec_flop / 1e12,
                         "executed_frac": img_s / world * exec_flop / 1e12 / peak_tf32,
-                        "tensor_pipe_active_pct_ncu": prof.get("k_lost_gram_tc2_tensor_pipe_active_pct"),
-                        "traffic": prof.get("k_lost_gram_tc2_traffic_bytes"),
-                        "peak_source": "0.5 x measured bf16 burst (nominal tf32:bf16 ratio; no measured tf32 peak); achieved counts the "
-                                       "algorithmic 2*N^2*d flop per image over the WHOLE LOST step (Gram + finish + launches); executed_tflops "
-                                       "counts what the tensor cores run: 3 tf32 MMAs per product on the upper-triangular 256-row tiles"},
-           "e2e": {"value": world * LOST_B / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms,
+                        "kernel_us": gram_us,
+                        "kernel_achieved": None if not gram_us else LOST_B * LOST_FLOP_PER_IMAGE / (gram_us * 1e-6) / 1e12,
+                        "kernel_frac": None if not gram_us else LOST_B * LOST_FLOP_PER_IMAGE / (gram_us * 1e-6) / 1e12 / peak_tf32,
+                        "kernel_executed_frac": None if not gram_us else LOST_B * exec_flop / (gram_us * 1e-6) / 1e12 / peak_tf32,
+                        "tensor_pipe_active_pct_static": static_profile("k_lost_gram_tc2_tensor_pipe_active_pct"),
+                        "traffic": static_profile("k_lost_gram_tc2_traffic_bytes"),
+                        "static_note": "tensor_pipe_active_pct_static and traffic come from one committed ncu capture (profiles/), not from this run",
+                        "note": "achieved counts the algorithmic 2*N^2*d flop per image over the WHOLE LOST step (Gram + finish + launches); executed_tflops "
+                                "counts what the tensor cores run: 3 tf32 MMAs per product on the upper-triangular 256-row tiles; kernel_* use the Gram "
+                                "kernel's own duration (globaltimer stamps of the last call)"},
+           "trace": trace,
+           "e2e": {"value": world * LOST_B / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms, "steps": 10, "statistic": "median",
                    "h2d_bytes_per_step": LOST_B * LOST_N * LOST_D * 4, "d2h_bytes_per_step": LOST_B * (16 + 4 + 4)},
-           "gpu_launches_per_step": 3 + (LOST_B + 255) // 256,   # set_meta x ceil(B/256), tile table, Gram, finish (+ 1 memset node)
+           "gpu_launches_per_step": 4,   # gen_meta, tile table, Gram, finish (+ 1 memset node)
            "seed0_box0": [int(out["seed"][0].item()), out["box"][0].tolist()]}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # ---- VOC-shaped mix through the varlen path ---------------------------------------------------------------------------------
+    gm = torch.Generator().manual_seed(1000 + rank)
+    mix_feats, mix_dims, mix_sizes = [], [], []
+    for i in range(LOST_B):
+        dims, sz = VOC_MIX[i % len(VOC_MIX)]
+        mix_feats.append(torch.randn(dims[0] * dims[1], LOST_D, generator=gm))
+        mix_dims.append(dims); mix_sizes.append(sz)
+    flat = torch.cat(mix_feats).to(dev)                   # one producer buffer; the per-image views below are read in place
+    views, off = [], 0
+    for f in mix_feats:
+        views.append(flat[off:off + f.shape[0]]); off += f.shape[0]
+    runm = lambda: OD.lost_batched(views, mix_dims, [16, 16], mix_sizes, k_patches=100)
+    for _ in range(3):
+        om = runm()
+    torch.cuda.synchronize()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    msteps = max(5, steps // 2)
+    m0.record()
+    for _ in range(msteps):
+        om = runm()
+    m1.record(); torch.cuda.synchronize()
+    mms = m0.elapsed_time(m1) / msteps
+    mix_flop = sum(2.0 * (d[0] * d[1]) ** 2 * LOST_D for d in mix_dims)
+    parity = None
+    if rank == 0:
         from oracle import lost_oracle as LO
+        box, seed, status = om["box"].cpu().numpy(), om["seed"].cpu().numpy(), om["status"].cpu().numpy()
+        checked = mismatched = excused = 0
+        for i in range(0, LOST_B, 8):                     # every 8th image: all four shapes
+            f = mix_feats[i].numpy()
+            sd, pred, decidable = LO.lost_from_degrees(f, om["degree"][i].cpu().numpy(), mix_dims[i], [16, 16], mix_sizes[i], 100)
+            got = None if status[i] else [float(v) for v in box[i]]
+            exp = None if pred is None else [float(v) for v in pred]
+            checked += 1
+            if int(seed[i]) != sd or (got != exp and decidable):
+                mismatched += 1
+            elif got != exp:
+                excused += 1
+        parity = {"checked": checked, "mismatched": mismatched, "excused_undecidable": excused, "ok": mismatched == 0,
+                  "how": "seed and box of every 8th image against the fp64 replay of object_discovery.py:57-67 from the GPU's degrees (oracle/lost_oracle.lost_from_degrees)"}
+    if world > 1:
+        t = torch.tensor([mms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mms = float(t[0])
+    leg["voc_mix"] = {"value": world * LOST_B / (mms * 1e-3), "unit": "images/s", "ms_per_step": mms, "steps": msteps,
+                      "workload": f"{LOST_B} images per GPU, N in {{768, 875, 900, 1024}} patches (24x32, 35x25, 30x30, 32x32), d = {LOST_D}, per-image views "
+                                  "of one key buffer read in place (varlen records)",
+                      "achieved_tflops": mix_flop / (mms * 1e-3) / 1e12,
+                      "frac": mix_flop / (mms * 1e-3) / 1e12 / peak_tf32, "parity": parity}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, ref_od, kind = load_reference()
         n_img = 24
-        fs = feats_host[:n_img].numpy()
-        LO.lost(fs[0], LOST_DIMS, [16, 16], size, 100)
-        tt = time.perf_counter()
-        for i in range(n_img):
-            LO.lost(fs[i], LOST_DIMS, [16, 16], size, 100)
-        dt = time.perf_counter() - tt
-        leg["cpu_baseline"] = {"value": n_img / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                               "sample": f"{n_img} of the same images through oracle/lost_oracle.lost (numpy BLAS Gram + python flood fill)"}
+        fs = feats_host[:n_img]
+        if ref_od is not None:
+            import torch as _t
+            _t.set_num_threads(os.cpu_count() or 1)
+            ref_od.lost(fs[0:1], LOST_DIMS, [16, 16], size, 100)
+            tt = time.perf_counter()
+            same = 0
+            for i in range(n_img):
+                pred, _, _, sd = ref_od.lost(fs[i:i + 1], LOST_DIMS, [16, 16], size, 100)
+                same += int(int(sd) == int(out["seed"][i].item()) and [float(v) for v in pred] == out["box"][i].tolist())
+            dt = time.perf_counter() - tt
+            leg["cpu_baseline"] = {"value": n_img / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "reference",
+                                   "sample": f"{n_img} of the same images through the unmodified object_discovery.lost (oracle/_ref; torch CPU Gram + scipy label)",
+                                   "same_seed_and_box_as_gpu": f"{same}/{n_img} (the reference's argsort is unstable and its fp32 Gram rounds differently: "
+                                                               "images with tied degrees or undecidable entries may differ)"}
+        else:
+            from oracle import lost_oracle as LO
+            LO.lost(fs[0].numpy(), LOST_DIMS, [16, 16], size, 100)
+            tt = time.perf_counter()
+            for i in range(n_img):
+                LO.lost(fs[i].numpy(), LOST_DIMS, [16, 16], size, 100)
+            dt = time.perf_counter() - tt
+            leg["cpu_baseline"] = {"value": n_img / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"{n_img} of the same images through oracle/lost_oracle.lost ({kind})"}
     return leg
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/roofline_traffic.json), or None."""
+def static_profile(key):
+    """A number from the committed ncu capture summary (profiles/roofline_traffic.json), or None.  NOT measured in this run."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(kernel + "_traffic_bytes")
+            return json.load(f).get(key)
     except Exception:
         return None
 
 
 class StdoutGuard:
-    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; stdout carries only
+    """Everything libraries print to fd 1 (NCCL's banner, the reference's prints) goes to stderr; stdout carries only
     the one JSON line the driver parses."""
 
     def __init__(self):

@@ -52,6 +52,7 @@ extern "C" {
 #define B200P_SLOT_WEFF     4   /* fp32 effective (masked) weight = module.weight          */
 #define B200P_SLOT_MASKF    5   /* fp32 0/1 masks = module.weight_mask (checkpoint compat) */
 #define B200P_SLOT_WEFF16   6   /* bf16 effective weight for autocast forward              */
+#define B200P_SLOT_EMA      7   /* fp32 EMA of weight_orig (utils.py:159-170)               */
 #define B200P_NUM_SLOTS     8
 
 /* emit / select modes */
@@ -126,6 +127,10 @@ int  b200p_plan_bind_table(b200p_plan* plan, int slot, const b200p_ptrtable* tab
 #define B200P_SELECT_EXACT      1   /* 3-pass MSD radix select over the full data */
 #define B200P_OPT_TIME_SWEEP    2   /* value 1: record CUDA events around every fused score+sweep kernel of
                                        b200p_snip_mask_build / b200p_snip_score_select (measurement only) */
+#define B200P_OPT_REUSE_SAMPLE  3   /* value 1: selects over UNCHANGED keys (same key source, old mask, chunk range; e.g. a sparsity
+                                       sweep over fixed weights, BASELINE config 5) derive their bracket from the sample histogram the
+                                       first one cached instead of sampling (and, sharded, all-reducing) again.  The caller vouches
+                                       for "unchanged": weights updated in place must clear the option or re-bind the slot. */
 int  b200p_plan_set_option(b200p_plan* plan, int option, int64_t value);
 /* Mean duration (ms) and number of the fused score+sweep launches timed since the option was set or this was last
  * called; synchronises on the last recorded event.  *out_launches may be 0 (then *out_ms = 0). */
@@ -275,6 +280,19 @@ int  b200p_mask_grads(b200p_plan* plan, const uint32_t* d_mask, void* stream);
 #define B200P_SGD_EMIT_WEFF16 8   /* also write WEFF16 = bf16(mask ? w_new : 0)     */
 int  b200p_masked_sgd_step(b200p_plan* plan, const uint32_t* d_mask, float lr, float momentum,
                            float dampening, float weight_decay, int flags, void* stream);
+/* The same with a device-side control block d_ctl (2 floats, nullable): every gradient is multiplied by d_ctl[0] before
+ * use — the loss-scale removal of GradScaler.unscale_, the coefficient of clip_grad_norm_ and the 1/world of a gradient
+ * all-reduce folded into one factor (train.py:55-66) — and d_ctl[1] != 0 skips the whole step (a non-finite gradient
+ * was found: GradScaler.step).  Both are read on the device, so nothing between backward and step needs the host. */
+int  b200p_masked_sgd_step_ctl(b200p_plan* plan, const uint32_t* d_mask, float lr, float momentum, float dampening,
+                               float weight_decay, int flags, const float* d_ctl, void* stream);
+/* d_out2[0] = sum of g^2 over the KEPT entries of the G slot (= ||weight_orig.grad||^2 of the reference's masked
+ * gradients, the prunable tensors' share of clip_grad_norm_'s total norm), d_out2[1] = number of non-finite gradient
+ * entries (kept or pruned: inf * 0 = NaN reaches the reference's inf check too).  d_out2: 2 doubles, zeroed by the call. */
+int  b200p_grad_stats(b200p_plan* plan, const uint32_t* d_mask, double* d_out2, void* stream);
+/* EMA slot = copy ? W : decay * EMA + (1 - decay) * W   (ExponentialMovingAverage over weight_orig, utils.py:159-170;
+ * copy = the n_averaged == 0 case of torch.optim.swa_utils.AveragedModel.update_parameters) */
+int  b200p_ema_update(b200p_plan* plan, float decay, int copy, void* stream);
 
 /* ---- LOST (object_discovery.py:23-134) ---------------------------------------------- */
 /* Batched LOST over B images that share d.  Image b has n_b = dims[2b]*dims[2b+1] patch
@@ -286,7 +304,7 @@ int  b200p_masked_sgd_step(b200p_plan* plan, const uint32_t* d_mask, float lr, f
  * (0 ok, 1 = "The seed is in the background component", object_discovery.py:110-111; 2 = internal: the finish
  * kernel gave up waiting for the Gram kernel, never expected).
  * d_A (nullable): fp32 Gram matrices, image b at d_A + a_offset[b], n_b x n_b row-major.  With d_A == NULL and a pair
- * Gram (TC2 / TC2D, keys up to 768 wide) NO Gram matrix is materialised anywhere: the Gram epilogue only counts, and
+ * Gram (TC2 / TC2D) NO Gram matrix is materialised anywhere: the Gram epilogue only counts, and
  * A[seed, potentials] and M = K (sum of the similar keys) come from the keys (object_discovery.py:61-62 as two skinny
  * mat-vecs; same signs wherever an entry is decidable in fp32).
  * h_meta is a host array of B records; it is consumed before the call returns.  At most 4096
@@ -304,8 +322,9 @@ typedef struct b200p_lost_image_t {
 #define B200P_LOST_GRAM_TC     1   /* TMA + tcgen05 3xTF32 error-compensated Gram, one CTA per 128x128 tile */
 #define B200P_LOST_GRAM_TC2    2   /* the same on CTA pairs: tcgen05.mma.cta_group::2, 256x256 tiles, features pre-split into hi/lo arrays */
 #define B200P_LOST_GRAM_TC2D   3   /* default: CTA pairs reading the caller's features in place (TMA on d_feats, hi/lo tiles derived in
-                                      shared memory); falls back to TC2 when the layout is not TMA-addressable and to FFMA for keys wider
-                                      than 768 (the tensor cores' truncating accumulator drifts ~1.2e-8 d |k|^2: past the 1e-5 bar there) */
+                                      shared memory); falls back to TC2 when the layout is not TMA-addressable.  Keys wider than 384 are
+                                      accumulated in K segments of 384 (the tensor cores' truncating accumulator drifts ~1.2e-8 d |k|^2 in one
+                                      accumulation: past the 1e-5 bar from d = 768 on); keys wider than 6144 go to FFMA */
 int  b200p_lost_workspace_bytes(int n_images, int64_t total_patches, int64_t total_a, int d, int gram_impl, int64_t* out);
 int  b200p_lost_batched(int device, const float* d_feats, int64_t row_stride, int d,
                         const b200p_lost_image_t* h_meta, int n_images, int k_patches,

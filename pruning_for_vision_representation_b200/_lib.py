@@ -13,14 +13,14 @@ LIB_PATH = os.path.join(HERE, "libb200prune.so")
 # constants mirrored from include/b200prune.h
 CHUNK = 4096
 WORDS_PER_CHUNK = 128
-SLOT_W, SLOT_G, SLOT_SCORE, SLOT_BUF, SLOT_WEFF, SLOT_MASKF, SLOT_WEFF16 = range(7)
+SLOT_W, SLOT_G, SLOT_SCORE, SLOT_BUF, SLOT_WEFF, SLOT_MASKF, SLOT_WEFF16, SLOT_EMA = range(8)
 NUM_SLOTS = 8
 MODE_SNIP_STRICT, MODE_EXACT_K = 0, 1
 KEY_ABS_W, KEY_SCORE = 0, 1
 EMIT_MASKF, EMIT_WEFF = 1, 2
 SGD_NESTEROV, SGD_FIRST_STEP, SGD_EMIT_WEFF, SGD_EMIT_WEFF16 = 1, 2, 4, 8
 LOST_GRAM_FFMA, LOST_GRAM_TC, LOST_GRAM_TC2, LOST_GRAM_TC2D = 0, 1, 2, 3
-OPT_SELECT_IMPL, OPT_TIME_SWEEP = 1, 2
+OPT_SELECT_IMPL, OPT_TIME_SWEEP, OPT_REUSE_SAMPLE = 1, 2, 3
 SHARD_SAMPLE, SHARD_SWEEP, SHARD_FINISH, SHARD_TIES, SHARD_EMIT, SHARD_PUSH, SHARD_ALL = 1, 2, 4, 8, 16, 32, 63
 SELECT_SAMPLED, SELECT_EXACT = 0, 1
 
@@ -99,6 +99,9 @@ SIGNATURES = {
     "b200p_apply_mask": (_I, [_P, _P, _I, _P]),
     "b200p_mask_grads": (_I, [_P, _P, _P]),
     "b200p_masked_sgd_step": (_I, [_P, _P, _F, _F, _F, _F, _I, _P]),
+    "b200p_masked_sgd_step_ctl": (_I, [_P, _P, _F, _F, _F, _F, _I, _P, _P]),
+    "b200p_grad_stats": (_I, [_P, _P, _P, _P]),
+    "b200p_ema_update": (_I, [_P, _F, _I, _P]),
     "b200p_lost_workspace_bytes": (_I, [_I, _I64, _I64, _I, _I, ctypes.POINTER(_I64)]),
     "b200p_lost_batched": (_I, [_I, _P, _I64, _I, ctypes.POINTER(LostImage), _I, _I, _P, _P, _P, _P, _P,
                                 _P, _I64, _I, _P]),

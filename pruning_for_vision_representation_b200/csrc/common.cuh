@@ -16,7 +16,8 @@ constexpr int kThreads = 256;                    // threads per CTA of the strea
 constexpr int kVecPerThread = kChunk / (4 * kThreads);   // float4 per thread per chunk = 4
 constexpr int kWordsPerChunk = B200P_WORDS_PER_CHUNK;
 constexpr int kHistBins = 4096;                  // 12-bit digits
-constexpr int kHistExtra = 8;                    // scalar counters behind the bins: [0] alive keys (sample pass), [1] keys below the bracket
+constexpr int kHistExtra = 8;                    // scalar counters behind the bins: [0] alive keys (sample pass), [1] keys below the bracket,
+                                                 // [2] NaN keys cleared from the provisional mask, [7] ticket of the mask push
 constexpr uint32_t kNanKey = 0x7FFFFFFFu;        // every NaN sorts last (torch.sort semantics)
 
 // digit layout of the 31-bit key: pass 0 -> bits 30..19, pass 1 -> bits 18..7, pass 2 -> bits 6..0
@@ -122,7 +123,7 @@ struct SelState {
     uint32_t lo_bucket, hi_bucket;   // bracket in units of the 12-bit digit (inclusive)
     uint32_t win_lo;                 // first key of the 1024-key window chosen by the bracket pass
     uint32_t prov_ok;                // the provisional mask (bits: alive && key >= bracket base) and the candidate list are valid
-    uint32_t pad_[2];
+    uint32_t pad_[2];                // [0] ticket of the last-CTA pattern, [1] alive NaN keys pruned by the provisional mask (SNIP_STRICT)
 };
 
 }  // namespace b200p
@@ -159,6 +160,12 @@ struct b200p_plan {
     // emit-by-patch: valid for the emit that directly follows b200p_select_kth with the same arguments
     uint32_t* prov_target = nullptr;        // where the sweep writes the provisional mask (nullptr: d_prov)
     bool prov_armed = false; int prov_key_source = -1; int prov_mode = -1; const uint32_t* prov_old_mask = nullptr;
+    // B200P_OPT_REUSE_SAMPLE: cached sample histogram of the last sampled select
+    bool reuse_sample = false, sample_cache_valid = false; int sample_cache_key = -1; const uint32_t* sample_cache_mask = nullptr;
+    int64_t sample_cache_c0 = 0, sample_cache_c1 = 0; const void* sample_cache_tab = nullptr;
+    unsigned long long* d_sample_cache = nullptr;
+    bool fuse_emit = false;                 // b200p_mask_build / b200p_snip_mask_build: the finish kernel emits the mask itself
+    bool emit_done = false;                 // ... and did (the caller skips its emit launch)
     int64_t prov_c0 = 0, prov_c1 = 0;       // chunk range the sweep covered (the whole set on one GPU, the rank's slice when sharded)
     unsigned long long* d_rank_ties = nullptr;   // [8] sharded select: every rank's count of the threshold key (k_sharded_finish)
     // lazily created arena for the host-buffer entry points

@@ -21,7 +21,7 @@ namespace b200p {
 
 constexpr int kLostMaxPatches = 4096;     // per image (ViT-S/8 at 480x480 = 3600)
 constexpr int kFinThreads = 512;
-constexpr int kLostMaxTensorCoreWidth = 768;   // widest key the default (TC2D) Gram keeps on the tensor cores, see b200p_lost_batched
+constexpr int kLostMaxTensorCoreWidth = 6144;  // widest key the pair kernels take (16 K segments of 384): ViT-B 768, VGG16 512, ResNet-50 2048 all fit
 
 // image records travel as kernel arguments (no pageable-memcpy stream sync, no staging buffer)
 constexpr int kMetaPerLaunch = 256;
@@ -567,7 +567,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // The pair kernels (TC2 / TC2D on keys the tensor cores take) run count-only when the caller does not ask for A:
 // no Gram matrix is materialised anywhere, the finish kernel works from the keys.
 static bool lost_count_only(int gram_impl, int d) {
-    return gram_impl == B200P_LOST_GRAM_TC2 || (gram_impl == B200P_LOST_GRAM_TC2D && d <= kLostMaxTensorCoreWidth);
+    return (gram_impl == B200P_LOST_GRAM_TC2 || gram_impl == B200P_LOST_GRAM_TC2D) && d <= kLostMaxTensorCoreWidth;
 }
 
 static const unsigned int* g_last_done = nullptr;
@@ -606,10 +606,12 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     bool vec = (((uintptr_t)d_feats) & 15u) == 0 && (row_stride & 3) == 0;
     const bool count_only = d_A == nullptr && lost_count_only(gram_impl, d);
     // The tensor cores truncate every product to the accumulator's ulp, so a same-sign sum (the squared norms on the
-    // diagonal) drifts by ~1.2e-8 d |k|^2: 4.9e-6 at d = 384, 9.3e-6 at 768, 2.2e-5 at 2048 (tools/gram_error_probe.py),
-    // whatever the operand split.  The default keeps the 1e-5 parity bar by computing wide keys (ResNet-50 features,
-    // main_lost_original.py:277-280) on the fp32 FMA path (1.6e-6); an explicit TC / TC2 request is honoured as is.
-    if (gram_impl == B200P_LOST_GRAM_TC2D && d > kLostMaxTensorCoreWidth) gram_impl = B200P_LOST_GRAM_FFMA;
+    // diagonal) drifts by ~1.2e-8 d |k|^2: 4.9e-6 at d = 384, 9.3e-6 at 768, 2.2e-5 at 2048 in ONE accumulation
+    // (tools/gram_error_probe.py), whatever the operand split.  The pair kernels keep the 1e-5 bar for wide keys (ResNet-50
+    // features, main_lost_original.py:277-280) by accumulating K segments of 384 from zero and adding them in fp32
+    // (lost_tc.cu, kSegBlocks); only keys past 6144 go to the fp32 FMA Gram.  The single-CTA cross-check kernel (TC) does
+    // not segment: an explicit request for it is honoured as is.
+    if ((gram_impl == B200P_LOST_GRAM_TC2D || gram_impl == B200P_LOST_GRAM_TC2) && d > kLostMaxTensorCoreWidth) gram_impl = B200P_LOST_GRAM_FFMA;
     int tc_mode = gram_impl == B200P_LOST_GRAM_TC ? LOST_TC_SINGLE : LOST_TC_PAIR;
     if (gram_impl == B200P_LOST_GRAM_TC2D && lost_tc_direct_ok(d_feats, (long long)row_stride, d, h_meta, n_images)) tc_mode = LOST_TC_PAIR_DIRECT;
     for (int b = 0; b < n_images; ++b) {

@@ -40,7 +40,7 @@ struct LostGramPlan {
     alignas(64) unsigned char tm_hi[128], tm_lo[128];     // CUtensorMap storage (cuda.h stays out of this header)
     const Tile2* tab; const LostImageDev* d_meta;
     unsigned int* d_done;                                  // count-only: per-image completion counters (epilogue warps x tiles)
-    int n_tiles2, n_tiles1, n_images, mode, d_pad, sms;
+    int n_tiles2, n_tiles1, n_images, mode, d_pad, sms, nseg;
 };
 int lost_gram_prepare(LostGramPlan* gp, const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
                       const std::vector<LostImageDev>& meta, long long total_patches, int n_max, void* ws, size_t ws_bytes,

@@ -402,14 +402,22 @@ __device__ __forceinline__ TileCoord decode_tile2(const LostImageDev* __restrict
 // the TMA producer).
 struct __align__(16) Tile2 {
     int a_row0, b_row0;        // first operand row of the tile's row / column block (before the rank offset)
-    int info;                  // ncols | share << 9 | diag << 10 | ti << 12 | tj << 16
+    int info;                  // ncols | share << 9 | diag << 10 | ti << 12 | tj << 16 | K segment << 20 | last segment << 24
     int n;                     // patches of the image
     long long a_off, out_off;  // the image's offsets into A_base / degree_base
 };
-constexpr int kT2Share = 1 << 9, kT2Diag = 1 << 10;
+constexpr int kT2Share = 1 << 9, kT2Diag = 1 << 10, kT2Last = 1 << 24;
+// K segmentation (keys wider than 512 when A is returned): the tensor core truncates every product to the accumulator's
+// ulp, a bias of ~1.2e-8 d on same-sign sums (the squared norms on the diagonal: 2.2e-5 at d = 2048, bar 1e-5).  Segments
+// of at most 12 k-blocks (384 keys) are accumulated from a zeroed TMEM accumulator each and added in fp32 by the
+// epilogue (A in global memory carries the partial sum), which bounds the drift at the d = 384 level (4.9e-6).
+// Count-only launches never segment: only the SIGN of off-diagonal entries matters there, and a mixed-sign sum near
+// zero keeps a small accumulator (small ulp): its truncation error is ~1e-8 of |k_i||k_j| at any width.
+constexpr int kSegBlocks = 12;
 
 __global__ void __launch_bounds__(128)
-k_lost_tile_table(const LostImageDev* __restrict__ meta, int n_images, int n_tiles, Tile2* __restrict__ tab, unsigned int* __restrict__ done) {
+k_lost_tile_table(const LostImageDev* __restrict__ meta, int n_images, int n_tiles, Tile2* __restrict__ tab, unsigned int* __restrict__ done,
+                  int nseg) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (done && t < n_images) done[t] = 0u;          // count-only: per-image completion counters, see k_lost_finish
     if (done && t == 0) {                            // globaltimer trace in front of the counters: Gram start / end, finish start / end
@@ -426,7 +434,11 @@ k_lost_tile_table(const LostImageDev* __restrict__ meta, int n_images, int n_til
     const bool diag = tc.ti == tc.tj;
     e.info = ncols | (diag && ncols == T2_BN ? kT2Share : 0) | (diag ? kT2Diag : 0) | (tc.ti << 12) | (tc.tj << 16);
     e.n = im.n; e.a_off = done ? (long long)tc.img : im.a_off; e.out_off = im.out_off;      // count-only: no A, the slot carries the image index
-    tab[t] = e;
+    for (int sg = 0; sg < nseg; ++sg) {             // the segments of a tile are consecutive records: one cluster runs them back to back
+        Tile2 r = e;
+        r.info |= (sg << 20) | (sg == nseg - 1 ? kT2Last : 0);
+        tab[(long long)t * nseg + sg] = r;
+    }
 }
 __device__ __forceinline__ Tile2 load_tile2(const Tile2* __restrict__ tab, int t, int n_tiles) {
     Tile2 e;
@@ -467,7 +479,7 @@ template <bool DIRECT, bool WRITE_A, int T2_CONV_WARPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2_threads(DIRECT, T2_CONV_WARPS), 1)
 k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                 const Tile2* __restrict__ tab, int n_tiles, float* __restrict__ A_base,
-                int* __restrict__ degree_base, float threshold, int d_pad, unsigned int* __restrict__ done) {
+                int* __restrict__ degree_base, float threshold, int d_pad, unsigned int* __restrict__ done, int nseg) {
     extern __shared__ uint8_t smem_raw[];
     // a dependent kernel (the count-only finish) may be scheduled beside this grid as soon as all of its CTAs are running
     if (!WRITE_A) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -498,6 +510,11 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     const uint32_t rank = cluster_ctarank();                    // 0 = leader of the pair
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int num_kb = d_pad / TC_BK;
+    // work items of this cluster: (tile, K segment), the segments of a tile back to back; item j -> record index
+    const int my_tiles = cluster_id < n_tiles ? (n_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
+    const int n_items = my_tiles * nseg;
+    auto rec_of = [&](int j) { const int jj = j < n_items ? j : n_items - 1; return (cluster_id + (jj / nseg) * n_clusters) * nseg + jj % nseg; };
+    const int n_recs = n_tiles * nseg;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_hi);
@@ -522,15 +539,16 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     if (warp == 0 && lane == 0) {
         // ===== TMA producer (both CTAs): own A rows and own half of the tile's B columns
         int it = 0;
-        Tile2 nxt = load_tile2(tab, cluster_id, n_tiles);
-        for (int t = cluster_id; t < n_tiles; t += n_clusters) {
+        Tile2 nxt = load_tile2(tab, rec_of(0), n_recs);
+        for (int j = 0; j < n_items; ++j) {
             const Tile2 e = nxt;
-            nxt = load_tile2(tab, t + n_clusters, n_tiles);
+            nxt = load_tile2(tab, rec_of(j + 1), n_recs);
             const int ncols = e.info & 511;
             const int a_row = e.a_row0 + (int)rank * T2_BM;
             const int b_row = e.b_row0 + (int)rank * (ncols >> 1);
             const bool share = (e.info & kT2Share) != 0;           // full diagonal tile: the B halves are the A tiles
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int kb0 = nseg > 1 ? ((e.info >> 20) & 15) * kSegBlocks : 0, kb1 = nseg > 1 ? min(num_kb, kb0 + kSegBlocks) : num_kb;
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % NFULL;
                 const uint32_t ph = (uint32_t)(it / NFULL) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u);
@@ -555,19 +573,20 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     } else if (warp == 1 && lane == 0 && rank == 0) {
         // ===== MMA issuer (leader CTA only) =====
         int it = 0, tl = 0;
-        Tile2 nxt = load_tile2(tab, cluster_id, n_tiles);
-        for (int t = cluster_id; t < n_tiles; t += n_clusters, ++tl) {
+        Tile2 nxt = load_tile2(tab, rec_of(0), n_recs);
+        for (int j = 0; j < n_items; ++j, ++tl) {
             const Tile2 e = nxt;
-            nxt = load_tile2(tab, t + n_clusters, n_tiles);
+            nxt = load_tile2(tab, rec_of(j + 1), n_recs);
             const int ncols = e.info & 511;
             const bool share = (e.info & kT2Share) != 0;
             const uint32_t idesc = umma_idesc_tf32(2 * T2_BM, ncols);
+            const int kb0 = nseg > 1 ? ((e.info >> 20) & 15) * kSegBlocks : 0, kb1 = nseg > 1 ? min(num_kb, kb0 + kSegBlocks) : num_kb;
             const int acc = tl % T2_ACC;
             const uint32_t acc_ph = (uint32_t)(tl / T2_ACC) & 1u;
             mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T2_BN);
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 if (DIRECT) mbar_wait(conv_bar(it % T2_LO_STAGES), (uint32_t)(it / T2_LO_STAGES) & 1u);    // raw tiles landed, lo tiles derived, in both CTAs
                 else mbar_wait(full_bar(it % TC_STAGES), (uint32_t)(it / TC_STAGES) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -578,7 +597,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
                     const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
-                    umma_tf32_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_tf32_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     umma_tf32_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
                     umma_tf32_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
                 }
@@ -590,11 +609,12 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         // ===== converter (both CTAs, 4 warps): raw tile -> (hi in place, lo) =====
         const int ct = threadIdx.x - T2_THREADS;                     // 0..127
         int it = 0;
-        Tile2 nxt = load_tile2(tab, cluster_id, n_tiles);
-        for (int t = cluster_id; t < n_tiles; t += n_clusters) {
+        Tile2 nxt = load_tile2(tab, rec_of(0), n_recs);
+        for (int j = 0; j < n_items; ++j) {
             const bool share = (nxt.info & kT2Share) != 0;
-            nxt = load_tile2(tab, t + n_clusters, n_tiles);
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int kb0 = nseg > 1 ? ((nxt.info >> 20) & 15) * kSegBlocks : 0, kb1 = nseg > 1 ? min(num_kb, kb0 + kSegBlocks) : num_kb;
+            nxt = load_tile2(tab, rec_of(j + 1), n_recs);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 mbar_wait(full_bar(it % T2_RAW_STAGES), (uint32_t)(it / T2_RAW_STAGES) & 1u);          // this CTA's raw tiles have landed
                 // the lo stage is free once the MMAs of k-block it - 3 are done: the commit that freed THAT k-block's raw
                 // stage says so (a second tcgen05.commit per k-block for a separate barrier costs ~0.1 ms per call)
@@ -639,10 +659,11 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         const int q = warp & 3, hsel = (warp - 2) >> 2;
         const uint32_t stg = staging_base + (uint32_t)(warp - 2) * 4096u;      // this warp's 32x32 transpose buffer
         int tl = 0;
-        Tile2 nxt = load_tile2(tab, cluster_id, n_tiles);
-        for (int t = cluster_id; t < n_tiles; t += n_clusters, ++tl) {
+        Tile2 nxt = load_tile2(tab, rec_of(0), n_recs);
+        for (int j = 0; j < n_items; ++j, ++tl) {
             const Tile2 im = nxt;
-            nxt = load_tile2(tab, t + n_clusters, n_tiles);
+            nxt = load_tile2(tab, rec_of(j + 1), n_recs);
+            const bool seg_first = ((im.info >> 20) & 15) == 0, seg_last = (im.info & kT2Last) != 0;      // K segments (WRITE_A, wide keys)
             const int acc = tl % T2_ACC;
             const uint32_t acc_ph = (uint32_t)(tl / T2_ACC) & 1u;
             mbar_wait(tmem_full_bar(acc), acc_ph);
@@ -662,6 +683,27 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_BN + ch * 32), r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (WRITE_A && !seg_first && gi < im.n) {
+                    // later K segment: add the partial sum the earlier segments left in A (this lane's row, fp32 adds)
+                    const float* __restrict__ prow = A + (long long)gi * im.n + gj0;
+                    if (vec_store && gj0 + 32 <= im.n) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 pv4 = *reinterpret_cast<const float4*>(prow + c);
+                            r[c] = __float_as_uint(__uint_as_float(r[c]) + pv4.x); r[c + 1] = __float_as_uint(__uint_as_float(r[c + 1]) + pv4.y);
+                            r[c + 2] = __float_as_uint(__uint_as_float(r[c + 2]) + pv4.z); r[c + 3] = __float_as_uint(__uint_as_float(r[c + 3]) + pv4.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) if (gj0 + c < im.n) r[c] = __float_as_uint(__uint_as_float(r[c]) + prow[c]);
+                    }
+                }
+                if (WRITE_A && !seg_first) __syncwarp();             // everybody has read its partial row before the staged stores overwrite it
+                if (WRITE_A && !vec_store && gi < im.n) {            // unaligned A: scalar row stores
+                    float* dst = A + (long long)gi * im.n + gj0;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) if (gj0 + c < im.n) dst[c] = __uint_as_float(r[c]);
+                }
                 if (WRITE_A && vec_store) {
                     // row-major copy through shared memory: lane i parks its row (8 float4, 16-B groups XOR-swizzled by
                     // i & 7: conflict-free both ways), then lane l picks up columns 4 (l & 7) .. +3 of rows 4 p + (l >> 3)
@@ -685,6 +727,7 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                     }
                     __syncwarp();                                    // the buffer is rewritten by the next chunk
                 }
+                if (WRITE_A && !seg_last) continue;                  // partial sum parked in A; the last segment counts and mirrors
                 // Fast paths, decided per 32x32 chunk: every element inside the image and none on the diagonal (a diagonal tile
                 // holds the diagonal only in its chunks with gi0 == gj0).  The epilogue is bound by dependent ALU latency with two
                 // warps per scheduler (clock64: 3100 cycles for a diagonal-tile chunk on the general path, without a single store),
@@ -737,11 +780,6 @@ k_lost_gram_tc2(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                     }
                 }
                 if (mirror && colcnt && gj0 + lane < im.n) atomicAdd(deg + gj0 + lane, colcnt);
-                if (WRITE_A && !vec_store && gi < im.n) {          // unaligned A: scalar row stores
-                    float* dst = A + (long long)gi * im.n + gj0;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) if (gj0 + c < im.n) dst[c] = __uint_as_float(r[c]);
-                }
             }
             if (gi < im.n && cnt) atomicAdd(deg + gi, cnt);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -794,7 +832,7 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, int col
 // upper bound of the 256x256 tile records of a batch: an image of n <= 4096 patches has T = ceil(n / 256) <= 16
 // tile rows and T (T + 1) / 2 <= 8.5 T tiles
 static size_t tile_table_bytes(int n_images, long long total_patches) {
-    return ((size_t)(9 * (total_patches / T2_TILE + n_images)) + 16) * sizeof(Tile2) + 32 + (size_t)n_images * sizeof(unsigned int);
+    return ((size_t)(9 * (total_patches / T2_TILE + n_images)) + 16) * sizeof(Tile2) * 16 /* K segments */ + 32 + (size_t)n_images * sizeof(unsigned int);
 }
 
 size_t lost_tc_workspace_bytes(int n_images, long long total_patches, int d) {
@@ -824,7 +862,7 @@ int lost_gram_prepare(LostGramPlan* gp, const float* d_feats, long long row_stri
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    gp->mode = mode; gp->d_pad = d_pad; gp->sms = sms; gp->d_meta = d_meta; gp->n_images = n_images;
+    gp->mode = mode; gp->d_pad = d_pad; gp->sms = sms; gp->d_meta = d_meta; gp->n_images = n_images; gp->nseg = 1;
     CUtensorMap* tm_hi = reinterpret_cast<CUtensorMap*>(gp->tm_hi);
     CUtensorMap* tm_lo = reinterpret_cast<CUtensorMap*>(gp->tm_lo);
     const int T2 = (last.n + T2_TILE - 1) / T2_TILE;
@@ -836,10 +874,14 @@ int lost_gram_prepare(LostGramPlan* gp, const float* d_feats, long long row_stri
     gp->tab = tab;
     gp->d_done = nullptr;
     if (mode != LOST_TC_SINGLE) {
-        if (ws_bytes < tab_bytes || (size_t)gp->n_tiles2 * sizeof(Tile2) + 16 + 32 + (size_t)n_images * 4 > tab_bytes) { set_error("lost_batched: tensor-core workspace too small"); return B200P_EINVAL; }
-        if (count_only) gp->d_done = reinterpret_cast<unsigned int*>(tab + gp->n_tiles2) + 8;   // behind the tile records: 4 x u64 trace, counters
+        if (ws_bytes < tab_bytes) { set_error("lost_batched: tensor-core workspace too small"); return B200P_EINVAL; }
         const int work = gp->n_tiles2 > n_images ? gp->n_tiles2 : n_images;
-        k_lost_tile_table<<<(work + 127) / 128, 128, 0, st>>>(d_meta, n_images, gp->n_tiles2, tab, gp->d_done);
+        gp->nseg = 1;
+        const int num_kb = d_pad / TC_BK;
+        if (!count_only && num_kb > kSegBlocks) gp->nseg = (num_kb + kSegBlocks - 1) / kSegBlocks;
+        if ((size_t)gp->n_tiles2 * gp->nseg * sizeof(Tile2) + 16 + 32 + (size_t)n_images * 4 > tab_bytes) { set_error("lost_batched: tensor-core workspace too small"); return B200P_EINVAL; }
+        if (count_only) gp->d_done = reinterpret_cast<unsigned int*>(tab + (size_t)gp->n_tiles2 * gp->nseg) + 8;   // behind the tile records: 4 x u64 trace, counters
+        k_lost_tile_table<<<(work + 127) / 128, 128, 0, st>>>(d_meta, n_images, gp->n_tiles2, tab, gp->d_done, gp->nseg);
         B200P_LAUNCH_CHECK("k_lost_tile_table");
     }
     ws = (char*)ws + tab_bytes; ws_bytes -= ws_bytes < tab_bytes ? ws_bytes : tab_bytes;
@@ -894,14 +936,14 @@ int lost_gram_run(const LostGramPlan& gp, int t_begin, int t_end, float* A_base,
     const int nt = t_end - t_begin;
     if (nt <= 0) return B200P_OK;
     const int grid2 = 2 * (nt < gp.sms / 2 ? nt : gp.sms / 2);             // one cluster (CTA pair) per two SMs
-    const Tile2* tab = gp.tab + t_begin;
+    const Tile2* tab = gp.tab + (size_t)t_begin * gp.nseg;
     if (gp.mode == LOST_TC_PAIR_DIRECT) {
-        if (A_base) k_lost_gram_tc2<true, true, 4><<<grid2, t2_threads(true, 4), T2_SMEM_BYTES, st>>>(tm_hi, tm_hi, tab, nt, A_base, d_degree, 0.0f, gp.d_pad, nullptr);
-        else        k_lost_gram_tc2<true, false, 4><<<grid2, t2_threads(true, 4), T2_SMEM_COUNT_BYTES, st>>>(tm_hi, tm_hi, tab, nt, nullptr, d_degree, 0.0f, gp.d_pad, gp.d_done);
+        if (A_base) k_lost_gram_tc2<true, true, 4><<<grid2, t2_threads(true, 4), T2_SMEM_BYTES, st>>>(tm_hi, tm_hi, tab, nt, A_base, d_degree, 0.0f, gp.d_pad, nullptr, gp.nseg);
+        else        k_lost_gram_tc2<true, false, 4><<<grid2, t2_threads(true, 4), T2_SMEM_COUNT_BYTES, st>>>(tm_hi, tm_hi, tab, nt, nullptr, d_degree, 0.0f, gp.d_pad, gp.d_done, 1);
         B200P_LAUNCH_CHECK("k_lost_gram_tc2<direct>");
     } else {
-        if (A_base) k_lost_gram_tc2<false, true, 4><<<grid2, T2_THREADS, T2_SMEM_BYTES, st>>>(tm_hi, tm_lo, tab, nt, A_base, d_degree, 0.0f, gp.d_pad, nullptr);
-        else        k_lost_gram_tc2<false, false, 4><<<grid2, T2_THREADS, T2_SMEM_COUNT_BYTES, st>>>(tm_hi, tm_lo, tab, nt, nullptr, d_degree, 0.0f, gp.d_pad, gp.d_done);
+        if (A_base) k_lost_gram_tc2<false, true, 4><<<grid2, T2_THREADS, T2_SMEM_BYTES, st>>>(tm_hi, tm_lo, tab, nt, A_base, d_degree, 0.0f, gp.d_pad, nullptr, gp.nseg);
+        else        k_lost_gram_tc2<false, false, 4><<<grid2, T2_THREADS, T2_SMEM_COUNT_BYTES, st>>>(tm_hi, tm_lo, tab, nt, nullptr, d_degree, 0.0f, gp.d_pad, gp.d_done, 1);
         B200P_LAUNCH_CHECK("k_lost_gram_tc2");
     }
     return B200P_OK;

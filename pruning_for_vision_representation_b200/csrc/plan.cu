@@ -87,6 +87,7 @@ extern "C" int b200p_plan_create(int device, int n_segments, const int64_t* h_nu
     TRY(cudaMalloc(&p->d_chunk_ties, chunks * sizeof(uint32_t)));
     TRY(cudaMalloc(&p->d_prov, chunks * kWordsPerChunk * sizeof(uint32_t)));
     TRY(cudaMalloc(&p->d_rank_ties, 8 * sizeof(unsigned long long)));
+    TRY(cudaMalloc(&p->d_sample_cache, (kHistBins + kHistExtra) * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_rank_ties, 0, 8 * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_hist, 0, (kHistBins + kHistExtra) * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_state, 0, sizeof(SelState)));
@@ -103,7 +104,7 @@ extern "C" int b200p_plan_destroy(b200p_plan* p) {
     cudaFree(p->d_chunk_seg); cudaFree(p->d_chunk_n); cudaFree(p->d_chunk_elem0);
     for (int s = 0; s < B200P_NUM_SLOTS; ++s) cudaFree(p->d_tab_own[s]);
     cudaFree(p->d_hist); cudaFree(p->d_state); cudaFree(p->d_cand_key); cudaFree(p->d_cand_pos);
-    cudaFree(p->d_chunk_ties); cudaFree(p->d_prov); cudaFree(p->d_rank_ties);
+    cudaFree(p->d_chunk_ties); cudaFree(p->d_prov); cudaFree(p->d_rank_ties); cudaFree(p->d_sample_cache);
     for (int i = 0; i < 2; ++i) if (p->arena_gtab[i]) { b200p_ptrtable_destroy(p->arena_gtab[i]); p->arena_gtab[i] = nullptr; }
     cudaFree(p->arena_w); cudaFree(p->arena_g[0]); cudaFree(p->arena_g[1]); cudaFree(p->arena_score);
     cudaFree(p->arena_mask); cudaFree(p->arena_old_mask);
@@ -135,6 +136,11 @@ extern "C" int b200p_plan_set_option(b200p_plan* p, int option, int64_t value) {
     if (option == B200P_OPT_SELECT_IMPL) {
         B200P_REQUIRE(value == B200P_SELECT_SAMPLED || value == B200P_SELECT_EXACT, B200P_EINVAL, "plan_set_option: bad select implementation");
         p->select_impl = (int)value;
+        return B200P_OK;
+    }
+    if (option == B200P_OPT_REUSE_SAMPLE) {
+        p->reuse_sample = value != 0;
+        if (!p->reuse_sample) p->sample_cache_valid = false;
         return B200P_OK;
     }
     if (option == B200P_OPT_TIME_SWEEP) {
@@ -231,6 +237,7 @@ extern "C" int b200p_plan_bind(b200p_plan* p, int slot, const void* const* h_ptr
     p->d_tab[slot] = p->d_tab_own[slot];
     p->bound[slot] = true;
     p->vec_ok[slot] = vec;
+    if (slot == B200P_SLOT_W || slot == B200P_SLOT_SCORE) p->sample_cache_valid = false;      // other data behind the keys
     return B200P_OK;
 }
 

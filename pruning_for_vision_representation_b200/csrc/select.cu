@@ -19,6 +19,7 @@
 // histogram between them.
 #include "common.cuh"
 #include "comm.cuh"
+#include "emit_body.cuh"
 #include <cooperative_groups.h>
 
 namespace b200p {
@@ -232,6 +233,7 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
     if (lane == 0) s_wcount[warp] = 0;
     __syncwarp();
     unsigned long long below = 0;
+    unsigned int nan_cnt = 0;                 // alive NaN keys: they sort last but SNIP_STRICT prunes them, the kept count needs them
     if (blockIdx.x == 0 && threadIdx.x == 0) st->prov_ok = (a.prov != nullptr && collect) ? 1u : 0u;
 
     // one matching key: fine histogram + staged append (order inside the buffer is irrelevant)
@@ -286,7 +288,7 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
             if (nan_pruned && mx > 0x7F800000u) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    if ((__float_as_uint(sel16(v, i)) & 0x7FFFFFFFu) > 0x7F800000u) keep &= ~(1u << (15 - i));
+                    if ((__float_as_uint(sel16(v, i)) & 0x7FFFFFFFu) > 0x7F800000u) { nan_cnt += (keep >> (15 - i)) & 1u; keep &= ~(1u << (15 - i)); }
             }
             uint32_t* pw = a.prov + (size_t)(pos0 >> 12) * kWordsPerChunk;
 #pragma unroll
@@ -315,6 +317,7 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
             if (pw) {
                 const uint32_t word = __ballot_sync(0xFFFFFFFFu, alive && k >= base && !(nan_pruned && k == kNanKey));
                 if (lane == 0) pw[e >> 5] = word;
+                if (alive && nan_pruned && k == kNanKey) ++nan_cnt;
             }
             if (alive) {
                 if (k < base) ++below;
@@ -373,6 +376,7 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
         const int filled = __shfl_sync(0xFFFFFFFFu, s_wcount[warp], 0);
         flush(filled < kStage ? filled : kStage);
     }
+    if (nan_cnt) atomicAdd(a.hist + kHistBins + 2, (unsigned long long)nan_cnt);      // rare
     return below;
 }
 
@@ -488,14 +492,13 @@ __global__ void k_select_init(SelState* st, unsigned long long* hist, unsigned i
 // ---- tie resolution (EXACT_K with quota < n_equal) ---------------------------------------
 // chunk_ties[c] = number of alive keys == threshold in chunk c.  Collect mode: every tie is in the
 // candidate buffer (one atomic per tied candidate into a zeroed table); otherwise re-stream the keys.
-__device__ void tie_count_body(const int32_t* __restrict__ chunk_n, ChunkTab key_tab, const uint32_t* __restrict__ old_mask,
-                               const SelState* __restrict__ st, const uint32_t* __restrict__ cand_key,
+__device__ void tie_count_vals(const int32_t* __restrict__ chunk_n, ChunkTab key_tab, const uint32_t* __restrict__ old_mask,
+                               uint32_t need_ties, uint32_t thr, uint32_t collect, uint32_t cand_count, const uint32_t* __restrict__ cand_key,
                                const uint32_t* __restrict__ cand_pos, uint32_t* __restrict__ chunk_ties,
                                int64_t c_begin, int64_t c_end, int vec_ok) {
-    if (!st->need_ties) return;
-    const uint32_t thr = st->thr_key;
-    if (st->collect) {
-        const uint32_t n = st->cand_count;
+    if (!need_ties) return;
+    if (collect) {
+        const uint32_t n = cand_count;
         for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
             if (cand_key[i] == thr) atomicAdd(&chunk_ties[cand_pos[i] >> 12], 1u);
         return;
@@ -521,6 +524,13 @@ __device__ void tie_count_body(const int32_t* __restrict__ chunk_n, ChunkTab key
         if (threadIdx.x == 0) chunk_ties[c] = (uint32_t)s_cnt;
         __syncthreads();
     }
+}
+__device__ __forceinline__ void tie_count_body(const int32_t* __restrict__ chunk_n, ChunkTab key_tab, const uint32_t* __restrict__ old_mask,
+                                               const SelState* __restrict__ st, const uint32_t* __restrict__ cand_key,
+                                               const uint32_t* __restrict__ cand_pos, uint32_t* __restrict__ chunk_ties,
+                                               int64_t c_begin, int64_t c_end, int vec_ok) {
+    tie_count_vals(chunk_n, key_tab, old_mask, st->need_ties, st->thr_key, st->collect, st->cand_count, cand_key, cand_pos, chunk_ties,
+                   c_begin, c_end, vec_ok);
 }
 __global__ void __launch_bounds__(kThreads)
 k_tie_count(const int32_t* __restrict__ chunk_n, ChunkTab key_tab, const uint32_t* __restrict__ old_mask,
@@ -639,7 +649,12 @@ struct SampleArgs {
     uint32_t mode;
     uint32_t sigmas;         // bracket half-width in standard deviations of the sample rank (8; 12 for clustered granules)
     uint32_t comm_seq;       // != 0: parameter-sharded select, the last CTA all-reduces the histogram over the ranks first
+    unsigned long long* cache;   // nullable: where the last CTA keeps a copy of the final sample histogram
 };
+
+// bracket for a new rank k from the cached sample histogram of the same keys: one CTA, no sampling, no collective
+__global__ void __launch_bounds__(kThreads)
+k_sample_from_cache(SampleArgs a, const unsigned long long* __restrict__ cache);
 
 // exclusive prefix of this thread's 16 bins over the CTA (kScanThreads threads) and the grand total
 __device__ __forceinline__ unsigned long long block_prefix16(const unsigned long long (&local)[kBinsPerThread],
@@ -685,6 +700,13 @@ __device__ __forceinline__ void sample_tail(const SampleArgs& a, unsigned long l
     unsigned long long local[kBinsPerThread];
 #pragma unroll
     for (int i = 0; i < kBinsPerThread; ++i) local[i] = ((volatile unsigned long long*)a.hist)[threadIdx.x * kBinsPerThread + i];
+    if (a.cache) {
+        // keep the (global) sample histogram: another select over the SAME keys (a sparsity sweep) derives its bracket from
+        // it without sampling again (B200P_OPT_REUSE_SAMPLE)
+#pragma unroll
+        for (int i = 0; i < kBinsPerThread; ++i) a.cache[threadIdx.x * kBinsPerThread + i] = local[i];
+        if (threadIdx.x < kHistExtra) a.cache[kHistBins + threadIdx.x] = ((volatile unsigned long long*)a.hist)[kHistBins + threadIdx.x];
+    }
     unsigned long long S;
     unsigned long long running = block_prefix16(local, s_warp, S);
     const unsigned long long n_alive = a.old_mask ? ((volatile unsigned long long*)a.hist)[kHistBins + 0] : a.n_total;
@@ -796,6 +818,16 @@ k_select_sample(SampleArgs a, CommDev comm) {
     if (!comm_ok && threadIdx.x == 0) { a.st->sample_ok = 0u; a.st->miss = 1u; }
 }
 
+__global__ void __launch_bounds__(kThreads)
+k_sample_from_cache(SampleArgs a, const unsigned long long* __restrict__ cache) {
+    __shared__ unsigned long long s_warp[9];
+    __shared__ uint32_t s_bkt[2];
+    for (int b = threadIdx.x; b < kHistBins + kHistExtra; b += kThreads) a.hist[b] = cache[b];
+    __threadfence();
+    __syncthreads();
+    sample_tail(a, s_warp, s_bkt);
+}
+
 // last CTA of a bracket sweep: verify that rank k is inside the bracket, narrow to a 1024-key window
 __device__ __forceinline__ void bracket_tail(const PassArgs& a, uint32_t base, unsigned long long* s_warp /*[9]*/) {
     SelState* __restrict__ st = a.st;
@@ -806,6 +838,7 @@ __device__ __forceinline__ void bracket_tail(const PassArgs& a, uint32_t base, u
     unsigned long long running = block_prefix16(local, s_warp, total_in);
     const unsigned long long n_below = ((volatile unsigned long long*)a.hist)[kHistBins + 1];
     const unsigned long long k = st->k;
+    if (threadIdx.x == 0) st->pad_[1] = (uint32_t)((volatile unsigned long long*)a.hist)[kHistBins + 2];     // NaN keys pruned by the provisional mask
     __syncthreads();
     const bool inside = k > n_below && k <= n_below + total_in && total_in <= (unsigned long long)a.cand_capacity;
     if (!inside) {
@@ -1077,6 +1110,7 @@ k_snip_score_sweep(PassArgs a, ChunkTab w_tab, GradTabs g_tabs, int vec_all) {
     };
 
     unsigned long long below = 0;
+    unsigned int nan_cnt = 0;
     for (int64_t c = a.c_begin + blockIdx.x; c < a.c_end; c += gridDim.x) {
         const int n = __ldg(a.chunk_n + c);
         const float* __restrict__ w = chunk_ptr<const float>(w_tab, c);
@@ -1106,10 +1140,9 @@ k_snip_score_sweep(PassArgs a, ChunkTab w_tab, GradTabs g_tabs, int vec_all) {
                     below += __popc(lt);
                     if (pw) {
                         // NaN scores are pruned (NaN > thr is false, train.py:316): the patching emit never sees them
-                        if (r.x != r.x) lt |= 8u;
-                        if (r.y != r.y) lt |= 4u;
-                        if (r.z != r.z) lt |= 2u;
-                        if (r.w != r.w) lt |= 1u;
+                        const uint32_t nanb = (r.x != r.x ? 8u : 0u) | (r.y != r.y ? 4u : 0u) | (r.z != r.z ? 2u : 0u) | (r.w != r.w ? 1u : 0u);
+                        lt |= nanb;
+                        nan_cnt += __popc(nanb);
                         const uint32_t word = gather_nibbles(__brev(~lt & 0xFu) >> 28);      // bit q = key q at or above the bracket base
                         if ((tid & 7) == 0) pw[vec_word_index(j)] = word;
                     }
@@ -1137,6 +1170,7 @@ k_snip_score_sweep(PassArgs a, ChunkTab w_tab, GradTabs g_tabs, int vec_all) {
                     if (pw) {
                         const uint32_t word = __ballot_sync(0xFFFFFFFFu, valid && k >= base && k != kNanKey);
                         if (lane == 0) pw[e >> 5] = word;
+                        if (valid && k == kNanKey) ++nan_cnt;
                     }
                     if (valid) {
                         if (k < base) ++below;
@@ -1166,6 +1200,7 @@ k_snip_score_sweep(PassArgs a, ChunkTab w_tab, GradTabs g_tabs, int vec_all) {
         if (v) atomicAdd(a.hist + b, (unsigned long long)v);
     }
     if (tid == 0 && s_below) atomicAdd(a.hist + kHistBins + 1, s_below);
+    if (nan_cnt) atomicAdd(a.hist + kHistBins + 2, (unsigned long long)nan_cnt);
     if (!last_cta_arrives(a.ticket)) return;
     bracket_tail(a, base, s_warp);
 }
@@ -1173,13 +1208,22 @@ k_snip_score_sweep(PassArgs a, ChunkTab w_tab, GradTabs g_tabs, int vec_all) {
 // ---- B: finish (cooperative launch) ----------------------------------------------------------------
 __device__ __forceinline__ void grid_barrier() { cooperative_groups::this_grid().sync(); }
 
+// EMIT: the kernel also emits the mask (b200p_mask_build: the sweep wrote the provisional mask straight into the
+// destination): once a CTA knows the exact key it patches its share of the candidates' bits — every CTA derives the key
+// itself from the global window histogram, so there is no barrier between "key known" and "mask patched", and the
+// separate emit launch is gone.
+template <bool EMIT>
 __global__ void __launch_bounds__(kThreads, 3)
-k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks) {
+k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks, EmitArgs em) {
     __shared__ uint32_t s_hist[kHistBins];
     __shared__ unsigned long long s_part[kThreads];
     __shared__ unsigned long long s_warp[9];
+    __shared__ int s_last;
     SelState* __restrict__ st = a.st;
     const bool exact = st->miss != 0u;               // written by the previous kernel: uniform over the grid
+    const bool prov_ok = st->prov_ok != 0u;          // idem
+    PatchVals pv;
+    bool pv_valid = false;
     if (exact) {
         if (blockIdx.x == 0 && threadIdx.x == 0) init_state(st, a.k, a.mode, a.allow_collect, 1u);
         grid_barrier();
@@ -1195,11 +1239,20 @@ k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks)
             if (threadIdx.x == 0) st->passes_full = st->collect ? 3u : 4u;
         }
         grid_barrier();
+        // ties (EXACT_K with quota < n_equal): per-chunk counts, then the ordered scan
+        if (a.mode == B200P_MODE_EXACT_K && st->need_ties) {
+            tie_count_body(a.chunk_n, a.key_tab, a.old_mask, st, a.cand_key, a.cand_pos, chunk_ties, 0, n_chunks, a.vec_ok);
+            grid_barrier();
+            if (blockIdx.x == 0) tie_scan_body(st, chunk_ties, 0, n_chunks, 0ull, nullptr, 0, s_part);
+            if (EMIT) grid_barrier();
+        }
     } else {
-        // window pass over the candidates: exact key among the 1024 keys of the window
+        // window pass over the candidates: exact key among the 1024 keys of the window.  Everything a CTA needs from the
+        // state is read BEFORE the barrier: afterwards CTA 0 rewrites the state while the others are still deriving the key.
+        const uint32_t n = st->cand_count, win_lo = st->win_lo, mode = st->mode, n_nan = st->pad_[1];
+        const unsigned long long k = st->k, n_less0 = st->n_less, n_valid = st->n_valid;
         for (int b = threadIdx.x; b < kWindow; b += kThreads) s_hist[b] = 0;
         __syncthreads();
-        const uint32_t n = st->cand_count, win_lo = st->win_lo;
         const uint32_t stride = gridDim.x * kThreads;
         for (uint32_t i0 = blockIdx.x * kThreads + threadIdx.x; i0 < n; i0 += 8 * stride) {
             uint32_t kk[8];
@@ -1217,42 +1270,95 @@ k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks)
             if (v) atomicAdd(a.hist + b, (unsigned long long)v);
         }
         grid_barrier();
-        if (blockIdx.x == 0) {
-            unsigned long long local[kBinsPerThread];
+        // every CTA: prefix over the 1024 global counts -> the key that holds rank k
+        unsigned long long local[kBinsPerThread];
 #pragma unroll
-            for (int i = 0; i < kBinsPerThread; ++i) {
-                const int b = threadIdx.x * kBinsPerThread + i;
-                local[i] = b < kWindow ? ((volatile unsigned long long*)a.hist)[b] : 0ull;
-            }
-            unsigned long long total;
-            unsigned long long running = block_prefix16(local, s_warp, total);
-            const unsigned long long k = st->k;
-            __syncthreads();
-#pragma unroll
-            for (int i = 0; i < kBinsPerThread; ++i) {
-                const unsigned long long v = local[i];
-                if (v != 0 && running < k && k <= running + v) {
-                    const uint32_t key = win_lo + (uint32_t)(threadIdx.x * kBinsPerThread + i);
-                    st->n_less += running;
-                    st->k = k - running;
-                    st->prefix = key; st->thr_key = key; st->threshold = key_to_float(key);
-                    st->n_equal = v; st->quota = k - running;
-                    st->need_ties = (st->mode == B200P_MODE_EXACT_K && (k - running) < v) ? 1u : 0u;
-                    st->tie_chunk = -1; st->tie_resid = 0; st->tie_seen = 0;
-                }
-                running += v;
-            }
-            __syncthreads();
-            clear_hist(a.hist);
+        for (int i = 0; i < kBinsPerThread; ++i) {
+            const int b = threadIdx.x * kBinsPerThread + i;
+            local[i] = b < kWindow ? __ldcg(a.hist + b) : 0ull;
         }
-        grid_barrier();
+        unsigned long long total;
+        unsigned long long running = block_prefix16(local, s_warp, total);
+        __shared__ unsigned long long s_pick[3];      // bin, count before it, count in it
+        if (threadIdx.x == 0) s_pick[0] = ~0ull;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kBinsPerThread; ++i) {
+            const unsigned long long v = local[i];
+            if (v != 0 && running < k && k <= running + v) { s_pick[0] = threadIdx.x * kBinsPerThread + i; s_pick[1] = running; s_pick[2] = v; }
+            running += v;
+        }
+        __syncthreads();
+        // the last CTA to have read the histogram clears it for the next select (nobody waits for that)
+        if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+        __syncthreads();
+        if (s_last) { clear_hist(a.hist); if (threadIdx.x == 0) *a.ticket = 0u; }
+        const bool found = s_pick[0] != ~0ull;      // always, after a verified bracket
+        const uint32_t key = win_lo + (uint32_t)s_pick[0];
+        const unsigned long long before = s_pick[1], v = s_pick[2];
+        const uint32_t need_ties = (found && mode == B200P_MODE_EXACT_K && (k - before) < v) ? 1u : 0u;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && found) {
+            st->n_less = n_less0 + before;
+            st->k = k - before;
+            st->prefix = key; st->thr_key = key; st->threshold = key_to_float(key);
+            st->n_equal = v; st->quota = k - before;
+            st->need_ties = need_ties;
+            st->tie_chunk = -1; st->tie_resid = 0; st->tie_seen = 0;
+        }
+        if (need_ties) {
+            tie_count_vals(a.chunk_n, a.key_tab, a.old_mask, 1u, key, 1u, n, a.cand_key, a.cand_pos, chunk_ties, 0, n_chunks, a.vec_ok);
+            grid_barrier();
+            if (blockIdx.x == 0) tie_scan_body(st, chunk_ties, 0, n_chunks, 0ull, nullptr, 0, s_part);
+            if (EMIT) grid_barrier();
+        } else if (found) {
+            pv.cand_count = n; pv.thr_key = key; pv.need_ties = 0u; pv.tie_resid = 0u; pv.tie_chunk = -1;
+            pv.n_kept = n_valid - (n_less0 + before) - (mode == B200P_MODE_SNIP_STRICT ? v + (key != kNanKey ? n_nan : 0u) : (k - before));
+            pv_valid = true;
+        }
     }
-    // ties (EXACT_K with quota < n_equal): per-chunk counts, then the ordered scan
-    if (a.mode == B200P_MODE_EXACT_K && st->need_ties) {
-        tie_count_body(a.chunk_n, a.key_tab, a.old_mask, st, a.cand_key, a.cand_pos, chunk_ties, 0, n_chunks, a.vec_ok);
-        grid_barrier();
-        if (blockIdx.x == 0) tie_scan_body(st, chunk_ties, 0, n_chunks, 0ull, nullptr, 0, s_part);
+    if (!EMIT) return;
+    if (prov_ok && !exact) {
+        if (!pv_valid) pv = patch_vals_from_state(st, em.mode);          // after the tie barriers: the state is final
+        emit_patch_body(em.chunk_n, em.key_tab, em.old_mask, st, em.cand_key, em.cand_pos, em.prov, em.mode, em.n_chunks, pv);
+    } else {
+        // no candidate list to patch (exact select, histogram mode): full pass over the keys; the state is final here
+        if (!exact || !(a.mode == B200P_MODE_EXACT_K && st->need_ties)) grid_barrier();
+        emit_full_body(em, 0, n_chunks);
     }
+}
+
+static unsigned int* ticket_ptr(b200p_plan* p);
+static int coop_ctas(b200p_plan* p) {
+    if (p->coop_ctas_per_sm == 0) {
+        int coop = 0, occ = 0, occ2 = 0;
+        B200P_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+        if (coop) {
+            B200P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select_finish<false>, kThreads, 0));
+            B200P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_select_finish<true>, kThreads, 0));
+            if (occ2 < occ) occ = occ2;
+        }
+        p->coop_ctas_per_sm = occ > 0 ? (occ > 3 ? 3 : occ) : -1;
+    }
+    return B200P_OK;
+}
+// B: finish (cooperative: grid-wide barriers between its phases).  With p->fuse_emit the kernel also emits the mask.
+static int launch_finish(b200p_plan* p, PassArgs& a, int key_source, int mode, const uint32_t* d_old_mask, cudaStream_t st) {
+    int64_t work = p->n_chunks;
+    const int64_t cblocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
+    if (cblocks > work) work = cblocks;
+    // one CTA per SM: the phases between the grid-wide barriers are tiny, the barriers are not
+    int grid = p->num_sms;
+    if (work < grid) grid = (int)(work < 1 ? 1 : work);
+    uint32_t* ties = p->d_chunk_ties; int64_t n_chunks = p->n_chunks;
+    EmitArgs em;
+    uint32_t* prov = p->prov_target ? p->prov_target : p->d_prov;
+    fill_patch_emit_args(p, em, key_source, mode, d_old_mask, prov, prov);
+    void* args[] = {(void*)&a, (void*)&ties, (void*)&n_chunks, (void*)&em};
+    const bool fuse = p->fuse_emit && p->prov_target != nullptr;
+    B200P_CUDA(cudaLaunchCooperativeKernel(fuse ? (const void*)k_select_finish<true> : (const void*)k_select_finish<false>, dim3(grid), dim3(kThreads),
+                                           args, 0, st));
+    p->emit_done = fuse;
+    return B200P_OK;
 }
 
 static unsigned int* ticket_ptr(b200p_plan* p) {
@@ -1263,6 +1369,20 @@ static unsigned int* ticket_ptr(b200p_plan* p) {
 }  // namespace b200p
 
 using namespace b200p;
+
+// B200P_OPT_REUSE_SAMPLE: the caller promises that the keys (and the old mask) are unchanged since the select that
+// filled the cache — true inside a sparsity sweep over fixed weights (BASELINE config 5); re-binding the key slot or
+// any other key source / old mask / chunk range drops the cache.
+static bool sample_cache_hit(b200p_plan* p, int key_source, const uint32_t* d_old_mask, int64_t c0, int64_t c1) {
+    return p->reuse_sample && p->sample_cache_valid && p->sample_cache_key == key_source && p->sample_cache_mask == d_old_mask &&
+           p->sample_cache_c0 == c0 && p->sample_cache_c1 == c1 && p->sample_cache_tab == (const void*)p->d_tab[key_source == B200P_KEY_ABS_W ? B200P_SLOT_W : B200P_SLOT_SCORE];
+}
+static unsigned long long* sample_cache_arm(b200p_plan* p, int key_source, const uint32_t* d_old_mask, int64_t c0, int64_t c1) {
+    if (!p->reuse_sample) { p->sample_cache_valid = false; return nullptr; }
+    p->sample_cache_valid = true; p->sample_cache_key = key_source; p->sample_cache_mask = d_old_mask; p->sample_cache_c0 = c0; p->sample_cache_c1 = c1;
+    p->sample_cache_tab = (const void*)p->d_tab[key_source == B200P_KEY_ABS_W ? B200P_SLOT_W : B200P_SLOT_SCORE];
+    return p->d_sample_cache;
+}
 
 static int check_key_source(b200p_plan* p, int key_source, const char* who) {
     const int slot = key_source == B200P_KEY_ABS_W ? B200P_SLOT_W : B200P_SLOT_SCORE;
@@ -1415,37 +1535,28 @@ static int select_kth_exact(b200p_plan* p, int key_source, const uint32_t* d_old
 
 static int select_kth_sampled(b200p_plan* p, int key_source, const uint32_t* d_old_mask, uint64_t k, int mode, cudaStream_t st) {
     const int slot = key_slot(key_source);
-    if (p->coop_ctas_per_sm == 0) {
-        int coop = 0, occ = 0;
-        B200P_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
-        if (coop) B200P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select_finish, kThreads, 0));
-        p->coop_ctas_per_sm = occ > 0 ? (occ > 3 ? 3 : occ) : -1;
-    }
+    { int rc = coop_ctas(p); if (rc) return rc; }
     if (p->coop_ctas_per_sm < 0) return select_kth_exact(p, key_source, d_old_mask, k, mode, st);   // no cooperative launch
     // S: 1/16 sample
     SampleArgs sa;
     sa.chunk_n = p->d_chunk_n; sa.key_tab = p->tab(slot); sa.old_mask = d_old_mask; sa.hist = p->d_hist; sa.st = p->d_state;
-    sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.c_begin = 0; sa.comm_seq = 0u; sa.vec_ok = p->vec_ok[slot] ? 1 : 0;
+    sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.c_begin = 0; sa.comm_seq = 0u; sa.cache = nullptr; sa.vec_ok = p->vec_ok[slot] ? 1 : 0;
     sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)mode; sa.sigmas = 8u;
     const int64_t sblocks = (p->n_chunks * kSampleSlotsPerChunk + 4 * kThreads - 1) / (4 * kThreads);
-    k_select_sample<<<p->grid_for(sblocks, 1), kThreads, 0, st>>>(sa, CommDev());
-    B200P_LAUNCH_CHECK("k_select_sample");
+    if (sample_cache_hit(p, key_source, d_old_mask, 0, p->n_chunks)) {
+        k_sample_from_cache<<<1, kThreads, 0, st>>>(sa, p->d_sample_cache);
+        B200P_LAUNCH_CHECK("k_sample_from_cache");
+    } else {
+        sa.cache = sample_cache_arm(p, key_source, d_old_mask, 0, p->n_chunks);
+        k_select_sample<<<p->grid_for(sblocks, 1), kThreads, 0, st>>>(sa, CommDev());
+        B200P_LAUNCH_CHECK("k_select_sample");
+    }
     // A: bracket sweep
     PassArgs a;
     fill_pass_args(p, a, key_source, d_old_mask, 0, p->n_chunks, 1, 0, k, mode, 1, true);
     k_select_bracket<<<p->grid_for((p->n_chunks + 1) / 2, 4), kThreads, 0, st>>>(a, CommDev());
     B200P_LAUNCH_CHECK("k_select_bracket");
-    // B: finish (cooperative: grid-wide barriers between its phases)
-    int64_t work = p->n_chunks;
-    const int64_t cblocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
-    if (cblocks > work) work = cblocks;
-    // one CTA per SM: the phases between the grid-wide barriers are tiny, the barriers are not
-    int grid = p->num_sms;
-    if (work < grid) grid = (int)(work < 1 ? 1 : work);
-    uint32_t* ties = p->d_chunk_ties; int64_t n_chunks = p->n_chunks;
-    void* args[] = {(void*)&a, (void*)&ties, (void*)&n_chunks};
-    B200P_CUDA(cudaLaunchCooperativeKernel((const void*)k_select_finish, dim3(grid), dim3(kThreads), args, 0, st));
-    return B200P_OK;
+    return launch_finish(p, a, key_source, mode, d_old_mask, st);
 }
 
 extern "C" int b200p_select_kth(b200p_plan* p, int key_source, const uint32_t* d_old_mask,
@@ -1457,7 +1568,7 @@ extern "C" int b200p_select_kth(b200p_plan* p, int key_source, const uint32_t* d
     B200P_CUDA(cudaSetDevice(p->device));
     // the emit that follows with the same arguments can patch the provisional mask instead of re-reading the keys
     p->prov_armed = true; p->prov_key_source = key_source; p->prov_mode = mode; p->prov_old_mask = d_old_mask;
-    p->prov_c0 = 0; p->prov_c1 = p->n_chunks;
+    p->prov_c0 = 0; p->prov_c1 = p->n_chunks; p->emit_done = false;
     if (p->select_impl == B200P_SELECT_EXACT) return select_kth_exact(p, key_source, d_old_mask, k, mode, (cudaStream_t)stream);
     return select_kth_sampled(p, key_source, d_old_mask, k, mode, (cudaStream_t)stream);
 }
@@ -1494,10 +1605,17 @@ extern "C" int b200p_sharded_mask_build(b200p_plan* p, b200p_comm* c, int key_so
     sa.chunk_n = p->d_chunk_n; sa.key_tab = p->tab(slot); sa.old_mask = d_old_mask; sa.hist = p->d_hist; sa.st = p->d_state;
     sa.ticket = ticket_ptr(p); sa.n_chunks = nc; sa.c_begin = chunk_begin; sa.vec_ok = p->vec_ok[slot] ? 1 : 0;
     sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)mode; sa.sigmas = 8u;
-    sa.comm_seq = ++c->seq[CH_HIST];
+    sa.comm_seq = 0u; sa.cache = nullptr;
     const int64_t sblocks = (nc * kSampleSlotsPerChunk + 4 * kThreads - 1) / (4 * kThreads);
-    k_select_sample<<<p->grid_for(sblocks, 1), kThreads, 0, st>>>(sa, cd);
-    B200P_LAUNCH_CHECK("k_select_sample");
+    if (sample_cache_hit(p, key_source, d_old_mask, chunk_begin, chunk_end)) {      // the cache holds the all-reduced histogram: same decision on every rank
+        k_sample_from_cache<<<1, kThreads, 0, st>>>(sa, p->d_sample_cache);
+        B200P_LAUNCH_CHECK("k_sample_from_cache");
+    } else {
+        sa.comm_seq = ++c->seq[CH_HIST];
+        sa.cache = sample_cache_arm(p, key_source, d_old_mask, chunk_begin, chunk_end);
+        k_select_sample<<<p->grid_for(sblocks, 1), kThreads, 0, st>>>(sa, cd);
+        B200P_LAUNCH_CHECK("k_select_sample");
+    }
     }
     // A
     p->prov_target = d_mask;
@@ -1568,12 +1686,7 @@ extern "C" int b200p_snip_score_select(b200p_plan* p, const b200p_ptrtable* cons
         B200P_REQUIRE(g_tables[i] != nullptr && g_tables[i]->plan == p, B200P_EINVAL, "snip_mask_build: table belongs to another plan");
     B200P_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->coop_ctas_per_sm == 0) {
-        int coop = 0, occ = 0;
-        B200P_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
-        if (coop) B200P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_select_finish, kThreads, 0));
-        p->coop_ctas_per_sm = occ > 0 ? (occ > 3 ? 3 : occ) : -1;
-    }
+    { int rc = coop_ctas(p); if (rc) return rc; }
     // all but the last group of up to 8 sets are plain accumulate launches; the last group is fused with the select
     const int last0 = ((n_sets - 1) / kMaxSets) * kMaxSets, nb = n_sets - last0;
     const bool unfused = p->select_impl == B200P_SELECT_EXACT || p->coop_ctas_per_sm < 0;
@@ -1590,11 +1703,11 @@ extern "C" int b200p_snip_score_select(b200p_plan* p, const b200p_ptrtable* cons
     // an emit that follows with the same arguments patches the provisional mask the sweep writes (into d_prov_target if given)
     p->prov_target = d_prov_target;
     p->prov_armed = true; p->prov_key_source = B200P_KEY_SCORE; p->prov_mode = B200P_MODE_SNIP_STRICT; p->prov_old_mask = nullptr;
-    p->prov_c0 = 0; p->prov_c1 = p->n_chunks;
+    p->prov_c0 = 0; p->prov_c1 = p->n_chunks; p->emit_done = false;
     // S': sample
     SampleArgs sa;
     sa.chunk_n = p->d_chunk_n; sa.key_tab = p->tab(B200P_SLOT_SCORE); sa.old_mask = nullptr; sa.hist = p->d_hist; sa.st = p->d_state;
-    sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.c_begin = 0; sa.comm_seq = 0u; sa.vec_ok = vec ? 1 : 0;
+    sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.c_begin = 0; sa.comm_seq = 0u; sa.cache = nullptr; sa.vec_ok = vec ? 1 : 0;
     sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)B200P_MODE_SNIP_STRICT; sa.sigmas = 12u;
     const int64_t sblocks = (p->n_chunks * kSnipGranulesPerChunk + kThreads - 1) / kThreads;      // one granule per thread
     if (acc) launch_snip_sample<true>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE));
@@ -1608,23 +1721,20 @@ extern "C" int b200p_snip_score_select(b200p_plan* p, const b200p_ptrtable* cons
     else     launch_snip_sweep<false>(nb, p->grid_for(p->n_chunks, 4), st, a, p->tab(B200P_SLOT_W), g, vec ? 1 : 0);
     B200P_LAUNCH_CHECK("k_snip_score_sweep");
     { int rc = plan_time_mark(p, 1, st); if (rc) return rc; }
-    // B: finish
-    int64_t work = p->n_chunks;
-    const int64_t cblocks = (p->cand_capacity + 8 * kThreads - 1) / (8 * kThreads);
-    if (cblocks > work) work = cblocks;
-    int grid = p->num_sms;
-    if (work < grid) grid = (int)(work < 1 ? 1 : work);
-    uint32_t* ties = p->d_chunk_ties; int64_t n_chunks = p->n_chunks;
-    void* args[] = {(void*)&a, (void*)&ties, (void*)&n_chunks};
-    B200P_CUDA(cudaLaunchCooperativeKernel((const void*)k_select_finish, dim3(grid), dim3(kThreads), args, 0, st));
-    return B200P_OK;
+    return launch_finish(p, a, B200P_KEY_SCORE, B200P_MODE_SNIP_STRICT, nullptr, st);
 }
 
 extern "C" int b200p_snip_mask_build(b200p_plan* p, const b200p_ptrtable* const* g_tables, int n_sets, uint64_t k,
                                      uint32_t* d_new_mask, void* stream) {
-    B200P_REQUIRE(d_new_mask != nullptr, B200P_EINVAL, "snip_mask_build: null argument");
+    B200P_REQUIRE(d_new_mask != nullptr && p != nullptr, B200P_EINVAL, "snip_mask_build: null argument");
+    p->fuse_emit = true; p->emit_done = false;
     int rc = b200p_snip_score_select(p, g_tables, n_sets, k, d_new_mask, stream);
-    if (rc) { if (p) p->prov_target = nullptr; return rc; }
+    p->fuse_emit = false;
+    if (rc) { p->prov_target = nullptr; return rc; }
+    if (p->emit_done) {                       // the finish kernel patched the mask itself
+        p->emit_done = false; p->prov_armed = false; p->prov_target = nullptr;
+        return B200P_OK;
+    }
     return b200p_emit_masks(p, B200P_KEY_SCORE, B200P_MODE_SNIP_STRICT, 0, 0.f, nullptr, d_new_mask, 0, 0, -1, stream);
 }
 

@@ -37,8 +37,9 @@ def discover(names, keys, dims, init_image_sizes, patch_size=16, k_patches=100, 
     scales = [patch_size, patch_size]
     for i in range(0, len(names), max_batch):
         sl = slice(i, i + max_batch)
-        feats = [k if k.dim() == 2 else k.reshape(-1, k.shape[-1]) for k in keys[sl]]
-        feats = [f if f.is_contiguous() else f.contiguous() for f in feats]
+        # strided views (the k slice of a qkv output) are handed over as they are: the kernels read them in place
+        feats = [k if k.dim() == 2 else (k[0] if k.dim() == 3 and k.shape[0] == 1 else k.reshape(-1, k.shape[-1])) for k in keys[sl]]
+        feats = [f if f.stride(1) == 1 else f.contiguous() for f in feats]
         out = lost_batched(feats, dims[sl], scales, init_image_sizes[sl], k_patches=k_patches)
         box, status = out["box"].cpu().numpy(), out["status"].cpu().numpy()       # one sync per batch
         for name, b, st in zip(names[sl], box, status):

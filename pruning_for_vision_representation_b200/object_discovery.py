@@ -83,6 +83,16 @@ class _Split:
         return (self[i] for i in range(len(self.sizes)))
 
 
+class _RawBase:
+    """Stand-in for the `feats` tensor of a batch whose images live in separate tensors: the lowest key address."""
+
+    def __init__(self, ptr, device, keepalive):
+        self.ptr, self.device, self.keepalive = ptr, device, keepalive
+
+    def data_ptr(self):
+        return self.ptr
+
+
 class _Batch:
     """Device buffers of one b200p_lost_batched call."""
 
@@ -174,15 +184,23 @@ def lost_batched(feats, dims, scales, init_image_sizes, k_patches=100, return_A=
         dims_l = dims
         sizes_l = init_image_sizes
     else:
-        feats = list(feats)
+        feats = [f if f.dim() == 2 else f.reshape(-1, f.shape[-1]) for f in feats]
         for f in feats:
             _require_cuda_f32(f, "feats")
         d = feats[0].shape[1]
-        base = torch.cat([f.reshape(-1, d) for f in feats], dim=0)
-        row_stride = d
-        feat_offs, o = [], 0
-        for f in feats:
-            feat_offs.append(o * d); o += f.shape[0]
+        strides = {f.stride(0) for f in feats}
+        if len(strides) == 1 and all(f.stride(1) == 1 and f.shape[1] == d for f in feats):
+            # every image is read IN PLACE, wherever its keys live (views of one producer buffer, k slices of separate qkv
+            # outputs, ...): the records carry each image's offset from the lowest address; no concatenation, no copy
+            row_stride = feats[0].stride(0)
+            ptrs = np.array([f.data_ptr() for f in feats], dtype=np.int64)
+            lowest = int(ptrs.min())
+            base = _RawBase(lowest, feats[0].device, feats)
+            feat_offs = (ptrs - lowest) // 4
+        else:                                           # mixed row strides: gather once (not the driver's path)
+            base = torch.cat([f.reshape(-1, d) for f in feats], dim=0)
+            row_stride = d
+            feat_offs = np.concatenate(([0], np.cumsum([f.shape[0] for f in feats])[:-1])).astype(np.int64) * d
         B = len(feats)
         dims_l, sizes_l = list(dims), list(init_image_sizes)
     metas, ns = _meta_records(feat_offs, dims_l, scales, sizes_l)

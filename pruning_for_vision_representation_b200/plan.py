@@ -10,12 +10,12 @@ import torch
 
 from . import _lib
 from ._lib import (CHUNK, WORDS_PER_CHUNK, SLOT_W, SLOT_G, SLOT_SCORE, SLOT_BUF, SLOT_WEFF,
-                   SLOT_MASKF, SLOT_WEFF16, MODE_SNIP_STRICT, MODE_EXACT_K, KEY_ABS_W, KEY_SCORE,
+                   SLOT_MASKF, SLOT_WEFF16, SLOT_EMA, MODE_SNIP_STRICT, MODE_EXACT_K, KEY_ABS_W, KEY_SCORE,
                    EMIT_MASKF, EMIT_WEFF, B200PruneError, SelectResult, check)
 
 _SLOT_DTYPE = {SLOT_W: torch.float32, SLOT_G: torch.float32, SLOT_SCORE: torch.float32,
                SLOT_BUF: torch.float32, SLOT_WEFF: torch.float32, SLOT_MASKF: torch.float32,
-               SLOT_WEFF16: torch.bfloat16}
+               SLOT_WEFF16: torch.bfloat16, SLOT_EMA: torch.float32}
 
 
 def _stream_ptr(device):
@@ -63,6 +63,11 @@ class ParamPlan:
         (3-pass radix select).  Both return identical results."""
         value = {"sampled": _lib.SELECT_SAMPLED, "exact": _lib.SELECT_EXACT}[impl]
         check(self.lib.b200p_plan_set_option(self.handle, _lib.OPT_SELECT_IMPL, value), "plan_set_option")
+        return self
+
+    def reuse_sample(self, on=True):
+        """Selects over unchanged keys (a sparsity sweep over fixed weights) reuse the first one's sample histogram."""
+        check(self.lib.b200p_plan_set_option(self.handle, _lib.OPT_REUSE_SAMPLE, 1 if on else 0), "plan_set_option")
         return self
 
     def close(self):
@@ -262,9 +267,17 @@ class ParamPlan:
     def mask_grads(self, mask):
         check(self.lib.b200p_mask_grads(self.handle, _ptr(mask), _stream_ptr(self.device)), "mask_grads")
 
-    def masked_sgd_step(self, mask, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, flags=0):
-        check(self.lib.b200p_masked_sgd_step(self.handle, _ptr(mask), lr, momentum, dampening, weight_decay, flags,
-                                             _stream_ptr(self.device)), "masked_sgd_step")
+    def masked_sgd_step(self, mask, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, flags=0, ctl=None):
+        """ctl: optional fp32 CUDA tensor [2] = (gradient multiplier, skip flag), read on the device."""
+        check(self.lib.b200p_masked_sgd_step_ctl(self.handle, _ptr(mask), lr, momentum, dampening, weight_decay, flags,
+                                                 _ptr(ctl), _stream_ptr(self.device)), "masked_sgd_step")
+
+    def grad_stats(self, mask, out):
+        """out (float64 CUDA tensor [2]) = (sum of kept g^2, count of non-finite gradient entries)."""
+        check(self.lib.b200p_grad_stats(self.handle, _ptr(mask), _ptr(out), _stream_ptr(self.device)), "grad_stats")
+
+    def ema_update(self, decay, copy=False):
+        check(self.lib.b200p_ema_update(self.handle, float(decay), 1 if copy else 0, _stream_ptr(self.device)), "ema_update")
 
     # ---- workspace views (for collectives between select stages) -----------------------
     def device_view(self, ptr, count, dtype, owner=None):

@@ -136,6 +136,8 @@ def _get_state(model, modules):
     if dev.type != "cuda":
         raise B200PruneError("the B200 pruning path needs the model on a CUDA device (no CPU fallback)")
     st = getattr(model, "_b200p_state", None)
+    if st is not None and st.mask is not None and any("weight_orig" not in m._parameters or "weight_mask" not in m._buffers for m in st.modules):
+        st = None          # prune.remove() (main_lost.py:67, evaluate_models.py:401) took the reparametrisation away: start from all N weights
     if st is not None and st.maskf is not None and any(
             "weight_mask" in m._buffers and m._buffers["weight_mask"] is not buf for m, buf in zip(st.modules, st.maskf)):
         st = None          # torch.nn.utils.prune (or a checkpoint load) replaced the mask buffers underneath: re-adopt
@@ -247,6 +249,11 @@ def snip_pruning(model, data_loader, device, criterion, target_sparsity=0.9, num
 
 
 def _grad_param(m):
+    """The tensor that carries this module's weight gradient: the fused leaf under MaskedSGD (autograd differentiates
+    `module.weight` there, `weight_orig.grad` stays None), else weight_orig / weight."""
+    for hook in m._forward_pre_hooks.values():
+        if isinstance(hook, B200MaskMethod) and hook.fused_weight is not None:
+            return hook.fused_weight
     p = m._parameters.get("weight_orig", None)
     if p is None:
         p = m._parameters.get("weight", None)

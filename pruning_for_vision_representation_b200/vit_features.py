@@ -63,15 +63,18 @@ class ViTFeatures(nn.Module):
         nn.init.trunc_normal_(self.pos_embed, std=0.02)
         nn.init.trunc_normal_(self.cls_token, std=0.02)
 
-    def interpolate_pos(self, h, w):
-        """Bicubic interpolation of the patch position embeddings to an h x w grid (what dino's
-        interpolate_pos_encoding / the reference's interpolate_embeddings, vision_transformer.py:781-858, do)."""
+    def interpolate_pos(self, h, w, align_corners=True):
+        """Bicubic interpolation of the patch position embeddings to an h x w grid, class token untouched.
+        Default = the reference's own `interpolate_embeddings` (vision_transformer.py:781-858: reshape to the square
+        grid, `nn.functional.interpolate(..., mode="bicubic", align_corners=True)`, back) — PINNED against it by
+        tests/golden/vit_producer.npz.  align_corners=False is facebookresearch/dino's interpolate_pos_encoding, the
+        (unvendored, unpinned) producer of main_lost_original.py; weights from that code base want that variant."""
         if h == self.grid0 and w == self.grid0:
             return self.pos_embed
         cls, patch = self.pos_embed[:, :1], self.pos_embed[:, 1:]
-        patch = patch.reshape(1, self.grid0, self.grid0, self.dim).permute(0, 3, 1, 2)
-        patch = F.interpolate(patch, size=(h, w), mode="bicubic", align_corners=False)
-        return torch.cat([cls, patch.permute(0, 2, 3, 1).reshape(1, h * w, self.dim)], dim=1)
+        patch = patch.permute(0, 2, 1).reshape(1, self.dim, self.grid0, self.grid0)
+        patch = F.interpolate(patch, size=(h, w), mode="bicubic", align_corners=align_corners)
+        return torch.cat([cls, patch.reshape(1, self.dim, h * w).permute(0, 2, 1)], dim=1)
 
     def pad_to_patch(self, img):
         """Zero-pad H and W up to a multiple of the patch size (main_lost_original.py:188-196)."""

@@ -217,9 +217,33 @@ def gen_lost():
         json.dump(meta, fjs, indent=1)
 
 
+def gen_vit_producer():
+    """Pins of the LOST feature producer (SURVEY f-4): (a) the reference's own position-embedding interpolation
+    (vision_transformer.py:781-858) on a 14x14 -> 13x17 and -> 30x30 grid; (b) the k extraction of
+    main_lost_original.py:251-263, run verbatim on a random qkv tensor."""
+    from collections import OrderedDict
+    import vision_transformer as ref_vit          # /root/reference/vision_transformer.py
+    torch.manual_seed(11)
+    pe = torch.randn(1, 1 + 14 * 14, 12)
+    out = {"pos_embed": pe.numpy()}
+    for (h, w) in ((13, 17), (30, 30)):
+        st = OrderedDict({"encoder.pos_embedding": pe.clone()})
+        new = ref_vit.interpolate_embeddings((h * 16, w * 16), 16, st)["encoder.pos_embedding"]
+        out[f"interp_{h}x{w}"] = new.numpy()
+    nb_im, nb_tokens, nh, D = 2, 1 + 35, 6, 48
+    feat_out = {"qkv": torch.randn(nb_im, nb_tokens, 3 * D)}
+    qkv = (feat_out["qkv"].reshape(nb_im, nb_tokens, 3, nh, -1 // nh).permute(2, 0, 3, 1, 4))      # main_lost_original.py:251-255, verbatim
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    k = k.transpose(1, 2).reshape(nb_im, nb_tokens, -1)                                             # :257
+    out["qkv"] = feat_out["qkv"].numpy()
+    out["k_feats"] = k[:, 1:, :].contiguous().numpy()                                               # :263
+    np.savez_compressed(os.path.join(HERE, "vit_producer.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["magnitude_tiny", "magnitude_tiefree", "snip_tiny", "resnet18", "lost"]
+    which = sys.argv[1:] or ["magnitude_tiny", "magnitude_tiefree", "snip_tiny", "resnet18", "lost", "vit"]
+    if "vit" in which: gen_vit_producer()
     if "magnitude_tiny" in which: gen_magnitude_tiny()
     if "magnitude_tiefree" in which: gen_magnitude_tiefree()
     if "snip_tiny" in which: gen_snip_tiny()

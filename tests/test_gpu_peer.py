@@ -181,3 +181,33 @@ def test_peer_fullsize_resnet50_magnitude_levels():
         res = vr.build(L.KEY_ABS_W, None, k, L.MODE_EXACT_K)
         for r, b in enumerate(vr.builders):
             assert res[r]["miss"] == 0 and res[r]["threshold"] == r_ref["threshold"] and torch.equal(b.mask, m), (s, r)
+
+
+def test_sample_reuse_gives_identical_builds():
+    """B200P_OPT_REUSE_SAMPLE: a sparsity sweep over fixed weights derives every bracket after the first from the cached
+    sample histogram (one plan and 3 virtual ranks): same masks and thresholds as sampling every time; re-binding the
+    weights drops the cache."""
+    numels = [4096 * 90 + 3, 4096 * 40, 12345]
+    n = sum(numels)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    wt = torch.randn(n, device=DEV, generator=g) * 0.02
+    plain, reuse = ParamPlan(numels, DEV), ParamPlan(numels, DEV).reuse_sample()
+    plain.bind(L.SLOT_W, _views(wt, numels)); reuse.bind(L.SLOT_W, _views(wt, numels))
+    vr = VirtualRanks(numels, 3)
+    for p in vr.plans:
+        p.bind(L.SLOT_W, _views(wt, numels)); p.reuse_sample()
+    for s in (0.5, 0.9, 0.2, 0.99):
+        k = round(s * n)
+        m0, m1 = plain.new_mask(), reuse.new_mask()
+        plain.mask_build(L.KEY_ABS_W, k, L.MODE_EXACT_K, m0); r0 = plain.result()
+        reuse.mask_build(L.KEY_ABS_W, k, L.MODE_EXACT_K, m1); r1 = reuse.result()
+        assert torch.equal(m0, m1) and r0["threshold"] == r1["threshold"] and r1["miss"] == 0
+        res = vr.build(L.KEY_ABS_W, None, k, L.MODE_EXACT_K)
+        for r, b in enumerate(vr.builders):
+            assert res[r]["miss"] == 0 and torch.equal(b.mask, m0), (s, r)
+    w2 = wt * 1.5                                                   # other weights behind the slot: the cache must not survive the bind
+    reuse.bind(L.SLOT_W, _views(w2, numels)); plain.bind(L.SLOT_W, _views(w2, numels))
+    k = round(0.7 * n)
+    m0, m1 = plain.new_mask(), reuse.new_mask()
+    plain.mask_build(L.KEY_ABS_W, k, L.MODE_EXACT_K, m0); reuse.mask_build(L.KEY_ABS_W, k, L.MODE_EXACT_K, m1)
+    assert torch.equal(m0, m1) and plain.result()["threshold"] == reuse.result()["threshold"]

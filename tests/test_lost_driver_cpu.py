@@ -54,3 +54,20 @@ def test_vit_feature_producer_contract():
     assert torch.equal(keys, k.transpose(1, 2).reshape(B, T, -1)[:, 1:, :])
     # native grid: position embeddings are used as they are
     assert m.interpolate_pos(4, 4) is m.pos_embed and m.interpolate_pos(5, 7).shape == (1, 36, 48)
+
+
+def test_vit_producer_pinned_to_the_reference(golden_dir):
+    """SURVEY f-4: the producer's position-embedding interpolation equals the reference's own interpolate_embeddings
+    (vision_transformer.py:781-858) and its key view equals the k the reference extracts (main_lost_original.py:251-263):
+    fixtures written by tests/golden/make_golden.py from the unmodified reference."""
+    from pruning_for_vision_representation_b200.vit_features import ViTFeatures
+    z = np.load(os.path.join(golden_dir, "vit_producer.npz"))
+    vit = ViTFeatures(patch_size=16, dim=12, depth=1, heads=2, img_size=224)
+    with torch.no_grad():
+        vit.pos_embed.copy_(torch.from_numpy(z["pos_embed"]))
+        for (h, w) in ((13, 17), (30, 30)):
+            got = vit.interpolate_pos(h, w)
+            torch.testing.assert_close(got, torch.from_numpy(z[f"interp_{h}x{w}"]), rtol=0, atol=0)
+        assert vit.interpolate_pos(14, 14) is vit.pos_embed
+    k = D.keys_from_qkv(torch.from_numpy(z["qkv"]))
+    assert torch.equal(k, torch.from_numpy(z["k_feats"])) and not k.is_contiguous()
