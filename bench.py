@@ -730,7 +730,7 @@ def magnitude_legs(torch, L, ParamPlan, dev, peak, flush):
         w, numels, src = model_weights_cpu(name)
         n = sum(numels)
         wd = w.to(dev)
-        plan = ParamPlan(numels, dev)
+        plan = ParamPlan(numels, dev).reuse_sample()        # a sweep over fixed weights: levels after the first reuse the sample histogram
         plan.bind(L.SLOT_W, split_views(wd, numels))
         m = plan.new_mask()
         levels = {}
@@ -765,11 +765,15 @@ def sharded_legs(torch, dist, L, ParamPlan, dev, rank, world, peak, flush, rn50,
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return bool(t.item())
 
-    def timed_build(fn, reps):
+    def timed_build(fn, reps, comm):
+        """median over `reps` of the max-over-ranks CUDA-event time of fn(); L2 flushed first, and the ranks aligned ON THE
+        DEVICE (a spin barrier kernel over the peer windows) right before the first event, so that host-side launch skew
+        between the processes is not billed to the build"""
         ts = []
         for _ in range(reps):
-            flush()
             dist.barrier(); torch.cuda.synchronize()
+            flush()
+            comm.barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record(); torch.cuda.synchronize()
             ts.append(all_max(a.elapsed_time(b) * 1e3))
@@ -786,8 +790,8 @@ def sharded_legs(torch, dist, L, ParamPlan, dev, rank, world, peak, flush, rn50,
         score = torch.zeros(n, device=dev)
         local_tab = plan.pointer_table(L.SLOT_SCORE, split_views(score, numels))
         gt = [plan.pointer_table(L.SLOT_G, split_views(g, numels)) for g in g_my]
-        comm = PeerComm.from_process_group(plan, score_cap=(plan.n_chunks + world - 1) // world * L.CHUNK)
-        b = PeerShardedBuilder(plan, comm)
+        b = PeerShardedBuilder.from_process_group(plan, score_cap=(plan.n_chunks + world - 1) // world * L.CHUNK)
+        comm = b.comm
         b.snip_build(gt, k, score, local_tab)
         res = b.check()
         # reference on this GPU alone: per-rank partials, added in rank order, ordinary build
@@ -858,8 +862,8 @@ def sharded_legs(torch, dist, L, ParamPlan, dev, rank, world, peak, flush, rn50,
         plan.bind(L.SLOT_W, split_views(wd, numels))
         ref = ParamPlan(numels, dev)
         ref.bind(L.SLOT_W, split_views(wd, numels))
-        comm = PeerComm.from_process_group(plan)
-        b = PeerShardedBuilder(plan, comm)
+        b = PeerShardedBuilder.from_process_group(plan)
+        plan.reuse_sample(); ref.reuse_sample()             # a sweep over fixed weights: every level after the first reuses the sample histogram
         m_ref = ref.new_mask()
         levels, ident_all = {}, True
         for s in (0.5, 0.8, 0.9, 0.95, 0.99):
@@ -872,11 +876,29 @@ def sharded_legs(torch, dist, L, ParamPlan, dev, rank, world, peak, flush, rn50,
             ident_all = ident_all and ident
             one_us = timed_us(torch, lambda: ref.mask_build(L.KEY_ABS_W, kk, L.MODE_EXACT_K, m_ref), 5, flush)
             one_us = all_max(one_us)
-            sh_us = timed_build(lambda: b.magnitude_build(kk), 7)
+            sh_us = timed_build(lambda: b.magnitude_build(kk), 7, b.comm)
             levels[str(s)] = {"one_gpu_us": one_us, "sharded_us": sh_us, "speedup": one_us / sh_us,
                               "value": n / (sh_us * 1e-6) / 1e9, "bit_identical": ident}
+        # where the time goes: the six stages issued one by one (events between them, max over ranks; the production sequence
+        # runs finish + ties + emit + push as ONE cooperative launch, so the sum here exceeds sharded_us)
+        kk = round(0.9 * n)
+        names = ["sample", "sweep", "finish", "ties", "emit", "mask_push"]
+        acc = {nm: [] for nm in names}
+        plan.reuse_sample(False)
+        for _ in range(5):
+            dist.barrier(); torch.cuda.synchronize()
+            flush(); b.comm.barrier()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+            evs[0].record()
+            for i in range(6):
+                b._build(L.KEY_ABS_W, None, kk, L.MODE_EXACT_K, stages=1 << i)
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            for i, nm in enumerate(names):
+                acc[nm].append(all_max(evs[i].elapsed_time(evs[i + 1]) * 1e3))
+        stage_us = {nm: statistics.median(v) for nm, v in acc.items()}
         med = lambda key: statistics.median([v[key] for v in levels.values()])
-        out["config5"][name] = {"N": n, "levels": levels, "one_gpu_us": med("one_gpu_us"), "sharded_us": med("sharded_us"),
+        out["config5"][name] = {"N": n, "levels": levels, "stage_us_at_0.9_unmerged": stage_us, "one_gpu_us": med("one_gpu_us"), "sharded_us": med("sharded_us"),
                                 "speedup": med("one_gpu_us") / med("sharded_us"), "value": n / (med("sharded_us") * 1e-6) / 1e9,
                                 "unit": "Gparams/s", "bit_identical_to_single_gpu": all_true(ident_all), "weights": src,
                                 "slice_bytes": n * 4 // world, "mask_bytes_pushed_per_rank": (world - 1) * (n // 8) // world}

@@ -131,6 +131,8 @@ int  b200p_plan_bind_table(b200p_plan* plan, int slot, const b200p_ptrtable* tab
                                        sweep over fixed weights, BASELINE config 5) derive their bracket from the sample histogram the
                                        first one cached instead of sampling (and, sharded, all-reducing) again.  The caller vouches
                                        for "unchanged": weights updated in place must clear the option or re-bind the slot. */
+#define B200P_OPT_COOP_GRID     4   /* cap on the grid of this plan's cooperative launches (0 = one CTA per SM).  Several plans that share
+                                       ONE device and wait on each other (virtual ranks in tests) must fit on it together. */
 int  b200p_plan_set_option(b200p_plan* plan, int option, int64_t value);
 /* Mean duration (ms) and number of the fused score+sweep launches timed since the option was set or this was last
  * called; synchronises on the last recorded event.  *out_launches may be 0 (then *out_ms = 0). */

@@ -20,7 +20,7 @@ KEY_ABS_W, KEY_SCORE = 0, 1
 EMIT_MASKF, EMIT_WEFF = 1, 2
 SGD_NESTEROV, SGD_FIRST_STEP, SGD_EMIT_WEFF, SGD_EMIT_WEFF16 = 1, 2, 4, 8
 LOST_GRAM_FFMA, LOST_GRAM_TC, LOST_GRAM_TC2, LOST_GRAM_TC2D = 0, 1, 2, 3
-OPT_SELECT_IMPL, OPT_TIME_SWEEP, OPT_REUSE_SAMPLE = 1, 2, 3
+OPT_SELECT_IMPL, OPT_TIME_SWEEP, OPT_REUSE_SAMPLE, OPT_COOP_GRID = 1, 2, 3, 4
 SHARD_SAMPLE, SHARD_SWEEP, SHARD_FINISH, SHARD_TIES, SHARD_EMIT, SHARD_PUSH, SHARD_ALL = 1, 2, 4, 8, 16, 32, 63
 SELECT_SAMPLED, SELECT_EXACT = 0, 1
 

@@ -26,18 +26,9 @@ static CommLayout make_layout(int world, long long mask_words, long long score_c
 // ---- all-gather of the packed mask: every rank pushes the words of its chunk range into every window ----------------
 __global__ void __launch_bounds__(256)
 k_mask_push(CommDev c, long long w_begin, long long w_end, uint32_t seq, unsigned int* ticket) {
-    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(c.win[c.rank] + c.lay.mask);
-    // 16-byte pieces (chunk ranges start on multiples of 128 words)
-    const long long q0 = w_begin >> 2, q1 = w_end >> 2;
-    for (long long q = q0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += (long long)gridDim.x * blockDim.x) {
-        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src) + q);
-        for (int p = 0; p < c.world; ++p)
-            if (p != c.rank) reinterpret_cast<uint4*>(c.win[p] + c.lay.mask)[q] = v;
-    }
+    comm_push_mask_words(c, w_begin, w_end);
     // last CTA: everybody's stores are out (fence + ticket), tell the peers and wait for theirs
     __shared__ unsigned int s_ticket;
-    __threadfence_system();
-    __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;

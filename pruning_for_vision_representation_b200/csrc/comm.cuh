@@ -66,11 +66,12 @@ __device__ __forceinline__ uint32_t* comm_flag(const CommDev& c, int dst_rank, i
 // publishes seq to every rank, then waits for every rank's seq.  Returns false on a time-out (err flag set).
 __device__ __forceinline__ bool comm_signal_and_wait(const CommDev& c, int ch, uint32_t seq) {
     __shared__ int s_comm_ok;
-    __threadfence_system();
-    __syncthreads();
     if (threadIdx.x == 0) s_comm_ok = 1;
-    __syncthreads();
+    __syncthreads();                       // every payload store of the CTA is issued (CTA-scope happens-before)
     if ((int)threadIdx.x < c.world) {
+        // ONE system-scope fence per signalling thread, after the barrier: fences are cumulative, so it also orders the
+        // stores of the other threads it synchronised with (256 concurrent fence.sys cost ~15 us per collective)
+        __threadfence_system();
         st_release_sys_u32(comm_flag(c, threadIdx.x, ch, c.rank), seq);
         const uint32_t* f = comm_flag(c, c.rank, ch, threadIdx.x);
         bool ok = false;
@@ -83,6 +84,22 @@ __device__ __forceinline__ bool comm_signal_and_wait(const CommDev& c, int ch, u
     }
     __syncthreads();
     return s_comm_ok != 0;
+}
+
+// Copy the packed-mask words [w_begin, w_end) of the own window into every peer's window (grid-stride over the launching
+// grid, 16-byte pieces: chunk ranges start on multiples of 128 words); each CTA ends with one cumulative system fence.
+__device__ __forceinline__ void comm_push_mask_words(const CommDev& c, long long w_begin, long long w_end) {
+    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(c.win[c.rank] + c.lay.mask);
+    const long long q0 = w_begin >> 2, q1 = w_end >> 2;
+    if (c.world > 1)
+        for (long long q = q0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += (long long)gridDim.x * blockDim.x) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src) + q);
+            for (int p = 0; p < c.world; ++p)
+                if (p != c.rank) reinterpret_cast<uint4*>(c.win[p] + c.lay.mask)[q] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
+    __syncthreads();
 }
 
 // All-reduce (sum) of a 4096-bin u64 histogram + 8 u64 extras that lives in this rank's global memory, by ONE CTA of

@@ -138,6 +138,7 @@ struct b200p_plan {
     int64_t cand_capacity = 0;
     int num_sms = 148;
     int coop_ctas_per_sm = 0;      // co-resident CTAs of the cooperative finish kernel (0: not queried yet)
+    int coop_grid_limit = 0;       // B200P_OPT_COOP_GRID: cap on the grid of cooperative launches (several plans sharing one device)
     int select_impl = 0;           // 0 sampled (bracketed) select, 1 exact 3-pass radix select
     std::vector<int64_t> numel;
     std::vector<int64_t> seg_chunk_start;   // n_seg + 1

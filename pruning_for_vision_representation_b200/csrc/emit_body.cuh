@@ -64,16 +64,28 @@ static __device__ void emit_patch_body(const int32_t* __restrict__ chunk_n, Chun
     const bool strict = mode == B200P_MODE_SNIP_STRICT;
     const uint32_t need_ties = strict ? 0u : pv.need_ties;
     const long long tie_chunk = pv.tie_chunk;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-        const uint32_t key = __ldg(cand_key + i), pos = __ldg(cand_pos + i);
-        const long long c = pos >> 12;
-        bool prune;
-        if (strict) prune = key <= thr_key;                           // keep = score > threshold (train.py:316)
-        else {
-            const bool ties_pruned = !need_ties || tie_chunk < 0 || c < tie_chunk;
-            prune = key < thr_key || (key == thr_key && ties_pruned);
+    // eight candidates per thread and iteration: sixteen independent loads in flight, then the (fire-and-forget) bit clears —
+    // the loop is bound by load latency, and the fused finish kernel runs it on one CTA per SM
+    const uint32_t stride = gridDim.x * kThreads;
+    for (uint32_t i0 = blockIdx.x * kThreads + threadIdx.x; i0 < n; i0 += 8 * stride) {
+        uint32_t key[8], pos[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t i = i0 + u * stride;
+            key[u] = i < n ? __ldg(cand_key + i) : 0xFFFFFFFFu;       // above every threshold: never pruned
+            pos[u] = i < n ? __ldg(cand_pos + i) : 0u;
         }
-        if (prune) atomicAnd(prov + (size_t)c * kWordsPerChunk + ((pos & 4095u) >> 5), ~(1u << (pos & 31u)));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long c = pos[u] >> 12;
+            bool prune;
+            if (strict) prune = key[u] <= thr_key;                    // keep = score > threshold (train.py:316)
+            else {
+                const bool ties_pruned = !need_ties || tie_chunk < 0 || c < tie_chunk;
+                prune = key[u] < thr_key || (key[u] == thr_key && ties_pruned);
+            }
+            if (prune) atomicAnd(prov + (size_t)c * kWordsPerChunk + ((pos[u] & 4095u) >> 5), ~(1u << (pos[u] & 31u)));
+        }
     }
     if (blockIdx.x != 0) return;
     if (threadIdx.x == 0) st->n_kept = pv.n_kept;

@@ -378,9 +378,38 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
             __syncthreads();
         }
         n_pot = min(n_pot, 1024);
-        for (int i = warp; i < n_pot; i += nwarps) {
-            const float a = warp_dot(F + (long long)s_sorted[i] * row_stride, s_kseed, d, vec_ok != 0);
-            if (lane == 0) s_simflag[i] = a > 0.0f ? 1 : 0;              // object_discovery.py:61 on the unmodified A
+        if (vec_ok && (d & 3) == 0) {
+            // four potentials per warp and round: their loads are in flight together (the phase is pure latency)
+            const int d4 = d >> 2;
+            const float4* __restrict__ ks4 = reinterpret_cast<const float4*>(s_kseed);
+            for (int i0 = 4 * warp; i0 < n_pot; i0 += 4 * nwarps) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const float4* rowp[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rowp[u] = reinterpret_cast<const float4*>(F + (long long)s_sorted[min(i0 + u, n_pot - 1)] * row_stride);
+                for (int c = lane; c < d4; c += 32) {
+                    float4 x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) x[u] = __ldg(rowp[u] + c);
+                    const float4 y = ks4[c];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        acc[u] = fmaf(x[u].x, y.x, acc[u]); acc[u] = fmaf(x[u].y, y.y, acc[u]);
+                        acc[u] = fmaf(x[u].z, y.z, acc[u]); acc[u] = fmaf(x[u].w, y.w, acc[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xFFFFFFFFu, acc[u], o);
+                    if (lane == 0 && i0 + u < n_pot) s_simflag[i0 + u] = acc[u] > 0.0f ? 1 : 0;      // object_discovery.py:61 on the unmodified A
+                }
+            }
+        } else {
+            for (int i = warp; i < n_pot; i += nwarps) {
+                const float a = warp_dot(F + (long long)s_sorted[i] * row_stride, s_kseed, d, vec_ok != 0);
+                if (lane == 0) s_simflag[i] = a > 0.0f ? 1 : 0;          // object_discovery.py:61 on the unmodified A
+            }
         }
         __syncthreads();
         int n_sim = 0;
@@ -448,26 +477,28 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
         }
         __syncthreads();
         if (vec_ok && (d & 3) == 0) {
+            // one warp per group of ROWS rows: ROWS x (d / 128) independent 16-byte loads in flight per lane before the first FMA
+            constexpr int ROWS = 4;        // 62 registers: a 256-thread CTA of this kernel fits beside a Gram CTA (6 rows: 86 registers, it no longer does)
             const int d4 = d >> 2;
             const float4* __restrict__ v4 = reinterpret_cast<const float4*>(s_vsum);
-            for (int j0 = 4 * warp; j0 < n; j0 += 4 * nwarps) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                const float4* rowp[4];
+            for (int j0 = ROWS * warp; j0 < n; j0 += ROWS * nwarps) {
+                float acc[ROWS];
+                const float4* rowp[ROWS];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) rowp[u] = reinterpret_cast<const float4*>(F + (long long)min(j0 + u, n - 1) * row_stride);
+                for (int u = 0; u < ROWS; ++u) { acc[u] = 0.f; rowp[u] = reinterpret_cast<const float4*>(F + (long long)min(j0 + u, n - 1) * row_stride); }
                 for (int c = lane; c < d4; c += 32) {
-                    float4 x[4];
+                    float4 x[ROWS];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) x[u] = __ldg(rowp[u] + c);
+                    for (int u = 0; u < ROWS; ++u) x[u] = __ldg(rowp[u] + c);
                     const float4 y = v4[c];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < ROWS; ++u) {
                         acc[u] = fmaf(x[u].x, y.x, acc[u]); acc[u] = fmaf(x[u].y, y.y, acc[u]);
                         acc[u] = fmaf(x[u].z, y.z, acc[u]); acc[u] = fmaf(x[u].w, y.w, acc[u]);
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < ROWS; ++u) {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xFFFFFFFFu, acc[u], o);
                     if (lane == 0 && j0 + u < n) {

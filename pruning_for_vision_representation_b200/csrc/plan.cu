@@ -143,6 +143,11 @@ extern "C" int b200p_plan_set_option(b200p_plan* p, int option, int64_t value) {
         if (!p->reuse_sample) p->sample_cache_valid = false;
         return B200P_OK;
     }
+    if (option == B200P_OPT_COOP_GRID) {
+        B200P_REQUIRE(value >= 0 && value <= 4096, B200P_EINVAL, "plan_set_option: bad cooperative grid limit");
+        p->coop_grid_limit = (int)value;
+        return B200P_OK;
+    }
     if (option == B200P_OPT_TIME_SWEEP) {
         p->time_sweep = value != 0;
         return B200P_OK;

@@ -21,6 +21,7 @@
 #include "comm.cuh"
 #include "emit_body.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace b200p {
 
@@ -223,11 +224,21 @@ __device__ __forceinline__ float sel16(const float4 (&v)[kVecPerThread], int i) 
 // canon: the range reaches the inf/NaN buckets, keys must be canonicalised: element-wise path.
 // Two chunks are loaded per iteration (128 B in flight per thread, 4 CTAs per SM) so that the sweep
 // is bound by HBM and not by the latency of one 64-byte load per thread.
+// per-warp candidate staging (one instance per kernel, shared by both instantiations of sweep_loop)
+struct SweepStage {
+    uint32_t key[kThreads / 32][kStage];
+    uint32_t pos[kThreads / 32][kStage];
+    int wcount[kThreads / 32];
+};
+__device__ __forceinline__ SweepStage& sweep_stage() { __shared__ SweepStage s_stage; return s_stage; }
+
+template <bool NANP>
 __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint32_t base, uint32_t span, int fine_shift,
                                                          bool collect, bool canon, uint32_t* __restrict__ s_hist) {
-    __shared__ uint32_t sg_key[kThreads / 32][kStage];
-    __shared__ uint32_t sg_pos[kThreads / 32][kStage];
-    __shared__ int s_wcount[kThreads / 32];
+    SweepStage& stg = sweep_stage();
+    uint32_t (&sg_key)[kThreads / 32][kStage] = stg.key;
+    uint32_t (&sg_pos)[kThreads / 32][kStage] = stg.pos;
+    int (&s_wcount)[kThreads / 32] = stg.wcount;
     SelState* __restrict__ st = a.st;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) s_wcount[warp] = 0;
@@ -264,45 +275,46 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
     // below `base` are removed from the inside-mask afterwards.
     // SNIP_STRICT prunes NaN scores (NaN > thr is false, train.py:316) although they sort last: their provisional bits
     // must be clear, the patching emit never sees them.  One max per key finds the (rare) threads that hold one.
-    const bool nan_pruned = st->mode == B200P_MODE_SNIP_STRICT;      // the state was initialised by the kernel before this one
-    auto do_vec = [&](const float4 (&v)[kVecPerThread], uint32_t alive_rev, uint32_t pos0) {
+    // NANP (SNIP_STRICT): NaN keys sort last but are pruned; the magnitude select (EXACT_K) keeps them like any large key and
+    // skips the per-key max.  The keys are walked LAST TO FIRST, so that key i ends up in bit i of the 16-bit masks: memory
+    // order, the alive bitmap and the mask nibbles need no bit reversal.
+    constexpr bool nan_pruned = NANP;
+    auto do_vec = [&](const float4 (&v)[kVecPerThread], uint32_t alive, uint32_t pos0) {
         uint32_t lt = 0, in = 0, mx = 0;
 #pragma unroll
-        for (int j = 0; j < kVecPerThread; ++j) {
+        for (int j = kVecPerThread - 1; j >= 0; --j) {
             const float f[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 3; q >= 0; --q) {
                 const uint32_t key = __float_as_uint(f[q]) & 0x7FFFFFFFu;
                 const uint32_t d = key - base;
-                mx = max(mx, key);
+                if (NANP) mx = max(mx, key);
                 lt = __funnelshift_l(d, lt, 1);
                 in = __funnelshift_l(d - span, in, 1);
             }
         }
-        lt &= alive_rev;
+        lt &= alive;
         below += __popc(lt);
         if (a.prov) {
             // provisional mask: alive keys at or above the bracket base stay set; the emit only patches the
             // candidates afterwards instead of re-reading every key
-            uint32_t keep = alive_rev & ~lt;
-            if (nan_pruned && mx > 0x7F800000u) {
+            uint32_t keep = alive & ~lt & 0xFFFFu;
+            if (NANP && mx > 0x7F800000u) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    if ((__float_as_uint(sel16(v, i)) & 0x7FFFFFFFu) > 0x7F800000u) { nan_cnt += (keep >> (15 - i)) & 1u; keep &= ~(1u << (15 - i)); }
+                    if ((__float_as_uint(sel16(v, i)) & 0x7FFFFFFFu) > 0x7F800000u) { nan_cnt += (keep >> i) & 1u; keep &= ~(1u << i); }
             }
             uint32_t* pw = a.prov + (size_t)(pos0 >> 12) * kWordsPerChunk;
 #pragma unroll
             for (int j = 0; j < kVecPerThread; ++j) {
-                const uint32_t nib = __brev((keep >> (12 - 4 * j)) & 0xFu) >> 28;       // key 4j+q sits at bit 15-(4j+q)
-                const uint32_t word = gather_nibbles(nib);
+                const uint32_t word = gather_nibbles((keep >> (4 * j)) & 0xFu);        // key 4j+q sits at bit 4j+q
                 if ((threadIdx.x & 7) == 0) pw[vec_word_index(j)] = word;
             }
         }
-        uint32_t match = in & ~lt & alive_rev;
+        uint32_t match = in & ~lt & alive & 0xFFFFu;
         while (match) {                               // divergent, rare (~1-2 % of the keys)
-            const int bit = __ffs(match) - 1;
+            const int i = __ffs(match) - 1;           // index of the key inside the thread's 16
             match &= match - 1;
-            const int i = 15 - bit;                   // processing order of the key
             take(__float_as_uint(sel16(v, i)) & 0x7FFFFFFFu, pos0 + (uint32_t)slot_element<true>(i));
         }
     };
@@ -325,14 +337,13 @@ __device__ __forceinline__ unsigned long long sweep_loop(const PassArgs& a, uint
             }
         }
     };
-    // alive bitmap in do_vec's bit order (key i -> bit 15 - i)
+    // alive bitmap in do_vec's bit order (key i -> bit i)
     auto load_alive = [&](const uint32_t* __restrict__ mchunk) {
         uint32_t alive = 0xFFFFu;
         if (mchunk) {
             alive = 0;
 #pragma unroll
             for (int j = 0; j < kVecPerThread; ++j) alive |= nibble_of(__ldg(mchunk + vec_word_index(j))) << (4 * j);
-            alive = __brev(alive) >> 16;
         }
         return alive;
     };
@@ -399,7 +410,8 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, uint32_t* __restric
 
     if (PASS == 1) {
         // keys of the chosen 12-bit bucket: histogram of their next 12 bits, plus the candidate append
-        sweep_loop(a, prefix, 1u << 19, 7, collect != 0, (prefix >> 19) >= 0xFF0u, s_hist);
+        if (st->mode == B200P_MODE_SNIP_STRICT) sweep_loop<true>(a, prefix, 1u << 19, 7, collect != 0, (prefix >> 19) >= 0xFF0u, s_hist);
+        else                                    sweep_loop<false>(a, prefix, 1u << 19, 7, collect != 0, (prefix >> 19) >= 0xFF0u, s_hist);
     } else if (PASS == 2 && collect) {
         const uint32_t n = st->cand_count;
         for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
@@ -880,7 +892,9 @@ k_select_bracket(PassArgs a, CommDev comm) {
     for (int b = threadIdx.x; b < kHistBins; b += kThreads) s_hist[b] = 0;
     if (threadIdx.x == 0) s_below = 0;
     __syncthreads();
-    unsigned long long below = sweep_loop(a, base, span, kFineShift, true, false, s_hist);
+    // the state was initialised by the kernel before this one: the mode is uniform over the grid
+    unsigned long long below = st->mode == B200P_MODE_SNIP_STRICT ? sweep_loop<true>(a, base, span, kFineShift, true, false, s_hist)
+                                                                  : sweep_loop<false>(a, base, span, kFineShift, true, false, s_hist);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xFFFFFFFFu, below, o);
     if ((threadIdx.x & 31) == 0 && below) atomicAdd(&s_below, below);
@@ -895,6 +909,62 @@ k_select_bracket(PassArgs a, CommDev comm) {
     if (a.comm_seq) comm_ok = comm_allreduce_hist(comm, a.comm_seq, a.hist);
     bracket_tail(a, base, s_warp);
     if (!comm_ok && threadIdx.x == 0) { st->miss = 1u; st->collect = 0u; st->prov_ok = 0u; }
+}
+
+// One CTA: all-gather of the ranks' window histograms (a.hist[0..1024) holds this rank's), exact key of rank k, tie
+// bookkeeping (every rank's count of that key -> rank_ties).  Leaves a.hist cleared.
+__device__ __forceinline__ void sharded_gather_pick(const PassArgs& a, const CommDev& comm, uint32_t seq, unsigned long long* __restrict__ rank_ties,
+                                                    unsigned long long* s_warp /*[9]*/, int* s_bin) {
+    SelState* __restrict__ st = a.st;
+    const uint32_t win_lo = st->win_lo;
+    const int tid = threadIdx.x, slot = seq & 1u;
+    // push the own 1024 counts (4 per thread) into every window, wait for everybody's
+    {
+        uint4 v;
+        v.x = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 0]; v.y = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 1];
+        v.z = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 2]; v.w = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 3];
+        for (int p = 0; p < comm.world; ++p)
+            reinterpret_cast<uint4*>(comm.win[p] + comm.lay.gather)[(size_t)(slot * comm.world + comm.rank) * (kCommGatherWords / 4) + tid] = v;
+    }
+    const bool comm_ok = comm_signal_and_wait(comm, CH_GATHER, seq);
+    const uint32_t* __restrict__ g = reinterpret_cast<const uint32_t*>(comm.win[comm.rank] + comm.lay.gather) + (size_t)slot * comm.world * kCommGatherWords;
+    unsigned long long local[kBinsPerThread];
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) {
+        const int b = tid * kBinsPerThread + i;
+        unsigned long long sum = 0;
+        if (b < kWindow) for (int r = 0; r < comm.world; ++r) sum += __ldcg(g + (size_t)r * kCommGatherWords + b);
+        local[i] = sum;
+    }
+    unsigned long long total;
+    unsigned long long running = block_prefix16(local, s_warp, total);
+    const unsigned long long k = st->k;
+    if (tid == 0) *s_bin = -1;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) {
+        const unsigned long long v = local[i];
+        if (v != 0 && running < k && k <= running + v) {
+            const int b = tid * kBinsPerThread + i;
+            const uint32_t key = win_lo + (uint32_t)b;
+            st->n_less += running;
+            st->k = k - running;
+            st->prefix = key; st->thr_key = key; st->threshold = key_to_float(key);
+            st->n_equal = v; st->quota = k - running;
+            st->need_ties = (st->mode == B200P_MODE_EXACT_K && (k - running) < v) ? 1u : 0u;
+            st->tie_chunk = -1; st->tie_resid = 0; st->tie_seen = 0;
+            *s_bin = b;
+        }
+        running += v;
+    }
+    __syncthreads();
+    if (*s_bin < 0 || !comm_ok) {                    // cannot happen after a verified bracket; treated like a miss
+        if (tid == 0) { st->miss = 1u; st->collect = 0u; st->prov_ok = 0u; }
+    } else if (tid < kCommMaxWorld) {
+        rank_ties[tid] = tid < comm.world ? (unsigned long long)__ldcg(g + (size_t)tid * kCommGatherWords + *s_bin) : 0ull;
+    }
+    __syncthreads();
+    clear_hist(a.hist);
 }
 
 // ---- B (sharded): exact key from the window histograms of all ranks -----------------------------------------------
@@ -929,55 +999,8 @@ k_sharded_finish(PassArgs a, CommDev comm, uint32_t seq, unsigned long long* __r
         if (v) atomicAdd(a.hist + b, (unsigned long long)v);
     }
     if (!last_cta_arrives(a.ticket)) return;
-    const int tid = threadIdx.x, slot = seq & 1u;
-    // push the own 1024 counts (4 per thread) into every window, wait for everybody's
-    {
-        uint4 v;
-        v.x = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 0]; v.y = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 1];
-        v.z = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 2]; v.w = (uint32_t)((volatile unsigned long long*)a.hist)[4 * tid + 3];
-        for (int p = 0; p < comm.world; ++p)
-            reinterpret_cast<uint4*>(comm.win[p] + comm.lay.gather)[(size_t)(slot * comm.world + comm.rank) * (kCommGatherWords / 4) + tid] = v;
-    }
-    const bool comm_ok = comm_signal_and_wait(comm, CH_GATHER, seq);
-    const uint32_t* __restrict__ g = reinterpret_cast<const uint32_t*>(comm.win[comm.rank] + comm.lay.gather) + (size_t)slot * comm.world * kCommGatherWords;
-    unsigned long long local[kBinsPerThread];
-#pragma unroll
-    for (int i = 0; i < kBinsPerThread; ++i) {
-        const int b = tid * kBinsPerThread + i;
-        unsigned long long sum = 0;
-        if (b < kWindow) for (int r = 0; r < comm.world; ++r) sum += __ldcg(g + (size_t)r * kCommGatherWords + b);
-        local[i] = sum;
-    }
-    unsigned long long total;
-    unsigned long long running = block_prefix16(local, s_warp, total);
-    const unsigned long long k = st->k;
-    if (tid == 0) s_bin = -1;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < kBinsPerThread; ++i) {
-        const unsigned long long v = local[i];
-        if (v != 0 && running < k && k <= running + v) {
-            const int b = tid * kBinsPerThread + i;
-            const uint32_t key = win_lo + (uint32_t)b;
-            st->n_less += running;
-            st->k = k - running;
-            st->prefix = key; st->thr_key = key; st->threshold = key_to_float(key);
-            st->n_equal = v; st->quota = k - running;
-            st->need_ties = (st->mode == B200P_MODE_EXACT_K && (k - running) < v) ? 1u : 0u;
-            st->tie_chunk = -1; st->tie_resid = 0; st->tie_seen = 0;
-            s_bin = b;
-        }
-        running += v;
-    }
-    __syncthreads();
-    if (s_bin < 0 || !comm_ok) {                     // cannot happen after a verified bracket; treated like a miss
-        if (tid == 0) { st->miss = 1u; st->collect = 0u; st->prov_ok = 0u; }
-    } else if (tid < kCommMaxWorld) {
-        rank_ties[tid] = tid < comm.world ? (unsigned long long)__ldcg(g + (size_t)tid * kCommGatherWords + s_bin) : 0ull;
-    }
-    __syncthreads();
-    if (tid == 0) *a.ticket = 0u;
-    clear_hist(a.hist);
+    sharded_gather_pick(a, comm, seq, rank_ties, s_warp, &s_bin);
+    if (threadIdx.x == 0) *a.ticket = 0u;
 }
 
 // =============================================================================================
@@ -1327,6 +1350,60 @@ k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks,
     }
 }
 
+// ---- sharded tail: finish + ties + emit + mask push in ONE cooperative launch ----------------------------------------------
+// The stages after the sweep are tiny and strictly ordered; as five launches (finish, tie count, tie scan, emit, push)
+// they cost ~60 us of launch latency and tails on a slice that streams in 20.  Here grid-wide barriers separate them:
+//   window histogram -> [CTA 0: all-gather over the ranks, exact key] -> (ties: count -> [CTA 0: ordered scan]) ->
+//   patch the own candidates' bits -> push the own mask words into every window -> [CTA 0: tell the peers, wait for theirs]
+__global__ void __launch_bounds__(kThreads, 3)
+k_sharded_tail(PassArgs a, CommDev comm, uint32_t seq_gather, uint32_t seq_mask, unsigned long long* __restrict__ rank_ties,
+               uint32_t* __restrict__ chunk_ties, EmitArgs em, int64_t c0, int64_t c1) {
+    __shared__ uint32_t s_hist[kWindow];
+    __shared__ unsigned long long s_part[kThreads];
+    __shared__ unsigned long long s_warp[9];
+    __shared__ int s_bin;
+    SelState* __restrict__ st = a.st;
+    if (st->miss) return;                            // same on every rank (identical state): the builder reruns the staged exact select
+    for (int b = threadIdx.x; b < kWindow; b += kThreads) s_hist[b] = 0;
+    __syncthreads();
+    {
+        const uint32_t n = st->cand_count, win_lo = st->win_lo;
+        const uint32_t stride = gridDim.x * kThreads;
+        for (uint32_t i0 = blockIdx.x * kThreads + threadIdx.x; i0 < n; i0 += 8 * stride) {
+            uint32_t kk[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) kk[u] = i0 + u * stride < n ? __ldg(a.cand_key + i0 + u * stride) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t d = kk[u] - win_lo;
+                if (i0 + u * stride < n && d < (uint32_t)kWindow) atomicAdd(&s_hist[d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kWindow; b += kThreads) {
+        const uint32_t v = s_hist[b];
+        if (v) atomicAdd(a.hist + b, (unsigned long long)v);
+    }
+    grid_barrier();
+    if (blockIdx.x == 0) sharded_gather_pick(a, comm, seq_gather, rank_ties, s_warp, &s_bin);
+    grid_barrier();
+    if (st->miss) return;                            // uniform after the barrier
+    if (a.mode == B200P_MODE_EXACT_K && st->need_ties) {
+        tie_count_body(a.chunk_n, a.key_tab, a.old_mask, st, a.cand_key, a.cand_pos, chunk_ties, c0, c1, a.vec_ok);
+        grid_barrier();
+        if (blockIdx.x == 0) tie_scan_body(st, chunk_ties, c0, c1, 0ull, rank_ties, comm.rank, s_part);
+        grid_barrier();
+    }
+    if (st->prov_ok) emit_patch_body(em.chunk_n, em.key_tab, em.old_mask, st, em.cand_key, em.cand_pos, em.prov, em.mode, em.n_chunks,
+                                     patch_vals_from_state(st, em.mode));
+    else emit_full_body(em, c0, c1);
+    grid_barrier();                                  // every bit of the own slice is final
+    comm_push_mask_words(comm, c0 * kWordsPerChunk, c1 * kWordsPerChunk);
+    grid_barrier();                                  // every CTA's remote stores are issued and fenced
+    if (blockIdx.x == 0) comm_signal_and_wait(comm, CH_MASK, seq_mask);
+}
+
 static unsigned int* ticket_ptr(b200p_plan* p);
 static int coop_ctas(b200p_plan* p) {
     if (p->coop_ctas_per_sm == 0) {
@@ -1627,6 +1704,24 @@ extern "C" int b200p_sharded_mask_build(b200p_plan* p, b200p_comm* c, int key_so
         a.comm_seq = ++c->seq[CH_HIST];
         k_select_bracket<<<p->grid_for(nc > 1 ? (nc + 1) / 2 : 1, 4), kThreads, 0, st>>>(a, cd);
         B200P_LAUNCH_CHECK("k_select_bracket");
+    }
+    // B + T + E + P in one cooperative launch when the whole tail is wanted
+    const int tail_bits = B200P_SHARD_FINISH | B200P_SHARD_TIES | B200P_SHARD_EMIT | B200P_SHARD_PUSH;
+    if ((stages & tail_bits) == tail_bits && !getenv("B200P_SHARD_SPLIT_TAIL")) {
+        rc = coop_ctas(p); if (rc) return rc;
+        if (p->coop_ctas_per_sm > 0) {
+            EmitArgs em;
+            fill_patch_emit_args(p, em, key_source, mode, d_old_mask, d_mask, d_mask);
+            int grid = p->num_sms;
+            if (p->coop_grid_limit > 0 && grid > p->coop_grid_limit) grid = p->coop_grid_limit;
+            uint32_t sg = ++c->seq[CH_GATHER], sm = ++c->seq[CH_MASK];
+            CommDev cdv = cd;
+            unsigned long long* rt = p->d_rank_ties; uint32_t* ties = p->d_chunk_ties; int64_t cb = chunk_begin, ce = chunk_end;
+            void* args[] = {(void*)&a, (void*)&cdv, (void*)&sg, (void*)&sm, (void*)&rt, (void*)&ties, (void*)&em, (void*)&cb, (void*)&ce};
+            B200P_CUDA(cudaLaunchCooperativeKernel((const void*)k_sharded_tail, dim3(grid), dim3(kThreads), args, 0, st));
+            p->prov_armed = false; p->prov_target = nullptr;
+            return B200P_OK;
+        }
     }
     // B
     if (stages & B200P_SHARD_FINISH) {

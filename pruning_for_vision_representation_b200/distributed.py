@@ -275,6 +275,13 @@ class PeerShardedBuilder:
         self._PtrTable = PtrTable
         self._last = None
 
+    @classmethod
+    def from_process_group(cls, plan, group=None, score_cap=0):
+        """One process per GPU: comm windows opened through CUDA IPC, and the staged exact select over NCCL
+        (ShardedMaskBuilder) as the fallback `check()` runs when the sampled bracket missed (small or degenerate key sets)."""
+        comm = PeerComm.from_process_group(plan, group, score_cap)
+        return cls(plan, comm, fallback=ShardedMaskBuilder(plan, group))
+
     # ---- magnitude (replicated weights: nothing but histograms, 4 KB of counts and mask words crosses the ranks) -------
     def magnitude_build(self, k, old_mask=None):
         p = self.plan

@@ -65,6 +65,11 @@ class ParamPlan:
         check(self.lib.b200p_plan_set_option(self.handle, _lib.OPT_SELECT_IMPL, value), "plan_set_option")
         return self
 
+    def coop_grid_limit(self, n_ctas):
+        """Cap the grid of this plan's cooperative launches (plans that share one device and wait on each other)."""
+        check(self.lib.b200p_plan_set_option(self.handle, _lib.OPT_COOP_GRID, int(n_ctas)), "plan_set_option")
+        return self
+
     def reuse_sample(self, on=True):
         """Selects over unchanged keys (a sparsity sweep over fixed weights) reuse the first one's sample histogram."""
         check(self.lib.b200p_plan_set_option(self.handle, _lib.OPT_REUSE_SAMPLE, 1 if on else 0), "plan_set_option")

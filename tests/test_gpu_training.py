@@ -165,9 +165,30 @@ def _ref_groups(model, wd, norm_wd, bias_wd):
     return set_weight_decay(model, wd, norm_weight_decay=norm_wd, custom_keys_weight_decay=[("bias", bias_wd)])
 
 
-class _RefEMA(torch.optim.swa_utils.AveragedModel):
-    def __init__(self, model, decay, device):                        # utils.py:159-170
-        super().__init__(model, device, lambda avg, p, n: decay * avg + (1 - decay) * p, use_buffers=True)
+class _RefEMA:
+    """utils.py:159-170 (AveragedModel, `decay * avg + (1 - decay) * param`, use_buffers=True) restated over the tensors of
+    a torch-pruned model: AveragedModel itself deep-copies the model, which torch refuses for a module whose `weight` is
+    the non-leaf `weight_mask * weight_orig` that prune.custom_from_mask installs."""
+
+    def __init__(self, model, decay, device):
+        self.decay = decay
+        self.items = list(model.named_parameters()) + list(model.named_buffers())
+        self.avg = [t.detach().clone() for _, t in self.items]
+        self.n_averaged = torch.tensor(0, dtype=torch.long, device=device)
+
+    @torch.no_grad()
+    def update_parameters(self, model):
+        for a, (_, t) in zip(self.avg, self.items):
+            if int(self.n_averaged) == 0:
+                a.copy_(t.detach())                                   # AveragedModel.update_parameters, n_averaged == 0
+            else:
+                a.copy_((self.decay * a + (1 - self.decay) * t.detach()).to(a.dtype))
+        self.n_averaged += 1
+
+    def state_dict(self):
+        sd = {"n_averaged": self.n_averaged}
+        sd.update({"module." + name: a for (name, _), a in zip(self.items, self.avg)})
+        return sd
 
 
 @pytest.mark.parametrize("use_scaler", [False, True])

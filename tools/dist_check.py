@@ -1,8 +1,11 @@
-"""Multi-GPU parity check (run under torchrun, NCCL): the sharded mask build of
-distributed.ShardedMaskBuilder against the single-GPU kernels on the same data, bit for bit.
+"""Multi-GPU parity of the peer-memory sharded build, run under torchrun:
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
-"""
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+
+Every rank: CUDA IPC windows, ResNet-50-sized set.  (1) magnitude rounds on replicated weights with planted ties,
+(2) SNIP with the mini-batches split over the ranks (score kernel writes into the owners' windows), (3) the staged NCCL
+fallback.  Each compared bit for bit with the single-GPU build of the same data on every rank.  Prints PASS / FAIL per
+item on rank 0, exit code 1 on any failure."""
 import os
 import sys
 
@@ -11,84 +14,89 @@ import torch
 import torch.distributed as dist
 
 from pruning_for_vision_representation_b200 import _lib as L
-from pruning_for_vision_representation_b200.distributed import ShardedMaskBuilder
+from pruning_for_vision_representation_b200.distributed import PeerShardedBuilder
 from pruning_for_vision_representation_b200.plan import ParamPlan
 from pruning_for_vision_representation_b200.shapes import prunable_numels
 
 
 def views(flat, numels):
-    out, o = [], 0
+    out, off = [], 0
     for n in numels:
-        out.append(flat[o:o + n]); o += n
+        out.append(flat[off:off + n]); off += n
     return out
 
 
 def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    numels = prunable_numels("resnet18") + [351, 2808, 670, 1]          # plus awkward partial chunks
+    numels = prunable_numels(sys.argv[1] if len(sys.argv) > 1 else "resnet50")
     n = sum(numels)
-    g = torch.Generator(device=dev).manual_seed(1)
+    ok_all = True
+
+    def report(name, ok):
+        nonlocal ok_all
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok_all = ok_all and bool(t.item())
+        if rank == 0:
+            print(f"{'PASS' if t.item() else 'FAIL'}  {name}", flush=True)
+
+    g = torch.Generator(device=dev).manual_seed(1)               # same seed on every rank: replicated weights
     w = torch.randn(n, device=dev, generator=g) * 0.02
-    w[torch.randperm(n, device=dev, generator=g)[: n // 9]] = 0.0078125   # planted ties around the 10-20 % quantile
-    per_rank = 2
-    grads = [torch.randn(n, device=dev, generator=torch.Generator(device=dev).manual_seed(300 + b)) * 1e-3
-             for b in range(world * per_rank)]
-    plan = ParamPlan(numels, dev)
-    s = torch.empty(n, device=dev)
-    plan.bind(L.SLOT_W, views(w, numels)).bind(L.SLOT_SCORE, views(s, numels))
-    builder = ShardedMaskBuilder(plan)
-    ok = True
-    for sparsity in (0.9, 0.5, 1.0, 0.0):
-        k = int(n * sparsity)
-        # --- sharded
-        for i, b in enumerate(range(rank * per_rank, (rank + 1) * per_rank)):
-            plan.bind(L.SLOT_G, views(grads[b], numels)); plan.score_accumulate(i > 0)
-        mask_d = plan.new_mask()
-        builder.snip_select_emit(s, k, mask_d)
-        thr_d = plan.result()["threshold"]
-        # --- single GPU, same summation tree: per-rank partials, then rank-order sum
-        parts = torch.empty(world, n, device=dev)
-        for r in range(world):
-            plan.bind(L.SLOT_SCORE, views(parts[r], numels))
-            for i, b in enumerate(range(r * per_rank, (r + 1) * per_rank)):
-                plan.bind(L.SLOT_G, views(grads[b], numels)); plan.score_accumulate(i > 0)
-        plan.sum_parts(s, parts.view(-1), world, n, n)
-        plan.bind(L.SLOT_SCORE, views(s, numels))
-        mask_s = plan.new_mask()
-        if k >= n:
-            plan.select_begin(0, L.MODE_SNIP_STRICT); plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask_s, force=3, forced_threshold=float("inf"))
-        elif k <= 0:
-            plan.select_begin(0, L.MODE_SNIP_STRICT); plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask_s, force=3, forced_threshold=-1.0)
-        else:
-            plan.select_kth(L.KEY_SCORE, k, L.MODE_SNIP_STRICT); plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask_s)
-        thr_s = plan.result()["threshold"]
-        same = torch.equal(mask_d, mask_s) and (not (0 < k < n) or thr_d == thr_s)
-        ok &= same
-        if rank == 0:
-            print(f"snip sparsity={sparsity}: thr {thr_d} vs {thr_s}, kept {int(plan.count_zeros(mask_d, use_weights=False)[1])}, identical={same}", flush=True)
-    # --- magnitude, iterative, ties
-    old_d = old_s = None
+    w[::9] = 0.0135; w[4::13] = -0.0135                           # a tied set near the median of |w|
+    plan, ref = ParamPlan(numels, dev), ParamPlan(numels, dev)
+    plan.bind(L.SLOT_W, views(w, numels)); ref.bind(L.SLOT_W, views(w, numels))
+    b = PeerShardedBuilder.from_process_group(plan, score_cap=(plan.n_chunks + world - 1) // world * L.CHUNK)
+    old_s = old_r = None
     n_alive = n
-    for amount in (0.15, 0.2, 0.5):
+    for rnd, amount in enumerate((0.5, 0.2, 0.2)):
         k = round(amount * n_alive)
-        new_d = plan.new_mask(); builder.magnitude_select_emit(k, old_d, new_d); rd = plan.result()
-        new_s = plan.new_mask(); plan.select_kth(L.KEY_ABS_W, k, L.MODE_EXACT_K, old_s); plan.emit_masks(L.KEY_ABS_W, L.MODE_EXACT_K, new_s, old_s); rs = plan.result()
-        same = torch.equal(new_d, new_s) and rd["quota"] == rs["quota"] and rd["n_equal"] == rs["n_equal"]
-        ok &= same
-        if rank == 0:
-            print(f"magnitude amount={amount}: k={k} n_equal={rd['n_equal']} quota={rd['quota']} identical={same}", flush=True)
-        old_d, old_s, n_alive = new_d, new_s, n_alive - k
-    # every rank holds the same mask
-    ref = old_d.clone(); dist.broadcast(ref, 0)
-    ok &= torch.equal(ref, old_d)
-    t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        print("DIST_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", flush=True)
+        m_ref = ref.new_mask()
+        ref.mask_build(L.KEY_ABS_W, k, L.MODE_EXACT_K, m_ref, old_r)
+        r_ref = ref.result()
+        b.magnitude_build(k, old_s)
+        res = b.check()
+        report(f"magnitude round {rnd} (k={k}, n_equal={r_ref['n_equal']}, quota={r_ref['quota']}, miss={res['miss']})",
+               torch.equal(b.mask, m_ref) and res["threshold"] == r_ref["threshold"] and res["quota"] == r_ref["quota"])
+        old_r, old_s, n_alive = m_ref, b.mask.clone(), n_alive - k
+    # SNIP: 8 mini-batches split over the ranks
+    if 8 % world == 0:
+        per = 8 // world
+        mk = lambda bidx: torch.randn(n, device=dev, generator=torch.Generator(device=dev).manual_seed(300 + bidx)) * 1e-3
+        mine = [mk(bi) for bi in range(rank * per, (rank + 1) * per)]
+        score = torch.zeros(n, device=dev)
+        local_tab = plan.pointer_table(L.SLOT_SCORE, views(score, numels))
+        gt = [plan.pointer_table(L.SLOT_G, views(x, numels)) for x in mine]
+        k = int(n * 0.9)
+        b.snip_build(gt, k, score, local_tab)
+        res = b.check()
+        total, part = torch.empty(n, device=dev), torch.empty(n, device=dev)
+        for r in range(world):
+            gr = [mk(bi) for bi in range(r * per, (r + 1) * per)]
+            ref.bind(L.SLOT_SCORE, views(part if r else total, numels))
+            ref.score_accumulate_multi([ref.pointer_table(L.SLOT_G, views(x, numels)) for x in gr])
+            if r:
+                total.add_(part)
+        ref.bind(L.SLOT_SCORE, views(total, numels))
+        m_ref = ref.new_mask()
+        ref.mask_build(L.KEY_SCORE, k, L.MODE_SNIP_STRICT, m_ref)
+        r_ref = ref.result()
+        report(f"SNIP scores of the own slice (rank-order sum of {world} parts)", torch.equal(score[b.f0:b.f1], total[b.f0:b.f1]))
+        report(f"SNIP mask over {world} GPUs (thr={res['threshold']!r}, kept={res['n_kept']}, miss={res['miss']})",
+               torch.equal(b.mask, m_ref) and res["threshold"] == r_ref["threshold"] and res["n_kept"] == r_ref["n_kept"])
+    # the staged NCCL fallback on the same data
+    k = round(0.37 * n)
+    m_ref = ref.new_mask()
+    ref.bind(L.SLOT_W, views(w, numels))
+    ref.mask_build(L.KEY_ABS_W, k, L.MODE_EXACT_K, m_ref)
+    m = plan.new_mask()
+    b.fallback.magnitude_select_emit(k, None, m)
+    report("staged exact select over NCCL (fallback path)", torch.equal(m, m_ref) and plan.result()["threshold"] == ref.result()["threshold"])
+    dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if int(t.item()) == 1 else 1)
+    sys.exit(0 if ok_all else 1)
 
 
 if __name__ == "__main__":

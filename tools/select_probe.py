@@ -40,3 +40,28 @@ for impl in ("sampled", "exact"):
     print(f"{model} {impl}: select_score {t1:.1f} us (passes {r1['passes_full']}, cand {r1['collected']}) emit_snip {t2:.1f} | "
           f"select_absw {t3:.1f} (passes {r3['passes_full']}) emit_mag {t4:.1f} | round2 select {t5:.1f} (passes {r5['passes_full']}) | "
           f"magnitude build {t6:.1f} us = {N / t6 / 1e3:.1f} Gparams/s | snip select+emit {t7:.1f} us", flush=True)
+
+# the sharded sequence on ONE rank (world = 1: every in-kernel collective degenerates to a local copy): its fixed cost against
+# mask_build on the same data, stage by stage
+from pruning_for_vision_representation_b200.distributed import PeerComm, PeerShardedBuilder
+plan.set_select_impl("sampled")
+comm = PeerComm(plan, 0, 1)
+b = PeerShardedBuilder(plan, comm)
+tb = timed(lambda: b.magnitude_build(N // 2))
+print(f"{model} sharded sequence, world 1: magnitude build {tb:.1f} us ({b.check()})", flush=True)
+names = ["sample", "sweep", "finish", "ties", "emit", "push"]
+for bit, name in enumerate(names):
+    # run the earlier stages untimed, then time this one
+    def upto():
+        for j in range(bit):
+            b._build(L.KEY_ABS_W, None, N // 2, L.MODE_EXACT_K, stages=1 << j)
+    ts = []
+    for _ in range(reps):
+        junk.fill_(1); upto()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record(); b._build(L.KEY_ABS_W, None, N // 2, L.MODE_EXACT_K, stages=1 << bit); b_.record(); torch.cuda.synchronize()
+        ts.append(a_.elapsed_time(b_) * 1e3)
+        for j in range(bit + 1, 6):
+            b._build(L.KEY_ABS_W, None, N // 2, L.MODE_EXACT_K, stages=1 << j)
+        torch.cuda.synchronize()
+    print(f"   stage {name}: {sorted(ts)[len(ts) // 2]:.1f} us", flush=True)
