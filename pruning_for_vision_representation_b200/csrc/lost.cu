@@ -728,7 +728,7 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     // following images; only the last images' finish is exposed.  The Gram kernel never waits on the finish kernel, so
     // the pair cannot deadlock; without room on the SMs the finish CTAs simply start when Gram CTAs retire.
     int rc = lost_gram_run(gp, 0, gp.n_tiles2, nullptr, d_degree, st); if (rc) return rc;
-    const bool beside = fin_smem <= 30 * 1024;
+    const bool beside = fin_smem <= 30 * 1024 && lost_conv_warps() == 4;      // only the 4-converter-warp Gram leaves room for a finish CTA
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_images); cfg.blockDim = dim3(beside ? 256 : kFinThreads); cfg.dynamicSmemBytes = fin_smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];

@@ -45,6 +45,7 @@ struct LostGramPlan {
 int lost_gram_prepare(LostGramPlan* gp, const float* d_feats, long long row_stride, int d, const LostImageDev* d_meta,
                       const std::vector<LostImageDev>& meta, long long total_patches, int n_max, void* ws, size_t ws_bytes,
                       int vec_ok, cudaStream_t st, int mode, bool count_only);
+int lost_conv_warps();
 int lost_gram_run(const LostGramPlan& gp, int t_begin, int t_end, float* A_base, int* d_degree, cudaStream_t st);
 
 }  // namespace b200p

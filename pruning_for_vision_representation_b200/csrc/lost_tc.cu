@@ -908,6 +908,17 @@ int lost_gram_prepare(LostGramPlan* gp, const float* d_feats, long long row_stri
     return make_map(tm_lo, lo, total_patches, d_pad, d_pad);
 }
 
+// Converter warps of the count-only direct kernel.  8 (default): two per scheduler halve the time from "raw tile landed" to
+// "lo tile ready" — ncu: 414 us / 256 images, tensor pipe 84 %, against 439 us / 74 % with 4.  With 8 the kernel holds
+// 576 threads x 80 registers, and a CTA of the finish kernel no longer fits beside it (the register file is split four
+// ways between the schedulers); with 4 a 256-thread finish CTA does fit and runs under the Gram of the following
+// images, but that co-run costs the Gram kernel ~25 us and leaves a ~75 us tail: 0.522 ms per call against ~0.50 ms for
+// 8 warps + finish afterwards.  B200P_LOST_CONV_WARPS=4 selects the co-resident variant.
+int lost_conv_warps() {
+    static const int cw = [] { const char* e = getenv("B200P_LOST_CONV_WARPS"); return (e && atoi(e) == 4) ? 4 : 8; }();
+    return cw;
+}
+
 // Gram + degrees of the 256x256 tiles [t_begin, t_end) of the table (pair modes; images own consecutive tiles, so a
 // range of images is a range of tiles).  A_base == nullptr: count-only.  The single-CTA cross-check kernel always runs
 // the whole batch.
@@ -918,6 +929,8 @@ int lost_gram_run(const LostGramPlan& gp, int t_begin, int t_end, float* A_base,
     if (!attr_set) {
         B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
         B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_COUNT_BYTES));
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<true, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_COUNT_BYTES));
+        B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<true, false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
         B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc2<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_COUNT_BYTES));
         B200P_CUDA(cudaFuncSetAttribute(k_lost_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
@@ -939,7 +952,10 @@ int lost_gram_run(const LostGramPlan& gp, int t_begin, int t_end, float* A_base,
     const Tile2* tab = gp.tab + (size_t)t_begin * gp.nseg;
     if (gp.mode == LOST_TC_PAIR_DIRECT) {
         if (A_base) k_lost_gram_tc2<true, true, 4><<<grid2, t2_threads(true, 4), T2_SMEM_BYTES, st>>>(tm_hi, tm_hi, tab, nt, A_base, d_degree, 0.0f, gp.d_pad, nullptr, gp.nseg);
-        else        k_lost_gram_tc2<true, false, 4><<<grid2, t2_threads(true, 4), T2_SMEM_COUNT_BYTES, st>>>(tm_hi, tm_hi, tab, nt, nullptr, d_degree, 0.0f, gp.d_pad, gp.d_done, 1);
+        else if (lost_conv_warps() == 4)
+            k_lost_gram_tc2<true, false, 4><<<grid2, t2_threads(true, 4), T2_SMEM_COUNT_BYTES, st>>>(tm_hi, tm_hi, tab, nt, nullptr, d_degree, 0.0f, gp.d_pad, gp.d_done, 1);
+        else
+            k_lost_gram_tc2<true, false, 8><<<grid2, t2_threads(true, 8), T2_SMEM_COUNT_BYTES, st>>>(tm_hi, tm_hi, tab, nt, nullptr, d_degree, 0.0f, gp.d_pad, gp.d_done, 1);
         B200P_LAUNCH_CHECK("k_lost_gram_tc2<direct>");
     } else {
         if (A_base) k_lost_gram_tc2<false, true, 4><<<grid2, T2_THREADS, T2_SMEM_BYTES, st>>>(tm_hi, tm_lo, tab, nt, A_base, d_degree, 0.0f, gp.d_pad, nullptr, gp.nseg);

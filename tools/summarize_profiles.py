@@ -41,8 +41,8 @@ WANT = [("us", "gpu__time_duration.sum"), ("dram read MB", "dram__bytes_read.sum
 agg = launches(os.path.join(OUT, "launches_final.csv"))
 total = sum(t for _, t in agg.values())
 with open(os.path.join(PROF, f"{tag}_launch_summary.md"), "w") as o:
-    o.write(f"# ncu launch list, {tag}\n\nCommand: `ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 200 --csv python bench.py "
-            "--steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-clocks` (run after the same command exited 0 without ncu).\n"
+    o.write(f"# ncu launch list, {tag}\n\nCommand: `ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 300 --csv python bench.py "
+            "--steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-clocks --no-extra` (run after the same command exited 0 without ncu).\n"
             "Per-launch times are cold-cache and serialised: compare shares, not absolutes.\n\n| kernel | launches | total us | mean us | share |\n|---|---|---|---|---|\n")
     for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         o.write(f"| `{name}` | {c} | {t:.1f} | {t / c:.1f} | {100 * t / total:.1f} % |\n")
@@ -53,12 +53,12 @@ with open(os.path.join(PROF, f"{tag}_launch_summary.md"), "w") as o:
 os.replace(os.path.join(OUT, "launches_final.csv"), os.path.join(PROF, f"{tag}_launches_bench.csv")) if "--move" in sys.argv else None
 
 rows = []
-for rep in ("prof_final_snip.ncu-rep", "prof_final_lost.ncu-rep"):
+for rep in ("prof_final_snip.ncu-rep", "prof_final_lost.ncu-rep", "prof_final_select.ncu-rep"):
     p = os.path.join(OUT, rep)
     if os.path.exists(p):
         rows += raw(p)
 with open(os.path.join(PROF, f"{tag}_ncu_full_summary.md"), "w") as o:
-    o.write(f"# ncu --set full capture, {tag}\n\nCommands (each after the same command exited 0 without ncu): see `tools/gpu_profile_round.sh`.\n\n")
+    o.write(f"# ncu --set full capture, {tag}\n\nCommands (each after the same command exited 0 without ncu): see `tools/gpu_profile_round_r2.sh`.\n\n")
     o.write("| kernel | " + " | ".join(n for n, _ in WANT) + " |\n|---|" + "---|" * len(WANT) + "\n")
     for d in rows:
         name = d["Kernel Name"].split("(")[0].replace("void ", "")
@@ -74,11 +74,11 @@ sw = [d for d in rows if "k_snip_score_sweep" in d["Kernel Name"]]
 if sw:
     tr["k_snip_score_sweep_traffic_bytes"] = sum(unit_bytes(d, "dram__bytes_read.sum") + unit_bytes(d, "dram__bytes_write.sum") for d in sw) / len(sw)
     tr["k_snip_score_sweep_source"] = f"profiles/{tag}_ncu_full_summary.md (ncu --set full, dram read + write, mean of {len(sw)} launches)"
-lg = [d for d in rows if "k_lost_gram_tc2" in d["Kernel Name"]]
+lg = [d for d in rows if "k_lost_gram_tc2<1, 0" in d["Kernel Name"] or "k_lost_gram_tc2<true, false" in d["Kernel Name"]] or [d for d in rows if "k_lost_gram_tc2" in d["Kernel Name"]]
 if lg:
     tr["k_lost_gram_tc2_traffic_bytes"] = sum(unit_bytes(d, "dram__bytes_read.sum") + unit_bytes(d, "dram__bytes_write.sum") for d in lg) / len(lg)
     tr["k_lost_gram_tc2_tensor_pipe_active_pct"] = sum(f(d, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed") for d in lg) / len(lg)
-    tr["k_lost_gram_tc2_source"] = f"profiles/{tag}_ncu_full_summary.md (tools/lost_probe.py 256 2 3, 256 images of 900 x 384 keys per launch)"
+    tr["k_lost_gram_tc2_source"] = f"profiles/{tag}_ncu_full_summary.md (tools/lost_probe2.py 256 2, count-only launches, 256 images of 900 x 384 keys per launch)"
 json.dump(tr, open(traffic_path, "w"), indent=1)
 print(open(os.path.join(PROF, f"{tag}_ncu_full_summary.md")).read())
 print(json.dumps(tr, indent=1))
