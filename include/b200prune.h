@@ -337,6 +337,9 @@ int  b200p_lost_batched(int device, const float* d_feats, int64_t row_stride, in
 /* Measurement aid: globaltimer (ns) trace of the last count-only b200p_lost_batched call: [Gram first CTA start, Gram last
  * CTA end, first finish CTA past its wait, last finish CTA end].  Synchronises the device. */
 int  b200p_lost_last_trace(uint64_t* h_out4);
+/* Measurement aid: globaltimer (ns) stamps written by the last CTA of the most recent sample and sweep kernels on the
+ * current device (select.cu: g_sel_stamps), then cleared.  Synchronises the device. */
+int  b200p_select_last_trace(uint64_t* h_out16);
 
 /* patch_scoring(M, threshold) of object_discovery.py:72-90 on a given n x n matrix (row stride lda):
  * d_degree[i] = #{j : (i != j ? max(A_ij, 0) : 0) > threshold}; d_sel = patches by ascending degree,

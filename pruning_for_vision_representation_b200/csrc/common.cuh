@@ -18,6 +18,9 @@ constexpr int kWordsPerChunk = B200P_WORDS_PER_CHUNK;
 constexpr int kHistBins = 4096;                  // 12-bit digits
 constexpr int kHistExtra = 8;                    // scalar counters behind the bins: [0] alive keys (sample pass), [1] keys below the bracket,
                                                  // [2] NaN keys cleared from the provisional mask, [7] ticket of the mask push
+constexpr int kHistStride = kHistBins + kHistExtra;   // u64 words of one copy of the global histogram
+constexpr int kHistReplicas = 4;                 // copies of the global histogram the sample / sweep kernels spread their flush over (select.cu: flush_hist);
+                                                 // the scalar counters and every other user live in copy 0
 constexpr uint32_t kNanKey = 0x7FFFFFFFu;        // every NaN sorts last (torch.sort semantics)
 
 // digit layout of the 31-bit key: pass 0 -> bits 30..19, pass 1 -> bits 18..7, pass 2 -> bits 6..0

@@ -80,7 +80,7 @@ extern "C" int b200p_plan_create(int device, int n_segments, const int64_t* h_nu
     TRY(cudaMemcpy(p->d_chunk_n, chunk_n.data(), chunks * sizeof(int32_t), cudaMemcpyHostToDevice));
     TRY(cudaMemcpy(p->d_chunk_elem0, chunk_elem0.data(), chunks * sizeof(int64_t), cudaMemcpyHostToDevice));
     for (int s = 0; s < B200P_NUM_SLOTS; ++s) TRY(cudaMalloc(&p->d_tab_own[s], chunks * sizeof(void*)));
-    TRY(cudaMalloc(&p->d_hist, (kHistBins + kHistExtra) * sizeof(unsigned long long)));
+    TRY(cudaMalloc(&p->d_hist, (size_t)kHistReplicas * kHistStride * sizeof(unsigned long long)));
     TRY(cudaMalloc(&p->d_state, sizeof(SelState)));
     TRY(cudaMalloc(&p->d_cand_key, cand_capacity * sizeof(uint32_t)));
     TRY(cudaMalloc(&p->d_cand_pos, cand_capacity * sizeof(uint32_t)));
@@ -89,7 +89,7 @@ extern "C" int b200p_plan_create(int device, int n_segments, const int64_t* h_nu
     TRY(cudaMalloc(&p->d_rank_ties, 8 * sizeof(unsigned long long)));
     TRY(cudaMalloc(&p->d_sample_cache, (kHistBins + kHistExtra) * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_rank_ties, 0, 8 * sizeof(unsigned long long)));
-    TRY(cudaMemset(p->d_hist, 0, (kHistBins + kHistExtra) * sizeof(unsigned long long)));
+    TRY(cudaMemset(p->d_hist, 0, (size_t)kHistReplicas * kHistStride * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_state, 0, sizeof(SelState)));
     TRY(cudaMemset(p->d_chunk_ties, 0, chunks * sizeof(uint32_t)));
     TRY(cudaDeviceSynchronize());

@@ -459,6 +459,98 @@ __device__ __forceinline__ void pass_body(const PassArgs& a, uint32_t* __restric
     }
 }
 
+// measurement aid (b200p_select_last_trace): globaltimer stamps of the last sample / sweep kernel's last CTA
+//   [0..3] sample: tail entered, bins staged, bracket chosen, done   [4..7] sweep: the same   [8] sweep: first CTA start
+//   [9] sweep: last CTA's flush issued
+__device__ unsigned long long g_sel_stamps[16];
+__device__ __forceinline__ unsigned long long sel_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void sel_stamp(int i) { if (threadIdx.x == 0) g_sel_stamps[i] = sel_globaltimer(); }
+
+// ---- histogram flush and last-CTA read-back ----------------------------------------------------
+// Measured (tools/probes/hist_flush_probe.cu, hist_tail_probe.cu): 592 CTAs that each add their ~600-800 non-zero bins
+// of a shared histogram into ONE global histogram at the end of a balanced sweep need 8-16 us for those atomics to
+// drain (same-line serialisation in L2 plus ~100 atomics/ns chip-wide), and the last CTA then spent 2.5 us reading 16
+// bins per thread at a 128-byte stride (one sector per lane) and 1.5 us clearing them the same way.  ncu showed it as
+// sm__cycles_active.max - .min = 25 k cycles on every sample / sweep kernel.
+//  * tried: clusters of 8 / 2 CTAs that sum their shared histograms through DSMEM before the global atomics (8x / 2x
+//    fewer).  The flush got cheaper, the streaming body of the sweep 29 % / 8 % slower: a kernel that contains cluster
+//    instructions is placed contiguous-modular instead of round-robin over the GPCs (even with cluster size 1: +7 %), and
+//    clusters >= 4 strand SMs on the 16/18/20-SM GPCs.  Removed again;
+//  * the global histogram has kHistReplicas copies, CTA i adds into copy i % kHistReplicas (4x fewer atomics per line);
+//  * the last CTA reads the bins back coalesced into shared memory, summing and re-zeroing the copies on the way, and
+//    clears copy 0 coalesced.
+// track: the kernel does not know beforehand which bins it touches (the sample histogram): the range of non-zero bins is
+// kept in two scalar counters behind the bins (both grow from zero: kHistBins - lowest bin, highest bin + 1)
+constexpr int kExtraRangeLo = 3, kExtraRangeHi = 4;
+__device__ __forceinline__ void flush_hist(const uint32_t* s_hist, unsigned long long* __restrict__ hist, bool track) {
+    unsigned long long* dst = hist + (size_t)(blockIdx.x & (kHistReplicas - 1)) * kHistStride;
+    int lo = kHistBins, hi = 0;
+    for (int b = threadIdx.x; b < kHistBins; b += kThreads) {
+        const uint32_t v = s_hist[b];
+        if (v) { atomicAdd(dst + b, (unsigned long long)v); lo = min(lo, b); hi = b + 1; }
+    }
+    if (track) {
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if ((threadIdx.x & 31) == 0 && hi > 0) {
+            atomicMax(hist + kHistBins + kExtraRangeLo, (unsigned long long)(kHistBins - lo));
+            atomicMax(hist + kHistBins + kExtraRangeHi, (unsigned long long)hi);
+        }
+    }
+}
+
+// The last CTA works alone, and what it reads is usually not in L2 any more (the sweep streamed hundreds of MB through it
+// since the previous build zeroed these lines): reading all kHistReplicas x 32 KB took 7-16 us at the memory-level
+// parallelism of one SM (b200p_select_last_trace).  Only the bins [lo, hi) that can be non-zero are read, summed, zeroed.
+// Loads first, stores afterwards: a store into `hist` between the loads orders every later load behind it.
+__device__ __forceinline__ void zero_hist_copies(unsigned long long* __restrict__ hist, int lo, int hi) {
+#pragma unroll
+    for (int r = 1; r < kHistReplicas; ++r)
+#pragma unroll
+        for (int i = 0; i < kBinsPerThread; ++i) {
+            const int b = i * kThreads + threadIdx.x;
+            if (b >= lo && b < hi) hist[(size_t)r * kHistStride + b] = 0ull;
+        }
+}
+// sum of the copies -> copy 0 (the sharded select all-reduces copy 0 in place), copies 1.. zeroed again
+__device__ __forceinline__ void collapse_hist(unsigned long long* __restrict__ hist, int lo, int hi) {
+    unsigned long long sum[kBinsPerThread];
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) {
+        const int b = i * kThreads + threadIdx.x;
+        const bool in = b >= lo && b < hi;
+        unsigned long long v = 0;
+#pragma unroll
+        for (int r = 0; r < kHistReplicas; ++r) v += in ? __ldcg(hist + (size_t)r * kHistStride + b) : 0ull;
+        sum[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) {
+        const int b = i * kThreads + threadIdx.x;
+        if (b >= lo && b < hi) hist[b] = sum[i];
+    }
+    zero_hist_copies(hist, lo, hi);
+    __threadfence();
+    __syncthreads();
+}
+// bins [lo, hi) of copy 0 (copies: of all copies, summed; copies 1.. zeroed again) -> s_stage, zero elsewhere
+// (u32: a bin never holds 2^32 keys, positions are 32-bit)
+__device__ __forceinline__ void stage_hist(unsigned long long* __restrict__ hist, uint32_t* s_stage, bool copies, int lo, int hi) {
+    uint32_t sum[kBinsPerThread];
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) {
+        const int b = i * kThreads + threadIdx.x;
+        const bool in = b >= lo && b < hi;
+        unsigned long long v = in ? __ldcg(hist + b) : 0ull;
+#pragma unroll
+        for (int r = 1; r < kHistReplicas; ++r) v += (in && copies) ? __ldcg(hist + (size_t)r * kHistStride + b) : 0ull;
+        sum[i] = (uint32_t)v;
+    }
+#pragma unroll
+    for (int i = 0; i < kBinsPerThread; ++i) s_stage[i * kThreads + threadIdx.x] = sum[i];
+    if (copies) zero_hist_copies(hist, lo, hi);
+    __syncthreads();
+}
+
 // true in exactly one CTA: the last one to arrive (all other CTAs' global writes are visible to it)
 __device__ __forceinline__ bool last_cta_arrives(unsigned int* ticket) {
     __shared__ unsigned int s_ticket;
@@ -494,7 +586,7 @@ __global__ void k_select_scan(int pass, unsigned long long* hist, SelState* st, 
 
 __global__ void k_select_init(SelState* st, unsigned long long* hist, unsigned int* ticket,
                               unsigned long long k, uint32_t mode, uint32_t allow_collect) {
-    for (int b = threadIdx.x; b < kHistBins + kHistExtra; b += blockDim.x) hist[b] = 0ull;
+    for (int b = threadIdx.x; b < kHistReplicas * kHistStride; b += blockDim.x) hist[b] = 0ull;
     if (threadIdx.x == 0) {
         init_state(st, k, mode, allow_collect);
         *ticket = 0u;
@@ -700,35 +792,33 @@ __device__ __forceinline__ unsigned long long block_prefix16(const unsigned long
     return s_warp[tid >> 5] + (incl - sum);
 }
 
-__device__ __forceinline__ void clear_hist(unsigned long long* hist) {
+__device__ __forceinline__ void clear_hist(unsigned long long* hist, int lo = 0, int hi = kHistBins) {
 #pragma unroll
-    for (int i = 0; i < kBinsPerThread; ++i) hist[threadIdx.x * kBinsPerThread + i] = 0ull;
+    for (int i = 0; i < kBinsPerThread; ++i) {                                                  // coalesced
+        const int b = i * kThreads + threadIdx.x;
+        if (b >= lo && b < hi) hist[b] = 0ull;
+    }
     if (threadIdx.x < kHistExtra) hist[kHistBins + threadIdx.x] = 0ull;
 }
 
-// last CTA of a sample kernel: bracket of 1..8 buckets around the sample rank of k
-__device__ __forceinline__ void sample_tail(const SampleArgs& a, unsigned long long* s_warp /*[9]*/, uint32_t* s_bkt /*[2]*/) {
+// bracket of 1..8 buckets around the sample rank of k, from the sample histogram staged in s_stage
+__device__ __forceinline__ void sample_pick(const SampleArgs& a, const uint32_t* s_stage, unsigned long long n_alive,
+                                            unsigned long long* s_warp /*[9]*/, uint32_t* s_bkt /*[2]*/) {
     SelState* st = a.st;
     unsigned long long local[kBinsPerThread];
 #pragma unroll
-    for (int i = 0; i < kBinsPerThread; ++i) local[i] = ((volatile unsigned long long*)a.hist)[threadIdx.x * kBinsPerThread + i];
-    if (a.cache) {
-        // keep the (global) sample histogram: another select over the SAME keys (a sparsity sweep) derives its bracket from
-        // it without sampling again (B200P_OPT_REUSE_SAMPLE)
-#pragma unroll
-        for (int i = 0; i < kBinsPerThread; ++i) a.cache[threadIdx.x * kBinsPerThread + i] = local[i];
-        if (threadIdx.x < kHistExtra) a.cache[kHistBins + threadIdx.x] = ((volatile unsigned long long*)a.hist)[kHistBins + threadIdx.x];
-    }
+    for (int i = 0; i < kBinsPerThread; ++i) local[i] = s_stage[threadIdx.x * kBinsPerThread + i];
     unsigned long long S;
     unsigned long long running = block_prefix16(local, s_warp, S);
-    const unsigned long long n_alive = a.old_mask ? ((volatile unsigned long long*)a.hist)[kHistBins + 0] : a.n_total;
     if (threadIdx.x == 0) { s_bkt[0] = 0xFFFFFFFFu; s_bkt[1] = 0xFFFFFFFFu; init_state(st, a.k, a.mode, 1u); st->n_valid = n_alive; }
     __syncthreads();
     bool usable = S >= 1024 && a.k >= 1 && a.k <= n_alive;
     unsigned long long r_lo = 1, r_hi = 1;
     if (usable) {
         // sample rank of the population's k-th key: hypergeometric, sigma <= sqrt(S)/2; margin = 8 sigma_max + 2
-        const unsigned long long r = (unsigned long long)(((__uint128_t)a.k * S + n_alive - 1) / n_alive);
+        // (k <= N < 2^32 and S < 2^31 in every real case: the product fits 64 bits; the 128-bit division is ~1 us of one thread)
+        const unsigned long long r = ((a.k >> 32) | (S >> 31)) ? (unsigned long long)(((__uint128_t)a.k * S + n_alive - 1) / n_alive)
+                                                              : (a.k * S + n_alive - 1) / n_alive;
         // 8 sigma of the hypergeometric rank, sigma^2 <= S q (1-q), plus slack for tiny tails
         const double q = (double)a.k / (double)n_alive;
         const unsigned long long m = (unsigned long long)ceil((double)a.sigmas * sqrt((double)S * q * (1.0 - q))) + 16ull;
@@ -752,7 +842,38 @@ __device__ __forceinline__ void sample_tail(const SampleArgs& a, unsigned long l
         st->lo_bucket = lo; st->hi_bucket = hi;
         *a.ticket = 0u;
     }
-    clear_hist(a.hist);
+}
+
+// last CTA of a sample kernel.  comm: parameter-sharded select: the sample histograms (and alive counts) of all ranks are
+// summed first, then every rank derives the same bracket.  Returns false if the collective failed.
+__device__ __forceinline__ bool sample_tail(const SampleArgs& a, const CommDev* comm, unsigned long long* s_warp /*[9]*/, uint32_t* s_bkt /*[2]*/,
+                                            uint32_t* s_stage /*[kHistBins]*/) {
+    sel_stamp(0);
+    // scalar loads first: their latency hides behind the staging loads
+    const int lo = kHistBins - (int)((volatile unsigned long long*)a.hist)[kHistBins + kExtraRangeLo],
+              hi = (int)((volatile unsigned long long*)a.hist)[kHistBins + kExtraRangeHi];
+    bool comm_ok = true;
+    if (comm && a.comm_seq) {
+        collapse_hist(a.hist, lo, hi);
+        comm_ok = comm_allreduce_hist(*comm, a.comm_seq, a.hist);
+        stage_hist(a.hist, s_stage, false, 0, kHistBins);
+    } else {
+        stage_hist(a.hist, s_stage, true, lo, hi);
+    }
+    const unsigned long long n_alive = a.old_mask ? ((volatile unsigned long long*)a.hist)[kHistBins + 0] : a.n_total;
+    sel_stamp(1);
+    if (a.cache) {
+        // keep the (global) sample histogram: another select over the SAME keys (a sparsity sweep) derives its bracket from
+        // it without sampling again (B200P_OPT_REUSE_SAMPLE)
+#pragma unroll
+        for (int i = 0; i < kBinsPerThread; ++i) a.cache[i * kThreads + threadIdx.x] = s_stage[i * kThreads + threadIdx.x];
+        if (threadIdx.x == 0) a.cache[kHistBins + 0] = n_alive;
+    }
+    sample_pick(a, s_stage, n_alive, s_warp, s_bkt);
+    sel_stamp(2);
+    if (comm && a.comm_seq) clear_hist(a.hist); else clear_hist(a.hist, lo, hi);
+    sel_stamp(3);
+    return comm_ok;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -816,42 +937,47 @@ k_select_sample(SampleArgs a, CommDev comm) {
         }
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < kHistBins; b += kThreads) {
-        const uint32_t v = s_hist[b];
-        if (v) atomicAdd(a.hist + b, (unsigned long long)v);
-    }
+    flush_hist(s_hist, a.hist, true);
     if (threadIdx.x == 0 && s_alive) atomicAdd(a.hist + kHistBins + 0, s_alive);
     if (!last_cta_arrives(a.ticket)) return;
-    // parameter-sharded select: sum the sample histograms (and alive counts) of all ranks right here, then every rank
-    // derives the same bracket
-    bool comm_ok = true;
-    if (a.comm_seq) comm_ok = comm_allreduce_hist(comm, a.comm_seq, a.hist);
-    sample_tail(a, s_warp, s_bkt);
+    const bool comm_ok = sample_tail(a, &comm, s_warp, s_bkt, s_hist);
     if (!comm_ok && threadIdx.x == 0) { a.st->sample_ok = 0u; a.st->miss = 1u; }
 }
 
 __global__ void __launch_bounds__(kThreads)
 k_sample_from_cache(SampleArgs a, const unsigned long long* __restrict__ cache) {
+    __shared__ uint32_t s_stage[kHistBins];
     __shared__ unsigned long long s_warp[9];
     __shared__ uint32_t s_bkt[2];
-    for (int b = threadIdx.x; b < kHistBins + kHistExtra; b += kThreads) a.hist[b] = cache[b];
-    __threadfence();
+    for (int b = threadIdx.x; b < kHistBins; b += kThreads) s_stage[b] = (uint32_t)cache[b];
+    const unsigned long long n_alive = a.old_mask ? cache[kHistBins + 0] : a.n_total;
     __syncthreads();
-    sample_tail(a, s_warp, s_bkt);
+    sample_pick(a, s_stage, n_alive, s_warp, s_bkt);
 }
 
 // last CTA of a bracket sweep: verify that rank k is inside the bracket, narrow to a 1024-key window
-__device__ __forceinline__ void bracket_tail(const PassArgs& a, uint32_t base, unsigned long long* s_warp /*[9]*/) {
+__device__ __forceinline__ bool bracket_tail(const PassArgs& a, const CommDev* comm, uint32_t base, uint32_t span, unsigned long long* s_warp /*[9]*/,
+                                             uint32_t* s_stage /*[kHistBins]*/) {
     SelState* __restrict__ st = a.st;
+    sel_stamp(4);
+    const int lo = 0, hi = (int)(span >> kFineShift);                 // the only fine bins a key inside the bracket can land in
+    bool comm_ok = true;
+    if (comm && a.comm_seq) {
+        collapse_hist(a.hist, lo, hi);
+        comm_ok = comm_allreduce_hist(*comm, a.comm_seq, a.hist);
+    }
+    // scalar loads first: their latency hides behind the staging loads
+    const unsigned long long n_below = ((volatile unsigned long long*)a.hist)[kHistBins + 1];
+    const unsigned long long n_nan = ((volatile unsigned long long*)a.hist)[kHistBins + 2];
+    const unsigned long long k = st->k;
+    stage_hist(a.hist, s_stage, !(comm && a.comm_seq), lo, hi);
+    sel_stamp(5);
     unsigned long long local[kBinsPerThread];
 #pragma unroll
-    for (int i = 0; i < kBinsPerThread; ++i) local[i] = ((volatile unsigned long long*)a.hist)[threadIdx.x * kBinsPerThread + i];
+    for (int i = 0; i < kBinsPerThread; ++i) local[i] = s_stage[threadIdx.x * kBinsPerThread + i];
     unsigned long long total_in;
     unsigned long long running = block_prefix16(local, s_warp, total_in);
-    const unsigned long long n_below = ((volatile unsigned long long*)a.hist)[kHistBins + 1];
-    const unsigned long long k = st->k;
-    if (threadIdx.x == 0) st->pad_[1] = (uint32_t)((volatile unsigned long long*)a.hist)[kHistBins + 2];     // NaN keys pruned by the provisional mask
-    __syncthreads();
+    if (threadIdx.x == 0) st->pad_[1] = (uint32_t)n_nan;              // NaN keys pruned by the provisional mask
     const bool inside = k > n_below && k <= n_below + total_in && total_in <= (unsigned long long)a.cand_capacity;
     if (!inside) {
         if (threadIdx.x == 0) { st->miss = 1u; st->collect = 0u; st->cand_count = 0u; st->prov_ok = 0u; }
@@ -872,7 +998,10 @@ __device__ __forceinline__ void bracket_tail(const PassArgs& a, uint32_t base, u
         }
     }
     if (threadIdx.x == 0) *a.ticket = 0u;
-    clear_hist(a.hist);
+    sel_stamp(6);
+    clear_hist(a.hist, lo, (comm && a.comm_seq) ? kHistBins : hi);
+    sel_stamp(7);
+    return comm_ok;
 }
 
 // ---- A: one sweep: count below the bracket, fine histogram + collect inside it -----------------
@@ -891,6 +1020,7 @@ k_select_bracket(PassArgs a, CommDev comm) {
     const uint32_t base = lo_b << 19, span = (hi_b - lo_b + 1) << 19;
     for (int b = threadIdx.x; b < kHistBins; b += kThreads) s_hist[b] = 0;
     if (threadIdx.x == 0) s_below = 0;
+    if (blockIdx.x == 0) sel_stamp(8);
     __syncthreads();
     // the state was initialised by the kernel before this one: the mode is uniform over the grid
     unsigned long long below = st->mode == B200P_MODE_SNIP_STRICT ? sweep_loop<true>(a, base, span, kFineShift, true, false, s_hist)
@@ -899,15 +1029,11 @@ k_select_bracket(PassArgs a, CommDev comm) {
     for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xFFFFFFFFu, below, o);
     if ((threadIdx.x & 31) == 0 && below) atomicAdd(&s_below, below);
     __syncthreads();
-    for (int b = threadIdx.x; b < kHistBins; b += kThreads) {
-        const uint32_t v = s_hist[b];
-        if (v) atomicAdd(a.hist + b, (unsigned long long)v);
-    }
+    flush_hist(s_hist, a.hist, false);
     if (threadIdx.x == 0 && s_below) atomicAdd(a.hist + kHistBins + 1, s_below);
+    if (threadIdx.x == 0) atomicMax(&g_sel_stamps[9], sel_globaltimer());
     if (!last_cta_arrives(a.ticket)) return;
-    bool comm_ok = true;
-    if (a.comm_seq) comm_ok = comm_allreduce_hist(comm, a.comm_seq, a.hist);
-    bracket_tail(a, base, s_warp);
+    const bool comm_ok = bracket_tail(a, &comm, base, span, s_warp, s_hist);
     if (!comm_ok && threadIdx.x == 0) { st->miss = 1u; st->collect = 0u; st->prov_ok = 0u; }
 }
 
@@ -1083,12 +1209,9 @@ k_snip_sample(SampleArgs a, ChunkTab w_tab, GradTabs g_tabs, ChunkTab s_tab) {
             if (q < cnt) atomicAdd(&s_hist[key_of(v[q]) >> 19], 1u);
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < kHistBins; b += kThreads) {
-        const uint32_t v = s_hist[b];
-        if (v) atomicAdd(a.hist + b, (unsigned long long)v);
-    }
+    flush_hist(s_hist, a.hist, true);
     if (!last_cta_arrives(a.ticket)) return;
-    sample_tail(a, s_warp, s_bkt);
+    sample_tail(a, nullptr, s_warp, s_bkt, s_hist);
 }
 
 template <bool ACC, int B>
@@ -1218,14 +1341,11 @@ k_snip_score_sweep(PassArgs a, ChunkTab w_tab, GradTabs g_tabs, int vec_all) {
     for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xFFFFFFFFu, below, o);
     if (lane == 0 && below) atomicAdd(&s_below, below);
     __syncthreads();
-    for (int b = tid; b < kHistBins; b += kThreads) {
-        const uint32_t v = s_hist[b];
-        if (v) atomicAdd(a.hist + b, (unsigned long long)v);
-    }
+    flush_hist(s_hist, a.hist, false);
     if (tid == 0 && s_below) atomicAdd(a.hist + kHistBins + 1, s_below);
     if (nan_cnt) atomicAdd(a.hist + kHistBins + 2, (unsigned long long)nan_cnt);
     if (!last_cta_arrives(a.ticket)) return;
-    bracket_tail(a, base, s_warp);
+    bracket_tail(a, nullptr, base, span, s_warp, s_hist);
 }
 
 // ---- B: finish (cooperative launch) ----------------------------------------------------------------
@@ -1443,6 +1563,13 @@ static unsigned int* ticket_ptr(b200p_plan* p) {
     return (unsigned int*)((char*)p->d_state + offsetof(SelState, pad_));
 }
 
+// plain launch returning the error (the sample / sweep kernels; a cluster launch lived here for a while, see flush_hist)
+template <typename K, typename... Args>
+static cudaError_t launch_clustered(K kern, int grid, cudaStream_t st, Args... args) {
+    kern<<<grid, kThreads, 0, st>>>(args...);
+    return cudaGetLastError();
+}
+
 }  // namespace b200p
 
 using namespace b200p;
@@ -1625,13 +1752,13 @@ static int select_kth_sampled(b200p_plan* p, int key_source, const uint32_t* d_o
         B200P_LAUNCH_CHECK("k_sample_from_cache");
     } else {
         sa.cache = sample_cache_arm(p, key_source, d_old_mask, 0, p->n_chunks);
-        k_select_sample<<<p->grid_for(sblocks, 1), kThreads, 0, st>>>(sa, CommDev());
+        B200P_CUDA(launch_clustered(k_select_sample, p->grid_for(sblocks, 1), st, sa, CommDev()));
         B200P_LAUNCH_CHECK("k_select_sample");
     }
     // A: bracket sweep
     PassArgs a;
     fill_pass_args(p, a, key_source, d_old_mask, 0, p->n_chunks, 1, 0, k, mode, 1, true);
-    k_select_bracket<<<p->grid_for((p->n_chunks + 1) / 2, 4), kThreads, 0, st>>>(a, CommDev());
+    B200P_CUDA(launch_clustered(k_select_bracket, p->grid_for((p->n_chunks + 1) / 2, 4), st, a, CommDev()));
     B200P_LAUNCH_CHECK("k_select_bracket");
     return launch_finish(p, a, key_source, mode, d_old_mask, st);
 }
@@ -1690,7 +1817,7 @@ extern "C" int b200p_sharded_mask_build(b200p_plan* p, b200p_comm* c, int key_so
     } else {
         sa.comm_seq = ++c->seq[CH_HIST];
         sa.cache = sample_cache_arm(p, key_source, d_old_mask, chunk_begin, chunk_end);
-        k_select_sample<<<p->grid_for(sblocks, 1), kThreads, 0, st>>>(sa, cd);
+        B200P_CUDA(launch_clustered(k_select_sample, p->grid_for(sblocks, 1), st, sa, cd));
         B200P_LAUNCH_CHECK("k_select_sample");
     }
     }
@@ -1702,7 +1829,7 @@ extern "C" int b200p_sharded_mask_build(b200p_plan* p, b200p_comm* c, int key_so
     fill_pass_args(p, a, key_source, d_old_mask, chunk_begin, chunk_end, 1, 0, k, mode, 1, true);
     if (stages & B200P_SHARD_SWEEP) {
         a.comm_seq = ++c->seq[CH_HIST];
-        k_select_bracket<<<p->grid_for(nc > 1 ? (nc + 1) / 2 : 1, 4), kThreads, 0, st>>>(a, cd);
+        B200P_CUDA(launch_clustered(k_select_bracket, p->grid_for(nc > 1 ? (nc + 1) / 2 : 1, 4), st, a, cd));
         B200P_LAUNCH_CHECK("k_select_bracket");
     }
     // B + T + E + P in one cooperative launch when the whole tail is wanted
@@ -1745,29 +1872,29 @@ extern "C" int b200p_sharded_mask_build(b200p_plan* p, b200p_comm* c, int key_so
 
 // ---- fused SNIP mask build ------------------------------------------------------------------------
 template <bool ACC>
-static void launch_snip_sample(int nb, int grid, cudaStream_t st, const SampleArgs& sa, ChunkTab w, const GradTabs& g, ChunkTab s) {
+static cudaError_t launch_snip_sample(int nb, int grid, cudaStream_t st, const SampleArgs& sa, ChunkTab w, const GradTabs& g, ChunkTab s) {
     switch (nb) {
-        case 1: k_snip_sample<ACC, 1><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
-        case 2: k_snip_sample<ACC, 2><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
-        case 3: k_snip_sample<ACC, 3><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
-        case 4: k_snip_sample<ACC, 4><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
-        case 5: k_snip_sample<ACC, 5><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
-        case 6: k_snip_sample<ACC, 6><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
-        case 7: k_snip_sample<ACC, 7><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
-        default: k_snip_sample<ACC, 8><<<grid, kThreads, 0, st>>>(sa, w, g, s); break;
+        case 1: return launch_clustered(k_snip_sample<ACC, 1>, grid, st, sa, w, g, s);
+        case 2: return launch_clustered(k_snip_sample<ACC, 2>, grid, st, sa, w, g, s);
+        case 3: return launch_clustered(k_snip_sample<ACC, 3>, grid, st, sa, w, g, s);
+        case 4: return launch_clustered(k_snip_sample<ACC, 4>, grid, st, sa, w, g, s);
+        case 5: return launch_clustered(k_snip_sample<ACC, 5>, grid, st, sa, w, g, s);
+        case 6: return launch_clustered(k_snip_sample<ACC, 6>, grid, st, sa, w, g, s);
+        case 7: return launch_clustered(k_snip_sample<ACC, 7>, grid, st, sa, w, g, s);
+        default: return launch_clustered(k_snip_sample<ACC, 8>, grid, st, sa, w, g, s);
     }
 }
 template <bool ACC>
-static void launch_snip_sweep(int nb, int grid, cudaStream_t st, const PassArgs& a, ChunkTab w, const GradTabs& g, int vec) {
+static cudaError_t launch_snip_sweep(int nb, int grid, cudaStream_t st, const PassArgs& a, ChunkTab w, const GradTabs& g, int vec) {
     switch (nb) {
-        case 1: k_snip_score_sweep<ACC, 1><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
-        case 2: k_snip_score_sweep<ACC, 2><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
-        case 3: k_snip_score_sweep<ACC, 3><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
-        case 4: k_snip_score_sweep<ACC, 4><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
-        case 5: k_snip_score_sweep<ACC, 5><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
-        case 6: k_snip_score_sweep<ACC, 6><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
-        case 7: k_snip_score_sweep<ACC, 7><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
-        default: k_snip_score_sweep<ACC, 8><<<grid, kThreads, 0, st>>>(a, w, g, vec); break;
+        case 1: return launch_clustered(k_snip_score_sweep<ACC, 1>, grid, st, a, w, g, vec);
+        case 2: return launch_clustered(k_snip_score_sweep<ACC, 2>, grid, st, a, w, g, vec);
+        case 3: return launch_clustered(k_snip_score_sweep<ACC, 3>, grid, st, a, w, g, vec);
+        case 4: return launch_clustered(k_snip_score_sweep<ACC, 4>, grid, st, a, w, g, vec);
+        case 5: return launch_clustered(k_snip_score_sweep<ACC, 5>, grid, st, a, w, g, vec);
+        case 6: return launch_clustered(k_snip_score_sweep<ACC, 6>, grid, st, a, w, g, vec);
+        case 7: return launch_clustered(k_snip_score_sweep<ACC, 7>, grid, st, a, w, g, vec);
+        default: return launch_clustered(k_snip_score_sweep<ACC, 8>, grid, st, a, w, g, vec);
     }
 }
 
@@ -1805,15 +1932,15 @@ extern "C" int b200p_snip_score_select(b200p_plan* p, const b200p_ptrtable* cons
     sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.c_begin = 0; sa.comm_seq = 0u; sa.cache = nullptr; sa.vec_ok = vec ? 1 : 0;
     sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)B200P_MODE_SNIP_STRICT; sa.sigmas = 12u;
     const int64_t sblocks = (p->n_chunks * kSnipGranulesPerChunk + kThreads - 1) / kThreads;      // one granule per thread
-    if (acc) launch_snip_sample<true>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE));
-    else     launch_snip_sample<false>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE));
+    if (acc) B200P_CUDA(launch_snip_sample<true>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE)));
+    else     B200P_CUDA(launch_snip_sample<false>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE)));
     B200P_LAUNCH_CHECK("k_snip_sample");
     // A': score + sweep
     PassArgs a;
     fill_pass_args(p, a, B200P_KEY_SCORE, nullptr, 0, p->n_chunks, 1, 0, k, B200P_MODE_SNIP_STRICT, 1, true);
     { int rc = plan_time_mark(p, 0, st); if (rc) return rc; }
-    if (acc) launch_snip_sweep<true>(nb, p->grid_for(p->n_chunks, 4), st, a, p->tab(B200P_SLOT_W), g, vec ? 1 : 0);
-    else     launch_snip_sweep<false>(nb, p->grid_for(p->n_chunks, 4), st, a, p->tab(B200P_SLOT_W), g, vec ? 1 : 0);
+    if (acc) B200P_CUDA(launch_snip_sweep<true>(nb, p->grid_for(p->n_chunks, 4), st, a, p->tab(B200P_SLOT_W), g, vec ? 1 : 0));
+    else     B200P_CUDA(launch_snip_sweep<false>(nb, p->grid_for(p->n_chunks, 4), st, a, p->tab(B200P_SLOT_W), g, vec ? 1 : 0));
     B200P_LAUNCH_CHECK("k_snip_score_sweep");
     { int rc = plan_time_mark(p, 1, st); if (rc) return rc; }
     return launch_finish(p, a, B200P_KEY_SCORE, B200P_MODE_SNIP_STRICT, nullptr, st);
@@ -1831,6 +1958,15 @@ extern "C" int b200p_snip_mask_build(b200p_plan* p, const b200p_ptrtable* const*
         return B200P_OK;
     }
     return b200p_emit_masks(p, B200P_KEY_SCORE, B200P_MODE_SNIP_STRICT, 0, 0.f, nullptr, d_new_mask, 0, 0, -1, stream);
+}
+
+extern "C" int b200p_select_last_trace(uint64_t* h_out16) {
+    B200P_REQUIRE(h_out16 != nullptr, B200P_EINVAL, "select_last_trace: null output");
+    B200P_CUDA(cudaDeviceSynchronize());
+    B200P_CUDA(cudaMemcpyFromSymbol(h_out16, g_sel_stamps, sizeof(unsigned long long) * 16));
+    unsigned long long zero[16] = {0};
+    B200P_CUDA(cudaMemcpyToSymbol(g_sel_stamps, zero, sizeof(zero)));
+    return B200P_OK;
 }
 
 extern "C" int b200p_select_result(b200p_plan* p, b200p_select_result_t* h_out, void* stream) {
