@@ -21,6 +21,7 @@ constexpr int kHistExtra = 8;                    // scalar counters behind the b
 constexpr int kHistStride = kHistBins + kHistExtra;   // u64 words of one copy of the global histogram
 constexpr int kHistReplicas = 4;                 // copies of the global histogram the sample / sweep kernels spread their flush over (select.cu: flush_hist);
                                                  // the scalar counters and every other user live in copy 0
+constexpr int kTieListCap = 512;                 // short list of tied candidates behind the per-chunk tie table (select.cu: tie_list_gather)
 constexpr uint32_t kNanKey = 0x7FFFFFFFu;        // every NaN sorts last (torch.sort semantics)
 
 // digit layout of the 31-bit key: pass 0 -> bits 30..19, pass 1 -> bits 18..7, pass 2 -> bits 6..0

@@ -84,14 +84,14 @@ extern "C" int b200p_plan_create(int device, int n_segments, const int64_t* h_nu
     TRY(cudaMalloc(&p->d_state, sizeof(SelState)));
     TRY(cudaMalloc(&p->d_cand_key, cand_capacity * sizeof(uint32_t)));
     TRY(cudaMalloc(&p->d_cand_pos, cand_capacity * sizeof(uint32_t)));
-    TRY(cudaMalloc(&p->d_chunk_ties, chunks * sizeof(uint32_t)));
+    TRY(cudaMalloc(&p->d_chunk_ties, (chunks + kTieListCap + 8) * sizeof(uint32_t)));      // table + [count, positions...] of the tie list
     TRY(cudaMalloc(&p->d_prov, chunks * kWordsPerChunk * sizeof(uint32_t)));
     TRY(cudaMalloc(&p->d_rank_ties, 8 * sizeof(unsigned long long)));
     TRY(cudaMalloc(&p->d_sample_cache, (kHistBins + kHistExtra) * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_rank_ties, 0, 8 * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_hist, 0, (size_t)kHistReplicas * kHistStride * sizeof(unsigned long long)));
     TRY(cudaMemset(p->d_state, 0, sizeof(SelState)));
-    TRY(cudaMemset(p->d_chunk_ties, 0, chunks * sizeof(uint32_t)));
+    TRY(cudaMemset(p->d_chunk_ties, 0, (chunks + kTieListCap + 8) * sizeof(uint32_t)));
     TRY(cudaDeviceSynchronize());
 #undef TRY
     *out = p;

@@ -693,6 +693,55 @@ __device__ void tie_scan_body(SelState* __restrict__ st, uint32_t* __restrict__ 
     __syncthreads();
     for (int64_t c = lo; c < hi; ++c) chunk_ties[c] = 0;
 }
+// Few ties, all of them in the candidate buffer (the normal case: a handful of weights share the threshold's bit pattern):
+// their positions go to a short list instead of the per-chunk table, and one CTA ranks the list.  The table walk above
+// is one CTA striding through n_chunks counters three times — 75 us for ViT-L/16's 55 k chunks, 30 us for ResNet-152
+// (tools/select_probe.py), for 6 tied keys.  tie_list[0] = count (left zero), positions from tie_list[1].
+__device__ __forceinline__ void tie_list_gather(uint32_t thr, uint32_t cand_count, const uint32_t* __restrict__ cand_key,
+                                                const uint32_t* __restrict__ cand_pos, uint32_t* __restrict__ tie_list) {
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < cand_count; i += gridDim.x * kThreads)
+        if (__ldg(cand_key + i) == thr) {
+            const uint32_t slot = atomicAdd(tie_list, 1u);
+            if (slot < (uint32_t)kTieListCap) tie_list[1 + slot] = __ldg(cand_pos + i);
+        }
+}
+// One CTA, after a grid-wide barrier: same outcome as tie_scan_body (lowest flat index first; ties owned by the n_before
+// lower ranks count against the quota first).
+__device__ void tie_list_pick(SelState* __restrict__ st, uint32_t* __restrict__ tie_list, int64_t c_begin, int64_t c_end,
+                              unsigned long long tie_offset, const unsigned long long* __restrict__ d_counts, int n_before,
+                              uint32_t* s_pos /* [kTieListCap] */) {
+    __shared__ int s_sel;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (d_counts) for (int r = 0; r < n_before; ++r) tie_offset += d_counts[r];
+    uint32_t m = __ldcg(tie_list);
+    if (m > (uint32_t)kTieListCap) m = kTieListCap;
+    for (uint32_t i = tid; i < m; i += nt) s_pos[i] = __ldcg(tie_list + 1 + i);
+    if (tid == 0) s_sel = -1;
+    __syncthreads();
+    const long long target = (long long)st->quota - (long long)tie_offset;
+    if (target <= 0) {
+        if (tid == 0) { st->tie_chunk = c_begin; st->tie_resid = 0; st->tie_seen = 0; }
+    } else if ((unsigned long long)target > (unsigned long long)m) {
+        if (tid == 0) { st->tie_chunk = c_end; st->tie_resid = 0; st->tie_seen = m; }           // every local tie pruned
+    } else {
+        for (uint32_t i = tid; i < m; i += nt) {
+            const uint32_t pi = s_pos[i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < m; ++j) rank += s_pos[j] < pi ? 1u : 0u;                    // positions are distinct
+            if ((long long)rank == target - 1) s_sel = (int)i;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t chunk = s_pos[s_sel] >> 12;
+            uint32_t seen = 0;
+            for (uint32_t j = 0; j < m; ++j) seen += (s_pos[j] >> 12) < chunk ? 1u : 0u;
+            st->tie_chunk = (long long)chunk; st->tie_seen = seen; st->tie_resid = (uint32_t)(target - (long long)seen);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) tie_list[0] = 0u;
+}
+
 __global__ void __launch_bounds__(1024)
 k_tie_scan(SelState* __restrict__ st, uint32_t* __restrict__ chunk_ties, int64_t c_begin, int64_t c_end,
            unsigned long long tie_offset, const unsigned long long* __restrict__ d_counts, int n_before) {
@@ -754,6 +803,7 @@ struct SampleArgs {
     uint32_t sigmas;         // bracket half-width in standard deviations of the sample rank (8; 12 for clustered granules)
     uint32_t comm_seq;       // != 0: parameter-sharded select, the last CTA all-reduces the histogram over the ranks first
     unsigned long long* cache;   // nullable: where the last CTA keeps a copy of the final sample histogram
+    int slot_shift;          // k_select_sample: 2^slot_shift float4 sampled per chunk (sample_slot_shift)
 };
 
 // bracket for a new rank k from the cached sample histogram of the same keys: one CTA, no sampling, no collective
@@ -898,15 +948,16 @@ k_select_sample(SampleArgs a, CommDev comm) {
     // sample slot s = (chunk, i), i < 16: elements 256*i + 4*phase .. +3 (one float4 out of 64), the
     // phase varying with chunk and i.  Four slots per thread are in flight at once: table loads,
     // then data loads, then the shared-memory atomics.
-    const int64_t slots = a.n_chunks * kSampleSlotsPerChunk;
+    const int64_t slots = a.n_chunks << a.slot_shift;
+    const int slot_mask = (1 << a.slot_shift) - 1, slot_step = kSampleSlotsPerChunk >> a.slot_shift;
     for (int64_t s0 = gtid; s0 < slots; s0 += 4 * nthreads) {
         int n[4], e0[4]; const float* src[4]; int64_t cc[4]; bool on[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t sl = s0 + u * nthreads;
             on[u] = sl < slots;
-            cc[u] = a.c_begin + (on[u] ? (sl >> 4) : 0);
-            const int i = (int)(sl & 15);
+            cc[u] = a.c_begin + (on[u] ? (sl >> a.slot_shift) : 0);
+            const int i = (int)(sl & slot_mask) * slot_step + (int)(cc[u] & (slot_step - 1));      // thinned samples rotate through the 16 positions
             e0[u] = 256 * i + 4 * (int)((cc[u] + 5 * i) & 63);
             n[u] = __ldg(a.chunk_n + cc[u]);
             src[u] = chunk_ptr<const float>(a.key_tab, cc[u]);
@@ -1448,7 +1499,12 @@ k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks,
             st->need_ties = need_ties;
             st->tie_chunk = -1; st->tie_resid = 0; st->tie_seen = 0;
         }
-        if (need_ties) {
+        if (need_ties && v <= (unsigned long long)kTieListCap) {
+            tie_list_gather(key, n, a.cand_key, a.cand_pos, chunk_ties + n_chunks);
+            grid_barrier();
+            if (blockIdx.x == 0) tie_list_pick(st, chunk_ties + n_chunks, 0, n_chunks, 0ull, nullptr, 0, reinterpret_cast<uint32_t*>(s_part));
+            if (EMIT) grid_barrier();
+        } else if (need_ties) {
             tie_count_vals(a.chunk_n, a.key_tab, a.old_mask, 1u, key, 1u, n, a.cand_key, a.cand_pos, chunk_ties, 0, n_chunks, a.vec_ok);
             grid_barrier();
             if (blockIdx.x == 0) tie_scan_body(st, chunk_ties, 0, n_chunks, 0ull, nullptr, 0, s_part);
@@ -1510,9 +1566,15 @@ k_sharded_tail(PassArgs a, CommDev comm, uint32_t seq_gather, uint32_t seq_mask,
     grid_barrier();
     if (st->miss) return;                            // uniform after the barrier
     if (a.mode == B200P_MODE_EXACT_K && st->need_ties) {
-        tie_count_body(a.chunk_n, a.key_tab, a.old_mask, st, a.cand_key, a.cand_pos, chunk_ties, c0, c1, a.vec_ok);
-        grid_barrier();
-        if (blockIdx.x == 0) tie_scan_body(st, chunk_ties, c0, c1, 0ull, rank_ties, comm.rank, s_part);
+        if (st->collect && st->n_equal <= (unsigned long long)kTieListCap) {        // uniform: the state is final since the barrier
+            tie_list_gather(st->thr_key, st->cand_count, a.cand_key, a.cand_pos, chunk_ties + em.n_chunks);
+            grid_barrier();
+            if (blockIdx.x == 0) tie_list_pick(st, chunk_ties + em.n_chunks, c0, c1, 0ull, rank_ties, comm.rank, reinterpret_cast<uint32_t*>(s_part));
+        } else {
+            tie_count_body(a.chunk_n, a.key_tab, a.old_mask, st, a.cand_key, a.cand_pos, chunk_ties, c0, c1, a.vec_ok);
+            grid_barrier();
+            if (blockIdx.x == 0) tie_scan_body(st, chunk_ties, c0, c1, 0ull, rank_ties, comm.rank, s_part);
+        }
         grid_barrier();
     }
     if (st->prov_ok) emit_patch_body(em.chunk_n, em.key_tab, em.old_mask, st, em.cand_key, em.cand_pos, em.prov, em.mode, em.n_chunks,
@@ -1577,6 +1639,14 @@ using namespace b200p;
 // B200P_OPT_REUSE_SAMPLE: the caller promises that the keys (and the old mask) are unchanged since the select that
 // filled the cache — true inside a sparsity sweep over fixed weights (BASELINE config 5); re-binding the key slot or
 // any other key source / old mask / chunk range drops the cache.
+// The bracket is a whole number of 12-bit buckets (each holds a few % of the keys near the mode), so its width stops
+// shrinking once the sample is a few hundred thousand float4: the 16 per chunk that suit ResNet-50 (100 k float4) are
+// 892 k random 32-byte sector reads on ViT-L/16 — 56 us, a quarter of the sweep.  Large sets are sampled more thinly.
+static int sample_slot_shift(int64_t n_chunks) {
+    int shift = 4;                                                     // kSampleSlotsPerChunk = 16
+    while (shift > 1 && (n_chunks << shift) > 480 * 1024) --shift;
+    return shift;
+}
 static bool sample_cache_hit(b200p_plan* p, int key_source, const uint32_t* d_old_mask, int64_t c0, int64_t c1) {
     return p->reuse_sample && p->sample_cache_valid && p->sample_cache_key == key_source && p->sample_cache_mask == d_old_mask &&
            p->sample_cache_c0 == c0 && p->sample_cache_c1 == c1 && p->sample_cache_tab == (const void*)p->d_tab[key_source == B200P_KEY_ABS_W ? B200P_SLOT_W : B200P_SLOT_SCORE];
@@ -1746,7 +1816,8 @@ static int select_kth_sampled(b200p_plan* p, int key_source, const uint32_t* d_o
     sa.chunk_n = p->d_chunk_n; sa.key_tab = p->tab(slot); sa.old_mask = d_old_mask; sa.hist = p->d_hist; sa.st = p->d_state;
     sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.c_begin = 0; sa.comm_seq = 0u; sa.cache = nullptr; sa.vec_ok = p->vec_ok[slot] ? 1 : 0;
     sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)mode; sa.sigmas = 8u;
-    const int64_t sblocks = (p->n_chunks * kSampleSlotsPerChunk + 4 * kThreads - 1) / (4 * kThreads);
+    sa.slot_shift = sample_slot_shift(p->n_chunks);
+    const int64_t sblocks = ((p->n_chunks << sa.slot_shift) + 4 * kThreads - 1) / (4 * kThreads);
     if (sample_cache_hit(p, key_source, d_old_mask, 0, p->n_chunks)) {
         k_sample_from_cache<<<1, kThreads, 0, st>>>(sa, p->d_sample_cache);
         B200P_LAUNCH_CHECK("k_sample_from_cache");
@@ -1810,7 +1881,8 @@ extern "C" int b200p_sharded_mask_build(b200p_plan* p, b200p_comm* c, int key_so
     sa.ticket = ticket_ptr(p); sa.n_chunks = nc; sa.c_begin = chunk_begin; sa.vec_ok = p->vec_ok[slot] ? 1 : 0;
     sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)mode; sa.sigmas = 8u;
     sa.comm_seq = 0u; sa.cache = nullptr;
-    const int64_t sblocks = (nc * kSampleSlotsPerChunk + 4 * kThreads - 1) / (4 * kThreads);
+    sa.slot_shift = sample_slot_shift(p->n_chunks);                   // from the whole set: every rank samples at the same density
+    const int64_t sblocks = ((nc << sa.slot_shift) + 4 * kThreads - 1) / (4 * kThreads);
     if (sample_cache_hit(p, key_source, d_old_mask, chunk_begin, chunk_end)) {      // the cache holds the all-reduced histogram: same decision on every rank
         k_sample_from_cache<<<1, kThreads, 0, st>>>(sa, p->d_sample_cache);
         B200P_LAUNCH_CHECK("k_sample_from_cache");
@@ -1930,7 +2002,7 @@ extern "C" int b200p_snip_score_select(b200p_plan* p, const b200p_ptrtable* cons
     SampleArgs sa;
     sa.chunk_n = p->d_chunk_n; sa.key_tab = p->tab(B200P_SLOT_SCORE); sa.old_mask = nullptr; sa.hist = p->d_hist; sa.st = p->d_state;
     sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.c_begin = 0; sa.comm_seq = 0u; sa.cache = nullptr; sa.vec_ok = vec ? 1 : 0;
-    sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)B200P_MODE_SNIP_STRICT; sa.sigmas = 12u;
+    sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)B200P_MODE_SNIP_STRICT; sa.sigmas = 12u; sa.slot_shift = 4;
     const int64_t sblocks = (p->n_chunks * kSnipGranulesPerChunk + kThreads - 1) / kThreads;      // one granule per thread
     if (acc) B200P_CUDA(launch_snip_sample<true>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE)));
     else     B200P_CUDA(launch_snip_sample<false>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE)));
