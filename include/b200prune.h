@@ -337,6 +337,9 @@ int  b200p_lost_batched(int device, const float* d_feats, int64_t row_stride, in
 /* Measurement aid: globaltimer (ns) trace of the last count-only b200p_lost_batched call: [Gram first CTA start, Gram last
  * CTA end, first finish CTA past its wait, last finish CTA end].  Synchronises the device. */
 int  b200p_lost_last_trace(uint64_t* h_out4);
+/* Measurement aid: globaltimer (ns) stamps of one finish CTA at its phase boundaries (lost.cu: g_fin_stamps) from the
+ * last call; `image` selects the image the NEXT call traces.  Synchronises the device. */
+int  b200p_lost_finish_trace(int image, uint64_t* h_out16);
 /* Measurement aid: globaltimer (ns) stamps written by the last CTA of the most recent sample and sweep kernels on the
  * current device (select.cu: g_sel_stamps), then cleared.  Synchronises the device. */
 int  b200p_select_last_trace(uint64_t* h_out16);

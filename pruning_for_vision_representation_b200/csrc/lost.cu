@@ -260,6 +260,15 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ a, const flo
     return acc;
 }
 
+// measurement aid (b200p_lost_finish_trace): globaltimer stamps of the finish CTA of image `g_fin_trace_img` at its phase
+// boundaries: [0] ready (degrees complete) [1] degrees + histogram + seed [2] cut-off [3] potentials listed
+// [4] similars known [5] similars ordered [6] sum of the similar keys [7] M [8] component + box
+__device__ unsigned long long g_fin_stamps[16];
+__device__ int g_fin_trace_img = 0;
+__device__ __forceinline__ void fin_stamp(int i) {
+    if (threadIdx.x == 0 && (int)blockIdx.x == g_fin_trace_img) g_fin_stamps[i] = lost_globaltimer();      // block index within its launch
+}
+
 // FROM_KEYS = false: A was materialised (the caller asked for it): similars and M are read from it, rows added in the
 //                    reference's order (object_discovery.py:61-62).
 // FROM_KEYS = true:  count-only Gram, no A anywhere.  A[seed, p] = k_seed . k_p for the <= k_patches potentials and
@@ -271,7 +280,7 @@ __global__ void __launch_bounds__(kFinThreads)
 k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A_base, const int* __restrict__ degree_base,
               int k_patches, int n_max, int* __restrict__ seed_out, float* __restrict__ box_out, int* __restrict__ status_out,
               float* __restrict__ M_out, const float* __restrict__ feats, long long row_stride, int d, int vec_ok,
-              const unsigned int* __restrict__ done) {
+              const unsigned int* __restrict__ done, int img_base) {
     // dynamic shared memory, sized for the largest image of the batch (n_max):
     //   int deg[n_max] | int hist[n_max+1 (+pad)] | int list[1024] | int sorted[1024] | u8 flag[n_max] | u8 comp[n_max]
     //   | FROM_KEYS: float vsum[d_pad4] | float kseed[d_pad4] | u8 simflag[1024]
@@ -291,7 +300,7 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
     __shared__ int s_red[4];
     __shared__ int s_cut[3];
 
-    const int img = (int)blockIdx.x;
+    const int img = img_base + (int)blockIdx.x;
     const LostImageDev im = meta[img];
     const int n = im.n, tid = threadIdx.x, nt = blockDim.x;
     if (FROM_KEYS && done) {
@@ -317,6 +326,7 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
             return;
         }
     }
+    fin_stamp(0);
     const float* __restrict__ A = FROM_KEYS ? nullptr : A_base + im.a_off;
     const float* __restrict__ F = FROM_KEYS ? feats + im.feat_off : nullptr;
     const int* __restrict__ deg = degree_base + im.out_off;
@@ -341,6 +351,7 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
     const int seed = (int)(s_best & 0xFFFFFFFFu);
     if (FROM_KEYS) for (int c = tid; c < d; c += nt) s_kseed[c] = F[(long long)seed * row_stride + c];
 
+    fin_stamp(1);
     // cut-off degree D: the k lowest-degree patches are those with degree < D plus the first
     // `quota` (by index) of degree == D
     const int kk = min(k_patches, n);
@@ -361,6 +372,7 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
     }
     __syncthreads();
     const int D = s_cut[0], quota = s_cut[1];
+    fin_stamp(2);
     if (FROM_KEYS) {
         // potentials in index order -> s_sorted (scratch), then one warp per potential: A[seed, p] = k_seed . k_p
         int carry = 0, n_pot = 0;
@@ -378,6 +390,7 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
             __syncthreads();
         }
         n_pot = min(n_pot, 1024);
+        fin_stamp(3);
         if (vec_ok && (d & 3) == 0) {
             // four potentials per warp and round: their loads are in flight together (the phase is pure latency)
             const int d4 = d >> 2;
@@ -447,6 +460,7 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
     }
     __syncthreads();
     const int n_sim = s_cut[2];
+    fin_stamp(4);
     // order of the similars = order of `potentials` (ascending degree, index): rank by counting
     for (int i = tid; i < n_sim; i += nt) {
         const int p = s_list[i], dp = s_deg[p];
@@ -458,6 +472,7 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
         s_sorted[rank] = p;
     }
     __syncthreads();
+    fin_stamp(5);
     if (FROM_KEYS) {
         // v = sum of the similar keys, added in that order; then M_j = k_j . v, one warp per row, four rows in flight
         for (int c = tid; c < d_pad4; c += nt) {
@@ -476,6 +491,7 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
             s_vsum[c] = v;
         }
         __syncthreads();
+        fin_stamp(6);
         if (vec_ok && (d & 3) == 0) {
             // one warp per group of ROWS rows: ROWS x (d / 128) independent 16-byte loads in flight per lane before the first FMA
             constexpr int ROWS = 4;        // 62 registers: a 256-thread CTA of this kernel fits beside a Gram CTA (6 rows: 86 registers, it no longer does)
@@ -531,8 +547,10 @@ k_lost_finish(const LostImageDev* __restrict__ meta, const float* __restrict__ A
         }
     }
     __syncthreads();
+    fin_stamp(7);
     int box[4];
     const bool ok = component_box(s_flag, s_comp, n, im.dim0, im.dim1, seed, s_red, box);
+    fin_stamp(8);
     if (tid == 0) {
         seed_out[img] = seed;
         status_out[img] = ok ? 0 : 1;
@@ -608,6 +626,14 @@ extern "C" int b200p_lost_last_trace(uint64_t* h_out4) {
     B200P_REQUIRE(h_out4 != nullptr && g_last_done != nullptr, B200P_ESTATE, "lost_last_trace: no count-only call yet");
     B200P_CUDA(cudaDeviceSynchronize());
     B200P_CUDA(cudaMemcpy(h_out4, reinterpret_cast<const unsigned long long*>(g_last_done) - 4, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return B200P_OK;
+}
+
+extern "C" int b200p_lost_finish_trace(int image, uint64_t* h_out16) {
+    B200P_REQUIRE(h_out16 != nullptr && image >= 0, B200P_EINVAL, "lost_finish_trace: bad argument");
+    B200P_CUDA(cudaDeviceSynchronize());
+    B200P_CUDA(cudaMemcpyFromSymbol(h_out16, g_fin_stamps, sizeof(unsigned long long) * 16));
+    B200P_CUDA(cudaMemcpyToSymbol(g_fin_trace_img, &image, sizeof(int)));      // image traced by the NEXT call
     return B200P_OK;
 }
 
@@ -717,31 +743,46 @@ extern "C" int b200p_lost_batched(int device, const float* d_feats, int64_t row_
     if (!count_only) {
         if (gram_impl != B200P_LOST_GRAM_FFMA) { int rc = lost_gram_run(gp, 0, gp.n_tiles2, A_base, d_degree, st); if (rc) return rc; }
         k_lost_finish<false><<<n_images, kFinThreads, fin_smem, st>>>(d_meta, A_base, d_degree, k_patches, n_max, d_seed, d_box, d_status, nullptr,
-                                                                      d_feats, (long long)row_stride, d, vec ? 1 : 0, nullptr);
+                                                                      d_feats, (long long)row_stride, d, vec ? 1 : 0, nullptr, 0);
         B200P_LAUNCH_CHECK("k_lost_finish");
         return B200P_OK;
     }
-    // Count-only: the finish kernel is launched as a programmatic dependent of the Gram kernel (which triggers right at
-    // its start, i.e. once all of its persistent CTAs are resident): finish CTAs slip onto the SMs beside the Gram CTAs
-    // (384 threads, ~22 KB of shared memory next to 193 KB) and CTA b waits on image b's completion counter, which the Gram
-    // epilogue releases per tile.  The finish of an image runs while its keys are still in L2 and under the Gram of the
-    // following images; only the last images' finish is exposed.  The Gram kernel never waits on the finish kernel, so
-    // the pair cannot deadlock; without room on the SMs the finish CTAs simply start when Gram CTAs retire.
+    // Count-only.  The finish kernel's cost is the mat-vec M = K v: it re-reads every key (355 MB per 256 images) and runs at
+    // DRAM speed when all images do it at once after the Gram kernel (58 of its 81 us per image, tools/lost_finish_trace.py:
+    // 6.1 TB/s); the other phases are latency.  It is launched as a programmatic dependent of the Gram kernel (which
+    // triggers at its start) and CTA b waits on image b's completion counter, which the Gram epilogue releases per tile:
+    // with 512-thread CTAs it cannot be co-resident with the 8-converter-warp Gram (registers), so its CTAs start as Gram
+    // CTAs retire — the launch latency is hidden, the ~0.1 ms of work is not.
+    // Tried (B200P_LOST_SPLIT_PCT / B200P_LOST_SMALL_THREADS keep the experiment): the first 25-100 % of the images in
+    // 128-192-thread CTAs that DO fit beside a Gram CTA (4-6 warps x 62 registers next to 18 x 80) and work in the shadow
+    // of the Gram of the following images, the rest in full-size CTAs afterwards.  Co-residency works (first finish CTA
+    // ready 22 us after the Gram starts), but a small CTA next to a Gram CTA that saturates the shared-memory pipe needs
+    // ~300 us per image and the Gram kernel loses 15-25 us: 0.501 ms at best (50 %, 192 threads) against 0.503 ms for the
+    // single launch, 0.56-0.73 ms for 40-100 % at 128 threads.
     int rc = lost_gram_run(gp, 0, gp.n_tiles2, nullptr, d_degree, st); if (rc) return rc;
-    const bool beside = fin_smem <= 30 * 1024 && lost_conv_warps() == 4;      // only the 4-converter-warp Gram leaves room for a finish CTA
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)n_images); cfg.blockDim = dim3(beside ? 256 : kFinThreads); cfg.dynamicSmemBytes = fin_smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    static const int fin_env = [] { const char* e = getenv("B200P_LOST_FINISH"); return e ? atoi(e) : 1; }();      // experiments: 0 skip, 2 no PDL
+    static const int fin_env = [] { const char* e = getenv("B200P_LOST_FINISH"); return e ? atoi(e) : 1; }();      // experiments: 0 skip, 2 one launch after the Gram kernel
+    static const int split_pct = [] { const char* e = getenv("B200P_LOST_SPLIT_PCT"); return e ? atoi(e) : 100; }();
+    static const int small_threads = [] { const char* e = getenv("B200P_LOST_SMALL_THREADS"); const int v = e ? atoi(e) : kFinThreads; return v >= 64 && v <= kFinThreads ? (v / 32) * 32 : kFinThreads; }();
     if (fin_env == 0) return B200P_OK;
-    if (fin_env == 2) { cfg.numAttrs = 0; cfg.blockDim = dim3(kFinThreads); }
+    int split = fin_env == 1 ? (int)((long long)n_images * split_pct / 100) : 0;                 // images of the programmatic dependent launch
+    if (split < 0) split = 0; if (split > n_images) split = n_images;
     g_last_done = gp.d_done;
-    B200P_CUDA(cudaLaunchKernelEx(&cfg, k_lost_finish<true>, (const LostImageDev*)d_meta, (const float*)nullptr, (const int*)d_degree, k_patches, n_max,
-                                  d_seed, d_box, d_status, (float*)nullptr, d_feats, (long long)row_stride, d, vec ? 1 : 0,
-                                  (const unsigned int*)gp.d_done));
+    if (split > 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)split); cfg.blockDim = dim3((unsigned)small_threads); cfg.dynamicSmemBytes = fin_smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        B200P_CUDA(cudaLaunchKernelEx(&cfg, k_lost_finish<true>, (const LostImageDev*)d_meta, (const float*)nullptr, (const int*)d_degree, k_patches, n_max,
+                                      d_seed, d_box, d_status, (float*)nullptr, d_feats, (long long)row_stride, d, vec ? 1 : 0,
+                                      (const unsigned int*)gp.d_done, 0));
+    }
+    if (split < n_images) {
+        k_lost_finish<true><<<n_images - split, kFinThreads, fin_smem, st>>>(d_meta, nullptr, d_degree, k_patches, n_max, d_seed, d_box, d_status, nullptr,
+                                                                             d_feats, (long long)row_stride, d, vec ? 1 : 0, gp.d_done, split);
+        B200P_LAUNCH_CHECK("k_lost_finish");
+    }
     return B200P_OK;
 }
 
