@@ -197,6 +197,36 @@ def test_magnitude_planted_ties_policy(golden_dir):
     assert res["n_kept"] == plan.total - k
 
 
+@pytest.mark.parametrize("n_ties", [3, 40, 511, 512, 513, 3000])
+def test_magnitude_tie_list_and_table_paths(n_ties):
+    """A planted tied set at the cut: up to 512 ties go through the short position list (tie_list_pick), more through the
+    per-chunk table (tie_scan_body); both must drop the lowest flat indices first, bit exact vs the oracle, wherever the
+    quota cuts the set (prune.py:1145-1153 semantics pinned by SURVEY 8c)."""
+    rng = np.random.default_rng(11 + n_ties)
+    sizes = [4096 * 9 + 17, 300, 4096 * 30, 4096 * 4 + 4095]
+    total = sum(sizes)
+    flat = (rng.standard_normal(total) * 0.05).astype(np.float32)
+    tie_val = np.float32(0.0337)
+    pos = np.sort(rng.choice(total, n_ties, replace=False))
+    flat[pos] = tie_val * rng.choice(np.array([1.0, -1.0], np.float32), n_ties)
+    w, o = [], 0
+    for n in sizes:
+        w.append(flat[o:o + n].copy()); o += n
+    plan = make_plan(w)
+    plan.bind(L.SLOT_W, to_dev(w))
+    n_less = int((np.abs(flat) < tie_val).sum())
+    for quota in sorted({1, 2, n_ties // 2, n_ties - 1}):
+        if not 0 < quota < n_ties:
+            continue
+        k = n_less + quota
+        new, res = run_magnitude(plan, k)
+        exp, info = PO.magnitude_masks(w, None, int(k))
+        assert (res["n_less"], res["n_equal"], res["quota"]) == (info["n_less"], info["n_equal"], info["quota"]) == (n_less, n_ties, quota)
+        for m, e in zip(gpu_masks(plan, new), exp):
+            assert np.array_equal(m, e.reshape(-1)), (n_ties, quota)
+        assert res["n_kept"] == total - k
+
+
 @pytest.mark.parametrize("cand_capacity", [0, 64])
 @pytest.mark.parametrize("case", ["random", "constant", "few_values", "nan_tail", "denormal"])
 def test_select_edge_cases(case, cand_capacity):

@@ -106,6 +106,42 @@ def test_peer_magnitude_rounds_match_single_plan_and_oracle(world, ties, merged)
         assert cut_inside_ties >= 1          # at least one round had to split a tied set across the ranks' slices
 
 
+@pytest.mark.parametrize("merged", [True, False])
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("n_ties", [5, 300])
+def test_peer_small_tied_set_across_ranks(world, n_ties, merged):
+    """A handful of tied keys spread over the ranks' slices (what real fp32 weight sets have at the cut: ViT-L/16 ties 6
+    keys at 50 %): the one-launch sharded tail (merged) resolves them through the tie list, the staged launches through
+    the per-chunk table; ties owned by lower ranks count against the quota first either way."""
+    numels = [4096 * 37 + 5, 1000, 4096 * 64, 333, 4096 * 21 + 4095, 77777]
+    total = sum(numels)
+    rng = np.random.default_rng(100 + n_ties)
+    w = (rng.standard_normal(total) * 0.05).astype(np.float32)
+    tie_val = np.float32(0.0337)
+    pos = np.sort(rng.choice(total, n_ties, replace=False))
+    w[pos] = tie_val
+    n_less = int((np.abs(w) < tie_val).sum())
+    wt = torch.from_numpy(w).to(DEV)
+    ref = ParamPlan(numels, DEV)
+    ref.bind(L.SLOT_W, _views(wt, numels))
+    vr = VirtualRanks(numels, world, merged=merged)
+    for p in vr.plans:
+        p.bind(L.SLOT_W, _views(wt, numels))
+    for quota in (1, n_ties // 2, n_ties - 1):
+        k = n_less + quota
+        new_ref = ref.new_mask()
+        ref.mask_build(L.KEY_ABS_W, k, L.MODE_EXACT_K, new_ref, None)
+        r_ref = ref.result()
+        assert (r_ref["n_less"], r_ref["n_equal"], r_ref["quota"]) == (n_less, n_ties, quota)
+        res = vr.build(L.KEY_ABS_W, None, k, L.MODE_EXACT_K)
+        exp, _ = PO.magnitude_masks(_views(w, numels), None, int(k))
+        for got, e in zip(ref.unpack_mask_host(new_ref), exp):
+            assert np.array_equal(got, e.reshape(-1))
+        for r in range(world):
+            assert res[r]["miss"] == 0 and res[r]["n_kept"] == total - k
+            assert torch.equal(vr.builders[r].mask, new_ref), (world, n_ties, quota, r)
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_peer_snip_matches_single_plan(world):
     """Batches shard over the ranks; the score kernel writes each chunk's partial scores into the owner's window, the owner
