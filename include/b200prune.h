@@ -228,6 +228,9 @@ int  b200p_snip_score_select(b200p_plan* plan, const b200p_ptrtable* const* g_ta
 typedef struct b200p_comm b200p_comm;
 int  b200p_comm_create(int device, int rank, int world, int64_t mask_words, int64_t score_cap, b200p_comm** out);
 int  b200p_comm_destroy(b200p_comm* comm);
+/* Measurement aid: globaltimer (ns) stamps of the last in-kernel collective per channel and sequence parity
+ * (comm.cuh: comm_signal_and_wait), u64 [4][2][8].  Synchronises the device. */
+int  b200p_comm_trace(b200p_comm* c, uint64_t* h_out64);
 int64_t b200p_comm_window_bytes(const b200p_comm* comm);
 void* b200p_comm_window(const b200p_comm* comm);                 /* device address of the own window            */
 void* b200p_comm_mask_ptr(const b200p_comm* comm);               /* the full packed mask inside the own window  */

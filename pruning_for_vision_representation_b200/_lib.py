@@ -107,6 +107,7 @@ SIGNATURES = {
                                 _P, _I64, _I, _P]),
     "b200p_lost_last_trace": (_I, [ctypes.POINTER(_U64)]),
     "b200p_lost_finish_trace": (_I, [_I, ctypes.POINTER(_U64)]),
+    "b200p_comm_trace": (_I, [_P, ctypes.POINTER(_U64)]),
     "b200p_select_last_trace": (_I, [ctypes.POINTER(_U64)]),
     "b200p_lost_patch_scoring": (_I, [_I, _P, _I, _I64, _F, _P, _P, _P]),
     "b200p_lost_detect_box": (_I, [_I, _P, _I, _I, _I, _F, _F, _I, _I, _P, _P, _P, _P]),

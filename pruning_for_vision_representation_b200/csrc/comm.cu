@@ -14,6 +14,7 @@ static CommLayout make_layout(int world, long long mask_words, long long score_c
     long long o = 0;
     l.flags = o;      o = align256(o + (long long)CH_COUNT * kCommMaxWorld * 4);
     l.err = o;        o = align256(o + 4);
+    l.trace = o;      o = align256(o + (long long)CH_COUNT * 2 * 8 * 8);
     l.hist_bins = o;  o = align256(o + 2ll * world * kCommHistBins * 4);
     l.hist_extra = o; o = align256(o + 2ll * world * kCommHistExtra * 8);
     l.gather = o;     o = align256(o + 2ll * world * kCommGatherWords * 4);
@@ -83,6 +84,14 @@ extern "C" int b200p_comm_destroy(b200p_comm* c) {
     cudaFree(c->window);
     cudaGetLastError();
     delete c;
+    return B200P_OK;
+}
+
+extern "C" int b200p_comm_trace(b200p_comm* c, uint64_t* h_out64) {
+    B200P_REQUIRE(c != nullptr && h_out64 != nullptr, B200P_EINVAL, "comm_trace: null argument");
+    B200P_CUDA(cudaSetDevice(c->device));
+    B200P_CUDA(cudaDeviceSynchronize());
+    B200P_CUDA(cudaMemcpy(h_out64, c->window + c->lay.trace, (size_t)CH_COUNT * 2 * 8 * 8, cudaMemcpyDeviceToHost));
     return B200P_OK;
 }
 

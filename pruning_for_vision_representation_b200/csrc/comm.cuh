@@ -35,6 +35,7 @@ constexpr int kCommGatherWords = 1024 + 8;                         // u32 window
 struct CommLayout {
     long long flags;        // u32 [CH_COUNT][kCommMaxWorld]
     long long err;          // u32 error flag (own window only)
+    long long trace;        // u64 [CH_COUNT][2][8] globaltimer stamps of the last collective per channel and seq parity (own window only)
     long long hist_bins;    // u32 [2][world][kCommHistBins]
     long long hist_extra;   // u64 [2][world][kCommHistExtra]
     long long gather;       // u32 [2][world][kCommGatherWords]
@@ -64,15 +65,25 @@ __device__ __forceinline__ uint32_t* comm_flag(const CommDev& c, int dst_rank, i
 
 // Called by ALL threads of one CTA after they have stored their part of the payload into the peers' windows:
 // publishes seq to every rank, then waits for every rank's seq.  Returns false on a time-out (err flag set).
+__device__ __forceinline__ unsigned long long comm_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// measurement aid (b200p_comm_trace): [0] payload stores issued [1] own fence done [2] own flag stored [3] last peer's flag seen
+// [4] leaving; written by the signalling threads of the last collective on (channel, seq parity)
+__device__ __forceinline__ unsigned long long* comm_trace_slot(const CommDev& c, int ch, uint32_t seq) {
+    return reinterpret_cast<unsigned long long*>(c.win[c.rank] + c.lay.trace) + (ch * 2 + (int)(seq & 1u)) * 8;
+}
 __device__ __forceinline__ bool comm_signal_and_wait(const CommDev& c, int ch, uint32_t seq) {
     __shared__ int s_comm_ok;
-    if (threadIdx.x == 0) s_comm_ok = 1;
+    unsigned long long* tr = comm_trace_slot(c, ch, seq);
+    if (threadIdx.x == 0) { s_comm_ok = 1; tr[3] = 0ull; }
     __syncthreads();                       // every payload store of the CTA is issued (CTA-scope happens-before)
+    if (threadIdx.x == 0) tr[0] = comm_globaltimer();
     if ((int)threadIdx.x < c.world) {
         // ONE system-scope fence per signalling thread, after the barrier: fences are cumulative, so it also orders the
         // stores of the other threads it synchronised with (256 concurrent fence.sys cost ~15 us per collective)
         __threadfence_system();
+        if (threadIdx.x == 0) tr[1] = comm_globaltimer();
         st_release_sys_u32(comm_flag(c, threadIdx.x, ch, c.rank), seq);
+        if (threadIdx.x == 0) tr[2] = comm_globaltimer();
         const uint32_t* f = comm_flag(c, c.rank, ch, threadIdx.x);
         bool ok = false;
         for (unsigned spin = 0; spin < (1u << 24); ++spin) {
@@ -80,9 +91,11 @@ __device__ __forceinline__ bool comm_signal_and_wait(const CommDev& c, int ch, u
             if ((int32_t)(ld_acquire_sys_u32(f) - seq) >= 0) { ok = true; break; }
             if (spin > 64) __nanosleep(128);
         }
+        atomicMax(tr + 3, comm_globaltimer());
         if (!ok) { s_comm_ok = 0; *reinterpret_cast<volatile uint32_t*>(c.win[c.rank] + c.lay.err) = 1u + (uint32_t)ch; }
     }
     __syncthreads();
+    if (threadIdx.x == 0) tr[4] = comm_globaltimer();
     return s_comm_ok != 0;
 }
 
@@ -91,12 +104,21 @@ __device__ __forceinline__ bool comm_signal_and_wait(const CommDev& c, int ch, u
 __device__ __forceinline__ void comm_push_mask_words(const CommDev& c, long long w_begin, long long w_end) {
     const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(c.win[c.rank] + c.lay.mask);
     const long long q0 = w_begin >> 2, q1 = w_end >> 2;
-    if (c.world > 1)
-        for (long long q = q0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += (long long)gridDim.x * blockDim.x) {
-            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src) + q);
-            for (int p = 0; p < c.world; ++p)
-                if (p != c.rank) reinterpret_cast<uint4*>(c.win[p] + c.lay.mask)[q] = v;
+    if (c.world > 1) {
+        // four 16-byte pieces per thread in flight: with one, the loop was a chain of load latencies (31 us for 14 MB to one peer)
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long q = q0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += 4 * stride) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (q + u * stride < q1) v[u] = __ldcg(reinterpret_cast<const uint4*>(src) + q + u * stride);
+            for (int p = 0; p < c.world; ++p) {
+                if (p == c.rank) continue;
+                uint4* dst = reinterpret_cast<uint4*>(c.win[p] + c.lay.mask);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (q + u * stride < q1) dst[q + u * stride] = v[u];
+            }
         }
+    }
     __syncthreads();
     if (threadIdx.x == 0) __threadfence_system();
     __syncthreads();
@@ -107,6 +129,7 @@ __device__ __forceinline__ void comm_push_mask_words(const CommDev& c, long long
 // On return `hist` holds the sums on every rank (bit-identical: integer adds).
 __device__ __forceinline__ bool comm_allreduce_hist(const CommDev& c, uint32_t seq, unsigned long long* __restrict__ hist) {
     const int tid = threadIdx.x, nt = blockDim.x, slot = seq & 1u;
+    if (tid == 0) comm_trace_slot(c, CH_HIST, seq)[5] = comm_globaltimer();          // [5] all-reduce entered, [6] sums written
     // pack own bins to u32 once, then push to every window
     for (int b4 = tid; b4 < kCommHistBins / 4; b4 += nt) {
         uint4 v;
@@ -123,11 +146,17 @@ __device__ __forceinline__ bool comm_allreduce_hist(const CommDev& c, uint32_t s
             reinterpret_cast<unsigned long long*>(c.win[p] + c.lay.hist_extra)[(size_t)(slot * c.world + c.rank) * kCommHistExtra + tid] = e;
     }
     if (!comm_signal_and_wait(c, CH_HIST, seq)) return false;
-    const uint32_t* bins = reinterpret_cast<const uint32_t*>(c.win[c.rank] + c.lay.hist_bins) + (size_t)slot * c.world * kCommHistBins;
-    for (int b = tid; b < kCommHistBins; b += nt) {
-        unsigned long long s = 0;
-        for (int r = 0; r < c.world; ++r) s += __ldcg(bins + (size_t)r * kCommHistBins + b);
-        hist[b] = s;
+    // loads first, stores afterwards: a store into `hist` inside the loop orders every later load behind it and the 16
+    // rounds of L2 latency run one after the other (b200p_comm_trace: 9-10 us for this sum, 2 GPUs)
+    const uint4* bins4 = reinterpret_cast<const uint4*>(c.win[c.rank] + c.lay.hist_bins) + (size_t)slot * c.world * (kCommHistBins / 4);
+    for (int b4 = tid; b4 < kCommHistBins / 4; b4 += nt) {          // nt = 256: four rounds of `world` 16-byte loads each
+        uint4 v[kCommMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kCommMaxWorld; ++r) v[r] = r < c.world ? __ldcg(bins4 + (size_t)r * (kCommHistBins / 4) + b4) : make_uint4(0u, 0u, 0u, 0u);
+        unsigned long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+        for (int r = 0; r < kCommMaxWorld; ++r) { s0 += v[r].x; s1 += v[r].y; s2 += v[r].z; s3 += v[r].w; }
+        hist[4 * b4 + 0] = s0; hist[4 * b4 + 1] = s1; hist[4 * b4 + 2] = s2; hist[4 * b4 + 3] = s3;
     }
     if (tid < kCommHistExtra) {
         const unsigned long long* ex = reinterpret_cast<const unsigned long long*>(c.win[c.rank] + c.lay.hist_extra) + (size_t)slot * c.world * kCommHistExtra;
@@ -137,6 +166,7 @@ __device__ __forceinline__ bool comm_allreduce_hist(const CommDev& c, uint32_t s
     }
     __threadfence();
     __syncthreads();
+    if (tid == 0) comm_trace_slot(c, CH_HIST, seq)[6] = comm_globaltimer();
     return true;
 }
 

@@ -59,10 +59,13 @@ __device__ __forceinline__ PatchVals patch_vals_from_state(const SelState* __res
 
 static __device__ void emit_patch_body(const int32_t* __restrict__ chunk_n, ChunkTab key_tab, const uint32_t* __restrict__ old_mask,
                                 SelState* __restrict__ st, const uint32_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_pos,
-                                uint32_t* __restrict__ prov, int mode, int64_t n_chunks, const PatchVals& pv) {
+                                uint32_t* __restrict__ prov, int mode, int64_t n_chunks, const PatchVals& pv,
+                                uint32_t* __restrict__ tie_list = nullptr) {
+    // tie_list (EXACT_K, few ties): this pass prunes only the keys below the threshold and appends the positions of the tied
+    // candidates to the list (tie_list[0] = count); one CTA then prunes the right ones by position (select.cu: tie_list_pick)
     const uint32_t n = pv.cand_count, thr_key = pv.thr_key;
     const bool strict = mode == B200P_MODE_SNIP_STRICT;
-    const uint32_t need_ties = strict ? 0u : pv.need_ties;
+    const uint32_t need_ties = (strict || tie_list) ? 0u : pv.need_ties;
     const long long tie_chunk = pv.tie_chunk;
     // eight candidates per thread and iteration: sixteen independent loads in flight, then the (fire-and-forget) bit clears —
     // the loop is bound by load latency, and the fused finish kernel runs it on one CTA per SM
@@ -80,7 +83,13 @@ static __device__ void emit_patch_body(const int32_t* __restrict__ chunk_n, Chun
             const long long c = pos[u] >> 12;
             bool prune;
             if (strict) prune = key[u] <= thr_key;                    // keep = score > threshold (train.py:316)
-            else {
+            else if (tie_list) {
+                prune = key[u] < thr_key;
+                if (key[u] == thr_key) {
+                    const uint32_t slot = atomicAdd(tie_list, 1u);
+                    if (slot < (uint32_t)kTieListCap) tie_list[1 + slot] = pos[u];
+                }
+            } else {
                 const bool ties_pruned = !need_ties || tie_chunk < 0 || c < tie_chunk;
                 prune = key[u] < thr_key || (key[u] == thr_key && ties_pruned);
             }

@@ -717,9 +717,12 @@ __device__ __forceinline__ void tie_list_gather(uint32_t thr, uint32_t cand_coun
 }
 // One CTA, after a grid-wide barrier: same outcome as tie_scan_body (lowest flat index first; ties owned by the n_before
 // lower ranks count against the quota first).
+// prov != nullptr: the CTA also clears the bits of the ties it prunes (the patch pass left every tie alone), and the state
+// says "no tie handling left" (tie_chunk = c_begin, tie_resid = 0): nobody walks the tie chunk element by element any more
+// (20 us on the rank that owns it: 128 dependent loads by one warp, the other ranks waiting at the final flag).
 __device__ void tie_list_pick(SelState* __restrict__ st, uint32_t* __restrict__ tie_list, int64_t c_begin, int64_t c_end,
                               unsigned long long tie_offset, const unsigned long long* __restrict__ d_counts, int n_before,
-                              uint32_t* s_pos /* [kTieListCap] */) {
+                              uint32_t* s_pos /* [kTieListCap] */, uint32_t* __restrict__ prov = nullptr) {
     __shared__ int s_sel;
     const int tid = threadIdx.x, nt = blockDim.x;
     if (d_counts) for (int r = 0; r < n_before; ++r) tie_offset += d_counts[r];
@@ -729,7 +732,16 @@ __device__ void tie_list_pick(SelState* __restrict__ st, uint32_t* __restrict__ 
     if (tid == 0) s_sel = -1;
     __syncthreads();
     const long long target = (long long)st->quota - (long long)tie_offset;
-    if (target <= 0) {
+    if (prov) {
+        const long long tgt = target < 0 ? 0 : target > (long long)m ? (long long)m : target;
+        for (uint32_t i = tid; i < m; i += nt) {
+            const uint32_t pi = s_pos[i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < m; ++j) rank += s_pos[j] < pi ? 1u : 0u;                    // positions are distinct
+            if ((long long)rank < tgt) atomicAnd(prov + (size_t)(pi >> 12) * kWordsPerChunk + ((pi & 4095u) >> 5), ~(1u << (pi & 31u)));
+        }
+        if (tid == 0) { st->tie_chunk = c_begin; st->tie_resid = 0; st->tie_seen = (unsigned long long)tgt; }
+    } else if (target <= 0) {
         if (tid == 0) { st->tie_chunk = c_begin; st->tie_resid = 0; st->tie_seen = 0; }
     } else if ((unsigned long long)target > (unsigned long long)m) {
         if (tid == 0) { st->tie_chunk = c_end; st->tie_resid = 0; st->tie_seen = m; }           // every local tie pruned
@@ -1427,7 +1439,7 @@ k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks,
     const bool exact = st->miss != 0u;               // written by the previous kernel: uniform over the grid
     const bool prov_ok = st->prov_ok != 0u;          // idem
     PatchVals pv;
-    bool pv_valid = false;
+    bool pv_valid = false, use_list = false;
     if (exact) {
         if (blockIdx.x == 0 && threadIdx.x == 0) init_state(st, a.k, a.mode, a.allow_collect, 1u);
         grid_barrier();
@@ -1509,7 +1521,12 @@ k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks,
             st->need_ties = need_ties;
             st->tie_chunk = -1; st->tie_resid = 0; st->tie_seen = 0;
         }
-        if (need_ties && v <= (unsigned long long)kTieListCap) {
+        if (need_ties && v <= (unsigned long long)kTieListCap && EMIT && prov_ok) {
+            // few ties and the mask is patched right here: the patch pass gathers them, CTA 0 prunes them by position afterwards
+            pv.cand_count = n; pv.thr_key = key; pv.need_ties = 0u; pv.tie_resid = 0u; pv.tie_chunk = -1;
+            pv.n_kept = n_valid - (n_less0 + before) - (k - before);
+            pv_valid = true; use_list = true;
+        } else if (need_ties && v <= (unsigned long long)kTieListCap) {
             tie_list_gather(key, n, a.cand_key, a.cand_pos, chunk_ties + n_chunks);
             grid_barrier();
             if (blockIdx.x == 0) tie_list_pick(st, chunk_ties + n_chunks, 0, n_chunks, 0ull, nullptr, 0, reinterpret_cast<uint32_t*>(s_part));
@@ -1528,7 +1545,12 @@ k_select_finish(PassArgs a, uint32_t* __restrict__ chunk_ties, int64_t n_chunks,
     if (!EMIT) return;
     if (prov_ok && !exact) {
         if (!pv_valid) pv = patch_vals_from_state(st, em.mode);          // after the tie barriers: the state is final
-        emit_patch_body(em.chunk_n, em.key_tab, em.old_mask, st, em.cand_key, em.cand_pos, em.prov, em.mode, em.n_chunks, pv);
+        emit_patch_body(em.chunk_n, em.key_tab, em.old_mask, st, em.cand_key, em.cand_pos, em.prov, em.mode, em.n_chunks, pv,
+                        use_list ? chunk_ties + n_chunks : nullptr);
+        if (use_list) {
+            grid_barrier();
+            if (blockIdx.x == 0) tie_list_pick(st, chunk_ties + n_chunks, 0, n_chunks, 0ull, nullptr, 0, reinterpret_cast<uint32_t*>(s_part), em.prov);
+        }
     } else {
         // no candidate list to patch (exact select, histogram mode): full pass over the keys; the state is final here
         if (!exact || !(a.mode == B200P_MODE_EXACT_K && st->need_ties)) grid_barrier();
@@ -1549,6 +1571,11 @@ k_sharded_tail(PassArgs a, CommDev comm, uint32_t seq_gather, uint32_t seq_mask,
     __shared__ unsigned long long s_warp[9];
     __shared__ int s_bin;
     SelState* __restrict__ st = a.st;
+    // measurement aid (b200p_comm_trace, channel "barrier"): [0] start [1] window histogram flushed [2] exact key known
+    // [3] ties resolved [4] own bits patched [5] own words pushed [6] every rank's words here
+    unsigned long long* tr = comm_trace_slot(comm, CH_BARRIER, 0u);
+    auto stamp = [&](int i) { if (blockIdx.x == 0 && threadIdx.x == 0) tr[i] = comm_globaltimer(); };
+    stamp(0);
     if (st->miss) return;                            // same on every rank (identical state): the builder reruns the staged exact select
     for (int b = threadIdx.x; b < kWindow; b += kThreads) s_hist[b] = 0;
     __syncthreads();
@@ -1572,28 +1599,38 @@ k_sharded_tail(PassArgs a, CommDev comm, uint32_t seq_gather, uint32_t seq_mask,
         if (v) atomicAdd(a.hist + b, (unsigned long long)v);
     }
     grid_barrier();
+    stamp(1);
     if (blockIdx.x == 0) sharded_gather_pick(a, comm, seq_gather, rank_ties, s_warp, &s_bin);
     grid_barrier();
+    stamp(2);
     if (st->miss) return;                            // uniform after the barrier
-    if (a.mode == B200P_MODE_EXACT_K && st->need_ties) {
-        if (st->collect && st->n_equal <= (unsigned long long)kTieListCap) {        // uniform: the state is final since the barrier
-            tie_list_gather(st->thr_key, st->cand_count, a.cand_key, a.cand_pos, chunk_ties + em.n_chunks);
-            grid_barrier();
-            if (blockIdx.x == 0) tie_list_pick(st, chunk_ties + em.n_chunks, c0, c1, 0ull, rank_ties, comm.rank, reinterpret_cast<uint32_t*>(s_part));
-        } else {
-            tie_count_body(a.chunk_n, a.key_tab, a.old_mask, st, a.cand_key, a.cand_pos, chunk_ties, c0, c1, a.vec_ok);
-            grid_barrier();
-            if (blockIdx.x == 0) tie_scan_body(st, chunk_ties, c0, c1, 0ull, rank_ties, comm.rank, s_part);
-        }
+    // few ties (the normal case) and a candidate list to patch: the patch pass gathers the tied candidates, CTA 0 prunes the
+    // right ones by position afterwards — one pass over the candidates and one barrier less than resolving the ties first
+    const bool list_mode = a.mode == B200P_MODE_EXACT_K && st->need_ties && st->collect && st->prov_ok &&
+                           st->n_equal <= (unsigned long long)kTieListCap;         // uniform: the state is final since the barrier
+    if (a.mode == B200P_MODE_EXACT_K && st->need_ties && !list_mode) {
+        tie_count_body(a.chunk_n, a.key_tab, a.old_mask, st, a.cand_key, a.cand_pos, chunk_ties, c0, c1, a.vec_ok);
+        grid_barrier();
+        if (blockIdx.x == 0) tie_scan_body(st, chunk_ties, c0, c1, 0ull, rank_ties, comm.rank, s_part);
         grid_barrier();
     }
-    if (st->prov_ok) emit_patch_body(em.chunk_n, em.key_tab, em.old_mask, st, em.cand_key, em.cand_pos, em.prov, em.mode, em.n_chunks,
-                                     patch_vals_from_state(st, em.mode));
-    else emit_full_body(em, c0, c1);
+    stamp(3);
+    if (st->prov_ok) {
+        PatchVals pv = patch_vals_from_state(st, em.mode);
+        emit_patch_body(em.chunk_n, em.key_tab, em.old_mask, st, em.cand_key, em.cand_pos, em.prov, em.mode, em.n_chunks, pv,
+                        list_mode ? chunk_ties + em.n_chunks : nullptr);
+        if (list_mode) {
+            grid_barrier();
+            if (blockIdx.x == 0) tie_list_pick(st, chunk_ties + em.n_chunks, c0, c1, 0ull, rank_ties, comm.rank, reinterpret_cast<uint32_t*>(s_part), em.prov);
+        }
+    } else emit_full_body(em, c0, c1);
     grid_barrier();                                  // every bit of the own slice is final
+    stamp(4);
     comm_push_mask_words(comm, c0 * kWordsPerChunk, c1 * kWordsPerChunk);
     grid_barrier();                                  // every CTA's remote stores are issued and fenced
+    stamp(5);
     if (blockIdx.x == 0) comm_signal_and_wait(comm, CH_MASK, seq_mask);
+    stamp(6);
 }
 
 static unsigned int* ticket_ptr(b200p_plan* p);
