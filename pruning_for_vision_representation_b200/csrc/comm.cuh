@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace b200p {
 
@@ -49,6 +50,7 @@ struct CommDev {
     CommLayout lay;
     long long score_cap;           // elements per part of the score area
     int rank, world;
+    int push_lsu;                  // 1 (default): mask push with LSU stores; 0: through the bulk-copy engine (B200P_PUSH_BULK=1)
 };
 
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
@@ -100,12 +102,17 @@ __device__ __forceinline__ bool comm_signal_and_wait(const CommDev& c, int ch, u
 }
 
 // Copy the packed-mask words [w_begin, w_end) of the own window into every peer's window (grid-stride over the launching
-// grid, 16-byte pieces: chunk ranges start on multiples of 128 words); each CTA ends with one cumulative system fence.
+// grid; chunk ranges start on multiples of 128 words); each CTA ends with one cumulative system fence.
+// The all-gather is bound by NVLink ingress (every rank receives (G-1)/G of the mask: 25 MB for ViT-L/16 at 8 GPUs, 28 us at
+// 900 GB/s).  LSU stores — 16-byte pieces, four in flight per lane, every piece to every peer — reach 485-550 GB/s (51 us at
+// 8 GPUs, 26 us for 14 MB to one peer at 2 GPUs; b200p_comm_trace).  Tried: tiles staged in shared memory and handed to the
+// bulk-copy engine (cp.async.bulk global <- shared, one instruction per 8 KB tile and peer, two tiles in flight) — bit-identical
+// and exactly as fast, so the rate is the link's, not the store path's.  B200P_PUSH_BULK=1 (read at comm creation) selects it.
+constexpr int kPushTileQ = 512;                                     // 16-byte pieces per tile (8 KB)
 __device__ __forceinline__ void comm_push_mask_words(const CommDev& c, long long w_begin, long long w_end) {
     const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(c.win[c.rank] + c.lay.mask);
     const long long q0 = w_begin >> 2, q1 = w_end >> 2;
-    if (c.world > 1) {
-        // four 16-byte pieces per thread in flight: with one, the loop was a chain of load latencies (31 us for 14 MB to one peer)
+    if (c.world > 1 && c.push_lsu) {
         const long long stride = (long long)gridDim.x * blockDim.x;
         for (long long q = q0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += 4 * stride) {
             uint4 v[4];
@@ -118,6 +125,30 @@ __device__ __forceinline__ void comm_push_mask_words(const CommDev& c, long long
                 for (int u = 0; u < 4; ++u) if (q + u * stride < q1) dst[q + u * stride] = v[u];
             }
         }
+    } else if (c.world > 1) {
+        __shared__ __align__(128) uint4 s_push[2][kPushTileQ];
+        const long long n_tiles = (q1 - q0 + kPushTileQ - 1) / kPushTileQ;
+        int buf = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, buf ^= 1) {
+            const long long qa = q0 + t * kPushTileQ;
+            const int cnt = (int)((q1 - qa) < kPushTileQ ? (q1 - qa) : kPushTileQ);
+            // the copies issued from this buffer two tiles ago have read it (at most one newer group may still be reading the other)
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+            for (int i = threadIdx.x; i < cnt; i += blockDim.x) s_push[buf][i] = __ldcg(reinterpret_cast<const uint4*>(src) + qa + i);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk-copy engine
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(&s_push[buf][0]);
+                for (int p = 0; p < c.world; ++p) {
+                    if (p == c.rank) continue;
+                    const uint4* dst = reinterpret_cast<const uint4*>(c.win[p] + c.lay.mask) + qa;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(saddr), "r"(cnt * 16) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // every bulk write of this CTA has been performed
     }
     __syncthreads();
     if (threadIdx.x == 0) __threadfence_system();
@@ -186,6 +217,8 @@ struct b200p_comm {
         b200p::CommDev d;
         for (int i = 0; i < b200p::kCommMaxWorld; ++i) d.win[i] = peers[i];
         d.lay = lay; d.score_cap = score_cap; d.rank = rank; d.world = world;
+        static const int lsu = [] { const char* e = getenv("B200P_PUSH_BULK"); return e && atoi(e) == 1 ? 0 : 1; }();
+        d.push_lsu = lsu;
         return d;
     }
 };
