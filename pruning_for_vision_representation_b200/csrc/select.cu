@@ -1113,7 +1113,7 @@ k_select_bracket(PassArgs a, CommDev comm) {
 // One CTA: all-gather of the ranks' window histograms (a.hist[0..1024) holds this rank's), exact key of rank k, tie
 // bookkeeping (every rank's count of that key -> rank_ties).  Leaves a.hist cleared.
 __device__ __forceinline__ void sharded_gather_pick(const PassArgs& a, const CommDev& comm, uint32_t seq, unsigned long long* __restrict__ rank_ties,
-                                                    unsigned long long* s_warp /*[9]*/, int* s_bin) {
+                                                    unsigned long long* s_warp /*[9]*/, int* s_bin, uint32_t* s_stage /*[kWindow]*/) {
     SelState* __restrict__ st = a.st;
     const uint32_t win_lo = st->win_lo;
     const int tid = threadIdx.x, slot = seq & 1u;
@@ -1127,17 +1127,30 @@ __device__ __forceinline__ void sharded_gather_pick(const PassArgs& a, const Com
     }
     const bool comm_ok = comm_signal_and_wait(comm, CH_GATHER, seq);
     const uint32_t* __restrict__ g = reinterpret_cast<const uint32_t*>(comm.win[comm.rank] + comm.lay.gather) + (size_t)slot * comm.world * kCommGatherWords;
+    // coalesced: thread t sums bins t, t + 256, ... over the ranks into shared memory (16 consecutive bins per thread straight
+    // from global memory are one 32-byte sector per lane and load: 8192 sector requests from 64 threads at 8 ranks)
+    const unsigned long long k = st->k;
+    {
+        uint32_t sum[kWindow / kThreads];
+#pragma unroll
+        for (int i = 0; i < kWindow / kThreads; ++i) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int r = 0; r < kCommMaxWorld; ++r) v += r < comm.world ? __ldcg(g + (size_t)r * kCommGatherWords + i * kThreads + tid) : 0u;
+            sum[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < kWindow / kThreads; ++i) s_stage[i * kThreads + tid] = sum[i];
+        __syncthreads();
+    }
     unsigned long long local[kBinsPerThread];
 #pragma unroll
     for (int i = 0; i < kBinsPerThread; ++i) {
         const int b = tid * kBinsPerThread + i;
-        unsigned long long sum = 0;
-        if (b < kWindow) for (int r = 0; r < comm.world; ++r) sum += __ldcg(g + (size_t)r * kCommGatherWords + b);
-        local[i] = sum;
+        local[i] = b < kWindow ? s_stage[b] : 0u;
     }
     unsigned long long total;
     unsigned long long running = block_prefix16(local, s_warp, total);
-    const unsigned long long k = st->k;
     if (tid == 0) *s_bin = -1;
     __syncthreads();
 #pragma unroll
@@ -1198,7 +1211,7 @@ k_sharded_finish(PassArgs a, CommDev comm, uint32_t seq, unsigned long long* __r
         if (v) atomicAdd(a.hist + b, (unsigned long long)v);
     }
     if (!last_cta_arrives(a.ticket)) return;
-    sharded_gather_pick(a, comm, seq, rank_ties, s_warp, &s_bin);
+    sharded_gather_pick(a, comm, seq, rank_ties, s_warp, &s_bin, s_hist);
     if (threadIdx.x == 0) *a.ticket = 0u;
 }
 
@@ -1600,7 +1613,7 @@ k_sharded_tail(PassArgs a, CommDev comm, uint32_t seq_gather, uint32_t seq_mask,
     }
     grid_barrier();
     stamp(1);
-    if (blockIdx.x == 0) sharded_gather_pick(a, comm, seq_gather, rank_ties, s_warp, &s_bin);
+    if (blockIdx.x == 0) sharded_gather_pick(a, comm, seq_gather, rank_ties, s_warp, &s_bin, s_hist);
     grid_barrier();
     stamp(2);
     if (st->miss) return;                            // uniform after the barrier
