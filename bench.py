@@ -20,7 +20,7 @@ Both arms use the same inputs: torchvision ResNet-50 init (seed 1) and g_b = 1e-
              no multi-batch mode), then train.snip_pruning itself on a 54-module stand-in whose weights are
              the accumulated scores and whose loss is sum(w) (the hooks see g = 1, so its score is the accumulated
              score bit for bit and its sort / threshold / custom_from_mask run on the real sizes).
-Extra legs in the same line: `with_fp32_masks` (the drop-in's fused fp32 weight_mask emit), `magnitude` (configs 1, 4, 5
+Extra legs in the same line: `with_fp32_masks` (the drop-in's sequence: build + fp32 weight_mask tensors expanded from the packed mask), `magnitude` (configs 1, 4, 5
 on one GPU), `lost` (config 3, uniform 900 x 384 and the VOC-shaped mix), and for N > 1 `sharded`: ONE ResNet-50 SNIP
 build over the N GPUs and the config-5 sweeps parameter-sharded, through the peer-memory path (no NCCL inside a build),
 each with a bit-identity flag against the single-GPU build of the same data.
@@ -564,8 +564,8 @@ def run_b200(args):
         plan.bind(L.SLOT_MASKF, split_views(maskf, numels))
         def with_f32():
             refresh_tables_fast()
-            plan.snip_score_select(g_tables, k)
-            plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, mask, None, outputs=L.EMIT_MASKF)
+            plan.snip_mask_build(g_tables, k, mask)
+            plan.mask_unpack_to_f32(mask)
         for _ in range(3):
             with_f32()
         torch.cuda.synchronize()
@@ -575,10 +575,10 @@ def run_b200(args):
             with_f32()
         c1.record(); torch.cuda.synchronize()
         fms = c0.elapsed_time(c1) / cs
-        with_masks = {"what": "fused score + select, then the full emit with the fp32 weight_mask output (pruning.snip_pruning's sequence)",
+        with_masks = {"what": "the fused build, then the fp32 weight_mask tensors expanded from the packed mask (pruning.snip_pruning's sequence on a fresh model: 0.125 B/param read + 4 B/param written on top of the build)",
                       "ms_per_step": fms, "value": n_total / (fms * 1e-3) / 1e9, "unit": "Gparams/s", "steps": cs,
-                      "bytes_per_param": FUSED_BYTES_PER_PARAM + 8.0,
-                      "step_GBps": n_total * (FUSED_BYTES_PER_PARAM + 8.0) / (fms * 1e-3) / 1e9}
+                      "bytes_per_param": FUSED_BYTES_PER_PARAM + 4.125,
+                      "step_GBps": n_total * (FUSED_BYTES_PER_PARAM + 4.125) / (fms * 1e-3) / 1e9}
         del maskf
         step(False)                                      # leave `mask` = the default build's mask for the e2e comparison
 

@@ -226,8 +226,15 @@ def snip_pruning(model, data_loader, device, criterion, target_sparsity=0.9, num
     if 0 < k < n:
         # one fused pass: score = sum_b |w * g_b|, added in batch order (bit-identical to per-batch accumulation),
         # classified against the sampled bracket while it is written; dead entries score 0 and count, as in the reference
-        plan.snip_score_select(tables, k)
-        plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, new_mask, st.mask, outputs=L.EMIT_MASKF)
+        if st.mask is None:
+            # fresh model (the usual SNIP case): the sweep writes the provisional packed mask, the finish kernel patches it,
+            # and the fp32 `weight_mask` buffers (checkpoint format) are expanded from the 0.125 B/param packed mask —
+            # the scores are never re-read (a full emit with fp32 outputs would: 8 B/param more)
+            plan.snip_mask_build(tables, k, new_mask)
+            plan.mask_unpack_to_f32(new_mask)
+        else:
+            plan.snip_score_select(tables, k)
+            plan.emit_masks(L.KEY_SCORE, L.MODE_SNIP_STRICT, new_mask, st.mask, outputs=L.EMIT_MASKF)
         threshold = None
     else:
         plan.score_accumulate_multi(tables, accumulate=False)
