@@ -483,9 +483,10 @@ __device__ __forceinline__ void sel_stamp(int i) { if (threadIdx.x == 0) g_sel_s
 // bins per thread at a 128-byte stride (one sector per lane) and 1.5 us clearing them the same way.  ncu showed it as
 // sm__cycles_active.max - .min = 25 k cycles on every sample / sweep kernel.
 //  * tried: clusters of 8 / 2 CTAs that sum their shared histograms through DSMEM before the global atomics (8x / 2x
-//    fewer).  The flush got cheaper, the streaming body of the sweep 29 % / 8 % slower: a kernel that contains cluster
-//    instructions is placed contiguous-modular instead of round-robin over the GPCs (even with cluster size 1: +7 %), and
-//    clusters >= 4 strand SMs on the 16/18/20-SM GPCs.  Removed again;
+//    fewer).  Clusters of 8 strand SMs on the 16/18/20-SM GPCs: the streaming body of the sweep ran 20 % slower; clusters
+//    of 2 made no measurable difference.  Removed again;
+//  * tried: an L2 access-policy window (persisting) over the histogram copies for these launches: no change (tail staged
+//    in 4.2 against 4.0 us), so the cold part of the tail is not the histogram data;
 //  * the global histogram has kHistReplicas copies, CTA i adds into copy i % kHistReplicas (4x fewer atomics per line);
 //  * the last CTA reads the bins back coalesced into shared memory, summing and re-zeroing the copies on the way, and
 //    clears copy 0 coalesced.
