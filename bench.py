@@ -529,6 +529,22 @@ def run_b200(args):
     result = {"threshold": res["threshold"], "n_less": res["n_less"], "n_equal": res["n_equal"], "n_kept": res["n_kept"],
               "passes_full": res["passes_full"], "mask_sha256": flat_mask_sha256(plan.unpack_mask_host(mask))}
 
+    # globaltimer stamps written by the last CTA of the last sample / sweep kernels (b200p_select_last_trace): where the part of
+    # the dominant kernel that is not streaming goes
+    tails = None
+    try:
+        import ctypes
+        st16 = (ctypes.c_uint64 * 16)()
+        if L.load().b200p_select_last_trace(st16) == 0 and st16[0] and st16[4]:
+            t = [int(v) for v in st16]
+            tails = {"sample_tail_us": (t[3] - t[0]) / 1e3,
+                     "sweep_first_cta_to_last_flush_us": (t[9] - t[8]) / 1e3 if t[8] and t[9] else None,
+                     "sweep_tail_us": {"ticket": (t[4] - t[9]) / 1e3 if t[9] else None, "stage_bins": (t[5] - t[4]) / 1e3,
+                                       "window": (t[6] - t[5]) / 1e3, "clear": (t[7] - t[6]) / 1e3},
+                     "how": "globaltimer stamps of the last build of the timed region (select.cu: g_sel_stamps); the tail is one CTA working alone, mostly on cold lines"}
+    except Exception:
+        tails = None
+
     acc_ms = [a.elapsed_time(b) for is_acc, a, b in score_events if is_acc]
     kernel_ms = sum(acc_ms) / max(1, len(acc_ms))
     n_timed = len(acc_ms)
@@ -651,7 +667,7 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": static_profile("k_snip_score_sweep_traffic_bytes") if mode == "sweep" else None,
                          "traffic_source": "static: profiles/roofline_traffic.json (one ncu --set full capture, not measured in this run)",
-                         "peak_source": peak_src, "kernel_ms": kernel_ms,
+                         "peak_source": peak_src, "kernel_ms": kernel_ms, "kernel_tails": tails,
                          "algorithmic_bytes_per_param": kernel_bpp, "algorithmic_bytes_per_launch": n_total * kernel_bpp,
                          "launches_timed": n_timed,
                          "residency_bytes": N_BATCHES * n_total * 4,
@@ -946,6 +962,12 @@ def lost_leg(args, dev, world, rank, dist):
         if L.load().b200p_lost_last_trace(tr) == 0:
             trace = {"gram_kernel_us": (tr[1] - tr[0]) / 1e3, "first_finish_cta_ready_us": (tr[2] - tr[0]) / 1e3, "last_finish_cta_end_us": (tr[3] - tr[0]) / 1e3,
                      "how": "globaltimer stamps written by the kernels of the last call (Gram first CTA start = 0)"}
+            f16 = (ctypes.c_uint64 * 16)()
+            if L.load().b200p_lost_finish_trace(0, f16) == 0 and f16[0] and f16[8]:
+                ft = [int(v) for v in f16]
+                names = ["degrees_hist_seed", "cutoff", "potentials", "seed_row_and_similars", "order", "sum_of_similar_keys", "M_matvec", "component_box"]
+                trace["finish_phases_us_image0"] = {n: (ft[i + 1] - ft[i]) / 1e3 for i, n in enumerate(names)}
+                trace["finish_M_matvec_GBps_all_images"] = LOST_B * LOST_N * LOST_D * 4 / ((ft[7] - ft[6]) * 1e-9) / 1e9
     except Exception:
         pass
     # e2e: pinned host keys in, boxes / seeds / status back on the host

@@ -1319,6 +1319,7 @@ k_snip_score_sweep(PassArgs a, ChunkTab w_tab, GradTabs g_tabs, int vec_all) {
     if (tid == 0) s_below = 0;
     if (lane == 0) s_wcount[warp] = 0;
     if (blockIdx.x == 0 && tid == 0) st->prov_ok = (a.prov != nullptr && classify) ? 1u : 0u;
+    if (blockIdx.x == 0) sel_stamp(8);
     __syncthreads();
 
     auto take = [&](uint32_t key, uint32_t pos) {
@@ -1431,6 +1432,7 @@ k_snip_score_sweep(PassArgs a, ChunkTab w_tab, GradTabs g_tabs, int vec_all) {
     flush_hist(s_hist, a.hist, false);
     if (tid == 0 && s_below) atomicAdd(a.hist + kHistBins + 1, s_below);
     if (nan_cnt) atomicAdd(a.hist + kHistBins + 2, (unsigned long long)nan_cnt);
+    if (tid == 0) atomicMax(&g_sel_stamps[9], sel_globaltimer());
     if (!last_cta_arrives(a.ticket)) return;
     bracket_tail(a, nullptr, base, span, s_warp, s_hist);
 }
