@@ -1690,7 +1690,7 @@ static unsigned int* ticket_ptr(b200p_plan* p) {
 
 // plain launch returning the error (the sample / sweep kernels; a cluster launch lived here for a while, see flush_hist)
 template <typename K, typename... Args>
-static cudaError_t launch_clustered(K kern, int grid, cudaStream_t st, Args... args) {
+static cudaError_t launch_kernel(K kern, int grid, cudaStream_t st, Args... args) {
     kern<<<grid, kThreads, 0, st>>>(args...);
     return cudaGetLastError();
 }
@@ -1886,13 +1886,13 @@ static int select_kth_sampled(b200p_plan* p, int key_source, const uint32_t* d_o
         B200P_LAUNCH_CHECK("k_sample_from_cache");
     } else {
         sa.cache = sample_cache_arm(p, key_source, d_old_mask, 0, p->n_chunks);
-        B200P_CUDA(launch_clustered(k_select_sample, p->grid_for(sblocks, 1), st, sa, CommDev()));
+        B200P_CUDA(launch_kernel(k_select_sample, p->grid_for(sblocks, 1), st, sa, CommDev()));
         B200P_LAUNCH_CHECK("k_select_sample");
     }
     // A: bracket sweep
     PassArgs a;
     fill_pass_args(p, a, key_source, d_old_mask, 0, p->n_chunks, 1, 0, k, mode, 1, true);
-    B200P_CUDA(launch_clustered(k_select_bracket, p->grid_for((p->n_chunks + 1) / 2, 4), st, a, CommDev()));
+    B200P_CUDA(launch_kernel(k_select_bracket, p->grid_for((p->n_chunks + 1) / 2, 4), st, a, CommDev()));
     B200P_LAUNCH_CHECK("k_select_bracket");
     return launch_finish(p, a, key_source, mode, d_old_mask, st);
 }
@@ -1952,7 +1952,7 @@ extern "C" int b200p_sharded_mask_build(b200p_plan* p, b200p_comm* c, int key_so
     } else {
         sa.comm_seq = ++c->seq[CH_HIST];
         sa.cache = sample_cache_arm(p, key_source, d_old_mask, chunk_begin, chunk_end);
-        B200P_CUDA(launch_clustered(k_select_sample, p->grid_for(sblocks, 1), st, sa, cd));
+        B200P_CUDA(launch_kernel(k_select_sample, p->grid_for(sblocks, 1), st, sa, cd));
         B200P_LAUNCH_CHECK("k_select_sample");
     }
     }
@@ -1964,7 +1964,7 @@ extern "C" int b200p_sharded_mask_build(b200p_plan* p, b200p_comm* c, int key_so
     fill_pass_args(p, a, key_source, d_old_mask, chunk_begin, chunk_end, 1, 0, k, mode, 1, true);
     if (stages & B200P_SHARD_SWEEP) {
         a.comm_seq = ++c->seq[CH_HIST];
-        B200P_CUDA(launch_clustered(k_select_bracket, p->grid_for(nc > 1 ? (nc + 1) / 2 : 1, 4), st, a, cd));
+        B200P_CUDA(launch_kernel(k_select_bracket, p->grid_for(nc > 1 ? (nc + 1) / 2 : 1, 4), st, a, cd));
         B200P_LAUNCH_CHECK("k_select_bracket");
     }
     // B + T + E + P in one cooperative launch when the whole tail is wanted
@@ -2009,27 +2009,27 @@ extern "C" int b200p_sharded_mask_build(b200p_plan* p, b200p_comm* c, int key_so
 template <bool ACC>
 static cudaError_t launch_snip_sample(int nb, int grid, cudaStream_t st, const SampleArgs& sa, ChunkTab w, const GradTabs& g, ChunkTab s) {
     switch (nb) {
-        case 1: return launch_clustered(k_snip_sample<ACC, 1>, grid, st, sa, w, g, s);
-        case 2: return launch_clustered(k_snip_sample<ACC, 2>, grid, st, sa, w, g, s);
-        case 3: return launch_clustered(k_snip_sample<ACC, 3>, grid, st, sa, w, g, s);
-        case 4: return launch_clustered(k_snip_sample<ACC, 4>, grid, st, sa, w, g, s);
-        case 5: return launch_clustered(k_snip_sample<ACC, 5>, grid, st, sa, w, g, s);
-        case 6: return launch_clustered(k_snip_sample<ACC, 6>, grid, st, sa, w, g, s);
-        case 7: return launch_clustered(k_snip_sample<ACC, 7>, grid, st, sa, w, g, s);
-        default: return launch_clustered(k_snip_sample<ACC, 8>, grid, st, sa, w, g, s);
+        case 1: return launch_kernel(k_snip_sample<ACC, 1>, grid, st, sa, w, g, s);
+        case 2: return launch_kernel(k_snip_sample<ACC, 2>, grid, st, sa, w, g, s);
+        case 3: return launch_kernel(k_snip_sample<ACC, 3>, grid, st, sa, w, g, s);
+        case 4: return launch_kernel(k_snip_sample<ACC, 4>, grid, st, sa, w, g, s);
+        case 5: return launch_kernel(k_snip_sample<ACC, 5>, grid, st, sa, w, g, s);
+        case 6: return launch_kernel(k_snip_sample<ACC, 6>, grid, st, sa, w, g, s);
+        case 7: return launch_kernel(k_snip_sample<ACC, 7>, grid, st, sa, w, g, s);
+        default: return launch_kernel(k_snip_sample<ACC, 8>, grid, st, sa, w, g, s);
     }
 }
 template <bool ACC>
 static cudaError_t launch_snip_sweep(int nb, int grid, cudaStream_t st, const PassArgs& a, ChunkTab w, const GradTabs& g, int vec) {
     switch (nb) {
-        case 1: return launch_clustered(k_snip_score_sweep<ACC, 1>, grid, st, a, w, g, vec);
-        case 2: return launch_clustered(k_snip_score_sweep<ACC, 2>, grid, st, a, w, g, vec);
-        case 3: return launch_clustered(k_snip_score_sweep<ACC, 3>, grid, st, a, w, g, vec);
-        case 4: return launch_clustered(k_snip_score_sweep<ACC, 4>, grid, st, a, w, g, vec);
-        case 5: return launch_clustered(k_snip_score_sweep<ACC, 5>, grid, st, a, w, g, vec);
-        case 6: return launch_clustered(k_snip_score_sweep<ACC, 6>, grid, st, a, w, g, vec);
-        case 7: return launch_clustered(k_snip_score_sweep<ACC, 7>, grid, st, a, w, g, vec);
-        default: return launch_clustered(k_snip_score_sweep<ACC, 8>, grid, st, a, w, g, vec);
+        case 1: return launch_kernel(k_snip_score_sweep<ACC, 1>, grid, st, a, w, g, vec);
+        case 2: return launch_kernel(k_snip_score_sweep<ACC, 2>, grid, st, a, w, g, vec);
+        case 3: return launch_kernel(k_snip_score_sweep<ACC, 3>, grid, st, a, w, g, vec);
+        case 4: return launch_kernel(k_snip_score_sweep<ACC, 4>, grid, st, a, w, g, vec);
+        case 5: return launch_kernel(k_snip_score_sweep<ACC, 5>, grid, st, a, w, g, vec);
+        case 6: return launch_kernel(k_snip_score_sweep<ACC, 6>, grid, st, a, w, g, vec);
+        case 7: return launch_kernel(k_snip_score_sweep<ACC, 7>, grid, st, a, w, g, vec);
+        default: return launch_kernel(k_snip_score_sweep<ACC, 8>, grid, st, a, w, g, vec);
     }
 }
 
