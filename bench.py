@@ -452,11 +452,16 @@ def run_b200(args):
         L.check(plan.lib.b200p_ptrtables_update(tab_arr, ptr_arr, len(g_tables), L.SLOT_G, stream_ptr()), "ptrtables_update")
         launches[0] += 1
 
+    mask_ptr = ctypes.c_void_p(mask.data_ptr())
+
     def step(record, smode=mode):
-        refresh_tables_fast()
         if smode == "sweep":
-            plan.snip_mask_build(g_tables, k, mask); launches[0] += 4      # sample, score+sweep, finish, patching emit
+            # fresh gradient tensors per build: the sample kernel re-points the 8 tables itself (b200p_snip_mask_build_refresh)
+            L.check(plan.lib.b200p_snip_mask_build_refresh(plan.handle, tab_arr, ptr_arr, len(g_tables), int(k), mask_ptr, stream_ptr()),
+                    "snip_mask_build_refresh")
+            launches[0] += 3                                                # table refresh + sample, score + sweep, finish + patching emit
             return
+        refresh_tables_fast()
         if smode == "fused":
             if record:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -579,8 +584,8 @@ def run_b200(args):
         maskf = torch.empty(n_total, device=dev)
         plan.bind(L.SLOT_MASKF, split_views(maskf, numels))
         def with_f32():
-            refresh_tables_fast()
-            plan.snip_mask_build(g_tables, k, mask)
+            L.check(plan.lib.b200p_snip_mask_build_refresh(plan.handle, tab_arr, ptr_arr, len(g_tables), int(k), mask_ptr, stream_ptr()),
+                    "snip_mask_build_refresh")
             plan.mask_unpack_to_f32(mask)
         for _ in range(3):
             with_f32()
@@ -657,7 +662,7 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "N": n_total, "tensors": len(numels), "k": k, "weights": wsrc,
                        "score_mode": mode,
-                       "step": "refresh of the 8 gradient pointer tables (1 launch) + sample + fused score/sweep + finish + patching emit"
+                       "step": "sample kernel that also re-points the 8 gradient pointer tables at this build's tensors + fused score/sweep + finish with the patching emit (3 launches)"
                                if mode == "sweep" else mode,
                        "l2": f"inputs larger than L2: {N_BATCHES} gradient sets x {n_total * 4 >> 20} MiB streamed per step",
                        "parallelism": ("1 GPU" if world == 1 else

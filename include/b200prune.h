@@ -211,6 +211,13 @@ int  b200p_mask_build(b200p_plan* plan, int key_source, const uint32_t* d_old_ma
  * are never read back (a bracket miss runs the exact select over the SCORE slot).  W and SCORE must be bound. */
 int  b200p_snip_mask_build(b200p_plan* plan, const b200p_ptrtable* const* g_tables, int n_sets, uint64_t k,
                            uint32_t* d_new_mask, void* stream);
+/* The same for gradient tensors that are NEW since the tables were filled — the normal case: every backward pass
+ * (train.py:270-280) allocates its gradients.  h_ptrs[i][t] = device pointer of segment t of gradient set i
+ * (as for b200p_ptrtables_update).  The sample kernel writes the per-chunk tables on its way, so the build is
+ * one launch shorter than b200p_ptrtables_update + b200p_snip_mask_build; it falls back to that pair when
+ * n_sets > 8, n_sets * n_segments > 1024, or the fused path is unavailable. */
+int  b200p_snip_mask_build_refresh(b200p_plan* plan, b200p_ptrtable* const* g_tables, const void* const* const* h_ptrs,
+                                   int n_sets, uint64_t k, uint32_t* d_new_mask, void* stream);
 /* The score + select half of it (= b200p_score_accumulate_multi + b200p_select_kth(KEY_SCORE, NULL, k, SNIP_STRICT)):
  * the caller issues its own b200p_emit_masks afterwards (e.g. with an old mask to AND with, or fp32 mask outputs).
  * d_prov_target: nullable, where the provisional mask of the sweep goes (the d_new_mask of a following plain emit). */

@@ -92,6 +92,7 @@ SIGNATURES = {
     "b200p_emit_masks": (_I, [_P, _I, _I, _I, _F, _P, _P, _I, _I64, _I64, _P]),
     "b200p_mask_build": (_I, [_P, _I, _P, _U64, _I, _P, _P]),
     "b200p_snip_mask_build": (_I, [_P, ctypes.POINTER(_P), _I, _U64, _P, _P]),
+    "b200p_snip_mask_build_refresh": (_I, [_P, ctypes.POINTER(_P), ctypes.POINTER(_P), _I, _U64, _P, _P]),
     "b200p_snip_score_select": (_I, [_P, ctypes.POINTER(_P), _I, _U64, _P, _P]),
     "b200p_count_zeros": (_I, [_P, _P, _P, _I, _P]),
     "b200p_mask_pack_from_f32": (_I, [_P, _P, _P]),

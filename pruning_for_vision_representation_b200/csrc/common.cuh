@@ -59,6 +59,11 @@ __device__ __forceinline__ T* chunk_ptr(ChunkTab tab, int64_t c) {
     return reinterpret_cast<T*>(__ldg(reinterpret_cast<const unsigned long long*>(tab) + c));
 }
 
+// segment pointers that travel as kernel arguments (b200p_ptrtables_update; the SNIP sample kernel that refreshes the gradient
+// tables itself): table t's pointer of segment g sits at p[t * n_seg + g]
+constexpr int kMultiPtrs = 1024, kMultiTabs = 16;
+struct PtrPackBig { void* p[kMultiPtrs]; };
+
 // up to 8 gradient sets (one per-chunk pointer table each) folded by one score launch
 constexpr int kMaxSets = 8;
 struct GradTabs { ChunkTab t[kMaxSets]; };

@@ -265,8 +265,6 @@ extern "C" int b200p_ptrtable_create(b200p_plan* p, int slot, const void* const*
 
 namespace b200p {
 // several tables in one launch: up to 1024 segment pointers travel as kernel arguments
-constexpr int kMultiPtrs = 1024, kMultiTabs = 16;
-struct PtrPackBig { void* p[kMultiPtrs]; };
 struct TabPack { void** tab[kMultiTabs]; };
 __global__ void k_fill_chunk_ptrs_multi(TabPack tabs, const int32_t* __restrict__ chunk_seg, const int64_t* __restrict__ chunk_elem0,
                                         PtrPackBig pack, int n_seg, int n_tabs, int elem_size, int64_t n_chunks) {

@@ -1262,9 +1262,12 @@ __device__ __forceinline__ float snip_score1(const float* __restrict__ w, const 
 // (16 x 4 keys per chunk) took 33 us for ResNet-50, twice the plain sample.  Neighbouring keys are correlated
 // (same filter), so the bracket margin is 12 sigma instead of 8 (SampleArgs::sigmas).
 constexpr int kSnipGranulesPerChunk = 4;
-template <bool ACC, int B>
-__global__ void __launch_bounds__(kThreads)
-k_snip_sample(SampleArgs a, ChunkTab w_tab, GradTabs g_tabs, ChunkTab s_tab) {
+// REFRESH: the gradient tensors of this build are new (fresh backward passes): their per-chunk pointer tables are written by
+// this kernel — the thread that samples a chunk's first granule derives the chunk's pointers from the segment pointers in the
+// kernel arguments anyway — instead of by a launch of their own before it (b200p_snip_mask_build_refresh).
+struct RefreshArgs { PtrPackBig pack; const int32_t* chunk_seg; const int64_t* chunk_elem0; int n_seg; };
+template <bool ACC, int B, bool REFRESH>
+__device__ __forceinline__ void snip_sample_body(const SampleArgs& a, ChunkTab w_tab, const GradTabs& g_tabs, ChunkTab s_tab, const RefreshArgs* rf) {
     __shared__ uint32_t s_hist[kHistBins];
     __shared__ unsigned long long s_warp[9];
     __shared__ uint32_t s_bkt[2];
@@ -1280,8 +1283,18 @@ k_snip_sample(SampleArgs a, ChunkTab w_tab, GradTabs g_tabs, ChunkTab s_tab) {
         const float* w = chunk_ptr<const float>(w_tab, c);
         const float* sc = ACC ? chunk_ptr<const float>(s_tab, c) : nullptr;
         const float* g[B];
+        if (REFRESH) {
+            const int seg = __ldg(rf->chunk_seg + c);
+            const int64_t el = __ldg(rf->chunk_elem0 + c);
 #pragma unroll
-        for (int b = 0; b < B; ++b) g[b] = chunk_ptr<const float>(g_tabs.t[b], c);
+            for (int b = 0; b < B; ++b) {
+                g[b] = reinterpret_cast<const float*>(rf->pack.p[b * rf->n_seg + seg]) + el;
+                if (i == 0) const_cast<void**>(g_tabs.t[b])[c] = const_cast<float*>(g[b]);       // every chunk has a granule 0
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < B; ++b) g[b] = chunk_ptr<const float>(g_tabs.t[b], c);
+        }
         if (e0 >= n) continue;
         float v[8]; int cnt = 0;
         if (a.vec_ok && e0 + 7 < n) {
@@ -1299,6 +1312,16 @@ k_snip_sample(SampleArgs a, ChunkTab w_tab, GradTabs g_tabs, ChunkTab s_tab) {
     flush_hist(s_hist, a.hist, true);
     if (!last_cta_arrives(a.ticket)) return;
     sample_tail(a, nullptr, s_warp, s_bkt, s_hist);
+}
+template <bool ACC, int B>
+__global__ void __launch_bounds__(kThreads)
+k_snip_sample(SampleArgs a, ChunkTab w_tab, GradTabs g_tabs, ChunkTab s_tab) {
+    snip_sample_body<ACC, B, false>(a, w_tab, g_tabs, s_tab, nullptr);
+}
+template <bool ACC, int B>
+__global__ void __launch_bounds__(kThreads)
+k_snip_refresh_sample(SampleArgs a, ChunkTab w_tab, GradTabs g_tabs, ChunkTab s_tab, const __grid_constant__ RefreshArgs rf) {
+    snip_sample_body<ACC, B, true>(a, w_tab, g_tabs, s_tab, &rf);
 }
 
 template <bool ACC, int B>
@@ -2020,6 +2043,19 @@ static cudaError_t launch_snip_sample(int nb, int grid, cudaStream_t st, const S
     }
 }
 template <bool ACC>
+static cudaError_t launch_snip_refresh_sample(int nb, int grid, cudaStream_t st, const SampleArgs& sa, ChunkTab w, const GradTabs& g, ChunkTab s, const RefreshArgs& rf) {
+    switch (nb) {
+        case 1: return launch_kernel(k_snip_refresh_sample<ACC, 1>, grid, st, sa, w, g, s, rf);
+        case 2: return launch_kernel(k_snip_refresh_sample<ACC, 2>, grid, st, sa, w, g, s, rf);
+        case 3: return launch_kernel(k_snip_refresh_sample<ACC, 3>, grid, st, sa, w, g, s, rf);
+        case 4: return launch_kernel(k_snip_refresh_sample<ACC, 4>, grid, st, sa, w, g, s, rf);
+        case 5: return launch_kernel(k_snip_refresh_sample<ACC, 5>, grid, st, sa, w, g, s, rf);
+        case 6: return launch_kernel(k_snip_refresh_sample<ACC, 6>, grid, st, sa, w, g, s, rf);
+        case 7: return launch_kernel(k_snip_refresh_sample<ACC, 7>, grid, st, sa, w, g, s, rf);
+        default: return launch_kernel(k_snip_refresh_sample<ACC, 8>, grid, st, sa, w, g, s, rf);
+    }
+}
+template <bool ACC>
 static cudaError_t launch_snip_sweep(int nb, int grid, cudaStream_t st, const PassArgs& a, ChunkTab w, const GradTabs& g, int vec) {
     switch (nb) {
         case 1: return launch_kernel(k_snip_score_sweep<ACC, 1>, grid, st, a, w, g, vec);
@@ -2033,8 +2069,15 @@ static cudaError_t launch_snip_sweep(int nb, int grid, cudaStream_t st, const Pa
     }
 }
 
+// refresh: segment pointers of the (new) gradient tensors behind g_tables; the sample kernel writes the tables itself
+static int snip_score_select_impl(b200p_plan* p, const b200p_ptrtable* const* g_tables, int n_sets, uint64_t k,
+                                  uint32_t* d_prov_target, void* stream, const RefreshArgs* refresh);
 extern "C" int b200p_snip_score_select(b200p_plan* p, const b200p_ptrtable* const* g_tables, int n_sets, uint64_t k,
                                        uint32_t* d_prov_target, void* stream) {
+    return snip_score_select_impl(p, g_tables, n_sets, k, d_prov_target, stream, nullptr);
+}
+static int snip_score_select_impl(b200p_plan* p, const b200p_ptrtable* const* g_tables, int n_sets, uint64_t k,
+                                  uint32_t* d_prov_target, void* stream, const RefreshArgs* refresh) {
     B200P_REQUIRE(p != nullptr && g_tables != nullptr, B200P_EINVAL, "snip_mask_build: null argument");
     B200P_REQUIRE(n_sets >= 1, B200P_EINVAL, "snip_mask_build: need at least one gradient set");
     B200P_REQUIRE(p->bound[B200P_SLOT_W] && p->bound[B200P_SLOT_SCORE], B200P_ESTATE, "snip_mask_build: W and SCORE slots must be bound");
@@ -2067,8 +2110,13 @@ extern "C" int b200p_snip_score_select(b200p_plan* p, const b200p_ptrtable* cons
     sa.ticket = ticket_ptr(p); sa.n_chunks = p->n_chunks; sa.c_begin = 0; sa.comm_seq = 0u; sa.cache = nullptr; sa.vec_ok = vec ? 1 : 0;
     sa.k = k; sa.n_total = (unsigned long long)p->total; sa.mode = (uint32_t)B200P_MODE_SNIP_STRICT; sa.sigmas = 12u; sa.slot_shift = 4;
     const int64_t sblocks = (p->n_chunks * kSnipGranulesPerChunk + kThreads - 1) / kThreads;      // one granule per thread
-    if (acc) B200P_CUDA(launch_snip_sample<true>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE)));
-    else     B200P_CUDA(launch_snip_sample<false>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE)));
+    if (refresh) {
+        if (acc) B200P_CUDA(launch_snip_refresh_sample<true>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE), *refresh));
+        else     B200P_CUDA(launch_snip_refresh_sample<false>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE), *refresh));
+    } else {
+        if (acc) B200P_CUDA(launch_snip_sample<true>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE)));
+        else     B200P_CUDA(launch_snip_sample<false>(nb, p->grid_for(sblocks, 4), st, sa, p->tab(B200P_SLOT_W), g, p->tab(B200P_SLOT_SCORE)));
+    }
     B200P_LAUNCH_CHECK("k_snip_sample");
     // A': score + sweep
     PassArgs a;
@@ -2089,6 +2137,49 @@ extern "C" int b200p_snip_mask_build(b200p_plan* p, const b200p_ptrtable* const*
     p->fuse_emit = false;
     if (rc) { p->prov_target = nullptr; return rc; }
     if (p->emit_done) {                       // the finish kernel patched the mask itself
+        p->emit_done = false; p->prov_armed = false; p->prov_target = nullptr;
+        return B200P_OK;
+    }
+    return b200p_emit_masks(p, B200P_KEY_SCORE, B200P_MODE_SNIP_STRICT, 0, 0.f, nullptr, d_new_mask, 0, 0, -1, stream);
+}
+
+// b200p_snip_mask_build for gradient tensors that are new since the tables were filled (every real build: each backward pass
+// allocates its gradients): h_ptrs[i][t] is the device pointer of segment t of gradient set i.  One launch less than
+// b200p_ptrtables_update + b200p_snip_mask_build: the sample kernel writes the per-chunk tables on its way.  Falls back to
+// that pair when the pointers do not fit the kernel arguments (n_sets * n_seg > 1024), when there are more than 8 sets, or
+// when the fused path is not available (exact select, no cooperative launch).
+extern "C" int b200p_snip_mask_build_refresh(b200p_plan* p, b200p_ptrtable* const* g_tables, const void* const* const* h_ptrs, int n_sets,
+                                             uint64_t k, uint32_t* d_new_mask, void* stream) {
+    B200P_REQUIRE(p != nullptr && g_tables != nullptr && h_ptrs != nullptr && d_new_mask != nullptr, B200P_EINVAL, "snip_mask_build_refresh: null argument");
+    B200P_REQUIRE(n_sets >= 1, B200P_EINVAL, "snip_mask_build_refresh: need at least one gradient set");
+    for (int i = 0; i < n_sets; ++i)
+        B200P_REQUIRE(g_tables[i] != nullptr && g_tables[i]->plan == p && h_ptrs[i] != nullptr, B200P_EINVAL, "snip_mask_build_refresh: tables must belong to this plan");
+    { int rc = coop_ctas(p); if (rc) return rc; }
+    const bool fused_ok = n_sets <= kMaxSets && (long long)n_sets * p->n_seg <= kMultiPtrs && p->select_impl != B200P_SELECT_EXACT &&
+                          p->coop_ctas_per_sm > 0 && k >= 1 && k <= (uint64_t)p->total;
+    if (!fused_ok) {
+        int rc = b200p_ptrtables_update(g_tables, h_ptrs, n_sets, B200P_SLOT_G, stream); if (rc) return rc;
+        return b200p_snip_mask_build(p, (const b200p_ptrtable* const*)g_tables, n_sets, k, d_new_mask, stream);
+    }
+    RefreshArgs rf;
+    rf.chunk_seg = p->d_chunk_seg; rf.chunk_elem0 = p->d_chunk_elem0; rf.n_seg = p->n_seg;
+    for (int i = 0; i < n_sets; ++i) {
+        bool vec = true;
+        for (int t = 0; t < p->n_seg; ++t) {
+            const void* q = h_ptrs[i][t];
+            B200P_REQUIRE(q != nullptr, B200P_EINVAL, "snip_mask_build_refresh: null segment pointer");
+            rf.pack.p[i * p->n_seg + t] = const_cast<void*>(q);
+            if ((uintptr_t)q & 15u) vec = false;
+        }
+        g_tables[i]->vec_ok = vec;
+        for (int sl = 0; sl < B200P_NUM_SLOTS; ++sl)
+            if (p->d_tab[sl] == g_tables[i]->d_tab) p->vec_ok[sl] = vec;
+    }
+    p->fuse_emit = true; p->emit_done = false;
+    int rc = snip_score_select_impl(p, (const b200p_ptrtable* const*)g_tables, n_sets, k, d_new_mask, stream, &rf);
+    p->fuse_emit = false;
+    if (rc) { p->prov_target = nullptr; return rc; }
+    if (p->emit_done) {
         p->emit_done = false; p->prov_armed = false; p->prov_target = nullptr;
         return B200P_OK;
     }

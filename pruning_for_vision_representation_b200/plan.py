@@ -189,6 +189,20 @@ class ParamPlan:
         check(self.lib.b200p_snip_mask_build(self.handle, arr, n, int(k), _ptr(new_mask), _stream_ptr(self.device)),
               "snip_mask_build")
 
+    def snip_mask_build_refresh(self, tables, tensor_lists, k, new_mask):
+        """snip_mask_build for gradient tensors that are new since the tables were filled (fresh backward passes): the
+        sample kernel re-points the tables itself — one launch less than update_tables + snip_mask_build."""
+        arr, n = self._table_array(tables, "snip_mask_build_refresh")
+        arrs = []
+        for tab, tensors in zip(tables, tensor_lists):
+            tensors, ptrs = self._validate(SLOT_G, tensors)
+            tab.tensors = tensors
+            arrs.append(ptrs)
+        ptr_arr = (ctypes.c_void_p * n)(*[ctypes.cast(a, ctypes.c_void_p) for a in arrs])
+        self._update_keepalive = arrs
+        check(self.lib.b200p_snip_mask_build_refresh(self.handle, arr, ptr_arr, n, int(k), _ptr(new_mask), _stream_ptr(self.device)),
+              "snip_mask_build_refresh")
+
     def snip_score_select(self, tables, k, prov_target=None):
         """The score + select half of snip_mask_build; follow with emit_masks."""
         arr, n = self._table_array(tables, "snip_score_select")

@@ -261,6 +261,48 @@ def test_select_edge_cases(case, cand_capacity):
             assert res["passes_full"] == (3 if SELECT_IMPL == "exact" else 4)
 
 
+@pytest.mark.parametrize("misalign", [False, True])
+@pytest.mark.parametrize("n_sets", [1, 3, 8, 9])
+def test_snip_mask_build_refresh_repoints_the_tables(misalign, n_sets):
+    """b200p_snip_mask_build_refresh: the tables still point at LAST build's gradient tensors (overwritten with garbage
+    here); the sample kernel re-points them at the new ones itself.  Same scores, mask and result block as
+    update_tables + snip_mask_build; 9 sets take the documented fallback (table update + build)."""
+    rng = np.random.default_rng(500 + n_sets)
+    sizes = [500_001, 4096 * 21, 77_777, 33, 4096]
+    w = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    plan = make_plan(w)
+    plan.bind(L.SLOT_W, to_dev(w, misalign))
+    stale = [to_dev([np.full(n, 1e30, np.float32) for n in sizes]) for _ in range(n_sets)]
+    tables = [plan.pointer_table(L.SLOT_G, st) for st in stale]
+    for build in range(2):                                               # two builds: fresh tensors each time
+        g = [[(1e-3 * rng.standard_normal(n)).astype(np.float32) for n in sizes] for _ in range(n_sets)]
+        gd = [to_dev(gb, misalign) for gb in g]
+        k = PO.snip_k(plan.total, 0.9 if build == 0 else 0.5)
+        s_new = [torch.full((n,), -3.0, device=DEV) for n in sizes]
+        plan.bind(L.SLOT_SCORE, s_new)
+        m_new = plan.new_mask(); plan.snip_mask_build_refresh(tables, gd, k, m_new)
+        r_new = plan.result()
+        # reference: explicit table update, then the plain fused build, on a second plan
+        ref = make_plan(w)
+        ref.bind(L.SLOT_W, to_dev(w, misalign))
+        s_ref = [torch.zeros(n, device=DEV) for n in sizes]
+        ref.bind(L.SLOT_SCORE, s_ref)
+        rt = [ref.pointer_table(L.SLOT_G, gb) for gb in gd]
+        m_ref = ref.new_mask(); ref.snip_mask_build(rt, k, m_ref)
+        r_ref = ref.result()
+        for a, b in zip(s_new, s_ref):
+            assert torch.equal(a, b)
+        assert torch.equal(m_new, m_ref)
+        for key in ("k", "n_less", "n_equal", "n_kept", "threshold", "thr_key"):
+            assert r_new[key] == r_ref[key], key
+        exp, thr, _ = PO.snip_pruning(w, g, 0.9 if build == 0 else 0.5)
+        for got, e in zip(gpu_masks(plan, m_new), exp):
+            assert np.array_equal(got, np.asarray(e).reshape(-1).astype(bool))
+        # the tables now point at this build's tensors: the plain build gives the same mask again
+        m_again = plan.new_mask(); plan.snip_mask_build(tables, k, m_again)
+        assert torch.equal(m_again, m_new)
+
+
 def test_snip_strict_degenerate():
     """All scores zero -> threshold 0 -> everything pruned (fresh ViT head)."""
     sizes = [4096 * 2, 100]
